@@ -1,0 +1,99 @@
+"""Re-export the reference's own golden vectors for the PWC propagator path as .npz fixtures.
+
+Run HERE (the build container), where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+The reference pickles hold ``tf.EagerTensor`` objects; TensorFlow is not installable in this
+image, so they are read with a stub unpickler.  Nothing is computed
+except the dressed collapse operators of the two-qubit chip, which the pickle does not carry
+and which are rebuilt from test/conftest.py:259-320 via oracle/c3_model_oracle.py.
+
+Sources (relative to the reference checkout):
+  test/two_qubit_data.pickle      <- test/test_two_qubits.py:46-62,193-213
+  test/transmon_expanded.pickle   <- test/test_transmon_expanded.py:252-283
+  test/test_tf_utils.pickle       <- test/test_tf_utils.py:81-111
+"""
+import os
+import pickle
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+REF = os.environ.get("C3_REFERENCE", "/root/reference")
+
+from oracle import c3_model_oracle as mo  # noqa: E402
+
+
+class _StubUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if module.startswith("tensorflow"):
+            return lambda *a, **k: np.asarray(a[0])
+        if module.startswith("numpy.core"):
+            module = module.replace("numpy.core", "numpy._core")
+        return super().find_class(module, name)
+
+
+def load(name):
+    with open(os.path.join(REF, "test", name), "rb") as f:
+        return _StubUnpickler(f).load()
+
+
+def two_qubit():
+    d = load("two_qubit_data.pickle")
+    # collapse operators: dims [2,2], T1 = 20 us, T2* = 40 us for both qubits, dressed basis
+    dims = [2, 2]
+    a1, a2 = mo.annihilators(dims)
+    drift = (2 * np.pi * 5e9) * mo.resonator(a1) + (2 * np.pi * 5.6e9) * mo.resonator(a2) \
+        + (2 * np.pi * 20e6) * mo.int_XX(a1, a2)
+    _, T = mo.dressing_transform(drift)
+    col_ops = np.stack([mo.dress(T, mo.qubit_collapse_op(a, t1=20e-6, t2star=40e-6)) for a in (a1, a2)])
+    h0_rebuilt = mo.dress(T, drift)
+    hks_rebuilt = np.stack([mo.dress(T, mo.x_drive(a)) for a in (a1, a2)])
+    np.savez_compressed(
+        os.path.join(HERE, "two_qubit.npz"),
+        hdrift=d["hdrift"], hks=np.stack([d["hks"]["d1"], d["hks"]["d2"]]),
+        signals=np.stack([d["signal"]["d1"]["values"], d["signal"]["d2"]["values"]]),
+        ts=d["signal"]["d1"]["ts"], propagator=d["propagator"],
+        lindblad_propagator=d["lindblad_propagator"], col_ops=col_ops,
+        h0_rebuilt=h0_rebuilt, hks_rebuilt=hks_rebuilt,
+    )
+
+
+def transmon_expanded():
+    d = load("transmon_expanded.pickle")
+    np.savez_compressed(
+        os.path.join(HERE, "transmon_expanded.npz"),
+        dims=np.array([6, 4]), max_excitations=np.array(4),
+        ts_q1=d["signal_q1"]["ts"], ts_q2=d["signal_q2"]["ts"],
+        hamiltonians_q1=d["hamiltonians_q1"], hamiltonians_q2=d["hamiltonians_q2"],
+        partial_propagators_q1=d["partial_propagators_q1"],
+        partial_propagators_q2=d["partial_propagators_q2"],
+        propagators_q1=d["propagators_q1"], propagators_q2=d["propagators_q2"],
+    )
+
+
+def tf_utils():
+    d = load("test_tf_utils.pickle")
+    out = {}
+    for key in ("tf_kron", "tf_spre", "tf_spost", "Id_like"):
+        for i, el in enumerate(d[key]):
+            if key == "tf_kron":
+                out[f"{key}_{i}_inA"], out[f"{key}_{i}_inB"] = el["in"]
+            else:
+                out[f"{key}_{i}_in"] = el["in"]
+            out[f"{key}_{i}_desired"] = el["desired"]
+    el = d["tf_super"][0]   # the two tf_super cases are 5x100x100 each; one is kept
+    out["tf_super_0_in"], out["tf_super_0_desired"] = el["in"], el["desired"]
+    np.savez_compressed(os.path.join(HERE, "tf_utils.npz"), **out)
+
+
+if __name__ == "__main__":
+    two_qubit()
+    transmon_expanded()
+    tf_utils()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
