@@ -1,0 +1,70 @@
+"""ctypes binding of libc3b200.so (include/c3b200.h).  There is NO fallback: if the CUDA
+library is missing, importing the engine raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libc3b200.so")
+
+#: every symbol include/c3b200.h declares (checked by tests/test_cabi.py)
+SYMBOLS = [
+    "c3b_version", "c3b_last_error", "c3b_pwc_workspace_bytes", "c3b_pwc_closed", "c3b_pwc_closed_hlist",
+    "c3b_pwc_lindblad", "c3b_product_workspace_bytes", "c3b_ordered_product", "c3b_seq_product", "c3b_kron",
+    "c3b_set_tuning", "c3b_pwc_path", "c3b_measure_fp64_peak", "c3b_microbench",
+]
+
+_lib = None
+
+
+class C3BError(Exception):
+    """Raised when a C-ABI call returns a non-zero status; message starts with 'C3:ERROR:'
+    like the reference's own exceptions (c3/experiment.py:464-468)."""
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"C3:ERROR: {LIB_PATH} is missing. Build it with `python -m c3_b200.build` "
+            "(needs nvcc; there is no CPU fallback for the propagator path)."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, i, d = C.c_void_p, C.c_size_t, C.c_int, C.c_double
+    lib.c3b_version.restype = i
+    lib.c3b_last_error.restype = C.c_char_p
+    lib.c3b_pwc_workspace_bytes.restype = sz
+    lib.c3b_pwc_workspace_bytes.argtypes = [i, i, i, i, i, i]
+    lib.c3b_pwc_closed.restype = i
+    lib.c3b_pwc_closed.argtypes = [vp, vp, vp, d, i, i, i, i, i, vp, vp, vp, sz, vp]
+    lib.c3b_pwc_closed_hlist.restype = i
+    lib.c3b_pwc_closed_hlist.argtypes = [vp, d, i, i, i, vp, vp, vp, sz, vp]
+    lib.c3b_pwc_lindblad.restype = i
+    lib.c3b_pwc_lindblad.argtypes = [vp, vp, vp, i, vp, d, i, i, i, i, i, vp, vp, vp, sz, vp]
+    lib.c3b_product_workspace_bytes.restype = sz
+    lib.c3b_product_workspace_bytes.argtypes = [i, i, i]
+    lib.c3b_ordered_product.restype = i
+    lib.c3b_ordered_product.argtypes = [vp, i, i, i, vp, vp, sz, vp]
+    lib.c3b_seq_product.restype = i
+    lib.c3b_seq_product.argtypes = [vp, i, vp, vp, i, i, i, vp, vp, sz, vp]
+    lib.c3b_kron.restype = i
+    lib.c3b_kron.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, vp]
+    lib.c3b_set_tuning.restype = i
+    lib.c3b_set_tuning.argtypes = [C.c_char_p, C.c_longlong]
+    lib.c3b_pwc_path.restype = i
+    lib.c3b_pwc_path.argtypes = [i, i, i]
+    lib.c3b_measure_fp64_peak.restype = d
+    lib.c3b_measure_fp64_peak.argtypes = [i, i, d]
+    lib.c3b_microbench.restype = d
+    lib.c3b_microbench.argtypes = [i, i, i]
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().c3b_last_error().decode("utf-8", "replace")
+        raise C3BError(msg or f"C3:ERROR: libc3b200 call failed with status {rc}")

@@ -1,0 +1,436 @@
+// C ABI of libc3b200.so -- see include/c3b200.h for the contract of every entry point.
+// Single translation unit: nvcc -gencode arch=compute_100a,code=sm_100a.
+#include "../../include/c3b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "c3b_common.cuh"
+#include "pwc_cta.cuh"
+#include "pwc_rows.cuh"
+#include "product.cuh"
+#include "peak.cuh"
+
+using namespace c3b;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) return fail(C3B_ECUDA, "C3:ERROR: %s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- tuning (process-wide) -------------------------------------------------------------------
+long long g_target_units = 32768;  // rows kernel: aim for this many warp work units per launch
+long long g_force_cta = 0;         // route everything to the CTA kernel (testing)
+long long g_min_chunk = 8;         // rows kernel: minimum slices per lane group
+
+int num_sms() {
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+        cached = n;
+    else {
+        cudaGetLastError();
+        return 148;  // B200; used only for sizing when no device is visible
+    }
+    return cached;
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+constexpr int kRowsWarps = 4;
+const int kRowsDims[] = {2, 3, 4, 5, 6, 8, 9, 10, 12};
+
+int rows_template_dim(int D) {
+    for (int t : kRowsDims)
+        if (D <= t) return t;
+    return 0;
+}
+
+int pwc_path(int K, int D, int batched_model) {
+    (void)K;
+    if (!g_force_cta && !batched_model && rows_template_dim(D) != 0) return 1;
+    return D <= 32 ? 2 : 3;
+}
+
+size_t cta_smem_bytes(int D) { return (((size_t)D * sizeof(int) + 15) & ~(size_t)15) + (size_t)kCtaSlots * D * D * sizeof(cplx); }
+
+int cta_grid(int D, long long units) {
+    int per_sm = 1;
+    if (D <= 32) {
+        const size_t sm = cta_smem_bytes(D);
+        per_sm = (int)((size_t)220 * 1024 / (sm + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+    } else {
+        per_sm = 2;
+    }
+    long long g = (long long)num_sms() * per_sm;
+    if (g > units) g = units;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+struct Plan {
+    int path;      // 1 rows, 2 cta smem, 3 cta global
+    int S;         // segments per batch element
+    int seg_len;
+    int grid;      // CTA kernel grid (persistent)
+    size_t off_G, off_RS, off_seg, off_cta, off_prod, total;
+};
+
+Plan make_plan(int B, int K, int N, int D, int batched_model, bool hlist) {
+    Plan pl{};
+    pl.path = pwc_path(K, D, batched_model);
+    const int Bm = batched_model ? B : 1;
+    if (pl.path == 1) {
+        const int TD = rows_template_dim(D);
+        const int G = 32 / TD;
+        long long S = (g_target_units + B - 1) / B;
+        long long smax = N / (g_min_chunk * G);
+        if (smax < 1) smax = 1;
+        if (S > smax) S = smax;
+        if (S < 1) S = 1;
+        pl.S = (int)S;
+    } else {
+        const long long want = 4LL * num_sms() * (D <= 32 ? 2 : 2);
+        long long S = (want + B - 1) / B;
+        long long smax = N / 8;
+        if (smax < 1) smax = 1;
+        if (S > smax) S = smax;
+        if (S < 1) S = 1;
+        pl.S = (int)S;
+    }
+    pl.seg_len = (N + pl.S - 1) / pl.S;
+    pl.S = (N + pl.seg_len - 1) / pl.seg_len;  // drop empty trailing segments
+    if (pl.S < 1) pl.S = 1;
+    pl.grid = cta_grid(D, (long long)B * pl.S);
+    size_t off = 0;
+    pl.off_G = off;
+    if (!hlist) off += align_up((size_t)Bm * (K + 1) * D * D * sizeof(cplx));
+    pl.off_RS = off;
+    if (!hlist) off += align_up((size_t)Bm * (K + 1) * D * sizeof(double));
+    pl.off_seg = off;
+    if (pl.S > 1) off += align_up((size_t)B * pl.S * D * D * sizeof(cplx));
+    pl.off_cta = off;
+    if (pl.path == 3) off += align_up((size_t)pl.grid * kCtaSlots * D * D * sizeof(cplx));
+    pl.off_prod = off;
+    if (pl.S > 1 && D > 64) off += align_up((size_t)cta_grid(D, 1LL << 40) * 2 * D * D * sizeof(cplx));
+    pl.total = off < 256 ? 256 : off;
+    return pl;
+}
+
+// ---- launches ----------------------------------------------------------------------------------
+
+template <int D, int MINB>
+int launch_rows_t(const RowsParams& rp, cudaStream_t st) {
+    using L = RowsLayout<D, kRowsWarps>;
+    const size_t smem = L::smem_bytes(rp.K);
+    if (smem > 227 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: too many control lines (K=%d) for the d=%d register kernel", rp.K, rp.d);
+    auto kern = pwc_rows_kernel<D, kRowsWarps, MINB>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long units = (long long)rp.B * rp.S;
+    const int grid = (int)((units + kRowsWarps - 1) / kRowsWarps);
+    kern<<<grid, kRowsWarps * 32, smem, st>>>(rp);
+    CUDA_TRY(cudaGetLastError());
+    return C3B_OK;
+}
+
+int launch_rows(const RowsParams& rp, cudaStream_t st) {
+    switch (rows_template_dim(rp.d)) {
+        case 2: return launch_rows_t<2, 4>(rp, st);
+        case 3: return launch_rows_t<3, 4>(rp, st);
+        case 4: return launch_rows_t<4, 4>(rp, st);
+        case 5: return launch_rows_t<5, 4>(rp, st);
+        case 6: return launch_rows_t<6, 3>(rp, st);
+        case 8: return launch_rows_t<8, 3>(rp, st);
+        case 9: return launch_rows_t<9, 3>(rp, st);
+        case 10: return launch_rows_t<10, 2>(rp, st);
+        case 12: return launch_rows_t<12, 2>(rp, st);
+    }
+    return fail(C3B_EUNSUPPORTED, "C3:ERROR: no register kernel for d=%d", rp.d);
+}
+
+template <int CT, int TR, int TC>
+int launch_cta_t(const CtaParams& cp, int grid, cudaStream_t st) {
+    auto kern = pwc_cta_kernel<CT, TR, TC>;
+    size_t smem = cp.use_smem ? cta_smem_bytes(cp.D) : (((size_t)cp.D * sizeof(int) + 15) & ~(size_t)15);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kCtaThreads, smem, st>>>(cp);
+    CUDA_TRY(cudaGetLastError());
+    return C3B_OK;
+}
+
+int launch_cta(const CtaParams& cp, int grid, cudaStream_t st) {
+    const int D = cp.D;
+    if (D <= 16) return launch_cta_t<16, 1, 1>(cp, grid, st);
+    if (D <= 32) return launch_cta_t<32, 4, 1>(cp, grid, st);
+    if (D <= 64) return launch_cta_t<32, 4, 2>(cp, grid, st);
+    return launch_cta_t<32, 4, 3>(cp, grid, st);
+}
+
+template <int CT, int TR, int TC>
+int launch_product_t(const ProductParams& pp, int grid, cudaStream_t st) {
+    auto kern = product_kernel<CT, TR, TC>;
+    const size_t smem = pp.use_smem ? (size_t)2 * pp.D * pp.D * sizeof(cplx) : 0;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kCtaThreads, smem, st>>>(pp);
+    CUDA_TRY(cudaGetLastError());
+    return C3B_OK;
+}
+
+int launch_product(ProductParams pp, cudaStream_t st) {
+    const int D = pp.D;
+    pp.use_smem = D <= 64;
+    const long long units = (long long)pp.B * pp.S;
+    long long g = pp.use_smem ? (long long)num_sms() * 4 : cta_grid(D, pp.B);
+    if (g > units) g = units;
+    if (g < 1) g = 1;
+    if (D <= 16) return launch_product_t<16, 1, 1>(pp, (int)g, st);
+    if (D <= 32) return launch_product_t<32, 4, 1>(pp, (int)g, st);
+    if (D <= 64) return launch_product_t<32, 4, 2>(pp, (int)g, st);
+    return launch_product_t<32, 4, 3>(pp, (int)g, st);
+}
+
+// common tail of the three pwc entry points once G (or the H list) is in place
+int run_pwc(const Plan& pl, const cplx* G, const double* RS, const double* signals, const cplx* hlist, double dt,
+            int B, int K, int N, int D, int batched_model, cplx* U_out, cplx* dUs_out, char* ws, cudaStream_t st) {
+    cplx* seg = pl.S > 1 ? reinterpret_cast<cplx*>(ws + pl.off_seg) : nullptr;
+    if (pl.path == 1) {
+        RowsParams rp{};
+        rp.G = G; rp.RS = RS; rp.signals = signals; rp.hlist = hlist;
+        rp.hscale_re = 0.0; rp.hscale_im = -dt;
+        rp.model_stride = 0;
+        rp.B = B; rp.K = K; rp.N = N; rp.d = D; rp.S = pl.S; rp.seg_len = pl.seg_len;
+        rp.U_out = U_out; rp.seg_out = seg; rp.dUs_out = dUs_out;
+        int rc = launch_rows(rp, st);
+        if (rc) return rc;
+    } else {
+        CtaParams cp{};
+        cp.G = G; cp.signals = signals; cp.hlist = hlist;
+        cp.hscale_re = 0.0; cp.hscale_im = -dt;
+        cp.model_stride = batched_model ? (long long)(K + 1) * D * D : 0;
+        cp.B = B; cp.K = K; cp.N = N; cp.D = D; cp.S = pl.S; cp.seg_len = pl.seg_len;
+        cp.U_out = U_out; cp.seg_out = seg; cp.dUs_out = dUs_out;
+        cp.ws = reinterpret_cast<cplx*>(ws + pl.off_cta);
+        cp.use_smem = pl.path == 2;
+        int rc = launch_cta(cp, pl.grid, st);
+        if (rc) return rc;
+    }
+    if (pl.S > 1) {
+        ProductParams pp{};
+        pp.mats = seg; pp.idx = nullptr; pp.lens = nullptr;
+        pp.B = B; pp.M = pl.S; pp.D = D; pp.S = 1; pp.seg_len = pl.S;
+        pp.out = U_out; pp.ws = reinterpret_cast<cplx*>(ws + pl.off_prod);
+        int rc = launch_product(pp, st);
+        if (rc) return rc;
+    }
+    return C3B_OK;
+}
+
+int check_common(int B, int K, int N, int d, const void* U_out, const void* ws) {
+    if (B <= 0 || N <= 0 || d <= 0 || K < 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d N=%d d=%d)", B, K, N, d);
+    if (U_out == nullptr) return fail(C3B_EINVAL, "C3:ERROR: U_out is NULL");
+    if (ws == nullptr) return fail(C3B_EINVAL, "C3:ERROR: workspace is NULL");
+    if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return fail(C3B_EINVAL, "C3:ERROR: workspace must be 16-byte aligned");
+    return C3B_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int c3b_version(void) { return 100; }
+
+const char* c3b_last_error(void) { return g_err; }
+
+int c3b_set_tuning(const char* key, long long value) {
+    if (key == nullptr) return fail(C3B_EINVAL, "C3:ERROR: null tuning key");
+    if (!strcmp(key, "target_units")) { g_target_units = value < 1 ? 1 : value; return C3B_OK; }
+    if (!strcmp(key, "force_cta")) { g_force_cta = value; return C3B_OK; }
+    if (!strcmp(key, "min_chunk")) { g_min_chunk = value < 1 ? 1 : value; return C3B_OK; }
+    return fail(C3B_EINVAL, "C3:ERROR: unknown tuning key '%s'", key);
+}
+
+int c3b_pwc_path(int K, int D, int batched_model) { return pwc_path(K, D, batched_model); }
+
+size_t c3b_pwc_workspace_bytes(int B, int K, int N, int d, int lindblad, int batched_model) {
+    if (B <= 0 || N <= 0 || d <= 0 || K < 0) return 0;
+    const int D = lindblad ? d * d : d;
+    return make_plan(B, K, N, D, batched_model, false).total;
+}
+
+int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
+                   int batched_model, void* U_out, void* dUs_out, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+    int rc = check_common(B, K, N, d, U_out, workspace);
+    if (rc) return rc;
+    if (h0 == nullptr) return fail(C3B_EINVAL, "C3:ERROR: h0 is NULL");
+    if (K > 0 && (hks == nullptr || signals == nullptr)) return fail(C3B_EINVAL, "C3:ERROR: K=%d but hks/signals is NULL", K);
+    const Plan pl = make_plan(B, K, N, d, batched_model, false);
+    if (workspace_bytes < pl.total) return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small: %zu < %zu bytes", workspace_bytes, pl.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    cplx* G = reinterpret_cast<cplx*>(ws + pl.off_G);
+    double* RS = reinterpret_cast<double*>(ws + pl.off_RS);
+    const int Bm = batched_model ? B : 1;
+    {
+        const long long total = (long long)Bm * (K + 1) * d * d;
+        const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+        setup_closed_kernel<<<blocks, 256, 0, st>>>(static_cast<const cplx*>(h0), static_cast<const cplx*>(hks), G, Bm, K, d, dt);
+        CUDA_TRY(cudaGetLastError());
+        const long long nrows = (long long)Bm * (K + 1) * d;
+        rowsum_kernel<<<(int)((nrows * 32 + 255) / 256), 256, 0, st>>>(G, RS, nrows, d);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return run_pwc(pl, G, RS, signals, nullptr, dt, B, K, N, d, batched_model, static_cast<cplx*>(U_out),
+                   static_cast<cplx*>(dUs_out), ws, st);
+}
+
+int c3b_pwc_closed_hlist(const void* Hs, double dt, int B, int N, int d, void* U_out, void* dUs_out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(B, 0, N, d, U_out, workspace);
+    if (rc) return rc;
+    if (Hs == nullptr) return fail(C3B_EINVAL, "C3:ERROR: Hs is NULL");
+    const Plan pl = make_plan(B, 0, N, d, 0, true);
+    if (workspace_bytes < pl.total) return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small: %zu < %zu bytes", workspace_bytes, pl.total);
+    return run_pwc(pl, nullptr, nullptr, nullptr, static_cast<const cplx*>(Hs), dt, B, 0, N, d, 0,
+                   static_cast<cplx*>(U_out), static_cast<cplx*>(dUs_out), static_cast<char*>(workspace),
+                   static_cast<cudaStream_t>(stream));
+}
+
+int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C, const double* signals, double dt,
+                     int B, int K, int N, int d, int batched_model, void* U_out, void* dUs_out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    int rc = check_common(B, K, N, d, U_out, workspace);
+    if (rc) return rc;
+    if (h0 == nullptr) return fail(C3B_EINVAL, "C3:ERROR: h0 is NULL");
+    if (K > 0 && (hks == nullptr || signals == nullptr)) return fail(C3B_EINVAL, "C3:ERROR: K=%d but hks/signals is NULL", K);
+    if (C < 0 || (C > 0 && col_ops == nullptr)) return fail(C3B_EINVAL, "C3:ERROR: C=%d but col_ops is NULL", C);
+    if (d > 181) return fail(C3B_EUNSUPPORTED, "C3:ERROR: Lindblad d=%d too large", d);
+    const int D = d * d;
+    const Plan pl = make_plan(B, K, N, D, batched_model, false);
+    if (workspace_bytes < pl.total) return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small: %zu < %zu bytes", workspace_bytes, pl.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    cplx* G = reinterpret_cast<cplx*>(ws + pl.off_G);
+    double* RS = reinterpret_cast<double*>(ws + pl.off_RS);
+    const int Bm = batched_model ? B : 1;
+    {
+        const long long total = (long long)Bm * (K + 1) * D * D;
+        const int blocks = (int)((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
+        setup_lindblad_kernel<<<blocks, 256, 0, st>>>(static_cast<const cplx*>(h0), static_cast<const cplx*>(hks),
+                                                      C > 0 ? static_cast<const cplx*>(col_ops) : nullptr, G, Bm, K, C, d, dt);
+        CUDA_TRY(cudaGetLastError());
+        const long long nrows = (long long)Bm * (K + 1) * D;
+        rowsum_kernel<<<(int)((nrows * 32 + 255) / 256), 256, 0, st>>>(G, RS, nrows, D);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return run_pwc(pl, G, RS, signals, nullptr, dt, B, K, N, D, batched_model, static_cast<cplx*>(U_out),
+                   static_cast<cplx*>(dUs_out), ws, st);
+}
+
+static size_t product_scratch_bytes(int D) {
+    return D > 64 ? align_up((size_t)cta_grid(D, 1LL << 40) * 2 * D * D * sizeof(cplx)) : 0;
+}
+
+size_t c3b_product_workspace_bytes(int B, int M, int D) {
+    if (B <= 0 || M < 0 || D <= 0) return 0;
+    // [scratch for D > 64][level-1 segment results]
+    size_t off = product_scratch_bytes(D) + align_up((size_t)B * ((M + 7) / 8 + 1) * D * D * sizeof(cplx));
+    return off < 256 ? 256 : off;
+}
+
+int c3b_ordered_product(const void* mats, int B, int M, int D, void* out, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    if (B <= 0 || M <= 0 || D <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d M=%d D=%d)", B, M, D);
+    if (mats == nullptr || out == nullptr || workspace == nullptr) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (workspace_bytes < c3b_product_workspace_bytes(B, M, D)) return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    // choose segments so that the grid is filled when B is small
+    long long S = (4LL * num_sms() + B - 1) / B;
+    long long smax = (M + 7) / 8;
+    if (S > smax) S = smax;
+    if (S < 1) S = 1;
+    int seg_len = (int)((M + S - 1) / S);
+    S = (M + seg_len - 1) / seg_len;
+    cplx* scratch = reinterpret_cast<cplx*>(ws);
+    cplx* seg = reinterpret_cast<cplx*>(ws + product_scratch_bytes(D));
+    ProductParams pp{};
+    pp.mats = static_cast<const cplx*>(mats); pp.B = B; pp.M = M; pp.D = D;
+    pp.S = (int)S; pp.seg_len = seg_len; pp.out = (S > 1) ? seg : static_cast<cplx*>(out); pp.ws = scratch;
+    int rc = launch_product(pp, st);
+    if (rc) return rc;
+    if (S > 1) {
+        ProductParams p2{};
+        p2.mats = seg; p2.B = B; p2.M = (int)S; p2.D = D; p2.S = 1; p2.seg_len = (int)S;
+        p2.out = static_cast<cplx*>(out); p2.ws = scratch;
+        rc = launch_product(p2, st);
+    }
+    return rc;
+}
+
+int c3b_seq_product(const void* gates, int Gn, const int32_t* seq_idx, const int32_t* seq_len, int S, int Lmax,
+                    int D, void* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (S <= 0 || D <= 0 || Gn <= 0 || Lmax < 0) return fail(C3B_EINVAL, "C3:ERROR: bad size (S=%d D=%d Gn=%d Lmax=%d)", S, D, Gn, Lmax);
+    if (gates == nullptr || out == nullptr || seq_len == nullptr || (Lmax > 0 && seq_idx == nullptr))
+        return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (D > 64 && (workspace == nullptr || workspace_bytes < product_scratch_bytes(D)))
+        return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small");
+    ProductParams pp{};
+    pp.mats = static_cast<const cplx*>(gates); pp.idx = seq_idx; pp.lens = seq_len;
+    pp.B = S; pp.M = Lmax; pp.D = D; pp.S = 1; pp.seg_len = Lmax > 0 ? Lmax : 1;
+    pp.out = static_cast<cplx*>(out);
+    pp.ws = static_cast<cplx*>(workspace);
+    return launch_product(pp, static_cast<cudaStream_t>(stream));
+}
+
+int c3b_kron(const void* A, const void* Bm, void* out, int batch, int ra, int ca, int rb, int cb, int a_batched,
+             int b_batched, void* stream) {
+    if (batch <= 0 || ra <= 0 || ca <= 0 || rb <= 0 || cb <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size");
+    if (A == nullptr || Bm == nullptr || out == nullptr) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    const long long total = (long long)batch * ra * rb * ca * cb;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 65535) blocks = 65535;
+    kron_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const cplx*>(A), static_cast<const cplx*>(Bm), static_cast<cplx*>(out), batch, ra, ca, rb, cb,
+        a_batched ? (long long)ra * ca : 0, b_batched ? (long long)rb * cb : 0);
+    CUDA_TRY(cudaGetLastError());
+    return C3B_OK;
+}
+
+double c3b_measure_fp64_peak(int kind, int device, double seconds) {
+    double tf = 0.0;
+    int rc = measure_fp64_peak(kind, device, seconds, &tf);
+    if (rc != 0) return (double)fail(C3B_ECUDA, "C3:ERROR: fp64 peak measurement failed (cuda error %d)", rc);
+    return tf;
+}
+
+double c3b_microbench(int kind, int a, int b) {
+    double tf = 0.0;
+    int rc = -1;
+    if (kind == 0) rc = run_mmrow_bench<9>(a, b, &tf);
+    else if (kind == 1) rc = run_mmrow_bench<4>(a, b, &tf);
+    else if (kind == 2) rc = run_mmrow_bench<3>(a, b, &tf);
+    else return (double)fail(C3B_EINVAL, "C3:ERROR: unknown microbench kind %d", kind);
+    if (rc != 0) return (double)fail(C3B_ECUDA, "C3:ERROR: microbench failed (cuda error %d)", rc);
+    return tf;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// CTA-cooperative PWC propagator kernel for any dimension D (closed d > 12, Lindblad D = d^2).
+//
+// Same fused contract as pwc_rows.cuh (assemble -> expm -> ordered product in one launch,
+// replacing c3/libraries/propagation.py:426-440, 551-585 and c3/utils/tf_utils.py:120-193),
+// but one CTA of 256 threads owns a time segment and every D x D matrix lives either in
+// shared memory (D <= 32) or in a per-CTA global workspace that stays L2-resident (D = 81:
+// 9 x 105 KB per CTA).  The exponential follows Higham 2005 exactly: order from the exact
+// 1-norm (thresholds theta_3..theta_9, else 13 with s = ceil(log2(norm/theta_13))) and a
+// Gauss-Jordan solve WITH partial pivoting (row permutation kept in shared memory).
+#pragma once
+#include "c3b_common.cuh"
+
+namespace c3b {
+
+struct CtaParams {
+    const cplx* G;          // [(Bm), K+1, D, D] pre-scaled generators
+    const double* signals;  // [B, K, N]
+    const cplx* hlist;      // [B, N, D, D] or null
+    double hscale_re, hscale_im;
+    long long model_stride;  // elements between batch models in G (0 = shared)
+    int B, K, N, D;
+    int S, seg_len;
+    cplx* U_out;    // [B, D, D]
+    cplx* seg_out;  // [B, S, D, D]
+    cplx* dUs_out;  // [B, N, D, D] or null
+    cplx* ws;       // global workspace, gridDim.x * kCtaSlots * D * D (only when matrices do not fit smem)
+    int use_smem;   // 1: matrices in dynamic shared memory
+};
+
+constexpr int kCtaThreads = 256;
+constexpr int kCtaSlots = 9;  // M0..M7 scratch + P
+
+// ---- C = A * B (+ optional linear epilogue handled by callers) -----------------------------
+// (No __restrict__: the operands may live in the global workspace written earlier by this
+// same CTA, so the non-coherent load path must not be used.)
+// Thread (tr, tc) owns rows {r0 + tr + ii*RT} and columns {c0 + tc + jj*CT}: lanes walk
+// consecutive columns (conflict-free / coalesced 16-byte loads of B) and broadcast-read A.
+template <int CT, int TR, int TC>
+__device__ __forceinline__ void cta_gemm(cplx* C, const cplx* A, const cplx* B, const int D) {
+    constexpr int RT = kCtaThreads / CT;
+    const int tc = threadIdx.x % CT;
+    const int tr = threadIdx.x / CT;
+    for (int r0 = 0; r0 < D; r0 += RT * TR) {
+        for (int c0 = 0; c0 < D; c0 += CT * TC) {
+            int rows[TR], cols[TC];
+#pragma unroll
+            for (int ii = 0; ii < TR; ++ii) rows[ii] = min(r0 + tr + ii * RT, D - 1);
+#pragma unroll
+            for (int jj = 0; jj < TC; ++jj) cols[jj] = min(c0 + tc + jj * CT, D - 1);
+            cplx acc[TR][TC];
+#pragma unroll
+            for (int ii = 0; ii < TR; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < TC; ++jj) acc[ii][jj] = cmake(0.0, 0.0);
+#pragma unroll 2
+            for (int k = 0; k < D; ++k) {
+                cplx a[TR], b[TC];
+#pragma unroll
+                for (int ii = 0; ii < TR; ++ii) a[ii] = A[rows[ii] * D + k];
+#pragma unroll
+                for (int jj = 0; jj < TC; ++jj) b[jj] = B[k * D + cols[jj]];
+#pragma unroll
+                for (int ii = 0; ii < TR; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < TC; ++jj) cfma(acc[ii][jj], a[ii], b[jj]);
+            }
+#pragma unroll
+            for (int ii = 0; ii < TR; ++ii) {
+                const int i = r0 + tr + ii * RT;
+#pragma unroll
+                for (int jj = 0; jj < TC; ++jj) {
+                    const int j = c0 + tc + jj * CT;
+                    if (i < D && j < D) C[i * D + j] = acc[ii][jj];
+                }
+            }
+        }
+    }
+}
+
+// exact 1-norm (max column sum of |a_ij|), result broadcast to all threads
+__device__ __forceinline__ double cta_norm1(const cplx* A, const int D, double* red) {
+    double best = 0.0;
+    for (int c = threadIdx.x; c < D; c += kCtaThreads) {
+        double s = 0.0;
+        for (int i = 0; i < D; ++i) s += cabs1(A[i * D + c]);
+        best = fmax(best, s);
+    }
+    best = warp_max(best);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    double v = red[0];
+#pragma unroll
+    for (int w = 1; w < kCtaThreads / 32; ++w) v = fmax(v, red[w]);
+    __syncthreads();
+    return v;
+}
+
+// Solve Q X = R in place (X overwrites ... is written to Xout), Gauss-Jordan with partial
+// pivoting through a row permutation (no physical swaps, no per-step normalisation).
+__device__ __forceinline__ void cta_solve(cplx* Q, cplx* R, cplx* Xout,
+                                          const int D, int* perm, int* pivrow) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = kCtaThreads / 32;
+    for (int i = threadIdx.x; i < D; i += kCtaThreads) perm[i] = i;
+    __syncthreads();
+    for (int k = 0; k < D; ++k) {
+        if (warp == 0) {
+            // logical rows k..D-1 are the not-yet-used physical rows perm[k..D-1]
+            double best = -1.0;
+            int bi = k;
+            for (int i = k + lane; i < D; i += 32) {
+                const cplx q = Q[perm[i] * D + k];
+                const double m = fma(q.x, q.x, q.y * q.y);
+                if (m > best) { best = m; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (lane == 0) {
+                const int t = perm[k];
+                perm[k] = perm[bi];
+                perm[bi] = t;
+                *pivrow = perm[k];
+            }
+        }
+        __syncthreads();
+        const int pr = *pivrow;
+        const cplx inv = crcp(Q[pr * D + k]);
+        const int ncols = (D - k - 1) + D;
+        for (int i = warp; i < D; i += NW) {
+            if (i == pr) continue;
+            const cplx f = cmul(Q[i * D + k], inv);
+            for (int c = lane; c < ncols; c += 32) {
+                if (c < D - k - 1) {
+                    const int j = k + 1 + c;
+                    cplx v = Q[i * D + j];
+                    cfms(v, f, Q[pr * D + j]);
+                    Q[i * D + j] = v;
+                } else {
+                    const int j = c - (D - k - 1);
+                    cplx v = R[i * D + j];
+                    cfms(v, f, R[pr * D + j]);
+                    R[i * D + j] = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // X[k,:] = R[perm[k],:] / Q[perm[k],k]
+    for (int i = warp; i < D; i += NW) {
+        const int pr = perm[i];
+        const cplx inv = crcp(Q[pr * D + i]);
+        for (int j = lane; j < D; j += 32) Xout[i * D + j] = cmul(inv, R[pr * D + j]);
+    }
+    __syncthreads();
+}
+
+template <int CT, int TR, int TC>
+__global__ void __launch_bounds__(kCtaThreads) pwc_cta_kernel(const CtaParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[kCtaThreads / 32];
+    __shared__ int s_pivrow;
+    const int D = p.D, K = p.K;
+    const int DD = D * D;
+    const int tid = threadIdx.x;
+
+    int* perm = reinterpret_cast<int*>(smem_raw);  // [D] (padded to 16 bytes)
+    cplx* mats;
+    if (p.use_smem)
+        mats = reinterpret_cast<cplx*>(smem_raw + (((size_t)D * sizeof(int) + 15) & ~(size_t)15));
+    else
+        mats = p.ws + (size_t)blockIdx.x * kCtaSlots * DD;
+    cplx* M[kCtaSlots];
+#pragma unroll
+    for (int i = 0; i < kCtaSlots; ++i) M[i] = mats + (size_t)i * DD;
+    cplx* const P = M[8];
+
+    const long long units = (long long)p.B * p.S;
+    for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const int b = (int)(unit / p.S);
+        const int sidx = (int)(unit - (long long)b * p.S);
+        const int n_begin = sidx * p.seg_len;
+        const int n_end = min(p.N, n_begin + p.seg_len);
+        const cplx* Gb = p.G ? p.G + (size_t)b * p.model_stride : nullptr;
+        const double* sig_b = p.signals ? p.signals + (size_t)b * K * p.N : nullptr;
+        const cplx hs = cmake(p.hscale_re, p.hscale_im);
+
+        for (int n = n_begin; n < n_end; ++n) {
+            cplx* A = M[0];
+            // ---- assemble ------------------------------------------------------------------
+            if (p.hlist == nullptr) {
+                for (int e = tid; e < DD; e += kCtaThreads) {
+                    cplx v = Gb[e];
+                    for (int k = 0; k < K; ++k) {
+                        const double c = __ldg(sig_b + (size_t)k * p.N + n);
+                        const cplx gk = Gb[(size_t)(k + 1) * DD + e];
+                        v.x = fma(c, gk.x, v.x);
+                        v.y = fma(c, gk.y, v.y);
+                    }
+                    A[e] = v;
+                }
+            } else {
+                const cplx* H = p.hlist + ((size_t)b * p.N + n) * DD;
+                for (int e = tid; e < DD; e += kCtaThreads) A[e] = cmul(hs, H[e]);
+            }
+            __syncthreads();
+            const double nrm = cta_norm1(A, D, red);
+            int m_idx, s = 0;
+            if (nrm < C3B_THETA3) m_idx = 0;
+            else if (nrm < C3B_THETA5) m_idx = 1;
+            else if (nrm < C3B_THETA7) m_idx = 2;
+            else if (nrm < C3B_THETA9) m_idx = 3;
+            else {
+                m_idx = 4;
+                s = squarings_for(nrm, C3B_THETA13);
+                if (nrm * pow2neg(s) >= C3B_THETA13) ++s;  // (cannot happen; keeps the bound explicit)
+            }
+            if (s > 0) {
+                const double sc = pow2neg(s);
+                for (int e = tid; e < DD; e += kCtaThreads) { A[e].x *= sc; A[e].y *= sc; }
+                __syncthreads();
+            }
+            const double* cf = kPade[m_idx];
+            cplx *Um = M[6], *Vm = M[7];
+            if (m_idx < 4) {
+                // A2 = M1; higher even powers ping-pong M2/M3; W (odd coefficients) in M5; V in M7
+                cta_gemm<CT, TR, TC>(M[1], A, A, D);
+                __syncthreads();
+                for (int e = tid; e < DD; e += kCtaThreads) {
+                    const cplx a2 = M[1][e];
+                    const bool diag = (e / D) == (e % D);
+                    M[5][e] = cmake(cf[3] * a2.x + (diag ? cf[1] : 0.0), cf[3] * a2.y);
+                    Vm[e] = cmake(cf[2] * a2.x + (diag ? cf[0] : 0.0), cf[2] * a2.y);
+                }
+                cplx* cur = M[1];
+                for (int i = 0; i < m_idx; ++i) {
+                    cplx* nxt = (i & 1) ? M[3] : M[2];
+                    __syncthreads();
+                    cta_gemm<CT, TR, TC>(nxt, cur, M[1], D);
+                    __syncthreads();
+                    const double cw = cf[2 * i + 5], cv = cf[2 * i + 4];
+                    for (int e = tid; e < DD; e += kCtaThreads) {
+                        const cplx x = nxt[e];
+                        cplx w = M[5][e], v = Vm[e];
+                        w.x = fma(cw, x.x, w.x); w.y = fma(cw, x.y, w.y);
+                        v.x = fma(cv, x.x, v.x); v.y = fma(cv, x.y, v.y);
+                        M[5][e] = w; Vm[e] = v;
+                    }
+                    cur = nxt;
+                }
+                __syncthreads();
+                cta_gemm<CT, TR, TC>(Um, A, M[5], D);
+                __syncthreads();
+            } else {
+                cplx *A2 = M[1], *A4 = M[2], *A6 = M[3], *T = M[4];
+                cta_gemm<CT, TR, TC>(A2, A, A, D);
+                __syncthreads();
+                cta_gemm<CT, TR, TC>(A4, A2, A2, D);
+                __syncthreads();
+                cta_gemm<CT, TR, TC>(A6, A4, A2, D);
+                __syncthreads();
+                for (int e = tid; e < DD; e += kCtaThreads) {
+                    const cplx x2 = A2[e], x4 = A4[e], x6 = A6[e];
+                    T[e] = cmake(cf[13] * x6.x + cf[11] * x4.x + cf[9] * x2.x, cf[13] * x6.y + cf[11] * x4.y + cf[9] * x2.y);
+                }
+                __syncthreads();
+                cta_gemm<CT, TR, TC>(M[5], A6, T, D);
+                __syncthreads();
+                for (int e = tid; e < DD; e += kCtaThreads) {
+                    const cplx x2 = A2[e], x4 = A4[e], x6 = A6[e];
+                    const bool diag = (e / D) == (e % D);
+                    cplx w = M[5][e];
+                    w.x += cf[7] * x6.x + cf[5] * x4.x + cf[3] * x2.x + (diag ? cf[1] : 0.0);
+                    w.y += cf[7] * x6.y + cf[5] * x4.y + cf[3] * x2.y;
+                    M[5][e] = w;
+                    T[e] = cmake(cf[12] * x6.x + cf[10] * x4.x + cf[8] * x2.x, cf[12] * x6.y + cf[10] * x4.y + cf[8] * x2.y);
+                }
+                __syncthreads();
+                cta_gemm<CT, TR, TC>(Um, A, M[5], D);
+                cta_gemm<CT, TR, TC>(Vm, A6, T, D);
+                __syncthreads();
+                for (int e = tid; e < DD; e += kCtaThreads) {
+                    const cplx x2 = A2[e], x4 = A4[e], x6 = A6[e];
+                    const bool diag = (e / D) == (e % D);
+                    cplx v = Vm[e];
+                    v.x += cf[6] * x6.x + cf[4] * x4.x + cf[2] * x2.x + (diag ? cf[0] : 0.0);
+                    v.y += cf[6] * x6.y + cf[4] * x4.y + cf[2] * x2.y;
+                    Vm[e] = v;
+                }
+                __syncthreads();
+            }
+            // Q = V - U -> M1, R = V + U -> M2
+            for (int e = tid; e < DD; e += kCtaThreads) {
+                const cplx u = Um[e], v = Vm[e];
+                M[1][e] = cmake(v.x - u.x, v.y - u.y);
+                M[2][e] = cmake(v.x + u.x, v.y + u.y);
+            }
+            __syncthreads();
+            cplx* X = M[3];
+            cta_solve(M[1], M[2], X, D, perm, &s_pivrow);
+            for (int i = 0; i < s; ++i) {
+                cplx* nxt = (X == M[3]) ? M[4] : M[3];
+                cta_gemm<CT, TR, TC>(nxt, X, X, D);
+                __syncthreads();
+                X = nxt;
+            }
+            if (p.dUs_out != nullptr) {
+                cplx* o = p.dUs_out + ((size_t)b * p.N + n) * DD;
+                for (int e = tid; e < DD; e += kCtaThreads) o[e] = X[e];
+            }
+            if (n == n_begin) {
+                for (int e = tid; e < DD; e += kCtaThreads) P[e] = X[e];
+            } else {
+                cta_gemm<CT, TR, TC>(M[5], X, P, D);
+                __syncthreads();
+                for (int e = tid; e < DD; e += kCtaThreads) P[e] = M[5][e];
+            }
+            __syncthreads();
+        }
+        cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * DD) : (p.seg_out + ((size_t)b * p.S + sidx) * DD);
+        if (n_end > n_begin) {
+            for (int e = tid; e < DD; e += kCtaThreads) o[e] = P[e];
+        } else {
+            for (int e = tid; e < DD; e += kCtaThreads) o[e] = cmake((e / D) == (e % D) ? 1.0 : 0.0, 0.0);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace c3b

@@ -1,0 +1,297 @@
+// Register-resident PWC propagator kernel for small Hilbert dimensions (D <= 12).
+//
+// Replaces, for one whole batch of control signals, the reference chain
+//   tf_batch_propagate -> tf_propagation_vectorized -> tf.linalg.expm   (c3/libraries/propagation.py:460-515, 426-440)
+//   tf_matmul_n / tf_matmul_left                                        (c3/utils/tf_utils.py:120-193)
+// with ONE fused kernel: assemble A_n = G0 + sum_k c_k[n] G_k, exponentiate by
+// scaling-and-squaring Pade, and fold the ordered product U = dU_{N-1} ... dU_0 on chip.
+//
+// Mapping.  A "group" of D lanes owns one time slice at a time; lane r holds ROW r of every
+// matrix in registers (D complex = 4D 32-bit registers per matrix row).  floor(32/D) groups
+// share a warp and walk consecutive sub-chunks of the warp's time segment.  A product
+// C = X * Y takes X's row from registers and streams Y from a per-group shared-memory
+// buffer with broadcast LDS.128 (all lanes of a group read the same address), so each
+// 16-byte shared load feeds 4 DFMAs and no shuffles are needed.  Warps never synchronise
+// with each other (only __syncwarp), so the fp64 pipe is kept busy by 8-12 independent
+// warps per SM.
+//
+// Exponential.  Pade order m in {3,5,7,9} and squarings s are chosen per warp from an
+// inf-norm bound  ||A_n|| <= rs0[r] + sum_k |c_k| rs_k[r]  (no square roots on the hot
+// path).  s is taken so that the scaled norm is below 2 ln 2, which makes V-U strictly
+// diagonally dominant and lets the linear solve be an un-pivoted Gauss-Jordan sweep with
+// no divergence (see c3b_common.cuh).  For every BASELINE config this selects exactly
+// Higham's minimal (m, s); the accuracy is that of Higham 2005 for any input.
+#pragma once
+#include "c3b_common.cuh"
+
+namespace c3b {
+
+struct RowsParams {
+    const cplx* G;          // [(Bm), K+1, d, d]  pre-scaled generators: A = G0 + sum_k c_k G_k
+    const double* RS;       // [(Bm), K+1, d]     row sums of |G_k| (inf-norm bound pieces)
+    const double* signals;  // [B, K, N] real control fields, contiguous in N (may be null if K == 0)
+    const cplx* hlist;      // [B, N, d, d] explicit Hamiltonians (H-list mode) or null
+    double hscale_re, hscale_im;  // H-list mode: A = hscale * H   (-i dt for the closed system)
+    long long model_stride;       // elements between consecutive batch models in G (0 = shared)
+    int B, K, N, d;               // d = actual dimension (<= template D)
+    int S;                        // segments per batch element
+    int seg_len;                  // slices per segment
+    cplx* U_out;                  // [B, d, d]      (used when S == 1)
+    cplx* seg_out;                // [B, S, d, d]   (used when S > 1)
+    cplx* dUs_out;                // [B, N, d, d] or null
+};
+
+// C(row) = X(row) * Y, Y a D x D matrix in shared memory (row-major, broadcast reads).
+template <int D>
+__device__ __forceinline__ void mm_row(const cplx (&x)[D], const cplx* __restrict__ Y, cplx (&c)[D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) c[j] = cmake(0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const cplx xk = x[k];
+#pragma unroll
+        for (int j = 0; j < D; ++j) cfma(c[j], xk, Y[k * D + j]);
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void store_row(cplx* __restrict__ M, int r, const cplx (&x)[D], bool pred) {
+    if (pred) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) M[r * D + j] = x[j];
+    }
+}
+
+template <int D, int WARPS>
+struct RowsLayout {
+    static constexpr int G = 32 / D;                   // groups per warp
+    static constexpr int GROUP_ELEMS = 3 * D * D + 4 * D;  // bufA, bufA2, bufP, piv[2][2D]  (cplx units)
+    static constexpr int WARP_ELEMS = G * GROUP_ELEMS;
+    __host__ __device__ static size_t smem_bytes(int K) {
+        size_t model = (size_t)(K + 1) * D * D * sizeof(cplx) + (size_t)(((K + 1) * D + 1) & ~1) * sizeof(double);
+        return model + (size_t)WARPS * WARP_ELEMS * sizeof(cplx);
+    }
+};
+
+template <int D, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) pwc_rows_kernel(const RowsParams p) {
+    using L = RowsLayout<D, WARPS>;
+    constexpr int G = L::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = p.K;
+    const int d = p.d;
+    cplx* sG = reinterpret_cast<cplx*>(smem_raw);                    // [(K+1), D, D] zero padded
+    double* sRS = reinterpret_cast<double*>(sG + (K + 1) * D * D);   // [(K+1), D]
+    cplx* sWarps = reinterpret_cast<cplx*>(sRS + (((K + 1) * D + 1) & ~1));
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const bool hmode = p.hlist != nullptr;
+
+    // ---- stage the (shared) model once per CTA -------------------------------------------
+    // TODO(per-batch models): model_stride != 0 is routed to the CTA kernel by the host.
+    if (!hmode) {
+        for (int idx = tid; idx < (K + 1) * D * D; idx += WARPS * 32) {
+            const int k = idx / (D * D);
+            const int rem = idx - k * D * D;
+            const int r = rem / D, j = rem - r * D;
+            cplx v = cmake(0.0, 0.0);
+            if (r < d && j < d) v = p.G[(size_t)k * d * d + r * d + j];
+            sG[idx] = v;
+        }
+        for (int idx = tid; idx < (K + 1) * D; idx += WARPS * 32) {
+            const int k = idx / D, r = idx - k * D;
+            sRS[idx] = (r < d) ? p.RS[k * d + r] : 0.0;
+        }
+    }
+    __syncthreads();
+
+    const long long unit = (long long)blockIdx.x * WARPS + warp;
+    if (unit >= (long long)p.B * p.S) return;  // whole warp leaves; no CTA barrier after this point
+    const int b = (int)(unit / p.S);
+    const int sidx = (int)(unit - (long long)b * p.S);
+
+    const int g_raw = lane / D;
+    const bool lane_on = g_raw < G;           // lanes beyond G*D idle (they shadow group 0)
+    const int g = lane_on ? g_raw : 0;
+    const int r = lane_on ? (lane - g_raw * D) : 0;
+
+    cplx* gbase = sWarps + (size_t)warp * L::WARP_ELEMS + (size_t)g * L::GROUP_ELEMS;
+    cplx* bufA = gbase;
+    cplx* bufA2 = gbase + D * D;
+    cplx* bufP = gbase + 2 * D * D;
+    cplx* piv = gbase + 3 * D * D;
+
+    const int n_begin = sidx * p.seg_len;
+    const int n_end = min(p.N, n_begin + p.seg_len);
+    const int len = n_end - n_begin;
+    const int cl = (len + G - 1) / G;  // slices per group (last group may get fewer)
+    const int my_begin = n_begin + g * cl;
+    const int my_end = min(n_end, my_begin + cl);
+
+    const double* sig_b = p.signals ? p.signals + (size_t)b * K * p.N : nullptr;
+    const cplx hs = cmake(p.hscale_re, p.hscale_im);
+
+    for (int it = 0; it < cl; ++it) {
+        const int n = my_begin + it;
+        const bool on = lane_on && (n < my_end);
+
+        // ---- assemble row r of A_n and an inf-norm bound ---------------------------------
+        cplx A[D];
+        double nb = 0.0;
+        if (!hmode) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) A[j] = on ? sG[r * D + j] : cmake(0.0, 0.0);
+            nb = on ? sRS[r] : 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double c = on ? __ldg(sig_b + (size_t)k * p.N + n) : 0.0;
+                const cplx* gk = sG + (k + 1) * D * D + r * D;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const cplx gv = gk[j];
+                    A[j].x = fma(c, gv.x, A[j].x);
+                    A[j].y = fma(c, gv.y, A[j].y);
+                }
+                nb = fma(fabs(c), sRS[(k + 1) * D + r], nb);
+            }
+        } else {
+            const cplx* hrow = p.hlist + ((size_t)b * p.N + (on ? n : 0)) * d * d + (size_t)r * d;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                cplx h = cmake(0.0, 0.0);
+                if (on && r < d && j < d) h = hrow[j];
+                A[j] = cmul(hs, h);
+                nb += cabs1(A[j]);
+            }
+        }
+        nb = warp_max(nb);  // warp-uniform => no divergence in what follows
+
+        const int s = squarings_for(nb, C3B_NOPIVOT_LIMIT);
+        const double ns = nb * pow2neg(s);
+        const int mi = ns < C3B_THETA3 ? 0 : (ns < C3B_THETA5 ? 1 : (ns < C3B_THETA7 ? 2 : 3));  // m = 2 mi + 3
+        if (s > 0) {
+            const double sc = pow2neg(s);
+#pragma unroll
+            for (int j = 0; j < D; ++j) { A[j].x *= sc; A[j].y *= sc; }
+        }
+
+        // ---- Pade numerator parts: U = A * W (odd), V (even) -----------------------------
+        store_row<D>(bufA, r, A, lane_on);
+        __syncwarp();
+        cplx X[D], W[D], V[D];
+        mm_row<D>(A, bufA, X);  // X = A^2 (row r)
+        {
+            const double c1 = kPade[mi][1], c3 = kPade[mi][3], c0 = kPade[mi][0], c2 = kPade[mi][2];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                W[j] = cmake(c3 * X[j].x, c3 * X[j].y);
+                V[j] = cmake(c2 * X[j].x, c2 * X[j].y);
+            }
+            // identity contributions on the diagonal element of this row
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (j == r) { W[j].x += c1; V[j].x += c0; }
+        }
+        if (mi > 0) {
+            store_row<D>(bufA2, r, X, lane_on);
+            __syncwarp();
+            for (int i = 0; i < mi; ++i) {
+                cplx Xn[D];
+                mm_row<D>(X, bufA2, Xn);  // A^(2i+4)
+                const double cw = kPade[mi][2 * i + 5], cv = kPade[mi][2 * i + 4];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    W[j].x = fma(cw, Xn[j].x, W[j].x);
+                    W[j].y = fma(cw, Xn[j].y, W[j].y);
+                    V[j].x = fma(cv, Xn[j].x, V[j].x);
+                    V[j].y = fma(cv, Xn[j].y, V[j].y);
+                    X[j] = Xn[j];
+                }
+            }
+        }
+        cplx R[D];
+        mm_row<D>(W, bufA, R);  // U = W * A  (polynomials in A commute)
+        cplx Q[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            Q[j] = cmake(V[j].x - R[j].x, V[j].y - R[j].y);
+            R[j] = cmake(V[j].x + R[j].x, V[j].y + R[j].y);
+        }
+
+        // ---- R <- Q^{-1} R by un-pivoted Gauss-Jordan; pivot rows broadcast through smem ---
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            cplx* pv = piv + (k & 1) * 2 * D;
+            if (lane_on && r == k) {
+#pragma unroll
+                for (int j = k; j < D; ++j) pv[j] = Q[j];
+#pragma unroll
+                for (int j = 0; j < D; ++j) pv[D + j] = R[j];
+            }
+            __syncwarp();
+            const cplx inv = crcp(pv[k]);
+            cplx f = cmul(Q[k], inv);
+            if (r == k) f = cmake(1.0 - inv.x, -inv.y);  // owner: row <- row * inv == row - (1-inv) row
+#pragma unroll
+            for (int j = k + 1; j < D; ++j) cfms(Q[j], f, pv[j]);
+#pragma unroll
+            for (int j = 0; j < D; ++j) cfms(R[j], f, pv[D + j]);
+        }
+
+        // ---- undo the scaling: s squarings -------------------------------------------------
+        for (int i = 0; i < s; ++i) {
+            store_row<D>(bufA, r, R, lane_on);
+            __syncwarp();
+            cplx T[D];
+            mm_row<D>(R, bufA, T);
+#pragma unroll
+            for (int j = 0; j < D; ++j) R[j] = T[j];
+            __syncwarp();
+        }
+
+        // ---- optional partial propagators ---------------------------------------------------
+        if (p.dUs_out != nullptr && on && r < d) {
+            cplx* o = p.dUs_out + ((size_t)b * p.N + n) * d * d + (size_t)r * d;
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (j < d) o[j] = R[j];
+        }
+
+        // ---- running ordered product P <- dU_n * P -------------------------------------------
+        if (it == 0) {
+            store_row<D>(bufP, r, R, lane_on);
+        } else {
+            cplx T[D];
+            mm_row<D>(R, bufP, T);
+            __syncwarp();
+            store_row<D>(bufP, r, T, lane_on);
+        }
+    }
+    __syncwarp();
+
+    // ---- fold the G group products of this warp: P_{G-1} ... P_1 P_0 ------------------------
+    // (every group computes the same thing redundantly; lanes of group 0 write it out)
+    cplx* wbase = sWarps + (size_t)warp * L::WARP_ELEMS;
+    cplx T[D];
+    {
+        const cplx* last = wbase + (size_t)(G - 1) * L::GROUP_ELEMS + 2 * D * D;
+#pragma unroll
+        for (int j = 0; j < D; ++j) T[j] = last[r * D + j];
+    }
+#pragma unroll 1
+    for (int gg = G - 2; gg >= 0; --gg) {
+        cplx T2[D];
+        mm_row<D>(T, wbase + (size_t)gg * L::GROUP_ELEMS + 2 * D * D, T2);
+#pragma unroll
+        for (int j = 0; j < D; ++j) T[j] = T2[j];
+    }
+    if (lane_on && g == 0 && r < d) {
+        cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * d * d) : (p.seg_out + ((size_t)b * p.S + sidx) * d * d);
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            if (j < d) o[r * d + j] = T[j];
+    }
+}
+
+}  // namespace c3b

@@ -1,0 +1,214 @@
+"""Tensor-level entry points of the B200 propagator engine.
+
+Thin host code over the C ABI (include/c3b200.h): checks shapes/dtypes, owns the output and
+workspace tensors (the C library never allocates) and passes torch's current CUDA stream.
+PyTorch is used for device memory and streams only.  Everything here requires the CUDA
+library and a CUDA device; there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _as(t, dtype, device) -> torch.Tensor:
+    """Contiguous tensor of the wanted dtype on the wanted device (accepts numpy/lists)."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if t.dtype != dtype:
+        if dtype == torch.float64 and t.is_complex():
+            t = t.real
+        t = t.to(dtype)
+    return t.to(device, non_blocking=True).contiguous()
+
+
+def default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("C3:ERROR: c3_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Per-(device, stream) scratch buffer, grown on demand and reused across calls."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+def set_tuning(key: str, value: int) -> None:
+    _lib.check(_lib.load().c3b_set_tuning(key.encode(), int(value)))
+
+
+def pwc_path(K: int, D: int, batched_model: bool = False) -> int:
+    return _lib.load().c3b_pwc_path(int(K), int(D), int(batched_model))
+
+
+def pwc_closed(h0, hks, signals, dt: float, return_dUs: bool = False, device=None):
+    """U[b] = prod_n expm(-i (h0 + sum_k signals[b,k,n] hks[k]) dt), later slices on the left.
+
+    h0 [d,d] (or [B,d,d]), hks [K,d,d] (or [B,K,d,d]), signals [B,K,N] (or [K,N] -> B=1).
+    Returns U [B,d,d] and, if ``return_dUs``, dUs [B,N,d,d].
+    (c3/libraries/propagation.py:426-440,460-515; c3/utils/tf_utils.py:144-193)
+    """
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        signals = _as(signals, torch.float64, device)
+        if signals.dim() == 2:
+            signals = signals.unsqueeze(0)
+        B, K, N = signals.shape
+        h0 = _as(h0, torch.complex128, device)
+        batched = h0.dim() == 3
+        d = h0.shape[-1]
+        if K > 0:
+            hks = _as(hks, torch.complex128, device)
+            want = (B, K, d, d) if batched else (K, d, d)
+            if tuple(hks.shape) != want:
+                raise ValueError(f"C3:ERROR: hks has shape {tuple(hks.shape)}, expected {want}")
+        else:
+            hks = None
+        if batched and h0.shape[0] != B:
+            raise ValueError("C3:ERROR: batched h0 must have the batch size of signals")
+        U = torch.empty((B, d, d), dtype=torch.complex128, device=device)
+        dUs = torch.empty((B, N, d, d), dtype=torch.complex128, device=device) if return_dUs else None
+        nbytes = lib.c3b_pwc_workspace_bytes(B, K, N, d, 0, int(batched))
+        ws = _workspace(nbytes, device)
+        _lib.check(lib.c3b_pwc_closed(_ptr(h0), _ptr(hks), _ptr(signals), float(dt), B, K, N, d, int(batched),
+                                      _ptr(U), _ptr(dUs), _ptr(ws), ws.numel(), _stream()))
+    return (U, dUs) if return_dUs else U
+
+
+def pwc_closed_hlist(Hs, dt: float, return_dUs: bool = False, device=None):
+    """Same with explicit Hamiltonians Hs [B,N,d,d] (or [N,d,d]); the reference's
+    ``signals is None`` mode (c3/libraries/propagation.py:294-308, 437-438)."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        Hs = _as(Hs, torch.complex128, device)
+        if Hs.dim() == 3:
+            Hs = Hs.unsqueeze(0)
+        B, N, d, _ = Hs.shape
+        U = torch.empty((B, d, d), dtype=torch.complex128, device=device)
+        dUs = torch.empty((B, N, d, d), dtype=torch.complex128, device=device) if return_dUs else None
+        nbytes = lib.c3b_pwc_workspace_bytes(B, 0, N, d, 0, 0)
+        ws = _workspace(nbytes, device)
+        _lib.check(lib.c3b_pwc_closed_hlist(_ptr(Hs), float(dt), B, N, d, _ptr(U), _ptr(dUs), _ptr(ws), ws.numel(),
+                                            _stream()))
+    return (U, dUs) if return_dUs else U
+
+
+def pwc_lindblad(h0, hks, col_ops, signals, dt: float, return_dUs: bool = False, device=None):
+    """Lindblad superoperator propagators U [B,d^2,d^2] (c3/libraries/propagation.py:551-585)."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        signals = _as(signals, torch.float64, device)
+        if signals.dim() == 2:
+            signals = signals.unsqueeze(0)
+        B, K, N = signals.shape
+        h0 = _as(h0, torch.complex128, device)
+        batched = h0.dim() == 3
+        d = h0.shape[-1]
+        hks = _as(hks, torch.complex128, device) if K > 0 else None
+        if isinstance(col_ops, (list, tuple)):
+            col_ops = torch.stack([_as(c, torch.complex128, device) for c in col_ops]) if len(col_ops) else None
+        if col_ops is not None:
+            col_ops = _as(col_ops, torch.complex128, device)
+            C = col_ops.shape[-3]
+        else:
+            C = 0
+        D = d * d
+        U = torch.empty((B, D, D), dtype=torch.complex128, device=device)
+        dUs = torch.empty((B, N, D, D), dtype=torch.complex128, device=device) if return_dUs else None
+        nbytes = lib.c3b_pwc_workspace_bytes(B, K, N, d, 1, int(batched))
+        ws = _workspace(nbytes, device)
+        _lib.check(lib.c3b_pwc_lindblad(_ptr(h0), _ptr(hks), _ptr(col_ops), C, _ptr(signals), float(dt), B, K, N, d,
+                                        int(batched), _ptr(U), _ptr(dUs), _ptr(ws), ws.numel(), _stream()))
+    return (U, dUs) if return_dUs else U
+
+
+def ordered_product(mats, device=None) -> torch.Tensor:
+    """out[b] = mats[b,M-1] ... mats[b,0]  for mats [B,M,D,D] (or [M,D,D] -> [D,D])."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        mats = _as(mats, torch.complex128, device)
+        squeeze = mats.dim() == 3
+        if squeeze:
+            mats = mats.unsqueeze(0)
+        B, M, D, _ = mats.shape
+        out = torch.empty((B, D, D), dtype=torch.complex128, device=device)
+        nbytes = lib.c3b_product_workspace_bytes(B, M, D)
+        ws = _workspace(nbytes, device)
+        _lib.check(lib.c3b_ordered_product(_ptr(mats), B, M, D, _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    return out[0] if squeeze else out
+
+
+def seq_product(gates, seq_idx, seq_len, device=None) -> torch.Tensor:
+    """out[s] = gates[idx[s,len_s-1]] ... gates[idx[s,0]] (identity when len_s == 0)."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        gates = _as(gates, torch.complex128, device)
+        seq_idx = _as(seq_idx, torch.int32, device)
+        seq_len = _as(seq_len, torch.int32, device)
+        Gn, D, _ = gates.shape
+        S = seq_len.shape[0]
+        Lmax = seq_idx.shape[1] if seq_idx.dim() == 2 else 0
+        out = torch.empty((S, D, D), dtype=torch.complex128, device=device)
+        nbytes = lib.c3b_product_workspace_bytes(S, 1, D)
+        ws = _workspace(nbytes, device)
+        _lib.check(lib.c3b_seq_product(_ptr(gates), Gn, _ptr(seq_idx) if Lmax > 0 else None, _ptr(seq_len), S, Lmax,
+                                       D, _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def kron(A, B, device=None) -> torch.Tensor:
+    """(Batched) Kronecker product with the row-major convention of tf_kron."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        A = _as(A, torch.complex128, device)
+        B = _as(B, torch.complex128, device)
+        a_b, b_b = A.dim() > 2, B.dim() > 2
+        lead = A.shape[:-2] if a_b else (B.shape[:-2] if b_b else ())
+        if a_b and b_b and A.shape[:-2] != B.shape[:-2]:
+            raise ValueError("C3:ERROR: kron batch shapes differ")
+        batch = 1
+        for s in lead:
+            batch *= s
+        ra, ca = A.shape[-2:]
+        rb, cb = B.shape[-2:]
+        out = torch.empty(tuple(lead) + (ra * rb, ca * cb), dtype=torch.complex128, device=device)
+        _lib.check(lib.c3b_kron(_ptr(A), _ptr(B), _ptr(out), batch, ra, ca, rb, cb, int(a_b), int(b_b), _stream()))
+    return out
+
+
+def measure_fp64_peak(kind: str = "dfma", seconds: float = 0.5, device: Optional[int] = None) -> float:
+    """Measured fp64 TFLOP/s of this GPU ("dfma": vector pipe, "dmma": mma.sync m8n8k4)."""
+    lib = _lib.load()
+    dev = torch.cuda.current_device() if device is None else device
+    v = lib.c3b_measure_fp64_peak(0 if kind == "dfma" else 1, dev, float(seconds))
+    if v < 0:
+        _lib.check(int(v))
+    return v

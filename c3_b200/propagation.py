@@ -1,0 +1,245 @@
+"""Drop-in mirror of ``c3.libraries.propagation`` for the PWC propagator path, backed by the
+B200 engine (c3_b200.engine -> libc3b200.so).
+
+Same names, argument meaning, return dictionaries and error strings as the reference
+(c3/libraries/propagation.py @ 48b7917e), so the parity tests read like the reference's own:
+
+  unitary_provider / state_provider / solver_dict / step_dict   registries   (:18-68)
+  pwc(model, gen, instr, folding_stack, batch_size=None) -> {"U","dUs","ts"}   (:258-341)
+  tf_batch_propagate(hamiltonian, hks, signals, dt, batch_size, col_ops=None, lindbladian=False)  (:460-515)
+  tf_propagation_vectorized(h0, hks, cflds_t, dt)                               (:426-440)
+  tf_propagation_lind(h0, hks, col_ops, cflds_t, dt)                            (:551-585)
+  evaluate_sequences(propagators, sequences)                                    (:588-627)
+
+plus the batch axis the reference lacks (its callers loop serially over ORBIT sequences,
+noise trajectories and optimiser samples): ``signals`` may be ``[B,K,N]`` and
+:func:`pwc_batch` propagates a whole batch in one kernel launch.
+
+Tensors are torch complex128 CUDA tensors (``numpy()``-convertible after ``.cpu()``).  There is no
+CPU path: every function raises if the CUDA library or a GPU is missing.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import engine
+
+unitary_provider: Dict[str, Callable] = dict()
+state_provider: Dict[str, Callable] = dict()
+solver_dict: Dict[str, Callable] = dict()
+step_dict: Dict[str, Callable] = dict()
+
+
+def unitary_deco(func):
+    """Decorator for making registry of functions (propagation.py:39-44)."""
+    unitary_provider[str(func.__name__)] = func
+    return func
+
+
+def state_deco(func):
+    state_provider[str(func.__name__)] = func
+    return func
+
+
+def solver_deco(func):
+    solver_dict[str(func.__name__)] = func
+    return func
+
+
+def step_deco(func):
+    step_dict[str(func.__name__)] = func
+    return func
+
+
+def _np(x):
+    """Reference-style input (numpy, list, tf tensor, torch tensor) -> numpy array or torch tensor."""
+    if isinstance(x, torch.Tensor):
+        return x
+    if hasattr(x, "numpy") and not isinstance(x, np.ndarray):
+        return np.asarray(x.numpy())
+    return np.asarray(x)
+
+
+def _host(x) -> np.ndarray:
+    """Same, but always a host numpy array (small model matrices, time stamps)."""
+    x = _np(x)
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x
+
+
+def _real_signals(signals):
+    """The reference casts real control fields to complex128 before use (:287-293, :429);
+    the engine keeps them float64.  Complex inputs must have zero imaginary part."""
+    if isinstance(signals, torch.Tensor):
+        if signals.is_complex():
+            if bool((signals.imag != 0).any()):
+                raise ValueError("C3:ERROR: control signals must be real")
+            signals = signals.real
+        return signals.to(torch.float64)
+    s = np.asarray(signals)
+    if np.iscomplexobj(s):
+        if np.any(s.imag != 0):
+            raise ValueError("C3:ERROR: control signals must be real")
+        s = s.real
+    return np.ascontiguousarray(s, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+# array-level API
+# --------------------------------------------------------------------------------------------
+
+def tf_propagation_vectorized(h0, hks, cflds_t, dt):
+    """dU_n = expm(-i (h0 + sum_k c_k[n] hks[k]) dt) for every slice -> [n,d,d]
+    (propagation.py:426-440).  With ``hks is None`` ``h0`` is the list of Hamiltonians [n,d,d]."""
+    if hks is not None and cflds_t is not None:
+        _, dUs = engine.pwc_closed(_np(h0), _np(hks), _real_signals(cflds_t), float(np.real(dt)), return_dUs=True)
+    else:
+        _, dUs = engine.pwc_closed_hlist(_np(h0), float(np.real(dt)), return_dUs=True)
+    return dUs[0]
+
+
+def tf_propagation_lind(h0, hks, col_ops, cflds_t, dt, history=False):
+    """dU_n = expm(L_n dt) with the Lindblad superoperator L_n -> [n,d^2,d^2] (propagation.py:551-585)."""
+    if hks is None or cflds_t is None:
+        # dead in the reference as well: tf.cast(None) at propagation.py:552 via :511
+        raise Exception("C3:ERROR: Lindblad propagation needs control Hamiltonians and signals.")
+    _, dUs = engine.pwc_lindblad(_np(h0), _np(hks), [_np(c) for c in col_ops], _real_signals(cflds_t),
+                                 float(np.real(dt)), return_dUs=True)
+    return dUs[0]
+
+
+def tf_batch_propagate(hamiltonian, hks, signals, dt, batch_size, col_ops=None, lindbladian=False):
+    """All slice propagators dUs [N,d,d] (or [B,N,d,d] for batched ``signals [B,K,N]``).
+
+    The reference chunks the TIME axis into ceil(N / batch_size) pieces only to bound host
+    memory (propagation.py:482-515); the fused kernel has no such temporaries, so
+    ``batch_size`` is accepted and ignored -- the result is identical.
+    """
+    del batch_size
+    if signals is not None:
+        sig = _real_signals(signals)
+        batched = sig.ndim == 3
+        if lindbladian:
+            _, dUs = engine.pwc_lindblad(_np(hamiltonian), _np(hks), [_np(c) for c in col_ops], sig,
+                                         float(np.real(dt)), return_dUs=True)
+        else:
+            _, dUs = engine.pwc_closed(_np(hamiltonian), _np(hks), sig, float(np.real(dt)), return_dUs=True)
+        return dUs if batched else dUs[0]
+    if lindbladian:
+        raise Exception("C3:ERROR: Lindblad propagation needs control Hamiltonians and signals.")
+    h = _np(hamiltonian)
+    _, dUs = engine.pwc_closed_hlist(h, float(np.real(dt)), return_dUs=True)
+    return dUs if h.ndim == 4 else dUs[0]
+
+
+def pwc_batch(h0, hks, signals, dt, col_ops=None, lindbladian=False, return_dUs=False):
+    """The batched fast path: U [B,D,D] for ``signals [B,K,N]`` in one launch, no ``dUs`` store
+    unless asked.  This is what B serial reference calls of ``pwc`` compute."""
+    sig = _real_signals(signals)
+    if lindbladian:
+        return engine.pwc_lindblad(_np(h0), _np(hks), [_np(c) for c in col_ops], sig, float(np.real(dt)),
+                                   return_dUs=return_dUs)
+    return engine.pwc_closed(_np(h0), _np(hks), sig, float(np.real(dt)), return_dUs=return_dUs)
+
+
+# --------------------------------------------------------------------------------------------
+# gate-level API (duck-typed Model / Generator / Instruction exactly as the reference uses them)
+# --------------------------------------------------------------------------------------------
+
+@unitary_deco
+def pwc(model, gen, instr, folding_stack: list, batch_size=None) -> Dict:
+    """Solve the equation of motion (Lindblad or Schroedinger) for one gate
+    (propagation.py:258-341).  ``folding_stack`` and ``batch_size`` are accepted for call
+    compatibility (c3/experiment.py:472-478); the ordered product is folded on chip.
+
+    Returns ``{"U": [D,D], "dUs": [N,D,D], "ts": [N]}`` (torch CUDA tensors, ``ts`` as given).
+    """
+    del folding_stack, batch_size
+    signal = gen.generate_signals(instr)
+    ts = []
+    if model.controllability:
+        h0, hctrls = model.get_Hamiltonians()
+        signals = []
+        hks = []
+        for key in signal:
+            signals.append(_host(signal[key]["values"]))
+            ts = signal[key]["ts"]
+            hks.append(_host(hctrls[key]))
+        signals = np.stack(signals)
+        hks = np.stack(hks)
+        ts_np = _host(ts)
+    else:
+        h0 = model.get_Hamiltonian(signal)
+        ts_list = np.asarray([_host(sig["ts"])[1:] for sig in signal.values()])
+        ts_np = ts_list.mean(axis=0)
+        ts = ts_np
+        hks = None
+        signals = None
+        if not np.all(ts_list.var(axis=0) < 1e-5 * (ts_np[1] - ts_np[0])):
+            raise Exception("C3Error:Something with the times happend.")
+        if not np.all(np.var(ts_np[1:] - ts_np[:-1]) < 1e-5 * (ts_np[1] - ts_np[0])):
+            raise Exception("C3Error:Something with the times happend.")
+
+    dt = float(ts_np[1] - ts_np[0])
+
+    cutter = _host(model.ex_cutter) if model.max_excitations else None
+
+    if model.lindbladian:
+        col_ops = [_host(c) for c in model.get_Lindbladians()]
+        if cutter is not None:
+            col_ops = [cutter @ c @ cutter.T for c in col_ops]
+        if signals is None:
+            raise Exception("C3:ERROR: Lindblad propagation needs control Hamiltonians and signals.")
+        U, dUs = engine.pwc_lindblad(_np(h0), hks, col_ops, _real_signals(signals), dt, return_dUs=True)
+    elif signals is not None:
+        U, dUs = engine.pwc_closed(_np(h0), hks, _real_signals(signals), dt, return_dUs=True)
+    else:
+        U, dUs = engine.pwc_closed_hlist(_np(h0), dt, return_dUs=True)
+    U, dUs = U[0], dUs[0]
+
+    if cutter is not None:
+        # blow-up P^T A P is a scatter of the cut matrix into the full space (c3/model.py:222-224)
+        U = blowup_excitations(cutter, U)
+        dUs = blowup_excitations(cutter, dUs)
+    return {"U": U, "dUs": dUs, "ts": ts}
+
+
+def blowup_excitations(cutter, op: torch.Tensor) -> torch.Tensor:
+    """P^T op P for a 0/1 row-selection matrix P [d_cut, d] as an index scatter."""
+    c = _host(cutter)
+    keep = torch.as_tensor(np.argmax(np.real(c), axis=1), device=op.device)
+    d_full = c.shape[1]
+    out = torch.zeros(op.shape[:-2] + (d_full, d_full), dtype=op.dtype, device=op.device)
+    out[..., keep[:, None], keep[None, :]] = op
+    return out
+
+
+def cut_excitations(cutter, op: torch.Tensor) -> torch.Tensor:
+    """P op P^T as an index gather (c3/model.py:218-220)."""
+    c = _host(cutter)
+    keep = torch.as_tensor(np.argmax(np.real(c), axis=1), device=op.device)
+    return op[..., keep[:, None], keep[None, :]]
+
+
+def evaluate_sequences(propagators: Dict, sequences: list) -> list:
+    """Total propagator of each gate sequence, multiplied from the left
+    (``sequence = [U0, U1, U2]`` is applied as ``U2 U1 U0``); an empty sequence gives the
+    identity (propagation.py:588-627).  One kernel launch for all sequences."""
+    names = list(propagators.keys())
+    lookup = {n: i for i, n in enumerate(names)}
+    first = propagators[names[0]]
+    dev = first.device if isinstance(first, torch.Tensor) and first.is_cuda else engine.default_device()
+    gates = torch.stack([torch.as_tensor(_np(propagators[n])).to(torch.complex128).to(dev) for n in names])
+    S = len(sequences)
+    if S == 0:
+        return []
+    lens = np.array([len(s) for s in sequences], dtype=np.int32)
+    Lmax = int(lens.max())
+    idx = np.zeros((S, max(Lmax, 1)), dtype=np.int32)
+    for i, seq in enumerate(sequences):
+        for j, g in enumerate(seq):
+            idx[i, j] = lookup[g]
+    out = engine.seq_product(gates, idx if Lmax > 0 else np.zeros((S, 0), np.int32), lens, device=dev)
+    return [out[i] for i in range(S)]

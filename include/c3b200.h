@@ -1,0 +1,119 @@
+/* c3b200.h -- C ABI of the B200-native PWC propagator engine (libc3b200.so).
+ *
+ * Drop-in boundary for ONE hot path of q-optimize/c3: the piecewise-constant propagator
+ * computation behind Experiment.compute_propagators / c3.libraries.propagation.  The
+ * reference is pure Python on TensorFlow and has no FFI of its own; each entry point below
+ * names the reference function (file:line, relative to the reference checkout @ 48b7917e)
+ * whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the library never
+ *     allocates or frees: the caller owns inputs, outputs and the workspace;
+ *   - complex128 is interleaved (re, im) doubles, matrices are row-major, exactly the
+ *     memory image of a contiguous numpy/torch complex128 tensor;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing
+ *     synchronises, calls are re-entrant (one thread per GPU is the intended use);
+ *   - return value 0 = success, otherwise a negative C3B_E* code; c3b_last_error() gives the
+ *     message of the last failure on the calling thread;
+ *   - ordered products put LATER slices on the LEFT: U = dU_{N-1} ... dU_1 dU_0
+ *     (c3/utils/tf_utils.py:120-129,144-193).
+ */
+#ifndef C3B200_H
+#define C3B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C3B_OK 0
+#define C3B_EINVAL (-1)   /* bad argument (null pointer, non-positive size, ...) */
+#define C3B_EWORKSPACE (-2) /* workspace too small */
+#define C3B_ECUDA (-3)    /* a CUDA runtime call failed */
+#define C3B_EUNSUPPORTED (-4)
+
+/* Library version (major*10000 + minor*100 + patch). */
+int c3b_version(void);
+
+/* Message of the last error on this thread ("" if none). */
+const char* c3b_last_error(void);
+
+/* Bytes of device workspace needed by c3b_pwc_closed / _hlist / _lindblad for the given
+ * problem.  `lindblad` != 0 means d is the Hilbert dimension and the matrices are d^2 x d^2.
+ * `batched_model` != 0 means h0/hks (and col_ops) carry a leading batch axis of length B. */
+size_t c3b_pwc_workspace_bytes(int B, int K, int N, int d, int lindblad, int batched_model);
+
+/* Closed-system PWC propagators for a whole batch of control signals.
+ *   replaces  tf_batch_propagate + tf_propagation_vectorized + tf.linalg.expm
+ *             (c3/libraries/propagation.py:460-515, 426-440) and tf_matmul_n / tf_matmul_left
+ *             (c3/utils/tf_utils.py:120-193), called B times by the reference's serial loops.
+ *   h0       [d,d]     or [B,d,d]   if batched_model       drift Hamiltonian
+ *   hks      [K,d,d]   or [B,K,d,d] if batched_model       control Hamiltonians (may be NULL if K==0)
+ *   signals  [B,K,N]   float64, contiguous in N            control fields c_k[b,n]
+ *   dt                                                      slice length
+ *   U_out    [B,d,d]   product of all N slice propagators
+ *   dUs_out  [B,N,d,d] every slice propagator expm(-i H_n dt), or NULL to skip the store
+ */
+int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
+                   int batched_model, void* U_out, void* dUs_out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* Same with explicit per-slice Hamiltonians (the reference's `signals is None` branch,
+ * c3/libraries/propagation.py:294-308, 491-499, 437-438):  Hs [B,N,d,d]. */
+int c3b_pwc_closed_hlist(const void* Hs, double dt, int B, int N, int d, void* U_out, void* dUs_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Lindblad (open-system) superoperator propagators, D = d*d:
+ *   replaces tf_propagation_lind (c3/libraries/propagation.py:551-585) incl. the Kronecker
+ *   helpers tf_kron/tf_spre/tf_spost (c3/utils/tf_utils.py:257-280), which are never
+ *   materialised per slice.
+ *   col_ops [C,d,d] or [B,C,d,d];  U_out [B,D,D];  dUs_out [B,N,D,D] or NULL. */
+int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C, const double* signals, double dt,
+                     int B, int K, int N, int d, int batched_model, void* U_out, void* dUs_out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* Ordered product of M matrices per batch row: out[b] = mats[b,M-1] ... mats[b,0].
+ *   replaces tf_matmul_left (c3/utils/tf_utils.py:120-129) and tf_matmul_n (:144-193).
+ *   mats [B,M,D,D], out [B,D,D]. */
+size_t c3b_product_workspace_bytes(int B, int M, int D);
+int c3b_ordered_product(const void* mats, int B, int M, int D, void* out, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* Gate-sequence propagators: out[s] = gates[idx[s,len_s-1]] ... gates[idx[s,0]], identity
+ * for an empty sequence.
+ *   replaces evaluate_sequences (c3/libraries/propagation.py:588-627).
+ *   gates [Gn,D,D];  seq_idx [S,Lmax] int32 (entries >= seq_len[s] ignored);  seq_len [S] int32;
+ *   out [S,D,D]. */
+int c3b_seq_product(const void* gates, int Gn, const int32_t* seq_idx, const int32_t* seq_len, int S, int Lmax,
+                    int D, void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Batched Kronecker product out[b] = A[b] (x) Bm[b]  (tf_kron, c3/utils/tf_utils.py:257-267).
+ *   A [batch,ra,ca] (or [ra,ca] with a_batched==0), Bm likewise, out [batch, ra*rb, ca*cb]. */
+int c3b_kron(const void* A, const void* Bm, void* out, int batch, int ra, int ca, int rb, int cb, int a_batched,
+             int b_batched, void* stream);
+
+/* Tuning knobs (process-wide; for experiments).  key: "target_units", "force_cta",
+ * "rows_warps".  Returns C3B_EINVAL for an unknown key. */
+int c3b_set_tuning(const char* key, long long value);
+
+/* Which kernel c3b_pwc_* would pick for this shape: 1 = register-resident rows kernel,
+ * 2 = CTA kernel with shared-memory matrices, 3 = CTA kernel with global workspace. */
+int c3b_pwc_path(int K, int D, int batched_model);
+
+/* Measured fp64 throughput of this GPU in TFLOP/s (2 flops per FMA) -- the roofline
+ * denominators bench.py reports against.  kind 0: DFMA (fp64 vector pipe),
+ * kind 1: DMMA (mma.sync m8n8k4 f64).  Synchronises the device; not for hot paths.
+ * Returns a negative error code on failure. */
+double c3b_measure_fp64_peak(int kind, int device, double seconds);
+
+/* Development micro-benchmarks of kernel building blocks (TFLOP/s of the fp64 pipe).
+ * kind 0/1/2: the row-times-shared-matrix primitive for D = 9/4/3 with `a` warps per CTA and
+ * `b` CTAs per SM.  Synchronises the device. */
+double c3b_microbench(int kind, int a, int b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C3B200_H */

@@ -1,0 +1,314 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and against the
+reference's golden vectors.  Tolerance is the one BASELINE.json states:
+||U_gpu - U_ref||_F / ||U_ref||_F < 1e-10 (complex128)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_fro
+from oracle import c3_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from c3_b200 import engine
+    return engine
+
+
+def _rand_model(rng, d, K, scale, hermitian=True):
+    def herm():
+        h = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+        return h + h.conj().T if hermitian else h
+    h0 = herm()
+    hks = np.stack([herm() for _ in range(K)]) if K else np.zeros((0, d, d), complex)
+    h0 *= scale / np.abs(h0).sum(axis=0).max()
+    for k in range(K):
+        hks[k] *= 0.2 * scale / np.abs(hks[k]).sum(axis=0).max()
+    return h0, hks
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors of the reference
+# ---------------------------------------------------------------------------------------------
+
+def test_closed_two_qubit_golden(eng, golden_two_qubit):
+    """test/test_two_qubits.py:46-62 of the reference."""
+    g = golden_two_qubit
+    dt = g["ts"][1] - g["ts"][0]
+    U, dUs = eng.pwc_closed(g["hdrift"], g["hks"], g["signals"][None], dt, return_dUs=True)
+    assert rel_fro(U[0].cpu().numpy(), g["propagator"]) < TOL
+    want = orc.tf_batch_propagate(g["hdrift"], g["hks"], g["signals"], dt, 700)
+    assert rel_fro(dUs[0].cpu().numpy(), want) < TOL
+
+
+def test_lindblad_two_qubit_golden(eng, golden_two_qubit):
+    """test/test_two_qubits.py:193-213 of the reference (16x16 superoperator)."""
+    g = golden_two_qubit
+    dt = g["ts"][1] - g["ts"][0]
+    U = eng.pwc_lindblad(g["hdrift"], g["hks"], g["col_ops"], g["signals"][None], dt)
+    assert rel_fro(U[0].cpu().numpy(), g["lindblad_propagator"]) < TOL
+
+
+@pytest.mark.parametrize("q", ["q1", "q2"])
+def test_transmon_expanded_golden(eng, golden_transmon, q):
+    """test/test_transmon_expanded.py:252-283: H-list mode, excitation cut 24 -> 14, blow-up."""
+    from c3_b200 import propagation as prop
+    g = golden_transmon
+    cutter = orc.make_ex_cutter(g["dims"], 4)
+    hs = np.stack([orc.cut_excitations(cutter, h) for h in g[f"hamiltonians_{q}"]])
+    ts = g[f"ts_{q}"][1:]
+    dt = ts[1] - ts[0]
+    U, dUs = eng.pwc_closed_hlist(hs[None], dt, return_dUs=True)
+    dUs_big = prop.blowup_excitations(cutter, dUs[0]).cpu().numpy()
+    U_big = prop.blowup_excitations(cutter, U[0]).cpu().numpy()
+    assert rel_fro(dUs_big, g[f"partial_propagators_{q}"]) < TOL
+    assert rel_fro(U_big, g[f"propagators_{q}"]) < TOL
+
+
+def test_superoperator_helpers_golden(eng, golden_tf_utils):
+    """test/test_tf_utils.py:81-111 of the reference."""
+    from c3_b200 import tf_utils as tu
+    g = golden_tf_utils
+    for i in (0, 1):
+        np.testing.assert_allclose(tu.tf_kron(g[f"tf_kron_{i}_inA"], g[f"tf_kron_{i}_inB"]).cpu().numpy(),
+                                   g[f"tf_kron_{i}_desired"], rtol=1e-13)
+        np.testing.assert_allclose(tu.tf_spre(g[f"tf_spre_{i}_in"]).cpu().numpy(), g[f"tf_spre_{i}_desired"], rtol=1e-13)
+        np.testing.assert_allclose(tu.tf_spost(g[f"tf_spost_{i}_in"]).cpu().numpy(), g[f"tf_spost_{i}_desired"], rtol=1e-13)
+        np.testing.assert_allclose(tu.Id_like(g[f"Id_like_{i}_in"]).cpu().numpy(), g[f"Id_like_{i}_desired"])
+    np.testing.assert_allclose(tu.tf_super(g["tf_super_0_in"]).cpu().numpy(), g["tf_super_0_desired"], rtol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle parity on seeded inputs
+# ---------------------------------------------------------------------------------------------
+
+def test_headline_shape_d9(eng):
+    """BASELINE config 2 shape (d=9, K=2, N=1000) at a batch the oracle finishes in seconds."""
+    from c3_b200 import synth
+    m = synth.two_transmon()
+    sig = synth.controls(m, 6, 1000)
+    U, dUs = eng.pwc_closed(m.h0, m.hks, sig, 1e-11, return_dUs=True)
+    wantU, want_dUs = orc.propagate_batch(m.h0, m.hks, sig, 1e-11, return_dUs=True)
+    for b in range(6):
+        assert rel_fro(U[b].cpu().numpy(), wantU[b]) < TOL
+    assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
+    # without the dUs store the result must be the same bits
+    U2 = eng.pwc_closed(m.h0, m.hks, sig, 1e-11)
+    assert torch.equal(U, U2)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 7, 50, 800])
+def test_config1_single_qubit(eng, N):
+    """BASELINE config 1: one 3-level qubit, B=1, N=50 (and the 800 the hjson actually yields),
+    plus ragged tiny N."""
+    from c3_b200 import synth
+    m = synth.one_qubit()
+    sig = synth.controls(m, 1, N)
+    U, dUs = eng.pwc_closed(m.h0, m.hks, sig, 1e-11, return_dUs=True)
+    wantU, want_dUs = orc.propagate_batch(m.h0, m.hks, sig, 1e-11, return_dUs=True)
+    assert rel_fro(U.cpu().numpy(), wantU) < TOL
+    assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
+
+
+@pytest.mark.parametrize("force_cta", [0, 1])
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 20, 27, 33])
+def test_all_dimensions_and_paths(eng, d, force_cta):
+    """Every register-kernel instantiation (incl. zero-padded d=7, 11), the shared-memory CTA
+    kernel and the global-workspace CTA kernel (d=33), on the same seeded inputs."""
+    rng = np.random.default_rng(100 + d)
+    K, B, N = 2, 3, 37
+    h0, hks = _rand_model(rng, d, K, 1.2)
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    eng.set_tuning("force_cta", force_cta)
+    try:
+        U, dUs = eng.pwc_closed(h0, hks, sig, 1.0, return_dUs=True)
+    finally:
+        eng.set_tuning("force_cta", 0)
+    wantU, want_dUs = orc.propagate_batch(h0, hks, sig, 1.0, return_dUs=True)
+    assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
+    assert rel_fro(U.cpu().numpy(), wantU) < TOL
+
+
+@pytest.mark.parametrize("force_cta", [0, 1])
+@pytest.mark.parametrize("scale", [1e-3, 0.1, 0.5, 1.3, 1.45, 2.5, 4.0])
+def test_pade_orders_and_squarings(eng, scale, force_cta):
+    """Every Pade order / squaring count.  Norms stay below theta_13 = 5.37: above it
+    tf.linalg.expm under-scales and parity would mean matching TensorFlow's own truncation
+    error; that regime is covered against scipy below."""
+    rng = np.random.default_rng(7)
+    d, K, B, N = 9, 2, 2, 21
+    h0, hks = _rand_model(rng, d, K, scale)
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    eng.set_tuning("force_cta", force_cta)
+    try:
+        U, dUs = eng.pwc_closed(h0, hks, sig, 1.0, return_dUs=True)
+    finally:
+        eng.set_tuning("force_cta", 0)
+    wantU, want_dUs = orc.propagate_batch(h0, hks, sig, 1.0, return_dUs=True)
+    assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
+    assert rel_fro(U.cpu().numpy(), wantU) < TOL
+
+
+@pytest.mark.parametrize("force_cta", [0, 1])
+@pytest.mark.parametrize("scale", [8.0, 30.0, 200.0])
+def test_large_norm_against_scipy(eng, scale, force_cta):
+    import scipy.linalg
+    rng = np.random.default_rng(8)
+    d, K, B, N = 6, 1, 1, 5
+    h0, hks = _rand_model(rng, d, K, scale)
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    eng.set_tuning("force_cta", force_cta)
+    try:
+        _, dUs = eng.pwc_closed(h0, hks, sig, 1.0, return_dUs=True)
+    finally:
+        eng.set_tuning("force_cta", 0)
+    for n in range(N):
+        want = scipy.linalg.expm(-1j * (h0 + sig[0, 0, n] * hks[0]))
+        assert rel_fro(dUs[0, n].cpu().numpy(), want) < 1e-11
+
+
+def test_ragged_lengths_and_segments(eng):
+    """N not divisible by the lane-group count / segment length, with segmentation forced."""
+    rng = np.random.default_rng(3)
+    d, K = 9, 2
+    h0, hks = _rand_model(rng, d, K, 1.0)
+    for N in (5, 31, 64, 101):
+        sig = rng.uniform(-1, 1, size=(2, K, N))
+        want = orc.propagate_batch(h0, hks, sig, 1.0)
+        for target in (1, 32768, 10 ** 7):
+            eng.set_tuning("target_units", target)
+            eng.set_tuning("min_chunk", 2)
+            try:
+                U = eng.pwc_closed(h0, hks, sig, 1.0)
+            finally:
+                eng.set_tuning("target_units", 32768)
+                eng.set_tuning("min_chunk", 8)
+            assert rel_fro(U.cpu().numpy(), want) < TOL
+
+
+def test_lindblad_small_dims(eng):
+    """Lindblad with d=2 (D=4, register kernel on a NON-Hermitian generator), d=3 (D=9) and
+    d=5 (D=25, CTA kernel)."""
+    for d in (2, 3, 5):
+        rng = np.random.default_rng(20 + d)
+        K, B, N = 2, 2, 25
+        h0, hks = _rand_model(rng, d, K, 0.8)
+        col = 0.3 * (rng.normal(size=(2, d, d)) + 1j * rng.normal(size=(2, d, d)))
+        sig = rng.uniform(-1, 1, size=(B, K, N))
+        U, dUs = eng.pwc_lindblad(h0, hks, col, sig, 0.7, return_dUs=True)
+        for b in range(B):
+            want = orc.tf_batch_propagate(h0, hks, sig[b], 0.7, N, col_ops=col, lindbladian=True)
+            assert rel_fro(dUs[b].cpu().numpy(), want) < TOL
+            assert rel_fro(U[b].cpu().numpy(), orc.tf_matmul_n(want, orc.compute_folding_stack(N))) < TOL
+
+
+def test_lindblad_config3_shape(eng):
+    """BASELINE config 3 shape (two 3-level transmons, D=81) on a small batch / few slices."""
+    from c3_b200 import synth
+    m = synth.two_transmon()
+    B, N = 2, 12
+    sig = synth.controls(m, B, 1000)[:, :, 494:494 + N].copy()
+    U, dUs = eng.pwc_lindblad(m.h0, m.hks, m.col_ops, sig, 1e-11, return_dUs=True)
+    for b in range(B):
+        want = orc.tf_batch_propagate(m.h0, m.hks, sig[b], 1e-11, N, col_ops=m.col_ops, lindbladian=True)
+        assert rel_fro(dUs[b].cpu().numpy(), want) < TOL
+        assert rel_fro(U[b].cpu().numpy(), orc.tf_matmul_n(want, orc.compute_folding_stack(N))) < TOL
+
+
+def test_config5_shape_d27(eng):
+    """BASELINE config 5 shape (tunable coupler d=27, K=3) on a small batch."""
+    from c3_b200 import synth
+    m = synth.tunable_coupler()
+    sig = synth.controls(m, 3, 64)
+    U, dUs = eng.pwc_closed(m.h0, m.hks, sig, 1e-11, return_dUs=True)
+    wantU, want_dUs = orc.propagate_batch(m.h0, m.hks, sig, 1e-11, return_dUs=True)
+    assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
+    assert rel_fro(U.cpu().numpy(), wantU) < TOL
+
+
+def test_batched_model(eng):
+    """Per-sample models h0[B,d,d], hks[B,K,d,d] (optimiser samples that change the model)."""
+    rng = np.random.default_rng(11)
+    d, K, B, N = 9, 2, 4, 19
+    models = [_rand_model(rng, d, K, 1.0) for _ in range(B)]
+    h0 = np.stack([m[0] for m in models])
+    hks = np.stack([m[1] for m in models])
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    U = eng.pwc_closed(h0, hks, sig, 1.0)
+    for b in range(B):
+        want = orc.propagate_batch(h0[b], hks[b], sig[b:b + 1], 1.0)[0]
+        assert rel_fro(U[b].cpu().numpy(), want) < TOL
+
+
+@pytest.mark.parametrize("D", [2, 9, 16, 27, 70])
+@pytest.mark.parametrize("M", [1, 2, 9, 64, 301])
+def test_ordered_product(eng, D, M):
+    """tf_matmul_left / tf_matmul_n semantics (c3/utils/tf_utils.py:120-193)."""
+    from c3_b200 import tf_utils as tu
+    rng = np.random.default_rng(D * 1000 + M)
+    x = (rng.normal(size=(M, D, D)) + 1j * rng.normal(size=(M, D, D))) / np.sqrt(2 * D)
+    want = orc.tf_matmul_n(x, orc.compute_folding_stack(M))
+    got = tu.tf_matmul_n(x, tu.compute_folding_stack(M)).cpu().numpy()
+    assert rel_fro(got, want) < 1e-11
+    assert rel_fro(tu.tf_matmul_left(x).cpu().numpy(), orc.tf_matmul_left(x)) < 1e-11
+    if M > 1:
+        assert rel_fro(tu.tf_matmul_right(x).cpu().numpy(), orc.tf_matmul_right(x)) < 1e-11
+
+
+def test_evaluate_sequences(eng):
+    """c3/libraries/propagation.py:588-627 incl. the empty-sequence identity."""
+    from c3_b200 import propagation as prop
+    rng = np.random.default_rng(5)
+    d = 9
+    names = ["rx90p[0]", "ry90p[0]", "rx90m[0]", "ry90m[0]", "id[0]"]
+    gates = {}
+    for n in names:
+        q, _ = np.linalg.qr(rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d)))
+        gates[n] = q
+    seqs = [[], ["id[0]"], ["rx90p[0]", "ry90p[0]"]]
+    for _ in range(40):
+        L = int(rng.integers(1, 60))
+        seqs.append([names[i] for i in rng.integers(0, len(names), size=L)])
+    got = prop.evaluate_sequences({k: torch.as_tensor(v) for k, v in gates.items()}, seqs)
+    want = orc.evaluate_sequences(gates, seqs)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert rel_fro(a.cpu().numpy(), b) < 1e-11
+    np.testing.assert_array_equal(got[0].cpu().numpy(), np.eye(d))
+
+
+def test_full_size_properties(eng):
+    """BASELINE config 2 at full size (d=9, N=1000, B=256): size-independent properties.
+    U must be unitary; splitting the time axis must compose (U = U_second_half U_first_half);
+    and a sample of batch rows is checked against the oracle."""
+    from c3_b200 import synth
+    m = synth.two_transmon()
+    B, N = 256, 1000
+    sig = synth.controls_fast(m, B, N)
+    U = eng.pwc_closed(m.h0, m.hks, sig, 1e-11)
+    eye = torch.eye(9, dtype=torch.complex128, device=U.device)
+    err = (U.conj().transpose(-1, -2) @ U - eye).abs().amax().item()
+    assert err < 1e-11
+    U1 = eng.pwc_closed(m.h0, m.hks, sig[:, :, :500].copy(), 1e-11)
+    U2 = eng.pwc_closed(m.h0, m.hks, sig[:, :, 500:].copy(), 1e-11)
+    comp = torch.matmul(U2, U1)
+    assert rel_fro(comp.cpu().numpy(), U.cpu().numpy()) < 1e-11
+    for b in (0, 17, 255):
+        want = orc.propagate_batch(m.h0, m.hks, sig[b:b + 1], 1e-11)[0]
+        assert rel_fro(U[b].cpu().numpy(), want) < TOL
+
+
+def test_error_reporting(eng):
+    from c3_b200 import _lib
+    lib = _lib.load()
+    rc = lib.c3b_pwc_closed(None, None, None, 1.0, 1, 0, 1, 3, 0, None, None, None, 0, None)
+    assert rc != 0
+    assert lib.c3b_last_error().decode().startswith("C3:ERROR:")
+    with pytest.raises(ValueError):
+        eng.pwc_closed(np.eye(3), np.zeros((1, 4, 4)), np.zeros((1, 1, 5)), 1.0)
