@@ -36,6 +36,7 @@ int fail(int code, const char* fmt, ...) {
 long long g_target_units = 32768;  // rows kernel: aim for this many warp work units per launch
 long long g_force_cta = 0;         // route everything to the CTA kernel (testing)
 long long g_min_chunk = 8;         // rows kernel: minimum slices per lane group
+long long g_rows_variant = 1;      // 0: v1 kernel, 1: v2 (255 regs), 2: v2 V-in-smem (168 regs), 3: v2 (168 regs)
 
 int num_sms() {
     static int cached = 0;
@@ -151,7 +152,26 @@ int launch_rows_t(const RowsParams& rp, cudaStream_t st) {
     return C3B_OK;
 }
 
+template <int D, int MINB, bool VSMEM>
+int launch_rows2_t(const RowsParams& rp, cudaStream_t st) {
+    using L = Rows2Layout<D, kRowsWarps, VSMEM>;
+    const size_t smem = L::smem_bytes(rp.K);
+    if (smem > 227 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: too many control lines (K=%d) for the d=%d register kernel", rp.K, rp.d);
+    auto kern = pwc_rows2_kernel<D, kRowsWarps, MINB, VSMEM>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long units = (long long)rp.B * rp.S;
+    const int grid = (int)((units + kRowsWarps - 1) / kRowsWarps);
+    kern<<<grid, kRowsWarps * 32, smem, st>>>(rp);
+    CUDA_TRY(cudaGetLastError());
+    return C3B_OK;
+}
+
 int launch_rows(const RowsParams& rp, cudaStream_t st) {
+    if (rows_template_dim(rp.d) == 9 && g_rows_variant > 0) {
+        if (g_rows_variant == 1) return launch_rows2_t<9, 2, false>(rp, st);
+        if (g_rows_variant == 2) return launch_rows2_t<9, 3, true>(rp, st);
+        return launch_rows2_t<9, 3, false>(rp, st);
+    }
     switch (rows_template_dim(rp.d)) {
         case 2: return launch_rows_t<2, 4>(rp, st);
         case 3: return launch_rows_t<3, 4>(rp, st);
@@ -263,6 +283,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (key == nullptr) return fail(C3B_EINVAL, "C3:ERROR: null tuning key");
     if (!strcmp(key, "target_units")) { g_target_units = value < 1 ? 1 : value; return C3B_OK; }
     if (!strcmp(key, "force_cta")) { g_force_cta = value; return C3B_OK; }
+    if (!strcmp(key, "rows_variant")) { g_rows_variant = value; return C3B_OK; }
     if (!strcmp(key, "min_chunk")) { g_min_chunk = value < 1 ? 1 : value; return C3B_OK; }
     return fail(C3B_EINVAL, "C3:ERROR: unknown tuning key '%s'", key);
 }

@@ -294,4 +294,265 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_rows_kernel(const RowsPa
     }
 }
 
+// =============================================================================================
+// v2: the same algorithm as pwc_rows_kernel, restructured as a small state machine around ONE
+// instance of the row-times-matrix product so that the slice loop fits the instruction cache
+// and the live register set is {left operand row, product row, W row (+ V row)}.
+//   phase 0..mi      : C = A^(2ph+2); W += c_odd C, V += c_even C
+//   phase mi+1       : C = U = W A;   Q = V - U, R = V + U;  R <- Q^{-1} R  (Gauss-Jordan)
+//   next s phases    : C = R R  (squarings)
+//   last phase       : C = dU P  (running ordered product; skipped for the first slice)
+// VSMEM keeps the V row in shared memory (own row only) instead of registers.
+// =============================================================================================
+template <int D, int WARPS, bool VSMEM>
+struct Rows2Layout {
+    static constexpr int G = 32 / D;
+    static constexpr int GROUP_ELEMS = (VSMEM ? 4 : 3) * D * D + 4 * D;  // bufA, bufA2, bufP, [bufV], piv[2][2D]
+    static constexpr int WARP_ELEMS = G * GROUP_ELEMS;
+    __host__ __device__ static size_t smem_bytes(int K) {
+        size_t model = (size_t)(K + 1) * D * D * sizeof(cplx) + (size_t)(((K + 1) * D + 1) & ~1) * sizeof(double);
+        return model + (size_t)WARPS * WARP_ELEMS * sizeof(cplx);
+    }
+};
+
+template <int D, int WARPS, int MINB, bool VSMEM>
+__global__ void __launch_bounds__(WARPS * 32, MINB) pwc_rows2_kernel(const RowsParams p) {
+    using L = Rows2Layout<D, WARPS, VSMEM>;
+    constexpr int G = L::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = p.K;
+    const int d = p.d;
+    cplx* sG = reinterpret_cast<cplx*>(smem_raw);
+    double* sRS = reinterpret_cast<double*>(sG + (K + 1) * D * D);
+    cplx* sWarps = reinterpret_cast<cplx*>(sRS + (((K + 1) * D + 1) & ~1));
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const bool hmode = p.hlist != nullptr;
+
+    if (!hmode) {
+        for (int idx = tid; idx < (K + 1) * D * D; idx += WARPS * 32) {
+            const int k = idx / (D * D);
+            const int rem = idx - k * D * D;
+            const int r = rem / D, j = rem - r * D;
+            cplx v = cmake(0.0, 0.0);
+            if (r < d && j < d) v = p.G[(size_t)k * d * d + r * d + j];
+            sG[idx] = v;
+        }
+        for (int idx = tid; idx < (K + 1) * D; idx += WARPS * 32) {
+            const int k = idx / D, r = idx - k * D;
+            sRS[idx] = (r < d) ? p.RS[k * d + r] : 0.0;
+        }
+    }
+    __syncthreads();
+
+    const long long unit = (long long)blockIdx.x * WARPS + warp;
+    if (unit >= (long long)p.B * p.S) return;
+    const int b = (int)(unit / p.S);
+    const int sidx = (int)(unit - (long long)b * p.S);
+
+    const int g_raw = lane / D;
+    const bool lane_on = g_raw < G;
+    const int g = lane_on ? g_raw : 0;
+    const int r = lane_on ? (lane - g_raw * D) : 0;
+
+    cplx* gbase = sWarps + (size_t)warp * L::WARP_ELEMS + (size_t)g * L::GROUP_ELEMS;
+    cplx* bufA = gbase;
+    cplx* bufA2 = gbase + D * D;
+    cplx* bufP = gbase + 2 * D * D;
+    cplx* bufV = gbase + 3 * D * D + r * D;              // own row (VSMEM only)
+    cplx* piv = gbase + (VSMEM ? 4 : 3) * D * D;
+
+    const int n_begin = sidx * p.seg_len;
+    const int n_end = min(p.N, n_begin + p.seg_len);
+    const int len = n_end - n_begin;
+    const int cl = (len + G - 1) / G;
+    const int my_begin = n_begin + g * cl;
+    const int my_end = min(n_end, my_begin + cl);
+
+    const double* sig_b = p.signals ? p.signals + (size_t)b * K * p.N : nullptr;
+    const cplx hs = cmake(p.hscale_re, p.hscale_im);
+
+#pragma unroll 1
+    for (int it = 0; it < cl; ++it) {
+        const int n = my_begin + it;
+        const bool on = lane_on && (n < my_end);
+
+        cplx Xop[D];
+        double nb = 0.0;
+        if (!hmode) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) Xop[j] = on ? sG[r * D + j] : cmake(0.0, 0.0);
+            nb = on ? sRS[r] : 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double c = on ? __ldg(sig_b + (size_t)k * p.N + n) : 0.0;
+                const cplx* gk = sG + (k + 1) * D * D + r * D;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const cplx gv = gk[j];
+                    Xop[j].x = fma(c, gv.x, Xop[j].x);
+                    Xop[j].y = fma(c, gv.y, Xop[j].y);
+                }
+                nb = fma(fabs(c), sRS[(k + 1) * D + r], nb);
+            }
+        } else {
+            const cplx* hrow = p.hlist + ((size_t)b * p.N + (on ? n : 0)) * d * d + (size_t)r * d;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                cplx h = cmake(0.0, 0.0);
+                if (on && r < d && j < d) h = hrow[j];
+                Xop[j] = cmul(hs, h);
+                nb += cabs1(Xop[j]);
+            }
+        }
+        nb = warp_max(nb);
+
+        const int s = squarings_for(nb, C3B_NOPIVOT_LIMIT);
+        const double ns = nb * pow2neg(s);
+        const int mi = ns < C3B_THETA3 ? 0 : (ns < C3B_THETA5 ? 1 : (ns < C3B_THETA7 ? 2 : 3));
+        if (s > 0) {
+            const double sc = pow2neg(s);
+#pragma unroll
+            for (int j = 0; j < D; ++j) { Xop[j].x *= sc; Xop[j].y *= sc; }
+        }
+        store_row<D>(bufA, r, Xop, lane_on);
+        __syncwarp();
+
+        const cplx* Y = bufA;
+        cplx W[D];
+        cplx V[VSMEM ? 1 : D];
+        const int ph_solve = mi + 1;
+        const int ph_lastsq = mi + 1 + s;
+        const int ph_last = ph_lastsq + (it > 0 ? 1 : 0);
+        const double* cf = kPade[mi];
+
+#pragma unroll 1
+        for (int ph = 0; ph <= ph_last; ++ph) {
+            cplx C[D];
+            mm_row<D>(Xop, Y, C);
+            if (ph < ph_solve) {
+                const double cw = cf[2 * ph + 3], cv = cf[2 * ph + 2];
+                if (ph == 0) {
+                    const double c1 = cf[1], c0 = cf[0];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        W[j] = cmake(cw * C[j].x + (j == r ? c1 : 0.0), cw * C[j].y);
+                        const cplx v = cmake(cv * C[j].x + (j == r ? c0 : 0.0), cv * C[j].y);
+                        if (VSMEM) { if (lane_on) bufV[j] = v; } else V[VSMEM ? 0 : j] = v;
+                    }
+                    if (mi > 0) {
+                        store_row<D>(bufA2, r, C, lane_on);
+                        __syncwarp();
+                        Y = bufA2;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        W[j].x = fma(cw, C[j].x, W[j].x);
+                        W[j].y = fma(cw, C[j].y, W[j].y);
+                        if (VSMEM) {
+                            cplx v = bufV[j];
+                            v.x = fma(cv, C[j].x, v.x);
+                            v.y = fma(cv, C[j].y, v.y);
+                            if (lane_on) bufV[j] = v;
+                        } else {
+                            V[VSMEM ? 0 : j].x = fma(cv, C[j].x, V[VSMEM ? 0 : j].x);
+                            V[VSMEM ? 0 : j].y = fma(cv, C[j].y, V[VSMEM ? 0 : j].y);
+                        }
+                    }
+                }
+                if (ph < mi) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) Xop[j] = C[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) Xop[j] = W[j];
+                    Y = bufA;
+                }
+            } else if (ph == ph_solve) {
+                // C = U.  W <- Q = V - U,  Xop <- R = V + U, then R <- Q^{-1} R
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const cplx v = VSMEM ? bufV[j] : V[VSMEM ? 0 : j];
+                    W[j] = cmake(v.x - C[j].x, v.y - C[j].y);
+                    Xop[j] = cmake(v.x + C[j].x, v.y + C[j].y);
+                }
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    cplx* pv = piv + (k & 1) * 2 * D;
+                    if (lane_on && r == k) {
+#pragma unroll
+                        for (int j = k; j < D; ++j) pv[j] = W[j];
+#pragma unroll
+                        for (int j = 0; j < D; ++j) pv[D + j] = Xop[j];
+                    }
+                    __syncwarp();
+                    const cplx inv = crcp(pv[k]);
+                    cplx f = cmul(W[k], inv);
+                    if (r == k) f = cmake(1.0 - inv.x, -inv.y);
+#pragma unroll
+                    for (int j = k + 1; j < D; ++j) cfms(W[j], f, pv[j]);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) cfms(Xop[j], f, pv[D + j]);
+                }
+                if (s > 0) {
+                    store_row<D>(bufA, r, Xop, lane_on);
+                    __syncwarp();
+                    Y = bufA;
+                } else {
+                    Y = bufP;
+                }
+            } else if (ph <= ph_lastsq) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) Xop[j] = C[j];
+                if (ph < ph_lastsq) {
+                    __syncwarp();
+                    store_row<D>(bufA, r, Xop, lane_on);
+                    __syncwarp();
+                    Y = bufA;
+                } else {
+                    Y = bufP;
+                }
+            } else {
+                // C = dU_n * P
+                __syncwarp();
+                store_row<D>(bufP, r, C, lane_on);
+            }
+            if (ph == ph_lastsq) {
+                // Xop holds dU_n
+                if (p.dUs_out != nullptr && on && r < d) {
+                    cplx* o = p.dUs_out + ((size_t)b * p.N + n) * d * d + (size_t)r * d;
+#pragma unroll
+                    for (int j = 0; j < D; ++j)
+                        if (j < d) o[j] = Xop[j];
+                }
+                if (it == 0) store_row<D>(bufP, r, Xop, lane_on);
+            }
+        }
+    }
+    __syncwarp();
+
+    cplx* wbase = sWarps + (size_t)warp * L::WARP_ELEMS;
+    cplx T[D];
+    {
+        const cplx* last = wbase + (size_t)(G - 1) * L::GROUP_ELEMS + 2 * D * D;
+#pragma unroll
+        for (int j = 0; j < D; ++j) T[j] = last[r * D + j];
+    }
+#pragma unroll 1
+    for (int gg = G - 2; gg >= 0; --gg) {
+        cplx T2[D];
+        mm_row<D>(T, wbase + (size_t)gg * L::GROUP_ELEMS + 2 * D * D, T2);
+#pragma unroll
+        for (int j = 0; j < D; ++j) T[j] = T2[j];
+    }
+    if (lane_on && g == 0 && r < d) {
+        cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * d * d) : (p.seg_out + ((size_t)b * p.S + sidx) * d * d);
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            if (j < d) o[r * d + j] = T[j];
+    }
+}
+
 }  // namespace c3b
