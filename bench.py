@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- propagator slices/s on the BASELINE.json headline workload.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (default N=1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+    torchrun ... bench.py --gpus N ...                        # N > 1: one rank per GPU over NCCL
+
+Workload (BASELINE.json `metric`): two 3-level transmons, d = 9, K = 2
+control lines, N = 1000 PWC slices, B = 4096 control-signal sets PER GPU (the batch axis shards
+across GPUs with no data-path collective; one all-gather of the final unitaries per step is
+included for N > 1, as BASELINE.json's north_star specifies).  A "step" is one batched
+`compute_propagators`-equivalent pass: signals[B,K,N] -> U[B,9,9].
+
+One JSON line on stdout (rank 0).  `value` = whole-job slices/s with inputs resident in HBM;
+`e2e` = the same through the public API with HOST buffers (H2D of the signals and D2H of the
+unitaries inside the timed region); `roofline` = the fused kernel against the fp64 DFMA peak
+measured in this process (MEASURED_PEAKS.json carries no fp64 figure) and against measured
+HBM; `cpu_baseline` = the oracle port (the reference restated op-for-op in numpy; TensorFlow
+is not installable here) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D, K, N, B_PER_GPU, DT = 9, 2, 1000, 4096, 1e-11
+N_ROTATE = 3  # rotating input buffers: 3 x 65.5 MB > 126 MB L2
+WORKLOAD = "two-transmon d=9, K=2 controls, N=1000 PWC slices, B=4096 signal sets per GPU (cfg2 shape at the metric's 4k batch)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side (oracle port of the reference) -- the ONLY part of this file that touches oracle/
+# ------------------------------------------------------------------------------------------------
+
+def _cpu_worker(args):
+    seed, nb = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import numpy as np  # noqa: F401
+    from oracle import c3_oracle as orc
+    from c3_b200 import synth
+    m = synth.two_transmon()
+    sig = synth.controls_fast(m, nb, N, DT, seed=seed)
+    t0 = time.perf_counter()
+    U = orc.propagate_batch(m.h0, m.hks, sig, DT)
+    return time.perf_counter() - t0, float(abs(U).sum())
+
+
+class CpuPool:
+    """One worker process per host core, kept alive across steps (spawned, so it is safe to use
+    before or after CUDA initialisation)."""
+
+    def __init__(self, n_proc: int):
+        import multiprocessing as mp
+        self.n = n_proc
+        self.pool = mp.get_context("spawn").Pool(n_proc)
+        self.pool.map(_cpu_worker, [(10_000 + i, 1) for i in range(n_proc)])  # import warm-up
+
+    def run(self, per_proc: int, seed: int = 0):
+        """B = n_proc * per_proc signal sets through the oracle (reference restatement: per
+        signal set, batched expm over the N slices then the pairwise product tree, exactly the
+        reference's serial loop).  Returns (slices_per_s, wall_s)."""
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_worker, [(seed + i, per_proc) for i in range(self.n)], chunksize=1)
+        wall = time.perf_counter() - t0
+        return self.n * per_proc * N / wall, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    per_proc = 6
+    vals = []
+    pool = CpuPool(cores)
+    for _ in range(args.warmup):
+        pool.run(1)
+    t_all = 0.0
+    for s in range(args.steps):
+        v, wall = pool.run(per_proc, seed=100 * s)
+        vals.append(v)
+        t_all += wall
+    pool.close()
+    value = args.steps * cores * per_proc * N / t_all if t_all > 0 else 0.0
+    sample = f"{cores * per_proc} signal sets x {N} slices per step ({cores} processes x {per_proc})"
+    line = {
+        "impl": "reference", "metric": "propagator slices/sec", "value": value, "unit": "slices/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "each step is a bounded sample of the workload on host cores"},
+        "cpu_baseline": {"value": value, "unit": "slices/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_note": "TensorFlow (the reference's arithmetic backend) is not installable in this image; "
+                          "this is oracle/c3_oracle.py, the numpy restatement pinned to the reference's golden vectors",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": max(power) if power else None}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def run_engine(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and rank == 0 and world > 1:
+        print(f"[bench] WORLD_SIZE={world} != --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
+    n_gpus = world if world > 1 else 1
+
+    # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process
+    cpu_baseline = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        per_proc = 12
+        pool = CpuPool(cores)
+        v, wall = pool.run(per_proc)
+        pool.close()
+        cpu_baseline = {"value": v, "unit": "slices/s", "cores": cores, "kind": "port",
+                        "sample": f"{cores * per_proc} signal sets x {N} slices ({cores} processes x {per_proc}), "
+                                  f"{wall:.1f} s wall; oracle/c3_oracle.py (TensorFlow not installable)"}
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from c3_b200 import engine, synth, propagation
+    from c3_b200.distributed import all_gather_unitaries
+
+    model = synth.two_transmon()
+    B = B_PER_GPU
+    h0 = torch.as_tensor(model.h0, device=dev)
+    hks = torch.as_tensor(model.hks, device=dev)
+    host_sig = [torch.as_tensor(synth.controls_fast(model, B, N, DT, seed=1234 + 17 * i, b_offset=rank * 1000003))
+                .pin_memory() for i in range(N_ROTATE)]
+    dev_sig = [h.to(dev) for h in host_sig]
+    U_host = torch.empty((B, D, D), dtype=torch.complex128).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def step(i):
+        U = engine.pwc_closed(h0, hks, dev_sig[i % N_ROTATE], DT)
+        if world > 1:
+            return all_gather_unitaries(U)
+        return U
+
+    # ---- parity in the same run: sampled rows against the oracle ---------------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import c3_oracle as orc
+        rows = [0, 1, B // 2, B - 1]
+        Ug = engine.pwc_closed(h0, hks, dev_sig[0], DT)[rows].cpu().numpy()
+        want = orc.propagate_batch(model.h0, model.hks, host_sig[0][rows].numpy(), DT)
+        parity = max(float(np.linalg.norm(Ug[i] - want[i]) / np.linalg.norm(want[i])) for i in range(len(rows)))
+
+    # ---- fp64 peak (roofline denominator), measured live -----------------------------------
+    dfma_peak = engine.measure_fp64_peak("dfma", 0.5, device=local_rank)
+
+    for i in range(max(args.warmup, 3)):  # never fewer than 3 warm-up steps
+        step(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = engine.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = engine.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+
+    # ---- dominant kernel alone (events inside the library, on the launching stream) ----------
+    engine.set_tuning("profile", 1)
+    kms = []
+    for i in range(min(args.steps, 10)):
+        engine.pwc_closed(h0, hks, dev_sig[i % N_ROTATE], DT)
+        kms.append(engine.last_kernel_ms())
+    engine.set_tuning("profile", 0)
+    kernel_ms = statistics.mean(kms)
+
+    # ---- end to end through the public API with host buffers ---------------------------------
+    def e2e_step(i):
+        U = propagation.pwc_batch(h0, hks, host_sig[i % N_ROTATE], DT)   # H2D inside
+        if world > 1:
+            U = all_gather_unitaries(U)[rank * B:(rank + 1) * B]
+        U_host.copy_(U, non_blocking=True)                                # D2H inside
+        torch.cuda.synchronize()
+        return U_host
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_s * 1e3, kernel_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms, kernel_ms = [float(x) for x in t.tolist()]
+        e2e_s = e2e_ms * 1e-3
+
+    if rank == 0:
+        ms_per_step = ms_total / args.steps
+        value = n_gpus * B * N / (ms_per_step * 1e-3)
+        e2e_value = n_gpus * B * N * args.steps / e2e_s
+        # algorithmic flops per slice: Higham's minimal (m, s) for the slice norms of this workload
+        from c3_b200.flops import flops_per_slice_closed
+        fl = flops_per_slice_closed(model.h0, model.hks, host_sig[0][:8].numpy(), DT)
+        achieved_tf = B * N * fl / (kernel_ms * 1e-3) / 1e12
+        alg_bytes = B * N * (8 * K) + B * D * D * 16
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": "propagator slices/sec", "value": value, "unit": "slices/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64 FMA)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "d": D, "K": K, "N": N, "B_per_gpu": B, "global_batch": B * n_gpus,
+                       "dt": DT, "parallelism": f"batch-sharded x{n_gpus}" + (", one all-gather of U per step" if n_gpus > 1 else ""),
+                       "l2": f"{N_ROTATE} rotating input buffers ({N_ROTATE * B * K * N * 8 / 1e6:.0f} MB > 126 MB L2)",
+                       "kernel": "pwc_rows2_kernel<9> (fused assemble + Pade expm + ordered product)"},
+            "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": B * K * N * 8,
+                    "d2h_bytes_per_step": B * D * D * 16, "api": "c3_b200.propagation.pwc_batch(host signals) -> U.cpu()"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / dfma_peak, "traffic": None,
+                         "flops_per_slice": fl, "kernel_ms": kernel_ms,
+                         "peak_source": "DFMA micro-benchmark in this process (c3b_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no fp64 entry",
+                         "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                 "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "parity_rel_fro_max": parity,
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

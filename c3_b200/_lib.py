@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(HERE, "libc3b200.so")
 SYMBOLS = [
     "c3b_version", "c3b_last_error", "c3b_pwc_workspace_bytes", "c3b_pwc_closed", "c3b_pwc_closed_hlist",
     "c3b_pwc_lindblad", "c3b_product_workspace_bytes", "c3b_ordered_product", "c3b_seq_product", "c3b_kron",
-    "c3b_set_tuning", "c3b_pwc_path", "c3b_measure_fp64_peak", "c3b_microbench",
+    "c3b_set_tuning", "c3b_pwc_path", "c3b_measure_fp64_peak", "c3b_microbench", "c3b_launch_count",
+    "c3b_last_kernel_ms",
 ]
 
 _lib = None
@@ -58,6 +59,8 @@ def load() -> C.CDLL:
     lib.c3b_pwc_path.argtypes = [i, i, i]
     lib.c3b_measure_fp64_peak.restype = d
     lib.c3b_measure_fp64_peak.argtypes = [i, i, d]
+    lib.c3b_launch_count.restype = C.c_longlong
+    lib.c3b_last_kernel_ms.restype = d
     lib.c3b_microbench.restype = d
     lib.c3b_microbench.argtypes = [i, i, i]
     _lib = lib

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 
 #include "c3b_common.cuh"
 #include "pwc_cta.cuh"
@@ -31,6 +32,11 @@ int fail(int code, const char* fmt, ...) {
         cudaError_t _e = (expr);                                                                   \
         if (_e != cudaSuccess) return fail(C3B_ECUDA, "C3:ERROR: %s failed: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
+
+std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py's gpu_launches)
+long long g_profile = 0;               // when set, the main PWC kernel of each call is bracketed by events
+cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+bool g_ev_valid = false;
 
 // ---- tuning (process-wide) -------------------------------------------------------------------
 long long g_target_units = 32768;  // rows kernel: aim for this many warp work units per launch
@@ -149,6 +155,7 @@ int launch_rows_t(const RowsParams& rp, cudaStream_t st) {
     const int grid = (int)((units + kRowsWarps - 1) / kRowsWarps);
     kern<<<grid, kRowsWarps * 32, smem, st>>>(rp);
     CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
 }
 
@@ -163,6 +170,7 @@ int launch_rows2_t(const RowsParams& rp, cudaStream_t st) {
     const int grid = (int)((units + kRowsWarps - 1) / kRowsWarps);
     kern<<<grid, kRowsWarps * 32, smem, st>>>(rp);
     CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
 }
 
@@ -193,6 +201,7 @@ int launch_cta_t(const CtaParams& cp, int grid, cudaStream_t st) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kCtaThreads, smem, st>>>(cp);
     CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
 }
 
@@ -211,6 +220,7 @@ int launch_product_t(const ProductParams& pp, int grid, cudaStream_t st) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kCtaThreads, smem, st>>>(pp);
     CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
 }
 
@@ -231,6 +241,10 @@ int launch_product(ProductParams pp, cudaStream_t st) {
 int run_pwc(const Plan& pl, const cplx* G, const double* RS, const double* signals, const cplx* hlist, double dt,
             int B, int K, int N, int D, int batched_model, cplx* U_out, cplx* dUs_out, char* ws, cudaStream_t st) {
     cplx* seg = pl.S > 1 ? reinterpret_cast<cplx*>(ws + pl.off_seg) : nullptr;
+    if (g_profile) {
+        if (g_ev0 == nullptr) { CUDA_TRY(cudaEventCreate(&g_ev0)); CUDA_TRY(cudaEventCreate(&g_ev1)); }
+        CUDA_TRY(cudaEventRecord(g_ev0, st));
+    }
     if (pl.path == 1) {
         RowsParams rp{};
         rp.G = G; rp.RS = RS; rp.signals = signals; rp.hlist = hlist;
@@ -252,6 +266,7 @@ int run_pwc(const Plan& pl, const cplx* G, const double* RS, const double* signa
         int rc = launch_cta(cp, pl.grid, st);
         if (rc) return rc;
     }
+    if (g_profile) { CUDA_TRY(cudaEventRecord(g_ev1, st)); g_ev_valid = true; }
     if (pl.S > 1) {
         ProductParams pp{};
         pp.mats = seg; pp.idx = nullptr; pp.lens = nullptr;
@@ -283,6 +298,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (key == nullptr) return fail(C3B_EINVAL, "C3:ERROR: null tuning key");
     if (!strcmp(key, "target_units")) { g_target_units = value < 1 ? 1 : value; return C3B_OK; }
     if (!strcmp(key, "force_cta")) { g_force_cta = value; return C3B_OK; }
+    if (!strcmp(key, "profile")) { g_profile = value; return C3B_OK; }
     if (!strcmp(key, "rows_variant")) { g_rows_variant = value; return C3B_OK; }
     if (!strcmp(key, "min_chunk")) { g_min_chunk = value < 1 ? 1 : value; return C3B_OK; }
     return fail(C3B_EINVAL, "C3:ERROR: unknown tuning key '%s'", key);
@@ -315,9 +331,11 @@ int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, doubl
         const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
         setup_closed_kernel<<<blocks, 256, 0, st>>>(static_cast<const cplx*>(h0), static_cast<const cplx*>(hks), G, Bm, K, d, dt);
         CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
         const long long nrows = (long long)Bm * (K + 1) * d;
         rowsum_kernel<<<(int)((nrows * 32 + 255) / 256), 256, 0, st>>>(G, RS, nrows, d);
         CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     return run_pwc(pl, G, RS, signals, nullptr, dt, B, K, N, d, batched_model, static_cast<cplx*>(U_out),
                    static_cast<cplx*>(dUs_out), ws, st);
@@ -358,9 +376,11 @@ int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C
         setup_lindblad_kernel<<<blocks, 256, 0, st>>>(static_cast<const cplx*>(h0), static_cast<const cplx*>(hks),
                                                       C > 0 ? static_cast<const cplx*>(col_ops) : nullptr, G, Bm, K, C, d, dt);
         CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
         const long long nrows = (long long)Bm * (K + 1) * D;
         rowsum_kernel<<<(int)((nrows * 32 + 255) / 256), 256, 0, st>>>(G, RS, nrows, D);
         CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     return run_pwc(pl, G, RS, signals, nullptr, dt, B, K, N, D, batched_model, static_cast<cplx*>(U_out),
                    static_cast<cplx*>(dUs_out), ws, st);
@@ -433,6 +453,7 @@ int c3b_kron(const void* A, const void* Bm, void* out, int batch, int ra, int ca
         static_cast<const cplx*>(A), static_cast<const cplx*>(Bm), static_cast<cplx*>(out), batch, ra, ca, rb, cb,
         a_batched ? (long long)ra * ca : 0, b_batched ? (long long)rb * cb : 0);
     CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
 }
 
@@ -441,6 +462,16 @@ double c3b_measure_fp64_peak(int kind, int device, double seconds) {
     int rc = measure_fp64_peak(kind, device, seconds, &tf);
     if (rc != 0) return (double)fail(C3B_ECUDA, "C3:ERROR: fp64 peak measurement failed (cuda error %d)", rc);
     return tf;
+}
+
+long long c3b_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+double c3b_last_kernel_ms(void) {
+    if (!g_ev_valid) return (double)fail(C3B_EINVAL, "C3:ERROR: no profiled launch (set tuning 'profile' to 1 first)");
+    if (cudaEventSynchronize(g_ev1) != cudaSuccess) return (double)fail(C3B_ECUDA, "C3:ERROR: event synchronize failed");
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return (double)fail(C3B_ECUDA, "C3:ERROR: event elapsed failed");
+    return (double)ms;
 }
 
 double c3b_microbench(int kind, int a, int b) {

@@ -212,3 +212,16 @@ def measure_fp64_peak(kind: str = "dfma", seconds: float = 0.5, device: Optional
     if v < 0:
         _lib.check(int(v))
     return v
+
+
+def launch_count() -> int:
+    """Kernels launched by libc3b200 in this process so far."""
+    return int(_lib.load().c3b_launch_count())
+
+
+def last_kernel_ms() -> float:
+    """Duration of the main fused kernel of the last pwc_* call (needs set_tuning("profile", 1))."""
+    v = _lib.load().c3b_last_kernel_ms()
+    if v < 0:
+        _lib.check(int(v))
+    return v

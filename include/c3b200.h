@@ -94,8 +94,8 @@ int c3b_seq_product(const void* gates, int Gn, const int32_t* seq_idx, const int
 int c3b_kron(const void* A, const void* Bm, void* out, int batch, int ra, int ca, int rb, int cb, int a_batched,
              int b_batched, void* stream);
 
-/* Tuning knobs (process-wide; for experiments).  key: "target_units", "force_cta",
- * "rows_warps".  Returns C3B_EINVAL for an unknown key. */
+/* Tuning knobs (process-wide; for experiments).  key: "target_units", "min_chunk", "force_cta",
+ * "rows_variant", "profile".  Returns C3B_EINVAL for an unknown key. */
 int c3b_set_tuning(const char* key, long long value);
 
 /* Which kernel c3b_pwc_* would pick for this shape: 1 = register-resident rows kernel,
@@ -107,6 +107,14 @@ int c3b_pwc_path(int K, int D, int batched_model);
  * kind 1: DMMA (mma.sync m8n8k4 f64).  Synchronises the device; not for hot paths.
  * Returns a negative error code on failure. */
 double c3b_measure_fp64_peak(int kind, int device, double seconds);
+
+/* Number of CUDA kernels this library has launched in this process so far. */
+long long c3b_launch_count(void);
+
+/* With tuning key "profile" = 1, every c3b_pwc_* call brackets its main (fused) kernel with
+ * CUDA events on the caller's stream; this returns the duration in ms of the last one
+ * (synchronises on that event).  Negative on error. */
+double c3b_last_kernel_ms(void);
 
 /* Development micro-benchmarks of kernel building blocks (TFLOP/s of the fp64 pipe).
  * kind 0/1/2: the row-times-shared-matrix primitive for D = 9/4/3 with `a` warps per CTA and
