@@ -193,7 +193,7 @@ def run_engine(args):
     cpu_baseline = None
     if n_gpus == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        per_proc = 12
+        per_proc = 40
         pool = CpuPool(cores)
         v, wall = pool.run(per_proc)
         pool.close()

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <atomic>
 
 #include "c3b_common.cuh"
@@ -41,8 +42,8 @@ bool g_ev_valid = false;
 // ---- tuning (process-wide) -------------------------------------------------------------------
 long long g_target_units = 32768;  // rows kernel: aim for this many warp work units per launch
 long long g_force_cta = 0;         // route everything to the CTA kernel (testing)
-long long g_min_chunk = 8;         // rows kernel: minimum slices per lane group
-long long g_rows_variant = 1;      // 0: v1 kernel, 1: v2 (255 regs), 2: v2 V-in-smem (168 regs), 3: v2 (168 regs)
+long long g_min_chunk = getenv("C3B_MIN_CHUNK") ? atoll(getenv("C3B_MIN_CHUNK")) : 8;         // rows kernel: minimum slices per lane group
+long long g_rows_variant = getenv("C3B_ROWS_VARIANT") ? atoll(getenv("C3B_ROWS_VARIANT")) : 1;      // 0: v1 kernel, 1: v2 (255 regs), 2: v2 V-in-smem (168 regs), 3: v2 (168 regs)
 
 int num_sms() {
     static int cached = 0;
@@ -98,7 +99,7 @@ struct Plan {
     int S;         // segments per batch element
     int seg_len;
     int grid;      // CTA kernel grid (persistent)
-    size_t off_G, off_RS, off_seg, off_cta, off_prod, total;
+    size_t off_G, off_RS, off_seg, off_cta, off_prod, off_counter, total;
 };
 
 Plan make_plan(int B, int K, int N, int D, int batched_model, bool hlist) {
@@ -107,7 +108,8 @@ Plan make_plan(int B, int K, int N, int D, int batched_model, bool hlist) {
     const int Bm = batched_model ? B : 1;
     if (pl.path == 1) {
         const int TD = rows_template_dim(D);
-        const int G = 32 / TD;
+        int G = 32 / TD;
+        if (g_rows_variant >= 4 && (TD == 9 || TD == 3)) G = (TD == 9) ? (g_rows_variant >= 5 ? 6 : 10) : 32;   // v3: lane groups per warp
         long long S = (g_target_units + B - 1) / B;
         long long smax = N / (g_min_chunk * G);
         if (smax < 1) smax = 1;
@@ -138,6 +140,8 @@ Plan make_plan(int B, int K, int N, int D, int batched_model, bool hlist) {
     if (pl.path == 3) off += align_up((size_t)pl.grid * kCtaSlots * D * D * sizeof(cplx));
     pl.off_prod = off;
     if (pl.S > 1 && D > 64) off += align_up((size_t)cta_grid(D, 1LL << 40) * 2 * D * D * sizeof(cplx));
+    pl.off_counter = off;
+    off += 256;
     pl.total = off < 256 ? 256 : off;
     return pl;
 }
@@ -174,7 +178,33 @@ int launch_rows2_t(const RowsParams& rp, cudaStream_t st) {
     return C3B_OK;
 }
 
-int launch_rows(const RowsParams& rp, cudaStream_t st) {
+template <int D, int R, int WARPS>
+int launch_rows3_t(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
+    using L = Rows3Layout<D, R>;
+    const size_t smem = L::smem_bytes(rp.K, WARPS);
+    if (smem > 227 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: too many control lines (K=%d) for the d=%d register kernel", rp.K, rp.d);
+    auto kern = pwc_rows3_kernel<D, R, WARPS>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    const long long units = (long long)rp.B * rp.S;
+    int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    long long grid = (long long)num_sms() * per_sm;
+    const long long need = (units + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(int)grid, WARPS * 32, smem, st>>>(rp, counter);
+    CUDA_TRY(cudaGetLastError());
+    return C3B_OK;
+}
+
+int launch_rows(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
+    if (g_rows_variant >= 4) {
+        if (rows_template_dim(rp.d) == 9 && g_rows_variant == 5) return launch_rows3_t<9, 2, 7>(rp, counter, st);
+        if (rows_template_dim(rp.d) == 9 && g_rows_variant == 6) return launch_rows3_t<9, 2, 6>(rp, counter, st);
+        if (rows_template_dim(rp.d) == 9) return launch_rows3_t<9, 3, 4>(rp, counter, st);
+        if (rows_template_dim(rp.d) == 3) return launch_rows3_t<3, 3, 4>(rp, counter, st);
+    }
     if (rows_template_dim(rp.d) == 9 && g_rows_variant > 0) {
         if (g_rows_variant == 1) return launch_rows2_t<9, 2, false>(rp, st);
         if (g_rows_variant == 2) return launch_rows2_t<9, 3, true>(rp, st);
@@ -252,7 +282,7 @@ int run_pwc(const Plan& pl, const cplx* G, const double* RS, const double* signa
         rp.model_stride = 0;
         rp.B = B; rp.K = K; rp.N = N; rp.d = D; rp.S = pl.S; rp.seg_len = pl.seg_len;
         rp.U_out = U_out; rp.seg_out = seg; rp.dUs_out = dUs_out;
-        int rc = launch_rows(rp, st);
+        int rc = launch_rows(rp, reinterpret_cast<unsigned int*>(ws + pl.off_counter), st);
         if (rc) return rc;
     } else {
         CtaParams cp{};
