@@ -11,6 +11,7 @@
 #include "c3b_common.cuh"
 #include "pwc_cta.cuh"
 #include "pwc_rows.cuh"
+#include "pwc_blk.cuh"
 #include "product.cuh"
 #include "peak.cuh"
 
@@ -43,7 +44,8 @@ bool g_ev_valid = false;
 long long g_target_units = 32768;  // rows kernel: aim for this many warp work units per launch
 long long g_force_cta = 0;         // route everything to the CTA kernel (testing)
 long long g_min_chunk = getenv("C3B_MIN_CHUNK") ? atoll(getenv("C3B_MIN_CHUNK")) : 8;         // rows kernel: minimum slices per lane group
-long long g_rows_variant = getenv("C3B_ROWS_VARIANT") ? atoll(getenv("C3B_ROWS_VARIANT")) : 1;      // 0: v1 kernel, 1: v2 (255 regs), 2: v2 V-in-smem (168 regs), 3: v2 (168 regs)
+// 1: rows v2 (one row per lane) | 4-6: rows v3 (R rows per lane, experimental) | 7-9: block layout (8 = default for d=9)
+long long g_rows_variant = getenv("C3B_ROWS_VARIANT") ? atoll(getenv("C3B_ROWS_VARIANT")) : 8;      // 0: v1 kernel, 1: v2 (255 regs), 2: v2 V-in-smem (168 regs), 3: v2 (168 regs)
 
 int num_sms() {
     static int cached = 0;
@@ -109,7 +111,7 @@ Plan make_plan(int B, int K, int N, int D, int batched_model, bool hlist) {
     if (pl.path == 1) {
         const int TD = rows_template_dim(D);
         int G = 32 / TD;
-        if (g_rows_variant >= 4 && (TD == 9 || TD == 3)) G = (TD == 9) ? (g_rows_variant >= 5 ? 6 : 10) : 32;   // v3: lane groups per warp
+        if (g_rows_variant >= 4 && g_rows_variant <= 6 && (TD == 9 || TD == 3)) G = (TD == 9) ? (g_rows_variant >= 5 ? 6 : 10) : 32;   // v3: lane groups per warp
         long long S = (g_target_units + B - 1) / B;
         long long smax = N / (g_min_chunk * G);
         if (smax < 1) smax = 1;
@@ -198,8 +200,31 @@ int launch_rows3_t(const RowsParams& rp, unsigned int* counter, cudaStream_t st)
     return C3B_OK;
 }
 
+template <int D, int BS, int WARPS, int MINB>
+int launch_blk_t(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
+    using L = BlkLayout<D, BS>;
+    const size_t smem = L::smem_bytes(rp.K, WARPS);
+    if (smem > 227 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: too many control lines (K=%d) for the d=%d block kernel", rp.K, rp.d);
+    auto kern = pwc_blk_kernel<D, BS, WARPS, MINB>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    const long long units = (long long)rp.B * rp.S;
+    int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > MINB) per_sm = MINB;
+    long long grid = (long long)num_sms() * per_sm;
+    const long long need = (units + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(int)grid, WARPS * 32, smem, st>>>(rp, counter);
+    CUDA_TRY(cudaGetLastError());
+    return C3B_OK;
+}
+
 int launch_rows(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
-    if (g_rows_variant >= 4) {
+    if (rows_template_dim(rp.d) == 9 && g_rows_variant == 7) return launch_blk_t<9, 3, 4, 3>(rp, counter, st);
+    if (rows_template_dim(rp.d) == 9 && g_rows_variant == 8) return launch_blk_t<9, 3, 4, 2>(rp, counter, st);
+    if (rows_template_dim(rp.d) == 9 && g_rows_variant == 9) return launch_blk_t<9, 3, 6, 2>(rp, counter, st);
+    if (g_rows_variant >= 4 && g_rows_variant <= 6) {
         if (rows_template_dim(rp.d) == 9 && g_rows_variant == 5) return launch_rows3_t<9, 2, 7>(rp, counter, st);
         if (rows_template_dim(rp.d) == 9 && g_rows_variant == 6) return launch_rows3_t<9, 2, 6>(rp, counter, st);
         if (rows_template_dim(rp.d) == 9) return launch_rows3_t<9, 3, 4>(rp, counter, st);

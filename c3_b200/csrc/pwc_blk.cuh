@@ -1,0 +1,370 @@
+// Block-layout PWC propagator kernel for small Hilbert dimensions (D = NB * BS).
+//
+// Same fused contract as pwc_rows.cuh (assemble -> Pade expm -> ordered product, replacing
+// c3/libraries/propagation.py:426-440,460-515 and c3/utils/tf_utils.py:120-193), different mapping:
+// a group of NB x NB lanes owns one matrix, lane (bi, bj) holds the BS x BS block (bi, bj) of every
+// register-resident matrix (accumulator, W, V, Q, R: 4*BS*BS registers each).  A product streams
+// BOTH operands from shared memory: per k, BS elements of X's block-row and BS of Y's block-column
+// feed BS*BS complex MACs, i.e. BS/2 cfma per 16-byte operand instead of 1 in the one-row-per-lane
+// layout -- the shared-memory wavefront pipe (128 lane-bytes/clk/SM, every LDS.128 = 4 wavefronts)
+// is what bounds these kernels (profiles/README_r01.md).  Register use is ~1/2 of the row layout,
+// so 12 warps per SM stay resident and cover the serial phases (Gauss-Jordan, syncs).
+//
+// Gauss-Jordan runs in the block layout too: at step k every lane needs 1 + BS + 2*BS complex
+// numbers from three other lanes (pivot, its rows' multipliers, its columns' pivot-row entries),
+// fetched with warp shuffles from registers; no pivoting (norm scaled below 2 ln 2, see
+// c3b_common.cuh).  Orders m in {3,5,7,9}; powers A^2, A^4, A^6 = A^4 A^2, A^8 = A^4 A^4.
+#pragma once
+#include "c3b_common.cuh"
+#include "pwc_rows.cuh"   // RowsParams
+
+namespace c3b {
+
+template <int D, int BS>
+struct BlkLayout {
+    static constexpr int NB = D / BS;
+    static constexpr int LPM = NB * NB;             // lanes per matrix
+    static constexpr int MPW = 32 / LPM;            // matrices per warp
+    // Leading dimension of the per-matrix shared buffers.  With LD = 3 (mod 8) [D=9: 11] the NB*NB
+    // lanes of a group hit distinct 16-byte bank slots for block stores, block-row and block-column
+    // loads; with the group stride = 4 (mod 8) neighbouring groups in a quarter-warp do not collide
+    // either (ncu before: 5.7 wavefronts per LDS.128 and 9 per STS.128 instead of 4).
+    static constexpr int LD = (D % 8 == 1) ? D + 2 : ((D % 8 == 3) ? D : D + 1);
+    static constexpr int BUF = D * LD;
+    static constexpr int GROUP_PAD = (4 - (4 * BUF) % 8 + 8) % 8;
+    static constexpr int GROUP_ELEMS = 4 * BUF + GROUP_PAD; // bufA, bufA2, bufX, bufP
+    static constexpr int WARP_ELEMS = MPW * GROUP_ELEMS;
+    static_assert(D % BS == 0, "D must be a multiple of the block size");
+    __host__ __device__ static size_t smem_bytes(int K, int warps) {
+        size_t model = (size_t)(K + 1) * D * D * sizeof(cplx) + (size_t)(((K + 1) * D + 1) & ~1) * sizeof(double);
+        return model + (size_t)warps * WARP_ELEMS * sizeof(cplx);
+    }
+};
+
+// C(block) = X(block-row) * Y(block-column); Xr = &X[r0*D], Yc = &Y[c0]
+template <int D, int BS, int LD>
+__device__ __forceinline__ void mm_blk(const cplx* __restrict__ Xr, const cplx* __restrict__ Yc, cplx (&c)[BS][BS]) {
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+#pragma unroll
+        for (int b = 0; b < BS; ++b) c[a][b] = cmake(0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        cplx x[BS], y[BS];
+#pragma unroll
+        for (int a = 0; a < BS; ++a) x[a] = Xr[a * LD + k];
+#pragma unroll
+        for (int b = 0; b < BS; ++b) y[b] = Yc[k * LD + b];
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+#pragma unroll
+            for (int b = 0; b < BS; ++b) cfma(c[a][b], x[a], y[b]);
+    }
+}
+
+template <int D, int BS, int LD>
+__device__ __forceinline__ void store_blk(cplx* __restrict__ Mrc, const cplx (&x)[BS][BS], bool pred) {
+    if (pred) {
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+#pragma unroll
+            for (int b = 0; b < BS; ++b) Mrc[a * LD + b] = x[a][b];
+    }
+}
+
+__device__ __forceinline__ cplx shfl_c(const cplx v, const int src) {
+    cplx r;
+    r.x = __shfl_sync(0xffffffffu, v.x, src);
+    r.y = __shfl_sync(0xffffffffu, v.y, src);
+    return r;
+}
+
+template <int D, int BS, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_kernel(const RowsParams p, unsigned int* __restrict__ counter) {
+    using L = BlkLayout<D, BS>;
+    constexpr int NB = L::NB, LPM = L::LPM, MPW = L::MPW, LD = L::LD;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = p.K;
+    const int d = p.d;
+    cplx* sG = reinterpret_cast<cplx*>(smem_raw);                 // [(K+1), D, D] zero padded
+    double* sRS = reinterpret_cast<double*>(sG + (K + 1) * D * D);  // [(K+1), D]
+    cplx* sWarps = reinterpret_cast<cplx*>(sRS + (((K + 1) * D + 1) & ~1));
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const bool hmode = p.hlist != nullptr;
+
+    if (!hmode) {
+        for (int idx = tid; idx < (K + 1) * D * D; idx += WARPS * 32) {
+            const int k = idx / (D * D);
+            const int rem = idx - k * D * D;
+            const int r = rem / D, j = rem - r * D;
+            cplx v = cmake(0.0, 0.0);
+            if (r < d && j < d) v = p.G[(size_t)k * d * d + r * d + j];
+            sG[idx] = v;
+        }
+        for (int idx = tid; idx < (K + 1) * D; idx += WARPS * 32) {
+            const int k = idx / D, r = idx - k * D;
+            sRS[idx] = (r < d) ? p.RS[k * d + r] : 0.0;
+        }
+    }
+    __syncthreads();   // the only CTA-wide barrier
+
+    const int g_raw = lane / LPM;
+    const bool lane_on = g_raw < MPW;
+    // leftover lanes shadow the LAST lane of the LAST group (same addresses as their quarter-warp
+    // neighbours: no extra bank conflicts) and never store
+    const int g = lane_on ? g_raw : MPW - 1;
+    const int li = lane_on ? (lane - g_raw * LPM) : LPM - 1;
+    const int bi = li / NB, bj = li - bi * NB;
+    const int r0 = bi * BS, c0 = bj * BS;
+    const int gbase_lane = g * LPM;
+    const bool on_diag = (bi == bj);
+
+    cplx* gbase = sWarps + (size_t)warp * L::WARP_ELEMS + (size_t)g * L::GROUP_ELEMS;
+    cplx* bufA = gbase;
+    cplx* bufA2 = gbase + L::BUF;
+    cplx* bufX = gbase + 2 * L::BUF;
+    cplx* bufP = gbase + 3 * L::BUF;
+    const int rc_off = r0 * LD + c0;                   // this lane's block inside a per-matrix buffer
+    const int mg_off = r0 * D + c0;                    // ... and inside a model matrix (stride D)
+    const cplx hs = cmake(p.hscale_re, p.hscale_im);
+    const long long total_units = (long long)p.B * p.S;
+
+    for (;;) {
+        unsigned int unit_u = 0;
+        if (lane == 0) unit_u = atomicAdd(counter, 1u);
+        unit_u = __shfl_sync(0xffffffffu, unit_u, 0);
+        const long long unit = unit_u;
+        if (unit >= total_units) break;
+        const int b = (int)(unit / p.S);
+        const int sidx = (int)(unit - (long long)b * p.S);
+        const int n_begin = sidx * p.seg_len;
+        const int n_end = min(p.N, n_begin + p.seg_len);
+        const int len = n_end - n_begin;
+        const int cl = (len + MPW - 1) / MPW;
+        const int my_begin = n_begin + g * cl;
+        const int my_end = min(n_end, my_begin + cl);
+        const double* sig_b = p.signals ? p.signals + (size_t)b * K * p.N : nullptr;
+
+#pragma unroll 1
+        for (int it = 0; it < cl; ++it) {
+            const int n = my_begin + it;
+            const bool on = lane_on && (n < my_end);
+
+            // ---- assemble this lane's block of A_n and the inf-norm bound of its rows -----------
+            cplx C[BS][BS];
+            double nb = 0.0;
+            if (!hmode) {
+                double nba[BS];
+#pragma unroll
+                for (int a = 0; a < BS; ++a) {
+                    nba[a] = on ? sRS[r0 + a] : 0.0;
+#pragma unroll
+                    for (int c = 0; c < BS; ++c) C[a][c] = on ? sG[mg_off + a * D + c] : cmake(0.0, 0.0);
+                }
+                for (int k = 0; k < K; ++k) {
+                    const double cs = on ? __ldg(sig_b + (size_t)k * p.N + n) : 0.0;
+                    const cplx* gk = sG + (k + 1) * D * D + mg_off;
+#pragma unroll
+                    for (int a = 0; a < BS; ++a) {
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) {
+                            const cplx gv = gk[a * D + c];
+                            C[a][c].x = fma(cs, gv.x, C[a][c].x);
+                            C[a][c].y = fma(cs, gv.y, C[a][c].y);
+                        }
+                        nba[a] = fma(fabs(cs), sRS[(k + 1) * D + r0 + a], nba[a]);
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < BS; ++a) nb = fmax(nb, nba[a]);
+            } else {
+                // explicit Hamiltonians: partial row sums of this block, summed over the NB lanes of the block-row
+#pragma unroll
+                for (int a = 0; a < BS; ++a) {
+                    const int row = r0 + a;
+                    double rs = 0.0;
+#pragma unroll
+                    for (int c = 0; c < BS; ++c) {
+                        cplx h = cmake(0.0, 0.0);
+                        if (on && row < d && c0 + c < d)
+                            h = p.hlist[((size_t)b * p.N + n) * d * d + (size_t)row * d + c0 + c];
+                        C[a][c] = cmul(hs, h);
+                        rs += cabs1(C[a][c]);
+                    }
+                    double tot = 0.0;
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) tot += __shfl_sync(0xffffffffu, rs, gbase_lane + bi * NB + q);
+                    nb = fmax(nb, tot);
+                }
+            }
+            nb = warp_max(nb);
+
+            const int s = squarings_for(nb, C3B_NOPIVOT_LIMIT);
+            const double ns = nb * pow2neg(s);
+            const int mi = ns < C3B_THETA3 ? 0 : (ns < C3B_THETA5 ? 1 : (ns < C3B_THETA7 ? 2 : 3));  // m = 2 mi + 3
+            if (s > 0) {
+                const double sc = pow2neg(s);
+#pragma unroll
+                for (int a = 0; a < BS; ++a)
+#pragma unroll
+                    for (int c = 0; c < BS; ++c) { C[a][c].x *= sc; C[a][c].y *= sc; }
+            }
+            store_blk<D, BS, LD>(bufA + rc_off, C, lane_on);
+            __syncwarp();
+
+            const double* cf = kPade[mi];
+            cplx W[BS][BS], V[BS][BS];
+            // phases: 0..mi powers | mi+1: U = W A | then s squarings | then the running product
+            const int ph_solve = mi + 1;
+            const int ph_lastsq = mi + 1 + s;
+            const int ph_last = ph_lastsq + (it > 0 ? 1 : 0);
+            const cplx* Xr = bufA + r0 * LD;
+            const cplx* Yc = bufA + c0;
+
+#pragma unroll 1
+            for (int ph = 0; ph <= ph_last; ++ph) {
+                mm_blk<D, BS, LD>(Xr, Yc, C);
+                if (ph < ph_solve) {
+                    // C = A^(2 ph + 2)
+                    const double cw = cf[2 * ph + 3], cv = cf[2 * ph + 2];
+                    if (ph == 0) {
+                        const double c1 = cf[1], c0c = cf[0];
+#pragma unroll
+                        for (int a = 0; a < BS; ++a)
+#pragma unroll
+                            for (int c = 0; c < BS; ++c) {
+                                const bool dg = on_diag && (a == c);
+                                W[a][c] = cmake(cw * C[a][c].x + (dg ? c1 : 0.0), cw * C[a][c].y);
+                                V[a][c] = cmake(cv * C[a][c].x + (dg ? c0c : 0.0), cv * C[a][c].y);
+                            }
+                        if (mi > 0) store_blk<D, BS, LD>(bufA2 + rc_off, C, lane_on);       // A^2: operand of A^4, A^6
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BS; ++a)
+#pragma unroll
+                            for (int c = 0; c < BS; ++c) {
+                                W[a][c].x = fma(cw, C[a][c].x, W[a][c].x);
+                                W[a][c].y = fma(cw, C[a][c].y, W[a][c].y);
+                                V[a][c].x = fma(cv, C[a][c].x, V[a][c].x);
+                                V[a][c].y = fma(cv, C[a][c].y, V[a][c].y);
+                            }
+                        if (ph == 1 && mi > 1) store_blk<D, BS, LD>(bufX + rc_off, C, lane_on);  // A^4: operand of A^6, A^8
+                    }
+                    if (ph < mi) {
+                        __syncwarp();
+                        if (ph == 0) { Xr = bufA2 + r0 * LD; Yc = bufA2 + c0; }          // A^4 = A^2 A^2
+                        else if (ph == 1) { Xr = bufX + r0 * LD; Yc = bufA2 + c0; }      // A^6 = A^4 A^2
+                        else { Xr = bufX + r0 * LD; Yc = bufX + c0; }                    // A^8 = A^4 A^4
+                    } else {
+                        // all powers done: publish W as the left operand of U = W A
+                        __syncwarp();                                                   // bufX (A^4) no longer read
+                        store_blk<D, BS, LD>(bufX + rc_off, W, lane_on);
+                        __syncwarp();
+                        Xr = bufX + r0 * LD;
+                        Yc = bufA + c0;
+                    }
+                } else if (ph == ph_solve) {
+                    // C = U.  W <- Q = V - U,  C <- R = V + U;  then C <- Q^{-1} C
+#pragma unroll
+                    for (int a = 0; a < BS; ++a)
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) {
+                            const cplx v = V[a][c], u = C[a][c];
+                            W[a][c] = cmake(v.x - u.x, v.y - u.y);
+                            C[a][c] = cmake(v.x + u.x, v.y + u.y);
+                        }
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const int bk = k / BS, kc = k % BS;   // compile-time after unrolling
+                        const cplx pk = shfl_c(W[kc][kc], gbase_lane + bk * NB + bk);
+                        cplx qa[BS], pq[BS], pr[BS];
+#pragma unroll
+                        for (int a = 0; a < BS; ++a) qa[a] = shfl_c(W[a][kc], gbase_lane + bi * NB + bk);
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) {
+                            pq[c] = shfl_c(W[kc][c], gbase_lane + bk * NB + bj);
+                            pr[c] = shfl_c(C[kc][c], gbase_lane + bk * NB + bj);
+                        }
+                        const cplx inv = crcp(pk);
+                        cplx f[BS];
+#pragma unroll
+                        for (int a = 0; a < BS; ++a) f[a] = cmul(qa[a], inv);
+                        if (bi == bk) f[kc] = cmake(1.0 - inv.x, -inv.y);   // pivot row: row <- row * inv
+#pragma unroll
+                        for (int a = 0; a < BS; ++a)
+#pragma unroll
+                            for (int c = 0; c < BS; ++c) {
+                                cfms(W[a][c], f[a], pq[c]);
+                                cfms(C[a][c], f[a], pr[c]);
+                            }
+                    }
+                    // C = dU (scaled).  Publish it as the next left operand.
+                    store_blk<D, BS, LD>(bufX + rc_off, C, lane_on);
+                    __syncwarp();
+                    Xr = bufX + r0 * LD;
+                    Yc = (s > 0) ? (bufX + c0) : (bufP + c0);
+                } else if (ph <= ph_lastsq) {
+                    // C = (previous)^2
+                    __syncwarp();
+                    store_blk<D, BS, LD>(bufX + rc_off, C, lane_on);
+                    __syncwarp();
+                    Xr = bufX + r0 * LD;
+                    Yc = (ph < ph_lastsq) ? (bufX + c0) : (bufP + c0);
+                } else {
+                    // C = dU_n * P
+                    __syncwarp();
+                    store_blk<D, BS, LD>(bufP + rc_off, C, lane_on);
+                }
+                if (ph == ph_lastsq) {                 // C holds dU_n
+                    if (p.dUs_out != nullptr && on) {
+#pragma unroll
+                        for (int a = 0; a < BS; ++a) {
+                            const int row = r0 + a;
+                            if (row < d) {
+                                cplx* o = p.dUs_out + ((size_t)b * p.N + n) * d * d + (size_t)row * d + c0;
+#pragma unroll
+                                for (int c = 0; c < BS; ++c)
+                                    if (c0 + c < d) o[c] = C[a][c];
+                            }
+                        }
+                    }
+                    if (it == 0) store_blk<D, BS, LD>(bufP + rc_off, C, lane_on);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- fold the group products: P_{MPW-1} ... P_1 P_0 (every group computes it; group 0 writes) ----
+        cplx* wbase = sWarps + (size_t)warp * L::WARP_ELEMS;
+        const cplx* cur = wbase + (size_t)(MPW - 1) * L::GROUP_ELEMS + 3 * L::BUF;
+        int flip = 0;
+#pragma unroll 1
+        for (int gg = MPW - 2; gg >= 0; --gg) {
+            cplx T[BS][BS];
+            mm_blk<D, BS, LD>(cur + r0 * LD, wbase + (size_t)gg * L::GROUP_ELEMS + 3 * L::BUF + c0, T);
+            cplx* dst = flip ? bufA : bufX;
+            store_blk<D, BS, LD>(dst + rc_off, T, lane_on);
+            __syncwarp();
+            cur = dst;
+            flip ^= 1;
+        }
+        if (lane_on && g == 0) {
+            cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * d * d) : (p.seg_out + ((size_t)b * p.S + sidx) * d * d);
+#pragma unroll
+            for (int a = 0; a < BS; ++a) {
+                const int row = r0 + a;
+                if (row < d) {
+#pragma unroll
+                    for (int c = 0; c < BS; ++c)
+                        if (c0 + c < d) o[row * d + c0 + c] = cur[(r0 + a) * LD + c0 + c];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace c3b
