@@ -101,7 +101,7 @@ struct Plan {
     int S;         // segments per batch element
     int seg_len;
     int grid;      // CTA kernel grid (persistent)
-    size_t off_G, off_RS, off_seg, off_cta, off_prod, off_counter, total;
+    size_t off_G, off_RS, off_TR, off_seg, off_cta, off_prod, off_counter, total;
 };
 
 Plan make_plan(int B, int K, int N, int D, int batched_model, bool hlist) {
@@ -136,6 +136,8 @@ Plan make_plan(int B, int K, int N, int D, int batched_model, bool hlist) {
     if (!hlist) off += align_up((size_t)Bm * (K + 1) * D * D * sizeof(cplx));
     pl.off_RS = off;
     if (!hlist) off += align_up((size_t)Bm * (K + 1) * D * sizeof(double));
+    pl.off_TR = off;
+    if (!hlist) off += align_up((size_t)Bm * (K + 1) * sizeof(cplx));
     pl.off_seg = off;
     if (pl.S > 1) off += align_up((size_t)B * pl.S * D * D * sizeof(cplx));
     pl.off_cta = off;
@@ -220,10 +222,38 @@ int launch_blk_t(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
     return C3B_OK;
 }
 
+template <int D, int BS, int WARPS, int MINB>
+int launch_blk_t18_t(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
+    using L = BlkLayout<D, BS>;
+    const size_t smem = L::smem_bytes(rp.K, WARPS);
+    if (smem > 227 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: too many control lines (K=%d) for the d=%d block kernel", rp.K, rp.d);
+    auto kern = pwc_blk_t18_kernel<D, BS, WARPS, MINB>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    const long long units = (long long)rp.B * rp.S;
+    int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > MINB) per_sm = MINB;
+    long long grid = (long long)num_sms() * per_sm;
+    const long long need = (units + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(int)grid, WARPS * 32, smem, st>>>(rp, counter);
+    CUDA_TRY(cudaGetLastError());
+    return C3B_OK;
+}
+
+// does the kernel that launch_rows() would pick accept trace-shifted generators?
+bool rows_kernel_takes_shift(int d) { return rows_template_dim(d) == 9 && g_rows_variant >= 13; }
+
 int launch_rows(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
+    if (rows_template_dim(rp.d) == 9 && g_rows_variant == 13) return launch_blk_t18_t<9, 3, 4, 2>(rp, counter, st);
+    if (rows_template_dim(rp.d) == 9 && g_rows_variant == 14) return launch_blk_t18_t<9, 3, 4, 3>(rp, counter, st);
     if (rows_template_dim(rp.d) == 9 && g_rows_variant == 7) return launch_blk_t<9, 3, 4, 3>(rp, counter, st);
     if (rows_template_dim(rp.d) == 9 && g_rows_variant == 8) return launch_blk_t<9, 3, 4, 2>(rp, counter, st);
     if (rows_template_dim(rp.d) == 9 && g_rows_variant == 9) return launch_blk_t<9, 3, 6, 2>(rp, counter, st);
+    if (rows_template_dim(rp.d) == 9 && g_rows_variant == 10) return launch_blk_t<9, 3, 5, 2>(rp, counter, st);
+    if (rows_template_dim(rp.d) == 9 && g_rows_variant == 11) return launch_blk_t<9, 3, 9, 1>(rp, counter, st);
+    if (rows_template_dim(rp.d) == 9 && g_rows_variant == 12) return launch_blk_t<9, 3, 11, 1>(rp, counter, st);
     if (g_rows_variant >= 4 && g_rows_variant <= 6) {
         if (rows_template_dim(rp.d) == 9 && g_rows_variant == 5) return launch_rows3_t<9, 2, 7>(rp, counter, st);
         if (rows_template_dim(rp.d) == 9 && g_rows_variant == 6) return launch_rows3_t<9, 2, 6>(rp, counter, st);
@@ -293,7 +323,7 @@ int launch_product(ProductParams pp, cudaStream_t st) {
 }
 
 // common tail of the three pwc entry points once G (or the H list) is in place
-int run_pwc(const Plan& pl, const cplx* G, const double* RS, const double* signals, const cplx* hlist, double dt,
+int run_pwc(const Plan& pl, const cplx* G, const double* RS, const cplx* TR, const double* signals, const cplx* hlist, double dt,
             int B, int K, int N, int D, int batched_model, cplx* U_out, cplx* dUs_out, char* ws, cudaStream_t st) {
     cplx* seg = pl.S > 1 ? reinterpret_cast<cplx*>(ws + pl.off_seg) : nullptr;
     if (g_profile) {
@@ -302,7 +332,7 @@ int run_pwc(const Plan& pl, const cplx* G, const double* RS, const double* signa
     }
     if (pl.path == 1) {
         RowsParams rp{};
-        rp.G = G; rp.RS = RS; rp.signals = signals; rp.hlist = hlist;
+        rp.G = G; rp.RS = RS; rp.TR = TR; rp.signals = signals; rp.hlist = hlist;
         rp.hscale_re = 0.0; rp.hscale_im = -dt;
         rp.model_stride = 0;
         rp.B = B; rp.K = K; rp.N = N; rp.d = D; rp.S = pl.S; rp.seg_len = pl.seg_len;
@@ -380,6 +410,7 @@ int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, doubl
     char* ws = static_cast<char*>(workspace);
     cplx* G = reinterpret_cast<cplx*>(ws + pl.off_G);
     double* RS = reinterpret_cast<double*>(ws + pl.off_RS);
+    cplx* TR = (pl.path == 1 && rows_kernel_takes_shift(d)) ? reinterpret_cast<cplx*>(ws + pl.off_TR) : nullptr;
     const int Bm = batched_model ? B : 1;
     {
         const long long total = (long long)Bm * (K + 1) * d * d;
@@ -387,12 +418,18 @@ int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, doubl
         setup_closed_kernel<<<blocks, 256, 0, st>>>(static_cast<const cplx*>(h0), static_cast<const cplx*>(hks), G, Bm, K, d, dt);
         CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (TR != nullptr) {
+            const long long nmat = (long long)Bm * (K + 1);
+            trace_shift_kernel<<<(int)((nmat * 32 + 255) / 256), 256, 0, st>>>(G, TR, nmat, d);
+            CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
         const long long nrows = (long long)Bm * (K + 1) * d;
         rowsum_kernel<<<(int)((nrows * 32 + 255) / 256), 256, 0, st>>>(G, RS, nrows, d);
         CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     }
-    return run_pwc(pl, G, RS, signals, nullptr, dt, B, K, N, d, batched_model, static_cast<cplx*>(U_out),
+    return run_pwc(pl, G, RS, TR, signals, nullptr, dt, B, K, N, d, batched_model, static_cast<cplx*>(U_out),
                    static_cast<cplx*>(dUs_out), ws, st);
 }
 
@@ -403,7 +440,7 @@ int c3b_pwc_closed_hlist(const void* Hs, double dt, int B, int N, int d, void* U
     if (Hs == nullptr) return fail(C3B_EINVAL, "C3:ERROR: Hs is NULL");
     const Plan pl = make_plan(B, 0, N, d, 0, true);
     if (workspace_bytes < pl.total) return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small: %zu < %zu bytes", workspace_bytes, pl.total);
-    return run_pwc(pl, nullptr, nullptr, nullptr, static_cast<const cplx*>(Hs), dt, B, 0, N, d, 0,
+    return run_pwc(pl, nullptr, nullptr, nullptr, nullptr, static_cast<const cplx*>(Hs), dt, B, 0, N, d, 0,
                    static_cast<cplx*>(U_out), static_cast<cplx*>(dUs_out), static_cast<char*>(workspace),
                    static_cast<cudaStream_t>(stream));
 }
@@ -424,6 +461,7 @@ int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C
     char* ws = static_cast<char*>(workspace);
     cplx* G = reinterpret_cast<cplx*>(ws + pl.off_G);
     double* RS = reinterpret_cast<double*>(ws + pl.off_RS);
+    cplx* TR = (pl.path == 1 && rows_kernel_takes_shift(D)) ? reinterpret_cast<cplx*>(ws + pl.off_TR) : nullptr;
     const int Bm = batched_model ? B : 1;
     {
         const long long total = (long long)Bm * (K + 1) * D * D;
@@ -432,12 +470,18 @@ int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C
                                                       C > 0 ? static_cast<const cplx*>(col_ops) : nullptr, G, Bm, K, C, d, dt);
         CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (TR != nullptr) {
+            const long long nmat = (long long)Bm * (K + 1);
+            trace_shift_kernel<<<(int)((nmat * 32 + 255) / 256), 256, 0, st>>>(G, TR, nmat, D);
+            CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
         const long long nrows = (long long)Bm * (K + 1) * D;
         rowsum_kernel<<<(int)((nrows * 32 + 255) / 256), 256, 0, st>>>(G, RS, nrows, D);
         CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     }
-    return run_pwc(pl, G, RS, signals, nullptr, dt, B, K, N, D, batched_model, static_cast<cplx*>(U_out),
+    return run_pwc(pl, G, RS, TR, signals, nullptr, dt, B, K, N, D, batched_model, static_cast<cplx*>(U_out),
                    static_cast<cplx*>(dUs_out), ws, st);
 }
 

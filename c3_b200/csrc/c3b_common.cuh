@@ -33,6 +33,13 @@ __device__ __forceinline__ cplx crcp(const cplx a) {
     const double rd = 1.0 / fma(a.x, a.x, a.y * a.y);
     return cmake(a.x * rd, -a.y * rd);
 }
+// exp of a complex scalar (phase/scale factor of the trace shift)
+__device__ __forceinline__ cplx cexp_(const cplx a) {
+    double sn, cs;
+    sincos(a.y, &sn, &cs);
+    const double e = exp(a.x);
+    return cmake(e * cs, e * sn);
+}
 __device__ __forceinline__ double cabs1(const cplx a) { return sqrt(fma(a.x, a.x, a.y * a.y)); }
 
 // ---- Pade coefficients, SURVEY.md Appendix A (Higham 2005), normalised by b0 ------------
@@ -53,6 +60,38 @@ __constant__ double kPade[5][14] = {
      33522128640.0 / 64764752532480000.0, 1323241920.0 / 64764752532480000.0, 40840800.0 / 64764752532480000.0,
      960960.0 / 64764752532480000.0, 16380.0 / 64764752532480000.0, 182.0 / 64764752532480000.0,
      1.0 / 64764752532480000.0}};
+
+// ---- degree-18 Taylor polynomial of exp in 5 matrix products (Bader, Blanes, Casas, "Computing
+// the matrix exponential with an optimized Taylor polynomial approximation", Mathematics 7 (2019)
+// 1174, scheme (T18)).  Checked in scratch/proto_t18.py: the composed polynomial reproduces 1/k!
+// for k = 0..18 to the 20 digits given, and exp(A) to 3e-16 for ||A||_1 <= theta_18.
+//   A2 = A A, A3 = A2 A, A6 = A3 A3
+//   B1 = a11 A + a21 A2 + a31 A3            B5 = b24 A2 + b34 A3 + b64 A6
+//   B4 = b03 I + b13 A + b23 A2 + b33 A3 + b63 A6     A9 = B1 B5 + B4
+//   B3 = b02 I + b12 A + b22 A2 + b32 A3 + b62 A6     B2 = b11 A + b21 A2 + b31 A3 + b61 A6
+//   T18 = B2 + (B3 + A9) A9
+#define C3B_T18_A11 (-0.10036558103014462001)
+#define C3B_T18_A21 (-0.00802924648241156960)
+#define C3B_T18_A31 (-0.00089213849804572995)
+#define C3B_T18_B11 (0.39784974949964507614)
+#define C3B_T18_B21 (1.36783778460411719922)
+#define C3B_T18_B31 (0.49828962252538267755)
+#define C3B_T18_B61 (-0.00063789819459472330)
+#define C3B_T18_B02 (-10.9676396052962062593)
+#define C3B_T18_B12 (1.68015813878906197182)
+#define C3B_T18_B22 (0.05717798464788655127)
+#define C3B_T18_B32 (-0.00698210122488052084)
+#define C3B_T18_B62 (0.00003349750170860705)
+#define C3B_T18_B03 (-0.09043168323908105619)
+#define C3B_T18_B13 (-0.06764045190713819075)
+#define C3B_T18_B23 (0.06759613017704596460)
+#define C3B_T18_B33 (0.02955525704293155274)
+#define C3B_T18_B63 (-0.00001391802575160607)
+#define C3B_T18_B24 (-0.09233646193671185927)
+#define C3B_T18_B34 (-0.01693649390020817171)
+#define C3B_T18_B64 (-0.00001400867981820361)
+// backward error <= 2^-53 for ||A||_1 <= 1.09 (same paper, table of theta_m)
+#define C3B_THETA18 1.09
 
 #define C3B_THETA3 1.495585217958292e-2
 #define C3B_THETA5 2.539398330063230e-1

@@ -142,6 +142,25 @@ __global__ void setup_lindblad_kernel(const cplx* __restrict__ h0, const cplx* _
     }
 }
 
+// Trace shift (Higham's preprocessing): t_m = tr(G_m)/D is subtracted from the diagonal of G_m and
+// stored in TR[m]; the kernels re-apply exp(t_0 + sum_k c_k t_k).  One warp per matrix.
+__global__ void trace_shift_kernel(cplx* __restrict__ G, cplx* __restrict__ TR, long long nmat, int D) {
+    const long long m = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= nmat) return;
+    cplx* g = G + m * (long long)D * D;
+    double tr = 0.0, ti = 0.0;
+    for (int j = lane; j < D; j += 32) { tr += g[(long long)j * D + j].x; ti += g[(long long)j * D + j].y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+        ti += __shfl_xor_sync(0xffffffffu, ti, o);
+    }
+    tr /= D; ti /= D;
+    for (int j = lane; j < D; j += 32) { g[(long long)j * D + j].x -= tr; g[(long long)j * D + j].y -= ti; }
+    if (lane == 0) TR[m] = cmake(tr, ti);
+}
+
 // RS[m, r] = sum_j |G[m, r, j]|  for m over (Bm * (K+1)) matrices; one warp per row.
 __global__ void rowsum_kernel(const cplx* __restrict__ G, double* __restrict__ RS, long long nrows, int D) {
     const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;

@@ -33,10 +33,16 @@ struct BlkLayout {
     static constexpr int BUF = D * LD;
     static constexpr int GROUP_PAD = (4 - (4 * BUF) % 8 + 8) % 8;
     static constexpr int GROUP_ELEMS = 4 * BUF + GROUP_PAD; // bufA, bufA2, bufX, bufP
-    static constexpr int WARP_ELEMS = MPW * GROUP_ELEMS;
+    // D = 9 (3 groups of 9 lanes): group base offsets {0,5,3} (mod 8) and a rotation of the lane ->
+    // block assignment inside group 1 make every quarter-warp hit 8 distinct 16-byte bank slots for
+    // block stores AND both operand loads (brute-force checked: 4 wavefronts per LDS/STS.128, the minimum).
+    static constexpr bool TUNED9 = (D == 9 && BS == 3);
+    static constexpr int WARP_ELEMS = TUNED9 ? 1208 : MPW * GROUP_ELEMS;
+    __host__ __device__ static constexpr int group_off(int g) { return TUNED9 ? (g == 0 ? 0 : (g == 1 ? 405 : 803)) : g * GROUP_ELEMS; }
+    __host__ __device__ static constexpr int rot(int g) { return (TUNED9 && g == 1) ? 2 : 0; }
     static_assert(D % BS == 0, "D must be a multiple of the block size");
     __host__ __device__ static size_t smem_bytes(int K, int warps) {
-        size_t model = (size_t)(K + 1) * D * D * sizeof(cplx) + (size_t)(((K + 1) * D + 1) & ~1) * sizeof(double);
+        size_t model = (size_t)(K + 1) * D * LD * sizeof(cplx) + (size_t)(((K + 1) * D + 1) & ~1) * sizeof(double);
         return model + (size_t)warps * WARP_ELEMS * sizeof(cplx);
     }
 };
@@ -86,8 +92,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_kernel(const RowsPar
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K;
     const int d = p.d;
-    cplx* sG = reinterpret_cast<cplx*>(smem_raw);                 // [(K+1), D, D] zero padded
-    double* sRS = reinterpret_cast<double*>(sG + (K + 1) * D * D);  // [(K+1), D]
+    cplx* sG = reinterpret_cast<cplx*>(smem_raw);                 // [(K+1), D, LD] zero padded
+    double* sRS = reinterpret_cast<double*>(sG + (K + 1) * D * LD);  // [(K+1), D]
     cplx* sWarps = reinterpret_cast<cplx*>(sRS + (((K + 1) * D + 1) & ~1));
 
     const int tid = threadIdx.x;
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_kernel(const RowsPar
             const int r = rem / D, j = rem - r * D;
             cplx v = cmake(0.0, 0.0);
             if (r < d && j < d) v = p.G[(size_t)k * d * d + r * d + j];
-            sG[idx] = v;
+            sG[(k * D + r) * LD + j] = v;
         }
         for (int idx = tid; idx < (K + 1) * D; idx += WARPS * 32) {
             const int k = idx / D, r = idx - k * D;
@@ -116,19 +122,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_kernel(const RowsPar
     // leftover lanes shadow the LAST lane of the LAST group (same addresses as their quarter-warp
     // neighbours: no extra bank conflicts) and never store
     const int g = lane_on ? g_raw : MPW - 1;
-    const int li = lane_on ? (lane - g_raw * LPM) : LPM - 1;
+    const int li = ((lane_on ? (lane - g_raw * LPM) : LPM - 1) + L::rot(g)) % LPM;   // block index owned by this lane
     const int bi = li / NB, bj = li - bi * NB;
     const int r0 = bi * BS, c0 = bj * BS;
     const int gbase_lane = g * LPM;
+    const int grot = L::rot(g);
+    auto lane_of = [&](int blk) { return gbase_lane + (blk - grot + LPM) % LPM; };   // lane holding block index blk
     const bool on_diag = (bi == bj);
 
-    cplx* gbase = sWarps + (size_t)warp * L::WARP_ELEMS + (size_t)g * L::GROUP_ELEMS;
+    cplx* gbase = sWarps + (size_t)warp * L::WARP_ELEMS + L::group_off(g);
     cplx* bufA = gbase;
     cplx* bufA2 = gbase + L::BUF;
     cplx* bufX = gbase + 2 * L::BUF;
     cplx* bufP = gbase + 3 * L::BUF;
     const int rc_off = r0 * LD + c0;                   // this lane's block inside a per-matrix buffer
-    const int mg_off = r0 * D + c0;                    // ... and inside a model matrix (stride D)
+    const int mg_off = r0 * LD + c0;                   // ... and inside a model matrix (same padded stride)
     const cplx hs = cmake(p.hscale_re, p.hscale_im);
     const long long total_units = (long long)p.B * p.S;
 
@@ -162,16 +170,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_kernel(const RowsPar
                 for (int a = 0; a < BS; ++a) {
                     nba[a] = on ? sRS[r0 + a] : 0.0;
 #pragma unroll
-                    for (int c = 0; c < BS; ++c) C[a][c] = on ? sG[mg_off + a * D + c] : cmake(0.0, 0.0);
+                    for (int c = 0; c < BS; ++c) C[a][c] = on ? sG[mg_off + a * LD + c] : cmake(0.0, 0.0);
                 }
                 for (int k = 0; k < K; ++k) {
                     const double cs = on ? __ldg(sig_b + (size_t)k * p.N + n) : 0.0;
-                    const cplx* gk = sG + (k + 1) * D * D + mg_off;
+                    const cplx* gk = sG + (k + 1) * D * LD + mg_off;
 #pragma unroll
                     for (int a = 0; a < BS; ++a) {
 #pragma unroll
                         for (int c = 0; c < BS; ++c) {
-                            const cplx gv = gk[a * D + c];
+                            const cplx gv = gk[a * LD + c];
                             C[a][c].x = fma(cs, gv.x, C[a][c].x);
                             C[a][c].y = fma(cs, gv.y, C[a][c].y);
                         }
@@ -196,7 +204,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_kernel(const RowsPar
                     }
                     double tot = 0.0;
 #pragma unroll
-                    for (int q = 0; q < NB; ++q) tot += __shfl_sync(0xffffffffu, rs, gbase_lane + bi * NB + q);
+                    for (int q = 0; q < NB; ++q) tot += __shfl_sync(0xffffffffu, rs, lane_of(bi * NB + q));
                     nb = fmax(nb, tot);
                 }
             }
@@ -279,14 +287,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_kernel(const RowsPar
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
                         const int bk = k / BS, kc = k % BS;   // compile-time after unrolling
-                        const cplx pk = shfl_c(W[kc][kc], gbase_lane + bk * NB + bk);
+                        const cplx pk = shfl_c(W[kc][kc], lane_of(bk * NB + bk));
                         cplx qa[BS], pq[BS], pr[BS];
 #pragma unroll
-                        for (int a = 0; a < BS; ++a) qa[a] = shfl_c(W[a][kc], gbase_lane + bi * NB + bk);
+                        for (int a = 0; a < BS; ++a) qa[a] = shfl_c(W[a][kc], lane_of(bi * NB + bk));
 #pragma unroll
                         for (int c = 0; c < BS; ++c) {
-                            pq[c] = shfl_c(W[kc][c], gbase_lane + bk * NB + bj);
-                            pr[c] = shfl_c(C[kc][c], gbase_lane + bk * NB + bj);
+                            pq[c] = shfl_c(W[kc][c], lane_of(bk * NB + bj));
+                            pr[c] = shfl_c(C[kc][c], lane_of(bk * NB + bj));
                         }
                         const cplx inv = crcp(pk);
                         cplx f[BS];
@@ -339,12 +347,309 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_kernel(const RowsPar
 
         // ---- fold the group products: P_{MPW-1} ... P_1 P_0 (every group computes it; group 0 writes) ----
         cplx* wbase = sWarps + (size_t)warp * L::WARP_ELEMS;
-        const cplx* cur = wbase + (size_t)(MPW - 1) * L::GROUP_ELEMS + 3 * L::BUF;
+        const cplx* cur = wbase + L::group_off(MPW - 1) + 3 * L::BUF;
         int flip = 0;
 #pragma unroll 1
         for (int gg = MPW - 2; gg >= 0; --gg) {
             cplx T[BS][BS];
-            mm_blk<D, BS, LD>(cur + r0 * LD, wbase + (size_t)gg * L::GROUP_ELEMS + 3 * L::BUF + c0, T);
+            mm_blk<D, BS, LD>(cur + r0 * LD, wbase + L::group_off(gg) + 3 * L::BUF + c0, T);
+            cplx* dst = flip ? bufA : bufX;
+            store_blk<D, BS, LD>(dst + rc_off, T, lane_on);
+            __syncwarp();
+            cur = dst;
+            flip ^= 1;
+        }
+        if (lane_on && g == 0) {
+            cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * d * d) : (p.seg_out + ((size_t)b * p.S + sidx) * d * d);
+#pragma unroll
+            for (int a = 0; a < BS; ++a) {
+                const int row = r0 + a;
+                if (row < d) {
+#pragma unroll
+                    for (int c = 0; c < BS; ++c)
+                        if (c0 + c < d) o[row * d + c0 + c] = cur[(r0 + a) * LD + c0 + c];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// =============================================================================================
+// Same mapping, exponential by the degree-18 Taylor scheme in 5 products (c3b_common.cuh) instead
+// of Pade + Gauss-Jordan: no division, no shuffles, no serial pivot chain -- every phase is a dense
+// block product or an element-wise combination, which is what a kernel with 2 warps per
+// scheduler needs (ncu: the Gauss-Jordan sweep took 33 % of the Pade kernel's time at 1/6 of its
+// flops).  The generators arrive TRACE-SHIFTED (G_k - tr(G_k)/d I, Higham's preprocessing step):
+// for lab-frame Hamiltonians with a large diagonal this halves ||A|| (headline: 1.33 -> 0.75), so
+// the slice needs no squaring; exp(mu_n) factors are accumulated as one complex sum per lane group
+// and applied once per segment (per slice only when the partial propagators are stored).
+// =============================================================================================
+template <int D, int BS, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_t18_kernel(const RowsParams p, unsigned int* __restrict__ counter) {
+    using L = BlkLayout<D, BS>;
+    constexpr int NB = L::NB, LPM = L::LPM, MPW = L::MPW, LD = L::LD;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = p.K;
+    const int d = p.d;
+    cplx* sG = reinterpret_cast<cplx*>(smem_raw);                 // [(K+1), D, LD] zero padded
+    double* sRS = reinterpret_cast<double*>(sG + (K + 1) * D * LD);
+    cplx* sWarps = reinterpret_cast<cplx*>(sRS + (((K + 1) * D + 1) & ~1));
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const bool hmode = p.hlist != nullptr;
+
+    if (!hmode) {
+        for (int idx = tid; idx < (K + 1) * D * D; idx += WARPS * 32) {
+            const int k = idx / (D * D);
+            const int rem = idx - k * D * D;
+            const int r = rem / D, j = rem - r * D;
+            cplx v = cmake(0.0, 0.0);
+            if (r < d && j < d) v = p.G[(size_t)k * d * d + r * d + j];
+            sG[(k * D + r) * LD + j] = v;
+        }
+        for (int idx = tid; idx < (K + 1) * D; idx += WARPS * 32) {
+            const int k = idx / D, r = idx - k * D;
+            sRS[idx] = (r < d) ? p.RS[k * d + r] : 0.0;
+        }
+    }
+    __syncthreads();
+
+    const int g_raw = lane / LPM;
+    const bool lane_on = g_raw < MPW;
+    const int g = lane_on ? g_raw : MPW - 1;
+    const int li = ((lane_on ? (lane - g_raw * LPM) : LPM - 1) + L::rot(g)) % LPM;   // block index owned by this lane
+    const int bi = li / NB, bj = li - bi * NB;
+    const int r0 = bi * BS, c0 = bj * BS;
+    const bool on_diag = (bi == bj);
+
+    cplx* gbase = sWarps + (size_t)warp * L::WARP_ELEMS + L::group_off(g);
+    cplx* bufA = gbase;
+    cplx* bufB = gbase + L::BUF;      // A^2, then B1, then the left operands of the later products
+    cplx* bufX = gbase + 2 * L::BUF;  // A^3, then B5, then A9
+    cplx* bufP = gbase + 3 * L::BUF;
+    const int rc_off = r0 * LD + c0;
+    const int mg_off = r0 * LD + c0;
+    const cplx hs = cmake(p.hscale_re, p.hscale_im);
+    const long long total_units = (long long)p.B * p.S;
+    const bool shifted = (p.TR != nullptr) && !hmode;
+
+    for (;;) {
+        unsigned int unit_u = 0;
+        if (lane == 0) unit_u = atomicAdd(counter, 1u);
+        unit_u = __shfl_sync(0xffffffffu, unit_u, 0);
+        const long long unit = unit_u;
+        if (unit >= total_units) break;
+        const int b = (int)(unit / p.S);
+        const int sidx = (int)(unit - (long long)b * p.S);
+        const int n_begin = sidx * p.seg_len;
+        const int n_end = min(p.N, n_begin + p.seg_len);
+        const int len = n_end - n_begin;
+        const int cl = (len + MPW - 1) / MPW;
+        const int my_begin = n_begin + g * cl;
+        const int my_end = min(n_end, my_begin + cl);
+        const double* sig_b = p.signals ? p.signals + (size_t)b * K * p.N : nullptr;
+        cplx mu_acc = cmake(0.0, 0.0);    // sum of the trace shifts of this group's slices
+
+#pragma unroll 1
+        for (int it = 0; it < cl; ++it) {
+            const int n = my_begin + it;
+            const bool on = lane_on && (n < my_end);
+
+            cplx R1[BS][BS];   // A, later B2
+            cplx mu = cmake(0.0, 0.0);
+            double nb = 0.0;
+            if (!hmode) {
+                double nba[BS];
+#pragma unroll
+                for (int a = 0; a < BS; ++a) {
+                    nba[a] = on ? sRS[r0 + a] : 0.0;
+#pragma unroll
+                    for (int c = 0; c < BS; ++c) R1[a][c] = on ? sG[mg_off + a * LD + c] : cmake(0.0, 0.0);
+                }
+                if (shifted && on) mu = p.TR[0];
+                for (int k = 0; k < K; ++k) {
+                    const double cs = on ? __ldg(sig_b + (size_t)k * p.N + n) : 0.0;
+                    const cplx* gk = sG + (k + 1) * D * LD + mg_off;
+#pragma unroll
+                    for (int a = 0; a < BS; ++a) {
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) {
+                            const cplx gv = gk[a * LD + c];
+                            R1[a][c].x = fma(cs, gv.x, R1[a][c].x);
+                            R1[a][c].y = fma(cs, gv.y, R1[a][c].y);
+                        }
+                        nba[a] = fma(fabs(cs), sRS[(k + 1) * D + r0 + a], nba[a]);
+                    }
+                    if (shifted) { const cplx t = p.TR[k + 1]; mu.x = fma(cs, t.x, mu.x); mu.y = fma(cs, t.y, mu.y); }
+                }
+#pragma unroll
+                for (int a = 0; a < BS; ++a) nb = fmax(nb, nba[a]);
+            } else {
+#pragma unroll
+                for (int a = 0; a < BS; ++a) {
+                    const int row = r0 + a;
+                    double rs = 0.0;
+#pragma unroll
+                    for (int c = 0; c < BS; ++c) {
+                        cplx h = cmake(0.0, 0.0);
+                        if (on && row < d && c0 + c < d)
+                            h = p.hlist[((size_t)b * p.N + n) * d * d + (size_t)row * d + c0 + c];
+                        R1[a][c] = cmul(hs, h);
+                        rs += cabs1(R1[a][c]);
+                    }
+                    double tot = 0.0;
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) tot += __shfl_sync(0xffffffffu, rs, g * LPM + (bi * NB + q - L::rot(g) + LPM) % LPM);
+                    nb = fmax(nb, tot);
+                }
+            }
+            nb = warp_max(nb);
+            mu_acc.x += mu.x; mu_acc.y += mu.y;
+
+            const int s = squarings_for(nb, C3B_THETA18);
+            if (s > 0) {
+                const double sc = pow2neg(s);
+#pragma unroll
+                for (int a = 0; a < BS; ++a)
+#pragma unroll
+                    for (int c = 0; c < BS; ++c) { R1[a][c].x *= sc; R1[a][c].y *= sc; }
+            }
+            store_blk<D, BS, LD>(bufA + rc_off, R1, lane_on);
+            __syncwarp();
+
+            cplx R2[BS][BS], R3[BS][BS], R4[BS][BS], C[BS][BS];
+            // phases: 0 A2 | 1 A3 | 2 A6 (+ combinations) | 3 B1 B5 | 4 (B3+A9) A9 | s squarings | product
+            const int ph_lastsq = 4 + s;
+            const int ph_last = ph_lastsq + (it > 0 ? 1 : 0);
+            const cplx* Xr = bufA + r0 * LD;
+            const cplx* Yc = bufA + c0;
+
+#pragma unroll 1
+            for (int ph = 0; ph <= ph_last; ++ph) {
+                mm_blk<D, BS, LD>(Xr, Yc, C);
+                if (ph == 0) {                                  // C = A^2
+#pragma unroll
+                    for (int a = 0; a < BS; ++a)
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) R2[a][c] = C[a][c];
+                    store_blk<D, BS, LD>(bufB + rc_off, C, lane_on);
+                    __syncwarp();
+                    Xr = bufB + r0 * LD; Yc = bufA + c0;         // A^3 = A^2 A
+                } else if (ph == 1) {                           // C = A^3
+#pragma unroll
+                    for (int a = 0; a < BS; ++a)
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) R3[a][c] = C[a][c];
+                    store_blk<D, BS, LD>(bufX + rc_off, C, lane_on);
+                    __syncwarp();
+                    Xr = bufX + r0 * LD; Yc = bufX + c0;         // A^6 = A^3 A^3
+                } else if (ph == 2) {                           // C = A^6: form B1..B5
+                    __syncwarp();                               // bufX (A^3) and bufB (A^2) no longer read
+#pragma unroll
+                    for (int a = 0; a < BS; ++a)
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) {
+                            const cplx x1 = R1[a][c], x2 = R2[a][c], x3 = R3[a][c], x6 = C[a][c];
+                            const double dg = (on_diag && a == c) ? 1.0 : 0.0;
+                            cplx b1, b5, b4, b3, b2;
+                            b1.x = C3B_T18_A11 * x1.x + C3B_T18_A21 * x2.x + C3B_T18_A31 * x3.x;
+                            b1.y = C3B_T18_A11 * x1.y + C3B_T18_A21 * x2.y + C3B_T18_A31 * x3.y;
+                            b5.x = C3B_T18_B24 * x2.x + C3B_T18_B34 * x3.x + C3B_T18_B64 * x6.x;
+                            b5.y = C3B_T18_B24 * x2.y + C3B_T18_B34 * x3.y + C3B_T18_B64 * x6.y;
+                            b4.x = C3B_T18_B03 * dg + C3B_T18_B13 * x1.x + C3B_T18_B23 * x2.x + C3B_T18_B33 * x3.x + C3B_T18_B63 * x6.x;
+                            b4.y = C3B_T18_B13 * x1.y + C3B_T18_B23 * x2.y + C3B_T18_B33 * x3.y + C3B_T18_B63 * x6.y;
+                            b3.x = C3B_T18_B02 * dg + C3B_T18_B12 * x1.x + C3B_T18_B22 * x2.x + C3B_T18_B32 * x3.x + C3B_T18_B62 * x6.x;
+                            b3.y = C3B_T18_B12 * x1.y + C3B_T18_B22 * x2.y + C3B_T18_B32 * x3.y + C3B_T18_B62 * x6.y;
+                            b2.x = C3B_T18_B11 * x1.x + C3B_T18_B21 * x2.x + C3B_T18_B31 * x3.x + C3B_T18_B61 * x6.x;
+                            b2.y = C3B_T18_B11 * x1.y + C3B_T18_B21 * x2.y + C3B_T18_B31 * x3.y + C3B_T18_B61 * x6.y;
+                            R4[a][c] = b4;
+                            R1[a][c] = b2;
+                            if (lane_on) {
+                                bufB[rc_off + a * LD + c] = b1;     // left operand of B1 B5
+                                bufX[rc_off + a * LD + c] = b5;     // right operand
+                                bufA[rc_off + a * LD + c] = b3;     // own block only, re-read after the product
+                            }
+                        }
+                    __syncwarp();
+                    Xr = bufB + r0 * LD; Yc = bufX + c0;
+                } else if (ph == 3) {                           // C = B1 B5  ->  A9 = C + B4
+                    __syncwarp();                               // bufB / bufX fully read
+#pragma unroll
+                    for (int a = 0; a < BS; ++a)
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) {
+                            const cplx a9 = cmake(C[a][c].x + R4[a][c].x, C[a][c].y + R4[a][c].y);
+                            const cplx b3 = bufA[rc_off + a * LD + c];
+                            if (lane_on) {
+                                bufX[rc_off + a * LD + c] = a9;                                   // right operand A9
+                                bufB[rc_off + a * LD + c] = cmake(b3.x + a9.x, b3.y + a9.y);      // left operand B3 + A9
+                            }
+                        }
+                    __syncwarp();
+                    Xr = bufB + r0 * LD; Yc = bufX + c0;
+                } else {
+                    if (ph == 4) {                              // C = (B3 + A9) A9  ->  T18 = C + B2
+#pragma unroll
+                        for (int a = 0; a < BS; ++a)
+#pragma unroll
+                            for (int c = 0; c < BS; ++c) { C[a][c].x += R1[a][c].x; C[a][c].y += R1[a][c].y; }
+                    }
+                    if (ph <= ph_lastsq) {
+                        // C = exp(A_n / 2^s)^(2^(ph-4)); publish as the next left operand
+                        __syncwarp();
+                        store_blk<D, BS, LD>(bufB + rc_off, C, lane_on);
+                        __syncwarp();
+                        Xr = bufB + r0 * LD;
+                        Yc = (ph < ph_lastsq) ? (bufB + c0) : (bufP + c0);
+                        if (ph == ph_lastsq) {
+                            if (p.dUs_out != nullptr && on) {
+                                const cplx ph_n = shifted ? cexp_(mu) : cmake(1.0, 0.0);
+#pragma unroll
+                                for (int a = 0; a < BS; ++a) {
+                                    const int row = r0 + a;
+                                    if (row < d) {
+                                        cplx* o = p.dUs_out + ((size_t)b * p.N + n) * d * d + (size_t)row * d + c0;
+#pragma unroll
+                                        for (int c = 0; c < BS; ++c)
+                                            if (c0 + c < d) o[c] = shifted ? cmul(ph_n, C[a][c]) : C[a][c];
+                                    }
+                                }
+                            }
+                            if (it == 0) store_blk<D, BS, LD>(bufP + rc_off, C, lane_on);
+                        }
+                    } else {                                    // C = dU_n * P
+                        __syncwarp();
+                        store_blk<D, BS, LD>(bufP + rc_off, C, lane_on);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- re-apply this group's accumulated shift: P_g <- exp(sum mu) P_g -------------------------
+        if (shifted) {
+            const cplx ph_g = cexp_(mu_acc);
+#pragma unroll
+            for (int a = 0; a < BS; ++a)
+#pragma unroll
+                for (int c = 0; c < BS; ++c) {
+                    const cplx v = bufP[rc_off + a * LD + c];
+                    if (lane_on) bufP[rc_off + a * LD + c] = cmul(ph_g, v);
+                }
+            __syncwarp();
+        }
+
+        // ---- fold the group products: P_{MPW-1} ... P_1 P_0 (every group computes it; group 0 writes) ----
+        cplx* wbase = sWarps + (size_t)warp * L::WARP_ELEMS;
+        const cplx* cur = wbase + L::group_off(MPW - 1) + 3 * L::BUF;
+        int flip = 0;
+#pragma unroll 1
+        for (int gg = MPW - 2; gg >= 0; --gg) {
+            cplx T[BS][BS];
+            mm_blk<D, BS, LD>(cur + r0 * LD, wbase + L::group_off(gg) + 3 * L::BUF + c0, T);
             cplx* dst = flip ? bufA : bufX;
             store_blk<D, BS, LD>(dst + rc_off, T, lane_on);
             __syncwarp();

@@ -29,6 +29,9 @@ namespace c3b {
 struct RowsParams {
     const cplx* G;          // [(Bm), K+1, d, d]  pre-scaled generators: A = G0 + sum_k c_k G_k
     const double* RS;       // [(Bm), K+1, d]     row sums of |G_k| (inf-norm bound pieces)
+    const cplx* TR;         // [(Bm), K+1] trace shifts t_k = tr(G_k)/d already SUBTRACTED from G_k's diagonal, or null
+                            //   (exp(A) = exp(mu) exp(A - mu I), mu_n = t_0 + sum_k c_k[n] t_k; only kernels that
+                            //    re-apply exp(mu) accept shifted generators)
     const double* signals;  // [B, K, N] real control fields, contiguous in N (may be null if K == 0)
     const cplx* hlist;      // [B, N, d, d] explicit Hamiltonians (H-list mode) or null
     double hscale_re, hscale_im;  // H-list mode: A = hscale * H   (-i dt for the closed system)

@@ -17,9 +17,9 @@ sig_small = synth.controls(m, 4, 1000)
 want, want_d = orc.propagate_batch(m.h0, m.hks, sig_small, 1e-11, return_dUs=True)
 B = 4096
 sig = torch.as_tensor(synth.controls_fast(m, B, 1000)).cuda()
-for v in (1, 7, 8, 9):
+for v in (8, 13, 14):
     engine.set_tuning("rows_variant", v)
-    for mc in (8, 40):
+    for mc in (8,):
         engine.set_tuning("min_chunk", mc)
         U, dUs = engine.pwc_closed(h0, hks, sig_small, 1e-11, return_dUs=True)
         err = np.linalg.norm(U.cpu().numpy() - want) / np.linalg.norm(want)
