@@ -322,7 +322,7 @@ def run_engine(args):
             "config": {"workload": WORKLOAD, "d": D, "K": K, "N": N, "B_per_gpu": B, "global_batch": B * n_gpus,
                        "dt": DT, "parallelism": f"batch-sharded x{n_gpus}" + (", one all-gather of U per step" if n_gpus > 1 else ""),
                        "l2": f"{N_ROTATE} rotating input buffers ({N_ROTATE * B * K * N * 8 / 1e6:.0f} MB > 126 MB L2)",
-                       "kernel": "pwc_blk_kernel<9,3> (fused assemble + Pade expm + ordered product, 3x3 lane blocks)"},
+                       "kernel": "pwc_blk_t18_kernel<9,3> (fused assemble + degree-18 Taylor expm in 5 products + ordered product, 3x3 lane blocks)"},
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": B * K * N * 8,
                     "d2h_bytes_per_step": B * D * D * 16, "api": "c3_b200.propagation.pwc_batch(host signals) -> U.cpu()"},
             "gpu_launches": launches,

@@ -13,6 +13,7 @@
 #include "pwc_rows.cuh"
 #include "pwc_blk.cuh"
 #include "product.cuh"
+#include "pwc_gemm.cuh"
 #include "peak.cuh"
 
 using namespace c3b;
@@ -43,9 +44,11 @@ bool g_ev_valid = false;
 // ---- tuning (process-wide) -------------------------------------------------------------------
 long long g_target_units = 32768;  // rows kernel: aim for this many warp work units per launch
 long long g_force_cta = 0;         // route everything to the CTA kernel (testing)
+long long g_cta_variant = getenv("C3B_CTA_VARIANT") ? atoll(getenv("C3B_CTA_VARIANT")) : 1;  // 0: Pade + pivoted Gauss-Jordan, 1: Taylor-18 on DMMA tiles
 long long g_min_chunk = getenv("C3B_MIN_CHUNK") ? atoll(getenv("C3B_MIN_CHUNK")) : 8;         // rows kernel: minimum slices per lane group
-// 1: rows v2 (one row per lane) | 4-6: rows v3 (R rows per lane, experimental) | 7-9: block layout (8 = default for d=9)
-long long g_rows_variant = getenv("C3B_ROWS_VARIANT") ? atoll(getenv("C3B_ROWS_VARIANT")) : 8;      // 0: v1 kernel, 1: v2 (255 regs), 2: v2 V-in-smem (168 regs), 3: v2 (168 regs)
+// 1: rows v2 (one row per lane, Pade) | 4-6: rows v3 (experimental) | 7-12: block layout, Pade + Gauss-Jordan (d=9)
+// 13 (default): block layout, degree-18 Taylor, trace shift, all d <= 12
+long long g_rows_variant = getenv("C3B_ROWS_VARIANT") ? atoll(getenv("C3B_ROWS_VARIANT")) : 13;      // 0: v1 kernel, 1: v2 (255 regs), 2: v2 V-in-smem (168 regs), 3: v2 (168 regs)
 
 int num_sms() {
     static int cached = 0;
@@ -72,6 +75,14 @@ int rows_template_dim(int D) {
     return 0;
 }
 
+// Block-kernel instantiations: padded dimension -> (D, BS).  Every d <= 12 maps to one of them.
+int blk_template_dim(int d) {
+    const int dims[] = {2, 3, 4, 6, 8, 9, 12};
+    for (int t : dims)
+        if (d <= t) return t;
+    return 0;
+}
+
 int pwc_path(int K, int D, int batched_model) {
     (void)K;
     if (!g_force_cta && !batched_model && rows_template_dim(D) != 0) return 1;
@@ -80,10 +91,13 @@ int pwc_path(int K, int D, int batched_model) {
 
 size_t cta_smem_bytes(int D) { return (((size_t)D * sizeof(int) + 15) & ~(size_t)15) + (size_t)kCtaSlots * D * D * sizeof(cplx); }
 
+int round8(int D) { return (D + 7) & ~7; }
+size_t gemm_smem_bytes(int D) { return (size_t)kGemmSlots * round8(D) * round8(D) * sizeof(cplx); }
+
 int cta_grid(int D, long long units) {
     int per_sm = 1;
     if (D <= 32) {
-        const size_t sm = cta_smem_bytes(D);
+        const size_t sm = g_cta_variant == 1 ? gemm_smem_bytes(D) : cta_smem_bytes(D);
         per_sm = (int)((size_t)220 * 1024 / (sm + 1024));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 4) per_sm = 4;
@@ -111,6 +125,14 @@ Plan make_plan(int B, int K, int N, int D, int batched_model, bool hlist) {
     if (pl.path == 1) {
         const int TD = rows_template_dim(D);
         int G = 32 / TD;
+        if (g_rows_variant >= 13) {
+            switch (blk_template_dim(D)) {
+                case 2: case 3: G = 32; break;
+                case 4: case 6: G = 8; break;
+                case 8: case 12: G = 2; break;
+                default: G = 3; break;
+            }
+        }
         if (g_rows_variant >= 4 && g_rows_variant <= 6 && (TD == 9 || TD == 3)) G = (TD == 9) ? (g_rows_variant >= 5 ? 6 : 10) : 32;   // v3: lane groups per warp
         long long S = (g_target_units + B - 1) / B;
         long long smax = N / (g_min_chunk * G);
@@ -141,7 +163,7 @@ Plan make_plan(int B, int K, int N, int D, int batched_model, bool hlist) {
     pl.off_seg = off;
     if (pl.S > 1) off += align_up((size_t)B * pl.S * D * D * sizeof(cplx));
     pl.off_cta = off;
-    if (pl.path == 3) off += align_up((size_t)pl.grid * kCtaSlots * D * D * sizeof(cplx));
+    if (pl.path == 3) off += align_up((size_t)pl.grid * kGemmSlots * round8(D) * round8(D) * sizeof(cplx));
     pl.off_prod = off;
     if (pl.S > 1 && D > 64) off += align_up((size_t)cta_grid(D, 1LL << 40) * 2 * D * D * sizeof(cplx));
     pl.off_counter = off;
@@ -243,11 +265,21 @@ int launch_blk_t18_t(const RowsParams& rp, unsigned int* counter, cudaStream_t s
 }
 
 // does the kernel that launch_rows() would pick accept trace-shifted generators?
-bool rows_kernel_takes_shift(int d) { return rows_template_dim(d) == 9 && g_rows_variant >= 13; }
+bool rows_kernel_takes_shift(int d) { return g_rows_variant >= 13 && blk_template_dim(d) != 0; }
 
 int launch_rows(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
-    if (rows_template_dim(rp.d) == 9 && g_rows_variant == 13) return launch_blk_t18_t<9, 3, 4, 2>(rp, counter, st);
-    if (rows_template_dim(rp.d) == 9 && g_rows_variant == 14) return launch_blk_t18_t<9, 3, 4, 3>(rp, counter, st);
+    if (g_rows_variant >= 13) {
+        switch (blk_template_dim(rp.d)) {
+            case 2: return launch_blk_t18_t<2, 2, 4, 3>(rp, counter, st);
+            case 3: return launch_blk_t18_t<3, 3, 4, 2>(rp, counter, st);
+            case 4: return launch_blk_t18_t<4, 2, 4, 3>(rp, counter, st);
+            case 6: return launch_blk_t18_t<6, 3, 4, 2>(rp, counter, st);
+            case 8: return launch_blk_t18_t<8, 2, 4, 3>(rp, counter, st);
+            case 9: return (g_rows_variant == 14) ? launch_blk_t18_t<9, 3, 4, 3>(rp, counter, st)
+                                                  : launch_blk_t18_t<9, 3, 4, 2>(rp, counter, st);
+            case 12: return launch_blk_t18_t<12, 3, 4, 2>(rp, counter, st);
+        }
+    }
     if (rows_template_dim(rp.d) == 9 && g_rows_variant == 7) return launch_blk_t<9, 3, 4, 3>(rp, counter, st);
     if (rows_template_dim(rp.d) == 9 && g_rows_variant == 8) return launch_blk_t<9, 3, 4, 2>(rp, counter, st);
     if (rows_template_dim(rp.d) == 9 && g_rows_variant == 9) return launch_blk_t<9, 3, 6, 2>(rp, counter, st);
@@ -288,6 +320,24 @@ int launch_cta_t(const CtaParams& cp, int grid, cudaStream_t st) {
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
+}
+
+template <int TM, int TN>
+int launch_gemm_t(const GemmParams& gp, int grid, cudaStream_t st) {
+    auto kern = pwc_t18_cta_kernel<TM, TN>;
+    const size_t smem = gp.c.use_smem ? gemm_smem_bytes(gp.c.D) : 0;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kCtaThreads, smem, st>>>(gp);
+    CUDA_TRY(cudaGetLastError());
+    return C3B_OK;
+}
+
+int launch_gemm(const CtaParams& cp, const cplx* TR, int grid, cudaStream_t st) {
+    GemmParams gp{};
+    gp.c = cp; gp.TR = TR; gp.DP = round8(cp.D);
+    if (gp.DP <= 16) return launch_gemm_t<1, 1>(gp, grid, st);
+    if (gp.DP <= 48) return launch_gemm_t<1, 2>(gp, grid, st);
+    return launch_gemm_t<2, 2>(gp, grid, st);
 }
 
 int launch_cta(const CtaParams& cp, int grid, cudaStream_t st) {
@@ -348,7 +398,7 @@ int run_pwc(const Plan& pl, const cplx* G, const double* RS, const cplx* TR, con
         cp.U_out = U_out; cp.seg_out = seg; cp.dUs_out = dUs_out;
         cp.ws = reinterpret_cast<cplx*>(ws + pl.off_cta);
         cp.use_smem = pl.path == 2;
-        int rc = launch_cta(cp, pl.grid, st);
+        int rc = (g_cta_variant == 1) ? launch_gemm(cp, TR, pl.grid, st) : launch_cta(cp, pl.grid, st);
         if (rc) return rc;
     }
     if (g_profile) { CUDA_TRY(cudaEventRecord(g_ev1, st)); g_ev_valid = true; }
@@ -383,6 +433,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (key == nullptr) return fail(C3B_EINVAL, "C3:ERROR: null tuning key");
     if (!strcmp(key, "target_units")) { g_target_units = value < 1 ? 1 : value; return C3B_OK; }
     if (!strcmp(key, "force_cta")) { g_force_cta = value; return C3B_OK; }
+    if (!strcmp(key, "cta_variant")) { g_cta_variant = value; return C3B_OK; }
     if (!strcmp(key, "profile")) { g_profile = value; return C3B_OK; }
     if (!strcmp(key, "rows_variant")) { g_rows_variant = value; return C3B_OK; }
     if (!strcmp(key, "min_chunk")) { g_min_chunk = value < 1 ? 1 : value; return C3B_OK; }
@@ -410,7 +461,7 @@ int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, doubl
     char* ws = static_cast<char*>(workspace);
     cplx* G = reinterpret_cast<cplx*>(ws + pl.off_G);
     double* RS = reinterpret_cast<double*>(ws + pl.off_RS);
-    cplx* TR = (pl.path == 1 && rows_kernel_takes_shift(d)) ? reinterpret_cast<cplx*>(ws + pl.off_TR) : nullptr;
+    cplx* TR = ((pl.path == 1 && rows_kernel_takes_shift(d)) || (pl.path != 1 && g_cta_variant == 1)) ? reinterpret_cast<cplx*>(ws + pl.off_TR) : nullptr;
     const int Bm = batched_model ? B : 1;
     {
         const long long total = (long long)Bm * (K + 1) * d * d;
@@ -461,7 +512,7 @@ int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C
     char* ws = static_cast<char*>(workspace);
     cplx* G = reinterpret_cast<cplx*>(ws + pl.off_G);
     double* RS = reinterpret_cast<double*>(ws + pl.off_RS);
-    cplx* TR = (pl.path == 1 && rows_kernel_takes_shift(D)) ? reinterpret_cast<cplx*>(ws + pl.off_TR) : nullptr;
+    cplx* TR = ((pl.path == 1 && rows_kernel_takes_shift(D)) || (pl.path != 1 && g_cta_variant == 1)) ? reinterpret_cast<cplx*>(ws + pl.off_TR) : nullptr;
     const int Bm = batched_model ? B : 1;
     {
         const long long total = (long long)Bm * (K + 1) * D * D;

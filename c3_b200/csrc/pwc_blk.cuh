@@ -29,7 +29,7 @@ struct BlkLayout {
     // lanes of a group hit distinct 16-byte bank slots for block stores, block-row and block-column
     // loads; with the group stride = 4 (mod 8) neighbouring groups in a quarter-warp do not collide
     // either (ncu before: 5.7 wavefronts per LDS.128 and 9 per STS.128 instead of 4).
-    static constexpr int LD = (D % 8 == 1) ? D + 2 : ((D % 8 == 3) ? D : D + 1);
+    static constexpr int LD = (D % 8 == 1) ? D + 2 : ((D % 8 == 3) ? D : ((D % 2 == 0) ? D + 1 : D));
     static constexpr int BUF = D * LD;
     static constexpr int GROUP_PAD = (4 - (4 * BUF) % 8 + 8) % 8;
     static constexpr int GROUP_ELEMS = 4 * BUF + GROUP_PAD; // bufA, bufA2, bufX, bufP

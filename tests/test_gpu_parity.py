@@ -208,6 +208,43 @@ def test_lindblad_small_dims(eng):
             assert rel_fro(U[b].cpu().numpy(), orc.tf_matmul_n(want, orc.compute_folding_stack(N))) < TOL
 
 
+@pytest.mark.parametrize("cta_variant", [0, 1])
+@pytest.mark.parametrize("d", [13, 16, 24, 27, 33, 40])
+def test_cta_kernels_pade_and_taylor(eng, d, cta_variant):
+    """Both CTA kernels on the same inputs: 0 = Higham Pade + pivoted Gauss-Jordan (the literal
+    restatement of tf.linalg.expm), 1 = degree-18 Taylor on DMMA tiles with trace shift (default)."""
+    rng = np.random.default_rng(200 + d)
+    K, B, N = 2, 2, 9
+    h0, hks = _rand_model(rng, d, K, 2.2)
+    h0 = h0 + 0.7 * np.eye(d)          # non-zero trace: exercises the shift / phase re-application
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    eng.set_tuning("cta_variant", cta_variant)
+    try:
+        U, dUs = eng.pwc_closed(h0, hks, sig, 1.0, return_dUs=True)
+    finally:
+        eng.set_tuning("cta_variant", 1)
+    wantU, want_dUs = orc.propagate_batch(h0, hks, sig, 1.0, return_dUs=True)
+    assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
+    assert rel_fro(U.cpu().numpy(), wantU) < TOL
+
+
+@pytest.mark.parametrize("variant", [1, 8, 13])
+def test_register_kernel_variants_d9(eng, variant):
+    """The three generations of the small-d kernel on the headline shape: rows/Pade (1),
+    blocks/Pade + Gauss-Jordan (8), blocks/Taylor-18 + trace shift (13, default)."""
+    from c3_b200 import synth
+    m = synth.two_transmon()
+    sig = synth.controls(m, 3, 203)
+    eng.set_tuning("rows_variant", variant)
+    try:
+        U, dUs = eng.pwc_closed(m.h0, m.hks, sig, 1e-11, return_dUs=True)
+    finally:
+        eng.set_tuning("rows_variant", 13)
+    wantU, want_dUs = orc.propagate_batch(m.h0, m.hks, sig, 1e-11, return_dUs=True)
+    assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
+    assert rel_fro(U.cpu().numpy(), wantU) < TOL
+
+
 def test_lindblad_config3_shape(eng):
     """BASELINE config 3 shape (two 3-level transmons, D=81) on a small batch / few slices."""
     from c3_b200 import synth
