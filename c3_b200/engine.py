@@ -63,7 +63,7 @@ def pwc_path(K: int, D: int, batched_model: bool = False) -> int:
     return _lib.load().c3b_pwc_path(int(K), int(D), int(batched_model))
 
 
-def pwc_closed(h0, hks, signals, dt: float, return_dUs: bool = False, device=None):
+def pwc_closed(h0, hks, signals, dt: float, return_dUs: bool = False, device=None, out=None):
     """U[b] = prod_n expm(-i (h0 + sum_k signals[b,k,n] hks[k]) dt), later slices on the left.
 
     h0 [d,d] (or [B,d,d]), hks [K,d,d] (or [B,K,d,d]), signals [B,K,N] (or [K,N] -> B=1).
@@ -89,13 +89,71 @@ def pwc_closed(h0, hks, signals, dt: float, return_dUs: bool = False, device=Non
             hks = None
         if batched and h0.shape[0] != B:
             raise ValueError("C3:ERROR: batched h0 must have the batch size of signals")
-        U = torch.empty((B, d, d), dtype=torch.complex128, device=device)
+        if out is not None:
+            if tuple(out.shape) != (B, d, d) or out.dtype != torch.complex128 or not out.is_contiguous() or out.device != device:
+                raise ValueError("C3:ERROR: `out` must be a contiguous complex128 [B,d,d] tensor on the compute device")
+            U = out
+        else:
+            U = torch.empty((B, d, d), dtype=torch.complex128, device=device)
         dUs = torch.empty((B, N, d, d), dtype=torch.complex128, device=device) if return_dUs else None
         nbytes = lib.c3b_pwc_workspace_bytes(B, K, N, d, 0, int(batched))
         ws = _workspace(nbytes, device)
         _lib.check(lib.c3b_pwc_closed(_ptr(h0), _ptr(hks), _ptr(signals), float(dt), B, K, N, d, int(batched),
                                       _ptr(U), _ptr(dUs), _ptr(ws), ws.numel(), _stream()))
     return (U, dUs) if return_dUs else U
+
+
+def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, device=None):
+    """Closed-system propagators for HOST-resident signals [B,K,N] (numpy or CPU tensor, ideally
+    pinned): the batch is cut into chunks and the host->device copy of chunk i+1 overlaps the kernel
+    of chunk i (two CUDA streams), so PCIe time hides behind compute.  Returns U [B,d,d] on the
+    device, ordered on the caller's current stream."""
+    device = torch.device(device) if device is not None else default_device()
+    if not isinstance(signals_host, torch.Tensor):
+        signals_host = torch.as_tensor(signals_host)
+    if signals_host.is_cuda:
+        return pwc_closed(h0, hks, signals_host, dt, device=device)
+    if signals_host.dim() == 2:
+        signals_host = signals_host.unsqueeze(0)
+    signals_host = signals_host.to(torch.float64).contiguous()
+    B, K, N = signals_host.shape
+    with torch.cuda.device(device):
+        h0 = _as(h0, torch.complex128, device)
+        hks = _as(hks, torch.complex128, device) if K > 0 else None
+        d = h0.shape[-1]
+        U = torch.empty((B, d, d), dtype=torch.complex128, device=device)
+        if B <= chunk or h0.dim() == 3:
+            return pwc_closed(h0, hks, signals_host.to(device, non_blocking=True), dt, device=device, out=U)
+        main = torch.cuda.current_stream()
+        streams = _side_streams(device)
+        start = torch.cuda.Event()
+        start.record(main)
+        done = []
+        for i, b0 in enumerate(range(0, B, chunk)):
+            b1 = min(B, b0 + chunk)
+            st = streams[i % 2]
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                sig = signals_host[b0:b1].to(device, non_blocking=True)
+                pwc_closed(h0, hks, sig, dt, device=device, out=U[b0:b1])
+                sig.record_stream(st)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done.append(ev)
+        for ev in done:
+            main.wait_event(ev)
+        U.record_stream(main)
+    return U
+
+
+_side = {}
+
+
+def _side_streams(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _side:
+        _side[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _side[key]
 
 
 def pwc_closed_hlist(Hs, dt: float, return_dUs: bool = False, device=None):

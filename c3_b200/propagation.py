@@ -141,6 +141,10 @@ def pwc_batch(h0, hks, signals, dt, col_ops=None, lindbladian=False, return_dUs=
     if lindbladian:
         return engine.pwc_lindblad(_np(h0), _np(hks), [_np(c) for c in col_ops], sig, float(np.real(dt)),
                                    return_dUs=return_dUs)
+    host = not (isinstance(sig, torch.Tensor) and sig.is_cuda)
+    if host and not return_dUs and sig.ndim == 3:
+        # host-resident signals: chunked copy/compute pipeline (PCIe hidden behind the kernel)
+        return engine.pwc_closed_from_host(_np(h0), _np(hks), sig, float(np.real(dt)))
     return engine.pwc_closed(_np(h0), _np(hks), sig, float(np.real(dt)), return_dUs=return_dUs)
 
 

@@ -341,6 +341,25 @@ def test_full_size_properties(eng):
         assert rel_fro(U[b].cpu().numpy(), want) < TOL
 
 
+def test_host_pipelined_path_matches_device_path(eng):
+    """propagation.pwc_batch with HOST signals (chunked H2D/compute pipeline, the e2e path of
+    bench.py) gives the same bits as the device-resident call."""
+    from c3_b200 import synth, propagation as prop
+    m = synth.two_transmon()
+    B, N = 2500, 120                     # not a multiple of the 1024-row chunk
+    sig = synth.controls_fast(m, B, N)
+    host = torch.as_tensor(sig).pin_memory()
+    U_host = prop.pwc_batch(m.h0, m.hks, host, 1e-11)
+    U_np = prop.pwc_batch(m.h0, m.hks, sig, 1e-11)          # pageable numpy input
+    U_dev = eng.pwc_closed(m.h0, m.hks, torch.as_tensor(sig).cuda(), 1e-11)
+    torch.cuda.synchronize()
+    assert U_host.shape == (B, 9, 9)
+    assert rel_fro(U_host.cpu().numpy(), U_dev.cpu().numpy()) < 1e-13
+    assert rel_fro(U_np.cpu().numpy(), U_dev.cpu().numpy()) < 1e-13
+    want = orc.propagate_batch(m.h0, m.hks, sig[[0, 1023, 1024, 2499]], 1e-11)
+    assert rel_fro(U_host[[0, 1023, 1024, 2499]].cpu().numpy(), want) < TOL
+
+
 def test_error_reporting(eng):
     from c3_b200 import _lib
     lib = _lib.load()
