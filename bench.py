@@ -315,6 +315,13 @@ def run_engine(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch of the fused kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+            traffic_src = tj["source"]
+        except Exception:
+            pass
         line = {
             "metric": "propagator slices/sec", "value": value, "unit": "slices/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -327,7 +334,8 @@ def run_engine(args):
                     "d2h_bytes_per_step": B * D * D * 16, "api": "c3_b200.propagation.pwc_batch(host signals) -> U.cpu()"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / dfma_peak, "traffic": None,
+                         "frac": achieved_tf / dfma_peak, "traffic": traffic, "traffic_unit": "bytes per launch",
+                         "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "flops_per_slice": fl, "kernel_ms": kernel_ms,
                          "peak_source": "DFMA micro-benchmark in this process (c3b_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no fp64 entry",
