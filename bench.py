@@ -115,7 +115,7 @@ def run_reference(args):
         "reference_note": "TensorFlow (the reference's arithmetic backend) is not installable in this image; "
                           "this is oracle/c3_oracle.py, the numpy restatement pinned to the reference's golden vectors",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -347,12 +347,32 @@ def run_engine(args):
             "parity_rel_fro_max": parity,
             "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Keep fd 1 for the ONE JSON line: everything else that writes to stdout from native code
+    (e.g. NCCL's version banner) is sent to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
