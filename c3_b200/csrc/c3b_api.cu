@@ -92,7 +92,7 @@ int pwc_path(int K, int D, int batched_model) {
 size_t cta_smem_bytes(int D) { return (((size_t)D * sizeof(int) + 15) & ~(size_t)15) + (size_t)kCtaSlots * D * D * sizeof(cplx); }
 
 int round8(int D) { return (D + 7) & ~7; }
-size_t gemm_smem_bytes(int D) { return (size_t)kGemmSlots * round8(D) * round8(D) * sizeof(cplx); }
+size_t gemm_smem_bytes(int D) { return (size_t)kGemmSlots * round8(D) * (round8(D) + 4) * sizeof(cplx); }
 
 int cta_grid(int D, long long units) {
     int per_sm = 1;
@@ -335,6 +335,7 @@ int launch_gemm_t(const GemmParams& gp, int grid, cudaStream_t st) {
 int launch_gemm(const CtaParams& cp, const cplx* TR, int grid, cudaStream_t st) {
     GemmParams gp{};
     gp.c = cp; gp.TR = TR; gp.DP = round8(cp.D);
+    gp.LD = cp.use_smem ? gp.DP + 4 : gp.DP;
     if (gp.DP <= 16) return launch_gemm_t<1, 1>(gp, grid, st);
     if (gp.DP <= 48) return launch_gemm_t<1, 2>(gp, grid, st);
     return launch_gemm_t<2, 2>(gp, grid, st);

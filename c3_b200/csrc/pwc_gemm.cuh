@@ -29,8 +29,11 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a
 // C = A * B for zero-padded DP x DP complex matrices (row-major, leading dimension DP, DP % 8 == 0).
 // Warp w owns macro tiles of TM x TN m8n8 blocks, assigned round-robin.  No __restrict__: operands
 // may be global-workspace buffers written earlier by this CTA.
+// LD is the leading dimension (>= DP); KP = D rounded up to 4 bounds the k loop (columns/rows beyond D
+// are zero).  In shared memory LD = DP + 4 (= 4 mod 8 in 16-byte units) makes the A-fragment loads
+// bank-conflict free and the B-fragment loads 2-way (with LD = DP = 32 they were 8-way / 4-way).
 template <int TM, int TN>
-__device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP) {
+__device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP, const int LD, const int KP) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = kCtaThreads / 32;
     const int nb = DP >> 3;                       // m8n8 blocks per dimension
@@ -46,16 +49,16 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
         // clamp block indices of partial macro tiles (results of clamped duplicates are not stored)
         int arow[TM], bcol[TN];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) arow[i] = (min(bi0 + i, nb - 1) * 8 + fr) * DP + fc;
+        for (int i = 0; i < TM; ++i) arow[i] = (min(bi0 + i, nb - 1) * 8 + fr) * LD + fc;
 #pragma unroll
-        for (int j = 0; j < TN; ++j) bcol[j] = fc * DP + min(bj0 + j, nb - 1) * 8 + fr;
+        for (int j = 0; j < TN; ++j) bcol[j] = fc * LD + min(bj0 + j, nb - 1) * 8 + fr;
 #pragma unroll 2
-        for (int k0 = 0; k0 < DP; k0 += 4) {
+        for (int k0 = 0; k0 < KP; k0 += 4) {
             cplx a[TM], b[TN];
 #pragma unroll
             for (int i = 0; i < TM; ++i) a[i] = A[arow[i] + k0];
 #pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = B[bcol[j] + k0 * DP];
+            for (int j = 0; j < TN; ++j) b[j] = B[bcol[j] + k0 * LD];
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -71,7 +74,7 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 if (bi0 + i < nb && bj0 + j < nb) {
-                    cplx* o = C + ((bi0 + i) * 8 + fr) * DP + (bj0 + j) * 8 + 2 * fc;
+                    cplx* o = C + ((bi0 + i) * 8 + fr) * LD + (bj0 + j) * 8 + 2 * fc;
                     o[0] = cmake(cr[i][j][0], ci[i][j][0]);
                     o[1] = cmake(cr[i][j][1], ci[i][j][1]);
                 }
@@ -100,7 +103,8 @@ __device__ __forceinline__ double cta_norm1_ld(const cplx* A, const int D, const
 struct GemmParams {
     CtaParams c;       // same fields as the Pade CTA kernel (G, signals, hlist, sizes, outputs, ws, use_smem)
     const cplx* TR;    // [(Bm), K+1] trace shifts already subtracted from G's diagonals, or null
-    int DP;            // D rounded up to a multiple of 8
+    int DP;            // D rounded up to a multiple of 8 (tile extent)
+    int LD;            // leading dimension of every workspace matrix (DP, or DP + 4 in shared memory)
 };
 
 template <int TM, int TN>
@@ -108,8 +112,9 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[kCtaThreads / 32];
     const CtaParams& p = gp.c;
-    const int D = p.D, K = p.K, DP = gp.DP;
-    const int PP = DP * DP;
+    const int D = p.D, K = p.K, DP = gp.DP, LD = gp.LD;
+    const int KP = (D + 3) & ~3;
+    const int PP = DP * LD;
     const int tid = threadIdx.x;
 
     cplx* mats = p.use_smem ? reinterpret_cast<cplx*>(smem_raw) : p.ws + (size_t)blockIdx.x * kGemmSlots * PP;
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                         v.x = fma(c, gk.x, v.x);
                         v.y = fma(c, gk.y, v.y);
                     }
-                    A[i * DP + j] = v;
+                    A[i * LD + j] = v;
                 }
                 if (shifted) {
                     cplx mu = TRb[0];
@@ -163,11 +168,11 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                 const cplx* H = p.hlist + ((size_t)b * p.N + n) * D * D;
                 for (int e = tid; e < D * D; e += kCtaThreads) {
                     const int i = e / D, j = e - i * D;
-                    A[i * DP + j] = cmul(hs, H[e]);
+                    A[i * LD + j] = cmul(hs, H[e]);
                 }
             }
             __syncthreads();
-            const double nrm = cta_norm1_ld(A, D, DP, red);
+            const double nrm = cta_norm1_ld(A, D, LD, red);
             const int s = squarings_for(nrm, C3B_THETA18);
             if (s > 0) {
                 const double sc = pow2neg(s);
@@ -175,15 +180,15 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                 __syncthreads();
             }
             // ---- T18: A2 = S1, A3 = S2, A6 = S3 -----------------------------------------------------
-            cta_zgemm<TM, TN>(S[1], A, A, DP);
+            cta_zgemm<TM, TN>(S[1], A, A, DP, LD, KP);
             __syncthreads();
-            cta_zgemm<TM, TN>(S[2], S[1], A, DP);
+            cta_zgemm<TM, TN>(S[2], S[1], A, DP, LD, KP);
             __syncthreads();
-            cta_zgemm<TM, TN>(S[3], S[2], S[2], DP);
+            cta_zgemm<TM, TN>(S[3], S[2], S[2], DP, LD, KP);
             __syncthreads();
             // B1 -> S4, B5 -> S5, B4 -> S6, B3 -> S7, B2 -> S8
             for (int e = tid; e < PP; e += kCtaThreads) {
-                const int i = e / DP, j = e - i * DP;
+                const int i = e / LD, j = e - i * LD;
                 const double dg = (i == j && i < D) ? 1.0 : 0.0;
                 const cplx x1 = A[e], x2 = S[1][e], x3 = S[2][e], x6 = S[3][e];
                 S[4][e] = cmake(C3B_T18_A11 * x1.x + C3B_T18_A21 * x2.x + C3B_T18_A31 * x3.x,
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                                 C3B_T18_B11 * x1.y + C3B_T18_B21 * x2.y + C3B_T18_B31 * x3.y + C3B_T18_B61 * x6.y);
             }
             __syncthreads();
-            cta_zgemm<TM, TN>(S[1], S[4], S[5], DP);      // B1 B5
+            cta_zgemm<TM, TN>(S[1], S[4], S[5], DP, LD, KP);      // B1 B5
             __syncthreads();
             for (int e = tid; e < PP; e += kCtaThreads) {  // A9 -> S2, B3 + A9 -> S3
                 const cplx a9 = cmake(S[1][e].x + S[6][e].x, S[1][e].y + S[6][e].y);
@@ -206,14 +211,14 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                 S[3][e] = cmake(S[7][e].x + a9.x, S[7][e].y + a9.y);
             }
             __syncthreads();
-            cta_zgemm<TM, TN>(S[1], S[3], S[2], DP);      // (B3 + A9) A9
+            cta_zgemm<TM, TN>(S[1], S[3], S[2], DP, LD, KP);      // (B3 + A9) A9
             __syncthreads();
             cplx* X = S[4];
             for (int e = tid; e < PP; e += kCtaThreads) X[e] = cmake(S[1][e].x + S[8][e].x, S[1][e].y + S[8][e].y);
             __syncthreads();
             for (int i = 0; i < s; ++i) {                  // undo the scaling
                 cplx* nxt = (X == S[4]) ? S[5] : S[4];
-                cta_zgemm<TM, TN>(nxt, X, X, DP);
+                cta_zgemm<TM, TN>(nxt, X, X, DP, LD, KP);
                 __syncthreads();
                 X = nxt;
             }
@@ -231,13 +236,13 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                 }
                 for (int e = tid; e < D * D; e += kCtaThreads) {
                     const int i = e / D, j = e - i * D;
-                    o[e] = cmul(phn, X[i * DP + j]);
+                    o[e] = cmul(phn, X[i * LD + j]);
                 }
             }
             if (n == n_begin) {
                 for (int e = tid; e < PP; e += kCtaThreads) P[e] = X[e];
             } else {
-                cta_zgemm<TM, TN>(S[6], X, P, DP);
+                cta_zgemm<TM, TN>(S[6], X, P, DP, LD, KP);
                 __syncthreads();
                 for (int e = tid; e < PP; e += kCtaThreads) P[e] = S[6][e];
             }
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
             const cplx phu = shifted ? cexp_(mu_acc) : cmake(1.0, 0.0);
             for (int e = tid; e < D * D; e += kCtaThreads) {
                 const int i = e / D, j = e - i * D;
-                o[e] = cmul(phu, P[i * DP + j]);
+                o[e] = cmul(phu, P[i * LD + j]);
             }
         } else {
             for (int e = tid; e < D * D; e += kCtaThreads) o[e] = cmake((e / D) == (e % D) ? 1.0 : 0.0, 0.0);
