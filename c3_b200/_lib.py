@@ -13,7 +13,7 @@ SYMBOLS = [
     "c3b_version", "c3b_last_error", "c3b_pwc_workspace_bytes", "c3b_pwc_closed", "c3b_pwc_closed_hlist",
     "c3b_pwc_lindblad", "c3b_product_workspace_bytes", "c3b_ordered_product", "c3b_seq_product", "c3b_kron",
     "c3b_set_tuning", "c3b_pwc_path", "c3b_measure_fp64_peak", "c3b_microbench", "c3b_launch_count",
-    "c3b_last_kernel_ms",
+    "c3b_last_kernel_ms", "c3b_pwc_grad_workspace_bytes", "c3b_pwc_closed_grad",
 ]
 
 _lib = None
@@ -45,6 +45,10 @@ def load() -> C.CDLL:
     lib.c3b_pwc_closed_hlist.argtypes = [vp, d, i, i, i, vp, vp, vp, sz, vp]
     lib.c3b_pwc_lindblad.restype = i
     lib.c3b_pwc_lindblad.argtypes = [vp, vp, vp, i, vp, d, i, i, i, i, i, vp, vp, vp, sz, vp]
+    lib.c3b_pwc_grad_workspace_bytes.restype = sz
+    lib.c3b_pwc_grad_workspace_bytes.argtypes = [i, i, i, i, i]
+    lib.c3b_pwc_closed_grad.restype = i
+    lib.c3b_pwc_closed_grad.argtypes = [vp, vp, vp, d, i, i, i, i, vp, vp, vp, i, vp, sz, vp]
     lib.c3b_product_workspace_bytes.restype = sz
     lib.c3b_product_workspace_bytes.argtypes = [i, i, i]
     lib.c3b_ordered_product.restype = i

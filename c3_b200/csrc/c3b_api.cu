@@ -14,6 +14,7 @@
 #include "pwc_blk.cuh"
 #include "product.cuh"
 #include "pwc_gemm.cuh"
+#include "grad.cuh"
 #include "peak.cuh"
 
 using namespace c3b;
@@ -613,6 +614,76 @@ double c3b_measure_fp64_peak(int kind, int device, double seconds) {
     int rc = measure_fp64_peak(kind, device, seconds, &tf);
     if (rc != 0) return (double)fail(C3B_ECUDA, "C3:ERROR: fp64 peak measurement failed (cuda error %d)", rc);
     return tf;
+}
+
+// ---- gradient -------------------------------------------------------------
+static size_t grad_chunk_bytes(int Bc, int K, int N, int d, size_t* off /*[9]*/) {
+    const size_t dd = (size_t)d * d * sizeof(cplx), dd2 = 4 * dd;
+    size_t o = 0;
+    off[0] = o; o += align_up(c3b_pwc_workspace_bytes(Bc, K, N, d, 0, 0));          // forward workspace
+    off[1] = o; o += align_up(c3b_pwc_workspace_bytes(Bc, 0, N, 2 * d, 0, 0));      // augmented H-list workspace
+    off[2] = o; o += align_up((size_t)Bc * dd);                                    // U (forward)
+    off[3] = o; o += align_up((size_t)Bc * N * dd);                                // dUs
+    off[4] = o; o += align_up((size_t)Bc * N * dd);                                // Psi
+    off[5] = o; o += align_up((size_t)Bc * sizeof(double));                        // alpha
+    off[6] = o; o += align_up((size_t)Bc * N * dd2);                               // Haug
+    off[7] = o; o += align_up((size_t)Bc * N * dd2);                               // exp(hscale Haug)
+    off[8] = o; o += align_up((size_t)Bc * dd2);                                   // product of the augmented slices (unused)
+    return o;
+}
+
+size_t c3b_pwc_grad_workspace_bytes(int B, int K, int N, int d, int chunk) {
+    if (B <= 0 || N <= 0 || d <= 0 || K <= 0) return 0;
+    const int Bc = (chunk > 0 && chunk < B) ? chunk : B;
+    size_t off[9];
+    return grad_chunk_bytes(Bc, K, N, d, off);
+}
+
+int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
+                        const void* Ubar, double* grad_out, void* U_out, int chunk, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if (B <= 0 || N <= 0 || d <= 0 || K <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d N=%d d=%d)", B, K, N, d);
+    if (!h0 || !hks || !signals || !Ubar || !grad_out || !workspace) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (d > 32) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gradient path supports d <= 32 (got %d)", d);
+    const int Bc = (chunk > 0 && chunk < B) ? chunk : B;
+    size_t off[9];
+    const size_t need = grad_chunk_bytes(Bc, K, N, d, off);
+    if (workspace_bytes < need) return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    const size_t dd = (size_t)d * d;
+    cplx* Utmp = reinterpret_cast<cplx*>(ws + off[2]);
+    cplx* dUs = reinterpret_cast<cplx*>(ws + off[3]);
+    cplx* Psi = reinterpret_cast<cplx*>(ws + off[4]);
+    double* alpha = reinterpret_cast<double*>(ws + off[5]);
+    cplx* Haug = reinterpret_cast<cplx*>(ws + off[6]);
+    cplx* Eaug = reinterpret_cast<cplx*>(ws + off[7]);
+    cplx* Uaug = reinterpret_cast<cplx*>(ws + off[8]);
+    const int wpb = 4;
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int nb = (B - b0 < Bc) ? (B - b0) : Bc;
+        const double* sig = signals + (size_t)b0 * K * N;
+        cplx* Udst = U_out ? static_cast<cplx*>(U_out) + (size_t)b0 * dd : Utmp;
+        int rc = c3b_pwc_closed(h0, hks, sig, dt, nb, K, N, d, 0, Udst, dUs, ws + off[0], off[1] - off[0], stream);
+        if (rc) return rc;
+        const int blocks = (nb + wpb - 1) / wpb;
+        grad_suffix_kernel<<<blocks, wpb * 32, (size_t)wpb * 3 * dd * sizeof(cplx), st>>>(
+            dUs, static_cast<const cplx*>(Ubar) + (size_t)b0 * dd, Psi, alpha, nb, N, d);
+        CUDA_TRY(cudaGetLastError());
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        grad_prefix_kernel<<<blocks, wpb * 32, (size_t)wpb * 4 * dd * sizeof(cplx), st>>>(
+            dUs, Psi, static_cast<const cplx*>(h0), static_cast<const cplx*>(hks), sig, Haug, dt, nb, K, N, d);
+        CUDA_TRY(cudaGetLastError());
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        rc = c3b_pwc_closed_hlist(Haug, dt, nb, N, 2 * d, Uaug, Eaug, ws + off[1], off[2] - off[1], stream);
+        if (rc) return rc;
+        const long long warps = (long long)nb * N;
+        grad_contract_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(
+            Eaug, static_cast<const cplx*>(hks), alpha, grad_out + (size_t)b0 * K * N, dt, nb, K, N, d);
+        CUDA_TRY(cudaGetLastError());
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return C3B_OK;
 }
 
 long long c3b_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -156,6 +156,39 @@ def _side_streams(device):
     return _side[key]
 
 
+def pwc_closed_grad(h0, hks, signals, dt: float, Ubar, max_workspace_bytes: int = 6 << 30, device=None):
+    """Forward U and the gradient of a real scalar loss w.r.t. the control fields.
+
+    ``Ubar`` [B,d,d] is the cotangent of U in torch's convention (dL = Re tr(Ubar^dag dU), i.e. what
+    ``autograd`` hands to ``backward``).  Returns (U [B,d,d], grad [B,K,N] float64).
+    Replaces tf.GradientTape through the propagator (c3/optimizers/optimizer.py:210-215)."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        signals = _as(signals, torch.float64, device)
+        if signals.dim() == 2:
+            signals = signals.unsqueeze(0)
+        B, K, N = signals.shape
+        h0 = _as(h0, torch.complex128, device)
+        hks = _as(hks, torch.complex128, device)
+        if h0.dim() != 2:
+            raise ValueError("C3:ERROR: the gradient path needs a shared model h0 [d,d]")
+        d = h0.shape[-1]
+        Ubar = _as(Ubar, torch.complex128, device)
+        if tuple(Ubar.shape) != (B, d, d):
+            raise ValueError(f"C3:ERROR: Ubar has shape {tuple(Ubar.shape)}, expected {(B, d, d)}")
+        U = torch.empty((B, d, d), dtype=torch.complex128, device=device)
+        grad = torch.empty((B, K, N), dtype=torch.float64, device=device)
+        chunk = B
+        while chunk > 1 and lib.c3b_pwc_grad_workspace_bytes(B, K, N, d, chunk) > max_workspace_bytes:
+            chunk = (chunk + 1) // 2
+        nbytes = lib.c3b_pwc_grad_workspace_bytes(B, K, N, d, chunk)
+        ws = _workspace(nbytes, device)
+        _lib.check(lib.c3b_pwc_closed_grad(_ptr(h0), _ptr(hks), _ptr(signals), float(dt), B, K, N, d, _ptr(Ubar),
+                                           _ptr(grad), _ptr(U), chunk, _ptr(ws), ws.numel(), _stream()))
+    return U, grad
+
+
 def pwc_closed_hlist(Hs, dt: float, return_dUs: bool = False, device=None):
     """Same with explicit Hamiltonians Hs [B,N,d,d] (or [N,d,d]); the reference's
     ``signals is None`` mode (c3/libraries/propagation.py:294-308, 437-438)."""

@@ -148,6 +148,36 @@ def pwc_batch(h0, hks, signals, dt, col_ops=None, lindbladian=False, return_dUs=
     return engine.pwc_closed(_np(h0), _np(hks), sig, float(np.real(dt)), return_dUs=return_dUs)
 
 
+class _PwcClosedFn(torch.autograd.Function):
+    """U = pwc_batch(h0, hks, signals, dt), differentiable w.r.t. ``signals``."""
+
+    @staticmethod
+    def forward(ctx, signals, h0, hks, dt):
+        U = engine.pwc_closed(h0, hks, signals.detach(), dt)
+        ctx.save_for_backward(signals.detach())
+        ctx.h0, ctx.hks, ctx.dt = h0, hks, dt
+        return U
+
+    @staticmethod
+    def backward(ctx, grad_U):
+        (signals,) = ctx.saved_tensors
+        _, g = engine.pwc_closed_grad(ctx.h0, ctx.hks, signals, ctx.dt, grad_U.contiguous())
+        return g.to(signals.dtype).reshape(signals.shape), None, None, None
+
+
+def pwc_batch_autograd(h0, hks, signals: torch.Tensor, dt) -> torch.Tensor:
+    """Differentiable batched propagators: ``signals`` is a CUDA float64 tensor [B,K,N] with
+    ``requires_grad``; gradients of any real loss of U flow back to it (what the reference gets from
+    tf.GradientTape, c3/optimizers/optimizer.py:210-215).  Closed system, shared model."""
+    if not (isinstance(signals, torch.Tensor) and signals.is_cuda):
+        raise ValueError("C3:ERROR: pwc_batch_autograd needs a CUDA tensor for `signals`")
+    dev = signals.device
+    h0_t = torch.as_tensor(_host(h0), dtype=torch.complex128).to(dev) if not isinstance(h0, torch.Tensor) else h0.to(dev)
+    hks_t = torch.as_tensor(_host(hks), dtype=torch.complex128).to(dev) if not isinstance(hks, torch.Tensor) else hks.to(dev)
+    sig = signals if signals.dim() == 3 else signals.unsqueeze(0)
+    return _PwcClosedFn.apply(sig, h0_t, hks_t, float(np.real(dt)))
+
+
 # --------------------------------------------------------------------------------------------
 # gate-level API (duck-typed Model / Generator / Instruction exactly as the reference uses them)
 # --------------------------------------------------------------------------------------------

@@ -74,6 +74,19 @@ int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C
                      int B, int K, int N, int d, int batched_model, void* U_out, void* dUs_out, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Gradient of a real scalar loss L through the closed-system propagators with respect to the control
+ * fields: what tf.GradientTape gives the reference's gradient optimisers
+ * (c3/optimizers/optimizer.py:210-215, 277-313; c3/libraries/algorithms.py:391-420).
+ *   Ubar     [B,d,d]  cotangent of U with dL = Re tr(Ubar^dag dU)  (torch's grad_output for U)
+ *   grad_out [B,K,N]  float64, dL/d signals[b,k,n]
+ *   U_out    [B,d,d]  or NULL: the forward result is produced on the way
+ *   chunk    batch rows processed per pass (bounds the workspace: ~10 N d^2 16 bytes per row); <= 0: all
+ * Shared model only (h0 [d,d], hks [K,d,d]), d <= 32. */
+size_t c3b_pwc_grad_workspace_bytes(int B, int K, int N, int d, int chunk);
+int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
+                        const void* Ubar, double* grad_out, void* U_out, int chunk, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* Ordered product of M matrices per batch row: out[b] = mats[b,M-1] ... mats[b,0].
  *   replaces tf_matmul_left (c3/utils/tf_utils.py:120-129) and tf_matmul_n (:144-193).
  *   mats [B,M,D,D], out [B,D,D]. */
