@@ -222,6 +222,7 @@ int launch_rows3_t(const RowsParams& rp, unsigned int* counter, cudaStream_t st)
     if (grid > need) grid = need;
     kern<<<(int)grid, WARPS * 32, smem, st>>>(rp, counter);
     CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
 }
 
@@ -242,6 +243,7 @@ int launch_blk_t(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
     if (grid > need) grid = need;
     kern<<<(int)grid, WARPS * 32, smem, st>>>(rp, counter);
     CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
 }
 
@@ -262,6 +264,7 @@ int launch_blk_t18_t(const RowsParams& rp, unsigned int* counter, cudaStream_t s
     if (grid > need) grid = need;
     kern<<<(int)grid, WARPS * 32, smem, st>>>(rp, counter);
     CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
 }
 
@@ -330,6 +333,7 @@ int launch_gemm_t(const GemmParams& gp, int grid, cudaStream_t st) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kCtaThreads, smem, st>>>(gp);
     CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
 }
 
