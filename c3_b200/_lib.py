@@ -14,6 +14,7 @@ SYMBOLS = [
     "c3b_pwc_lindblad", "c3b_product_workspace_bytes", "c3b_ordered_product", "c3b_seq_product", "c3b_kron",
     "c3b_set_tuning", "c3b_pwc_path", "c3b_measure_fp64_peak", "c3b_microbench", "c3b_launch_count",
     "c3b_last_kernel_ms", "c3b_pwc_grad_workspace_bytes", "c3b_pwc_closed_grad",
+    "c3b_gate_infid", "c3b_gate_infid_grad", "c3b_seq_populations",
 ]
 
 _lib = None
@@ -49,6 +50,12 @@ def load() -> C.CDLL:
     lib.c3b_pwc_grad_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.c3b_pwc_closed_grad.restype = i
     lib.c3b_pwc_closed_grad.argtypes = [vp, vp, vp, d, i, i, i, i, vp, vp, vp, i, vp, sz, vp]
+    lib.c3b_gate_infid.restype = i
+    lib.c3b_gate_infid.argtypes = [vp, i, i, vp, vp, i, i, vp, vp, vp]
+    lib.c3b_gate_infid_grad.restype = i
+    lib.c3b_gate_infid_grad.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, vp]
+    lib.c3b_seq_populations.restype = i
+    lib.c3b_seq_populations.argtypes = [vp, i, vp, vp, i, i, i, vp, i, vp, vp, vp]
     lib.c3b_product_workspace_bytes.restype = sz
     lib.c3b_product_workspace_bytes.argtypes = [i, i, i]
     lib.c3b_ordered_product.restype = i

@@ -15,6 +15,7 @@
 #include "product.cuh"
 #include "pwc_gemm.cuh"
 #include "grad.cuh"
+#include "fidelity.cuh"
 #include "peak.cuh"
 
 using namespace c3b;
@@ -687,6 +688,58 @@ int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, 
         CUDA_TRY(cudaGetLastError());
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
+    return C3B_OK;
+}
+
+// ---- goal functions on the propagators ------------------------------------
+int c3b_gate_infid(const void* U, int B, int D, const void* ideal, const int32_t* sel, int C, int mode,
+                   double* infid_out, void* overlap_out, void* stream) {
+    if (B <= 0 || D <= 0 || C <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d D=%d C=%d)", B, D, C);
+    if (C > D) return fail(C3B_EINVAL, "C3:ERROR: computational subspace (%d) larger than the matrix (%d)", C, D);
+    if (mode < 0 || mode > 3) return fail(C3B_EINVAL, "C3:ERROR: unknown fidelity mode %d", mode);
+    if (!U || !ideal || !sel || (!infid_out && !overlap_out)) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    const int wpb = 4;
+    gate_overlap_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const cplx*>(U), static_cast<const cplx*>(ideal), sel, B, D, C, mode, infid_out,
+        static_cast<cplx*>(overlap_out));
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return C3B_OK;
+}
+
+int c3b_gate_infid_grad(const void* overlap, const void* ideal, const int32_t* sel, const double* gbar, int B, int D,
+                        int C, int mode, void* Ubar_out, void* stream) {
+    if (B <= 0 || D <= 0 || C <= 0 || C > D) return fail(C3B_EINVAL, "C3:ERROR: bad size (B=%d D=%d C=%d)", B, D, C);
+    if (mode != 0 && mode != 1) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gradient only for unitary_infid / average_infid (mode 0/1), got %d", mode);
+    if (!overlap || !ideal || !sel || !Ubar_out) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(Ubar_out, 0, (size_t)B * D * D * sizeof(cplx), st));
+    const long long total = (long long)B * C * C;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    gate_overlap_grad_kernel<<<(int)blocks, 256, 0, st>>>(static_cast<const cplx*>(overlap), static_cast<const cplx*>(ideal),
+                                                         sel, gbar, B, D, C, mode, static_cast<cplx*>(Ubar_out));
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return C3B_OK;
+}
+
+int c3b_seq_populations(const void* gates, int Gn, const int32_t* seq_idx, const int32_t* seq_len, int S, int Lmax,
+                        int D, const void* psi0, int lindblad_d, double* pops_out, void* psi_out, void* stream) {
+    if (S <= 0 || D <= 0 || Gn <= 0 || Lmax < 0) return fail(C3B_EINVAL, "C3:ERROR: bad size (S=%d D=%d Gn=%d Lmax=%d)", S, D, Gn, Lmax);
+    if (!gates || !seq_len || (Lmax > 0 && !seq_idx) || (!pops_out && !psi_out)) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (lindblad_d < 0 || (lindblad_d > 0 && lindblad_d * lindblad_d != D))
+        return fail(C3B_EINVAL, "C3:ERROR: Lindblad populations need D = d^2 (D=%d, d=%d)", D, lindblad_d);
+    constexpr int W = 4;
+    const size_t smem = (size_t)W * 2 * D * sizeof(cplx);
+    if (smem > 200 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: state dimension %d too large", D);
+    auto kern = seq_state_kernel<W>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(S + W - 1) / W, W * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const cplx*>(gates), seq_idx, seq_len, static_cast<const cplx*>(psi0), S, Lmax > 0 ? Lmax : 1, D,
+        lindblad_d, pops_out, static_cast<cplx*>(psi_out));
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
 }
 

@@ -274,6 +274,71 @@ def seq_product(gates, seq_idx, seq_len, device=None) -> torch.Tensor:
     return out
 
 
+FID_MODES = {"unitary": 0, "average": 1, "lindbladian_unitary": 2, "lindbladian_average": 3}
+
+
+def gate_infid(U, ideal, sel, mode: str = "unitary", return_overlap: bool = False, device=None):
+    """infid[b] of every propagator U[b] against the ideal gate on the rows/columns ``sel``
+    (c3/libraries/fidelities.py:152-183, 221-249, 288-311, 377-399).  U [B,D,D] or [D,D]."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        U = _as(U, torch.complex128, device)
+        squeeze = U.dim() == 2
+        if squeeze:
+            U = U.unsqueeze(0)
+        B, D, _ = U.shape
+        ideal = _as(ideal, torch.complex128, device)
+        sel = _as(sel, torch.int32, device)
+        C = sel.shape[0]
+        if tuple(ideal.shape) != (C, C):
+            raise ValueError(f"C3:ERROR: ideal gate has shape {tuple(ideal.shape)}, expected {(C, C)}")
+        infid = torch.empty((B,), dtype=torch.float64, device=device)
+        ov = torch.empty((B,), dtype=torch.complex128, device=device) if return_overlap else None
+        _lib.check(lib.c3b_gate_infid(_ptr(U), B, D, _ptr(ideal), _ptr(sel), C, FID_MODES[mode], _ptr(infid), _ptr(ov),
+                                      _stream()))
+    if squeeze:
+        infid = infid[0]
+    return (infid, ov) if return_overlap else infid
+
+
+def gate_infid_grad(overlap, ideal, sel, gbar, D: int, mode: str = "unitary", device=None) -> torch.Tensor:
+    """Cotangent Ubar [B,D,D] of the propagators for the loss sum_b gbar[b] infid[b]."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        overlap = _as(overlap, torch.complex128, device)
+        ideal = _as(ideal, torch.complex128, device)
+        sel = _as(sel, torch.int32, device)
+        gbar = _as(gbar, torch.float64, device) if gbar is not None else None
+        B, C = overlap.shape[0], sel.shape[0]
+        Ubar = torch.empty((B, D, D), dtype=torch.complex128, device=device)
+        _lib.check(lib.c3b_gate_infid_grad(_ptr(overlap), _ptr(ideal), _ptr(sel), _ptr(gbar), B, D, C, FID_MODES[mode],
+                                           _ptr(Ubar), _stream()))
+    return Ubar
+
+
+def seq_populations(gates, seq_idx, seq_len, psi0=None, lindblad_d: int = 0, return_states: bool = False, device=None):
+    """Populations [S,D] (Lindblad: [S,d]) of psi0 after each gate sequence (c3/experiment.py:273-302, 603-624)."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        gates = _as(gates, torch.complex128, device)
+        seq_idx = _as(seq_idx, torch.int32, device)
+        seq_len = _as(seq_len, torch.int32, device)
+        Gn, D, _ = gates.shape
+        S = seq_len.shape[0]
+        Lmax = seq_idx.shape[1] if seq_idx.dim() == 2 else 0
+        psi0 = _as(psi0, torch.complex128, device).reshape(-1) if psi0 is not None else None
+        if psi0 is not None and psi0.shape[0] != D:
+            raise ValueError(f"C3:ERROR: psi0 has {psi0.shape[0]} entries, expected {D}")
+        pops = torch.empty((S, lindblad_d if lindblad_d else D), dtype=torch.float64, device=device)
+        psi = torch.empty((S, D), dtype=torch.complex128, device=device) if return_states else None
+        _lib.check(lib.c3b_seq_populations(_ptr(gates), Gn, _ptr(seq_idx) if Lmax > 0 else None, _ptr(seq_len), S, Lmax, D,
+                                           _ptr(psi0), int(lindblad_d), _ptr(pops), _ptr(psi), _stream()))
+    return (pops, psi) if return_states else pops
+
+
 def kron(A, B, device=None) -> torch.Tensor:
     """(Batched) Kronecker product with the row-major convention of tf_kron."""
     lib = _lib.load()

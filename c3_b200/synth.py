@@ -160,3 +160,59 @@ def rb_sequences(S: int, length: int, n_gates: int, seed: int = 0, mean_native: 
     Lmax = int(lens.max())
     idx = rng.integers(0, n_gates, size=(S, Lmax)).astype(np.int32)
     return idx, lens
+
+
+# ---- randomized-benchmarking sequences (c3/utils/qt_utils.py:448-498, 528-553) -------------------------
+_RB_NATIVE = {"X": "rx90p", "x": "rx90m", "Y": "ry90p", "y": "ry90m"}
+#: native-gate decomposition of the 24 single-qubit Cliffords C1..C24, applied left to right
+#: (upper case = +90 degrees, lower case = -90 degrees); same table as qt_utils.cliffords_decomp
+_RB_DECOMP = ("Xx YX xy YXX x Xyx XX yx Xy y X XYX YY yX XY yXX XYY XyX XXYY Yx xY Y xYY XYx").split()
+
+
+def _rb_native_matrix(code: str) -> np.ndarray:
+    s = 1.0 if code.isupper() else -1.0
+    if code.upper() == "X":
+        return np.array([[1, -1j * s], [-1j * s, 1]], dtype=np.complex128) / np.sqrt(2)
+    return np.array([[1, -s], [s, 1]], dtype=np.complex128) / np.sqrt(2)
+
+
+def clifford_decomp(n: int) -> List[str]:
+    """Native gate names of Clifford C_n, n = 1..24."""
+    return [_RB_NATIVE[c] for c in _RB_DECOMP[n - 1]]
+
+
+def clifford_matrix(n: int) -> np.ndarray:
+    """2x2 unitary of C_n: the product of its native gates, later gates on the left
+    (equals c3/libraries/constants.py:96-121 CLIFFORDS["C<n>"])."""
+    u = np.eye(2, dtype=np.complex128)
+    for c in _RB_DECOMP[n - 1]:
+        u = _rb_native_matrix(c) @ u
+    return u
+
+
+def inverse_clifford(seq: Sequence[int]) -> int:
+    """The Clifford that returns the sequence to the identity up to a phase (qt_utils.inverseC, :480-491)."""
+    op = np.eye(2, dtype=np.complex128)
+    for n in seq:
+        op = clifford_matrix(int(n)) @ op
+    for i in range(1, 25):
+        if abs(2 - abs(np.trace(clifford_matrix(i) @ op))) < 1e-4:
+            return i
+    raise RuntimeError("C3:ERROR: no inverting Clifford found")
+
+
+def single_length_RB(RB_number: int, RB_length: int, target: int = 0, rng=None) -> List[List[str]]:
+    """``RB_number`` sequences of ``RB_length`` Cliffords (the last one inverts the rest), as lists of
+    native gate names ``"<gate>[<target>]"`` (qt_utils.single_length_RB, :448-477).  ``rng``: a
+    ``numpy.random.Generator``/``RandomState``; default is numpy's global state like the reference."""
+    draw = (lambda size: np.random.choice(24, size=size)) if rng is None else (
+        (lambda size: rng.choice(24, size=size)))
+    S = []
+    for _ in range(RB_number):
+        seq = np.asarray(draw(RB_length - 1)) + 1
+        seq = np.append(seq, inverse_clifford(seq))
+        gates: List[str] = []
+        for n in seq:
+            gates.extend(f"{g}[{target}]" for g in clifford_decomp(int(n)))
+        S.append(gates)
+    return S

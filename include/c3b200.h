@@ -87,6 +87,36 @@ int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, 
                         const void* Ubar, double* grad_out, void* U_out, int chunk, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* Gate infidelities straight from a batch of propagators: every goal function
+ * of c3/libraries/fidelities.py on a single gate is a function of the gathered overlap
+ *     t[b] = sum_{I,J} U[b, sel[I], sel[J]] * conj(ideal[I,J])
+ * (tf_project_to_comp + trace, c3/utils/tf_utils.py:326-364, 380-413, 430-438).
+ *   U      [B,D,D]   propagators (D = d, or d^2 for Lindblad superoperators)
+ *   ideal  [C,C]     ideal gate G on the computational subspace (modes 2/3: G (x) G^*, C = c^2)
+ *   sel    [C] int32 rows/columns of U kept by the projector (qt_utils.projector, c3/utils/qt_utils.py:178-193)
+ *   mode   0 unitary_infid (fidelities.py:152-183)            1 - |t|^2 / C^2
+ *          1 average_infid (:288-311)                          1 - (|t|^2 / C + 1) / (C + 1)
+ *          2 lindbladian_unitary_infid (:221-249)              1 - |t| / C
+ *          3 lindbladian_average_infid (:377-399)              1 - |conj(t)/sqrt(C) + 1| / (sqrt(C) + 1)
+ *   infid_out [B] float64 (or NULL), overlap_out [B] complex128 (or NULL; needed by the gradient). */
+int c3b_gate_infid(const void* U, int B, int D, const void* ideal, const int32_t* sel, int C, int mode,
+                   double* infid_out, void* overlap_out, void* stream);
+
+/* Cotangent of U for the loss sum_b gbar[b] * infid[b] (modes 0 and 1), in the convention c3b_pwc_closed_grad
+ * takes (dL = Re tr(Ubar^dag dU)): what tf.GradientTape propagates from the goal function back to the
+ * propagator (c3/optimizers/optimalcontrol.py:200-228).  gbar [B] float64 or NULL (= ones); Ubar_out [B,D,D]. */
+int c3b_gate_infid_grad(const void* overlap, const void* ideal, const int32_t* sel, const double* gbar, int B, int D,
+                        int C, int mode, void* Ubar_out, void* stream);
+
+/* Final states and populations of gate sequences applied to psi0 (NULL: basis state 0):
+ *   psi_s = gates[idx[s,len_s-1]] ... gates[idx[s,0]] psi0  as a chain of matrix-vector products.
+ *   replaces the gate loop of Experiment.evaluate_legacy + populations (c3/experiment.py:273-302, 603-624) and
+ *   evaluate_sequences + matmul + pop0 in orbit_infid (c3/libraries/fidelities.py:753-790).
+ *   lindblad_d == 0: pops_out [S,D] = |psi|^2;  lindblad_d = d (D = d^2, psi = density vector):
+ *   pops_out [S,d] = Re diag(rho).  psi_out [S,D] or NULL; pops_out may be NULL if psi_out is given. */
+int c3b_seq_populations(const void* gates, int Gn, const int32_t* seq_idx, const int32_t* seq_len, int S, int Lmax,
+                        int D, const void* psi0, int lindblad_d, double* pops_out, void* psi_out, void* stream);
+
 /* Ordered product of M matrices per batch row: out[b] = mats[b,M-1] ... mats[b,0].
  *   replaces tf_matmul_left (c3/utils/tf_utils.py:120-129) and tf_matmul_n (:144-193).
  *   mats [B,M,D,D], out [B,D,D]. */
