@@ -70,3 +70,34 @@ def qubit_collapse_op(a: np.ndarray, t1: float = None, t2star: float = None) -> 
     if t2star is not None:
         L = L + (0.5 / t2star) ** 0.5 * 2.0 * (a.T.conj() @ a)
     return L
+
+
+def z_drive(a):              # c3/libraries/hamiltonians.py:166-182
+    return a.T.conj() @ a
+
+
+def transmon_factor(phi: float, phi_0: float, d: float) -> float:
+    """Flux dependence of a tunable transmon (c3/libraries/chip.py:355-372)."""
+    x = np.pi * phi / phi_0
+    return float(np.sqrt(np.sqrt(np.cos(x) ** 2 + d ** 2 * np.sin(x) ** 2)))
+
+
+def tunable_coupler_model():
+    """The three-body model of test/test_tunable_coupler.py:31-157 (subsystem order [coupler, Q1, Q2],
+    :152): drift = sum of subsystem and coupling Hamiltonians (c3/model.py:430-447), tunable transmon
+    frequency (freq - anhar) * factor + anhar (chip.py:378-383), dressed with eigh + reorder
+    (model.py:453-534).  Returns the dressed drift, the dressed flux-line (z-drive) Hamiltonian and the
+    eigenframe."""
+    tp = 2 * np.pi
+    dims = [3, 3, 3]
+    a_tc, a_q1, a_q2 = annihilators(dims)
+    freq_tc, anhar_tc = 8.1e9 * tp, -235e6 * tp
+    phi_0 = 10.0
+    f_tc = (freq_tc - anhar_tc) * transmon_factor(phi_0 * 0.23, phi_0, 0.36) + anhar_tc
+    drift = f_tc * resonator(a_tc) + anhar_tc * duffing(a_tc)
+    drift = drift + 6.189e9 * tp * resonator(a_q1) + (-286e6 * tp) * duffing(a_q1)
+    drift = drift + 5.089e9 * tp * resonator(a_q2) + (-310e6 * tp) * duffing(a_q2)
+    drift = drift + 142e6 * tp * int_XX(a_q1, a_tc) + 116e6 * tp * int_XX(a_q2, a_tc)   # Q1-Q2 strength is 0
+    eigenframe, T = dressing_transform(drift)
+    return {"h0": dress(T, drift), "hk_tc": dress(T, z_drive(a_tc)), "eigenframe": eigenframe, "transform": T,
+            "hk_q1": dress(T, x_drive(a_q1)), "hk_q2": dress(T, x_drive(a_q2))}

@@ -35,3 +35,13 @@ def golden_transmon():
 @pytest.fixture(scope="session")
 def golden_tf_utils():
     return dict(np.load(os.path.join(GOLDEN, "tf_utils.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_tunable_coupler():
+    return dict(np.load(os.path.join(GOLDEN, "tunable_coupler.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_generator():
+    return dict(np.load(os.path.join(GOLDEN, "generator.npz")))

@@ -13,6 +13,10 @@ Sources (relative to the reference checkout):
   test/two_qubit_data.pickle      <- test/test_two_qubits.py:46-62,193-213
   test/transmon_expanded.pickle   <- test/test_transmon_expanded.py:252-283
   test/test_tf_utils.pickle       <- test/test_tf_utils.py:81-111
+  test/tunable_coupler_data.pickle <- test/test_tunable_coupler.py:31-157,399-409 (d = 27; the model matrices
+                                      are rebuilt with oracle/c3_model_oracle.py, checked on the pickled
+                                      coupler_01 / coupler_12 eigenfrequencies)
+  test/generator_data.pickle      <- test/test_generator.py:21-190 (signal chain, stage by stage)
 """
 import os
 import pickle
@@ -90,8 +94,42 @@ def tf_utils():
     np.savez_compressed(os.path.join(HERE, "tf_utils.npz"), **out)
 
 
+def tunable_coupler():
+    """d = 27 (3-level tunable coupler + two 3-level qubits).  The pickle stores the flux-line control field
+    ``tc_signal`` and every 50th slice propagator; the dressed drift and the dressed z-drive Hamiltonian are
+    rebuilt (the two qubit drive lines carry ``no_drive``: their fields are identically zero)."""
+    d = load("tunable_coupler_data.pickle")
+    m = mo.tunable_coupler_model()
+    c01 = abs(abs(m["eigenframe"][0]) - abs(m["eigenframe"][9]))     # labels (0,0,0) -> (1,0,0)
+    c12 = abs(abs(m["eigenframe"][9]) - abs(m["eigenframe"][18]))
+    assert abs(c01 - d["coupler_01"]) / d["coupler_01"] < 1e-12     # test_tunable_coupler.py:295-302
+    assert abs(c12 - d["coupler_12"]) / d["coupler_12"] < 1e-12     # :305-312
+    keep = np.arange(0, 200, 2)                                      # slices 0, 100, 200, ... of 10 000
+    np.savez_compressed(
+        os.path.join(HERE, "tunable_coupler.npz"),
+        h0=m["h0"], hk_tc=m["hk_tc"], tc_signal=d["tc_signal"], tc_ts=d["tc_ts"],
+        dUs_index=keep * 50, dUs=np.asarray(d["dUs"])[keep],
+        tc_awg_I=d["tc_awg_I"], tc_awg_Q=d["tc_awg_Q"], tc_awg_ts=d["tc_awg_ts"],
+    )
+
+
+def generator_chain():
+    d = load("generator_data.pickle")
+    np.savez_compressed(
+        os.path.join(HERE, "generator.npz"),
+        lo_I=d["lo_sig"]["values"][0], lo_Q=d["lo_sig"]["values"][1], lo_ts=d["lo_sig"]["ts"],
+        awg_I=d["awg_sig"]["inphase"], awg_Q=d["awg_sig"]["quadrature"],
+        dac_I=d["dig_to_an_sig"]["inphase"], dac_Q=d["dig_to_an_sig"]["quadrature"],
+        resp_I=d["resp_sig"]["inphase"], resp_Q=d["resp_sig"]["quadrature"],
+        mixer=d["mixer_sig"], v2hz=d["v2hz_sig"],
+        full_values=d["full_signal"][0]["d1"]["values"], full_ts=d["full_signal"][0]["d1"]["ts"],
+    )
+
+
 if __name__ == "__main__":
     two_qubit()
+    tunable_coupler()
+    generator_chain()
     transmon_expanded()
     tf_utils()
     for f in sorted(os.listdir(HERE)):

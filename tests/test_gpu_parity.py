@@ -269,6 +269,30 @@ def test_config5_shape_d27(eng):
     assert rel_fro(U.cpu().numpy(), wantU) < TOL
 
 
+def test_tunable_coupler_golden_d27(eng, golden_tunable_coupler):
+    """test/test_tunable_coupler.py:399-409 of the reference: d = 27 slice propagators of the CPHASE flux
+    pulse (10 000 slices, stored every 100th here) through the DMMA CTA kernel, and the full product
+    against the oracle."""
+    g = golden_tunable_coupler
+    dt = float(g["tc_ts"][1] - g["tc_ts"][0])
+    U, dUs = eng.pwc_closed(g["h0"], g["hk_tc"][None], g["tc_signal"][None, None, :], dt, return_dUs=True)
+    got = dUs[0].cpu().numpy()
+    assert rel_fro(got[g["dUs_index"]], g["dUs"]) < TOL
+    # three control lines as in the reference (the two qubit drives carry no_drive = zeros)
+    from oracle import c3_model_oracle as mo
+    m = mo.tunable_coupler_model()
+    hks = np.stack([m["hk_q1"], m["hk_q2"], g["hk_tc"]])
+    sig3 = np.zeros((1, 3, 10000))
+    sig3[0, 2] = g["tc_signal"]
+    U3 = eng.pwc_closed(g["h0"], hks, sig3, dt)
+    assert rel_fro(U3.cpu().numpy(), U.cpu().numpy()) < 1e-12
+    want = np.eye(27, dtype=complex)
+    for n in range(10000):
+        want = got[n] @ want
+    assert rel_fro(U[0].cpu().numpy(), want) < TOL
+    assert rel_fro(U[0].cpu().numpy().conj().T @ U[0].cpu().numpy(), np.eye(27)) < 1e-10
+
+
 def test_batched_model(eng):
     """Per-sample models h0[B,d,d], hks[B,K,d,d] (optimiser samples that change the model)."""
     rng = np.random.default_rng(11)

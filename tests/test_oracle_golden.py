@@ -148,3 +148,27 @@ def test_evaluate_sequences():
     assert rel_fro(out[0], gates["c"] @ gates["b"] @ gates["a"]) < 1e-14
     np.testing.assert_array_equal(out[1], np.eye(3))
     np.testing.assert_array_equal(out[2], gates["c"])
+
+
+def test_tunable_coupler_d27_partial_propagators(golden_tunable_coupler):
+    """test/test_tunable_coupler.py:399-409 of the reference (d = 27, 10 000 slices, every 50th stored):
+    the oracle's TF-style expm on the rebuilt model reproduces the pickled slice propagators."""
+    g = golden_tunable_coupler
+    dt = g["tc_ts"][1] - g["tc_ts"][0]
+    idx = g["dUs_index"]
+    got = orc.tf_propagation_vectorized(g["h0"], g["hk_tc"][None], g["tc_signal"][None, idx], dt)
+    assert rel_fro(got, g["dUs"]) < 1e-12
+    assert abs(g["tc_ts"][0] - 0.5 * dt) < 1e-20 and len(g["tc_signal"]) == 10000
+
+
+def test_rebuilt_tunable_coupler_model():
+    """Dressed three-body model: Hermitian drift, diagonal in its own eigenbasis, coupler 0-1 and 1-2
+    transition frequencies as pickled by the reference (checked when the fixture is made, repeated here
+    on the stored numbers 45.100 and 43.785 Grad/s)."""
+    from oracle import c3_model_oracle as mo
+    m = mo.tunable_coupler_model()
+    h0 = m["h0"]
+    assert np.abs(h0 - np.diag(np.diag(h0))).max() < 1e-3 * np.abs(h0).max() * 1e-6
+    e = m["eigenframe"]
+    assert abs(abs(abs(e[0]) - abs(e[9])) - 45100118139.44866) / 45100118139.44866 < 1e-12
+    assert abs(abs(abs(e[9]) - abs(e[18])) - 43784918348.34318) / 43784918348.34318 < 1e-12
