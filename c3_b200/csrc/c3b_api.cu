@@ -16,6 +16,7 @@
 #include "pwc_gemm.cuh"
 #include "grad.cuh"
 #include "fidelity.cuh"
+#include "signal_chain.cuh"
 #include "peak.cuh"
 
 using namespace c3b;
@@ -738,6 +739,33 @@ int c3b_seq_populations(const void* gates, int Gn, const int32_t* seq_idx, const
     kern<<<(S + W - 1) / W, W * 32, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const cplx*>(gates), seq_idx, seq_len, static_cast<const cplx*>(psi0), S, Lmax > 0 ? Lmax : 1, D,
         lindblad_d, pops_out, static_cast<cplx*>(psi_out));
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return C3B_OK;
+}
+
+// ---- signal generation chain ----------------------------------------------------
+int c3b_signal_slice_num(double t_start, double t_end, double resolution) {
+    const double span = t_start - t_end;
+    return (int)((span < 0 ? -span : span) * resolution);   // Device.calc_slice_num, c3/generator/devices.py:73-85
+}
+
+int c3b_generate_signals(const double* env_params, const int32_t* env_shape, const int32_t* env_flags,
+                         const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
+                         int B, int K, int E, int N, double* signals_out, void* stream) {
+    if (B <= 0 || K <= 0 || E <= 0 || N <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d E=%d N=%d)", B, K, E, N);
+    if (!env_params || !env_shape || !env_flags || !lo_freq || !chain || !signals_out) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    SignalParams sp{};
+    sp.env = env_params; sp.shape = env_shape; sp.flags = env_flags; sp.lo_freq = lo_freq; sp.chain = chain;
+    sp.chain_batched = chain_batched; sp.t_start = t_start; sp.t_end = t_end;
+    sp.B = B; sp.K = K; sp.E = E; sp.N = N; sp.out = signals_out;
+    // the AWG grid and the response taps live in shared memory: bounded by the simulation grid / 4096 taps
+    sp.max_awg = N + 1;
+    sp.max_taps = 4096;
+    const size_t smem = ((size_t)2 * sp.max_awg + sp.max_taps) * sizeof(double);
+    if (smem > 200 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gate too long for the on-chip signal chain (N=%d)", N);
+    CUDA_TRY(cudaFuncSetAttribute(signal_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    signal_chain_kernel<<<B * K, 128, smem, static_cast<cudaStream_t>(stream)>>>(sp);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;

@@ -339,6 +339,40 @@ def seq_populations(gates, seq_idx, seq_len, psi0=None, lindblad_d: int = 0, ret
     return (pops, psi) if return_states else pops
 
 
+def signal_slice_num(t_start: float, t_end: float, resolution: float) -> int:
+    """Device.calc_slice_num (c3/generator/devices.py:73-85)."""
+    return int(_lib.load().c3b_signal_slice_num(float(t_start), float(t_end), float(resolution)))
+
+
+def generate_signals(env_params, env_shape, env_flags, lo_freq, chain, t_start: float, t_end: float, device=None,
+                     out=None) -> torch.Tensor:
+    """signals [B,K,N] from pulse parameters (c3b_generate_signals; see include/c3b200.h for the layouts)."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        env_params = _as(env_params, torch.float64, device)
+        B, K, E, P = env_params.shape
+        if P != 9:
+            raise ValueError("C3:ERROR: env_params must have 9 entries per envelope")
+        env_shape = _as(env_shape, torch.int32, device)
+        env_flags = _as(env_flags, torch.int32, device)
+        lo_freq = _as(lo_freq, torch.float64, device)
+        chain = _as(chain, torch.float64, device)
+        batched = chain.dim() == 3
+        if tuple(env_shape.shape) != (K, E) or tuple(env_flags.shape) != (K, E) or tuple(lo_freq.shape) != (B, K) \
+                or tuple(chain.shape) != ((B, K, 11) if batched else (K, 11)):
+            raise ValueError("C3:ERROR: inconsistent shapes in generate_signals")
+        sim_res = float(chain.reshape(-1, 11)[0, 0])
+        N = signal_slice_num(t_start, t_end, sim_res)
+        if N <= 0:
+            raise ValueError("C3:ERROR: empty time grid")
+        if out is None:
+            out = torch.empty((B, K, N), dtype=torch.float64, device=device)
+        _lib.check(lib.c3b_generate_signals(_ptr(env_params), _ptr(env_shape), _ptr(env_flags), _ptr(lo_freq), _ptr(chain),
+                                            int(batched), float(t_start), float(t_end), B, K, E, N, _ptr(out), _stream()))
+    return out
+
+
 def kron(A, B, device=None) -> torch.Tensor:
     """(Batched) Kronecker product with the row-major convention of tf_kron."""
     lib = _lib.load()

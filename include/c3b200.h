@@ -117,6 +117,27 @@ int c3b_gate_infid_grad(const void* overlap, const void* ideal, const int32_t* s
 int c3b_seq_populations(const void* gates, int Gn, const int32_t* seq_idx, const int32_t* seq_len, int S, int Lmax,
                         int D, const void* psi0, int lindblad_d, double* pops_out, void* psi_out, void* stream);
 
+/* Control fields from pulse parameters for a whole batch of parameter samples: the
+ * standard device chain of c3/generator/generator.py:172-229,
+ *   LO + AWG(envelopes) -> DigitalToAnalog -> Response|ResponseFFT -> Mixer -> VoltsToHertz|FluxTuning
+ * (c3/generator/devices.py:1063-1130, 1159-1197, 296-351, 585-701, 906-939, 187-221, 480-529; envelopes
+ * c3/signal/gates.py:341-370, c3/signal/pulse.py:93-180, c3/libraries/envelopes.py), one kernel, output written
+ * directly in the [B,K,N] layout c3b_pwc_closed reads.  All values are what Quantity.get_value() returns
+ * (angular frequencies).
+ *   env_params [B,K,E,9]  amp, t_final, sigma, xy_angle, freq_offset, delta, t_up, t_down, risefall
+ *   env_shape  [K,E] int32  0 no_drive, 1 rect, 2 gaussian_nonorm, 3 gaussian_sigma, 4 cosine, 5 flattop; < 0: unused
+ *   env_flags  [K,E] int32  bit 0: EnvelopeDrag quadrature (-delta * d env/dt * dt), bit 1: use_t_before
+ *   lo_freq    [B,K]        carrier frequency of the line
+ *   chain      [K,11] (or [B,K,11] if chain_batched): sim_res, awg_res, rise_time, response kind (0 none,
+ *              1 Response, 2 ResponseFFT), output kind (0 VoltsToHertz, 1 FluxTuning), V_to_Hz, phi, phi_0,
+ *              omega_0, anhar, d (NaN: no junction asymmetry)
+ *   N = c3b_signal_slice_num(t_start, t_end, sim_res) (Device.calc_slice_num); the AWG grid must not be finer
+ *   than the simulation grid.  signals_out [B,K,N] float64. */
+int c3b_signal_slice_num(double t_start, double t_end, double resolution);
+int c3b_generate_signals(const double* env_params, const int32_t* env_shape, const int32_t* env_flags,
+                         const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
+                         int B, int K, int E, int N, double* signals_out, void* stream);
+
 /* Ordered product of M matrices per batch row: out[b] = mats[b,M-1] ... mats[b,0].
  *   replaces tf_matmul_left (c3/utils/tf_utils.py:120-129) and tf_matmul_n (:144-193).
  *   mats [B,M,D,D], out [B,D,D]. */

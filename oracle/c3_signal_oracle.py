@@ -1,0 +1,227 @@
+"""CPU oracle for SURVEY.md section 8f row f-2: the signal-generation chain that produces the control
+fields ``signals[K,N]`` the propagator consumes.
+
+TEST INFRASTRUCTURE ONLY (see oracle/c3_oracle.py).  numpy restatement of the standard chain
+LO + AWG -> DigitalToAnalog -> Response -> Mixer -> VoltsToHertz / FluxTuning:
+
+  c3/generator/devices.py:73-122     Device.calc_slice_num / create_ts
+  c3/generator/devices.py:1063-1130  LO.process (noise-free branch)
+  c3/generator/devices.py:1159-1197  AWG.create_IQ  ->  c3/signal/gates.py:341-370 Instruction.get_awg_signal
+  c3/signal/pulse.py:93-142          Envelope.compute_mask / _get_shape_values_just / _before
+  c3/signal/pulse.py:171-180         EnvelopeDrag.get_shape_values (derivative quadrature)
+  c3/libraries/envelopes.py          no_drive :25, rect :194, flattop :253, gaussian_sigma :373, cosine :420,
+                                     gaussian_nonorm :469
+  c3/generator/devices.py:296-351    DigitalToAnalog.process (tf.image.resize, method "nearest")
+  c3/generator/devices.py:585-701    Response (tf_convolve_legacy) and ResponseFFT (tf_convolve)
+  c3/utils/tf_utils.py:441-515       tf_convolve, tf_convolve_legacy
+  c3/generator/devices.py:906-939    Mixer.process
+  c3/generator/devices.py:187-221    VoltsToHertz.process
+  c3/generator/devices.py:480-529    FluxTuning.get_factor / get_freq / process
+
+Pinned stage by stage to the reference's own fixtures (tests/golden/generator.npz from
+test/generator_data.pickle, test/test_generator.py:118-190; the AWG samples and the final flux-line field of
+test/tunable_coupler_data.pickle) in tests/test_signal_oracle.py.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+from scipy.special import erf, expit
+
+SHAPES = ("no_drive", "rect", "gaussian_nonorm", "gaussian_sigma", "cosine", "flattop")
+
+
+@dataclass
+class EnvelopeSpec:
+    """One Envelope component of an instruction channel (values as ``Quantity.get_value()`` returns them,
+    i.e. frequencies already multiplied by 2 pi)."""
+    shape: str = "gaussian_nonorm"
+    amp: float = 0.0
+    t_final: float = 0.0
+    sigma: float = 0.0
+    xy_angle: float = 0.0
+    freq_offset: float = 0.0
+    delta: float = 0.0
+    t_up: float = 0.0
+    t_down: float = 0.0
+    risefall: float = 1.0
+    drag: bool = False          # EnvelopeDrag: quadrature = -delta * d env/dt * dt
+    use_t_before: bool = False
+
+
+def create_ts(t_start: float, t_end: float, resolution: float, centered: bool = True) -> np.ndarray:
+    slice_num = int(np.abs(t_start - t_end) * resolution)
+    dt = 1 / resolution
+    if centered:
+        offset, num = dt / 2, slice_num
+    else:
+        offset, num = 0.0, slice_num + 1
+    return np.linspace(t_start + offset, t_end - offset, num)
+
+
+def lo_signal(ts: np.ndarray, omega_lo: float):
+    return np.cos(omega_lo * ts), np.sin(omega_lo * ts)
+
+
+def shape_values(shape: str, t: np.ndarray, e: EnvelopeSpec) -> np.ndarray:
+    """Real envelope shape functions (the reference returns them complexified with zero imaginary part)."""
+    t = np.asarray(t, dtype=np.float64)
+    if shape == "no_drive":
+        return np.zeros_like(t)
+    if shape == "rect":
+        return np.ones_like(t)
+    if shape == "gaussian_nonorm":
+        return np.exp(-((t - e.t_final / 2) ** 2) / (2 * e.sigma ** 2))
+    if shape == "gaussian_sigma":
+        gauss = np.exp(-((t - e.t_final / 2) ** 2) / (2 * e.sigma ** 2))
+        offset = np.exp(-(e.t_final ** 2) / (8 * e.sigma ** 2))
+        norm = np.sqrt(2 * np.pi * e.sigma ** 2) * erf(e.t_final / (np.sqrt(8) * e.sigma)) - e.t_final * offset
+        return (gauss - offset) / norm
+    if shape == "cosine":
+        return 0.5 * (1 - np.cos(2 * np.pi * t / e.t_final))
+    if shape == "flattop":
+        return (1 + erf((t - e.t_up) / e.risefall)) / 2 * (1 + erf((-t + e.t_down) / e.risefall)) / 2
+    raise ValueError(f"C3:ERROR: envelope shape '{shape}' is not restated")
+
+
+def shape_derivative(shape: str, t: np.ndarray, e: EnvelopeSpec) -> np.ndarray:
+    """d shape / dt (what tf.GradientTape gives EnvelopeDrag, pulse.py:173-178)."""
+    t = np.asarray(t, dtype=np.float64)
+    if shape in ("no_drive", "rect"):
+        return np.zeros_like(t)
+    if shape in ("gaussian_nonorm", "gaussian_sigma"):
+        g = np.exp(-((t - e.t_final / 2) ** 2) / (2 * e.sigma ** 2)) * (-(t - e.t_final / 2) / e.sigma ** 2)
+        if shape == "gaussian_sigma":
+            offset = np.exp(-(e.t_final ** 2) / (8 * e.sigma ** 2))
+            norm = np.sqrt(2 * np.pi * e.sigma ** 2) * erf(e.t_final / (np.sqrt(8) * e.sigma)) - e.t_final * offset
+            g = g / norm
+        return g
+    if shape == "cosine":
+        return 0.5 * np.sin(2 * np.pi * t / e.t_final) * 2 * np.pi / e.t_final
+    if shape == "flattop":
+        up, dn = (t - e.t_up) / e.risefall, (-t + e.t_down) / e.risefall
+        c = 2 / np.sqrt(np.pi) / e.risefall
+        return (c * np.exp(-up ** 2) * (1 + erf(dn)) - (1 + erf(up)) * c * np.exp(-dn ** 2)) / 4
+    raise ValueError(f"C3:ERROR: envelope shape '{shape}' is not restated")
+
+
+def compute_mask(ts: np.ndarray, t_final: float, t_end: float) -> np.ndarray:
+    tf_ = min(t_final, t_end)
+    dt = ts[1] - ts[0]
+    return expit((ts / dt + 0.001) * 1e6) * expit((0.999 * tf_ - ts) / dt * 1e6)
+
+
+def envelope_values(e: EnvelopeSpec, ts_off: np.ndarray, t_len: float) -> np.ndarray:
+    """Complex envelope samples: Envelope.get_shape_values (mask * shape, optionally minus the value one
+    sample before the start) and the DRAG quadrature of EnvelopeDrag."""
+    mask = compute_mask(ts_off, e.t_final, t_len)
+    env = mask * shape_values(e.shape, ts_off, e)
+    if e.use_t_before:
+        t_before = 2 * ts_off[0] - ts_off[1]
+        env = mask * (shape_values(e.shape, ts_off, e) - shape_values(e.shape, np.array([t_before]), e)[0])
+    if not e.drag:
+        return env.astype(np.complex128)
+    dt = ts_off[1] - ts_off[0]
+    denv = mask * shape_derivative(e.shape, ts_off, e) * dt
+    return env - 1j * denv * e.delta
+
+
+def awg_signal(envelopes: Sequence[EnvelopeSpec], ts: np.ndarray, t_start: float = 0.0):
+    """Instruction.get_awg_signal: sum over the channel's envelopes of amp * env * exp(i (xy - w_off t))."""
+    signal = np.zeros_like(ts, dtype=np.complex128)
+    for e in envelopes:
+        ts_off = ts - t_start
+        phase = e.xy_angle - e.freq_offset * ts_off
+        signal = signal + e.amp * envelope_values(e, ts_off, e.t_final) * np.exp(1j * phase)
+    return np.real(signal), np.imag(signal)
+
+
+def resize_nearest(x: np.ndarray, new_dim: int) -> np.ndarray:
+    """tf.image.resize(method="nearest") along one axis: TF2 samples at floor((i + 0.5) * old / new)
+    (half-pixel centres) -- pinned by the 2.4 GS/s -> 100 GS/s fixture (ratio 41.67)."""
+    old = x.shape[0]
+    idx = np.minimum(np.floor((np.arange(new_dim) + 0.5) * (old / new_dim)).astype(np.int64), old - 1)
+    return x[idx]
+
+
+def rise_function(rise_time: float, resolution: float, fft_variant: bool = False) -> np.ndarray:
+    n_ts = int(np.floor(rise_time * resolution))
+    ts = np.linspace(0.0, rise_time, n_ts)
+    cen = (rise_time - 1 / resolution) / 2 if fft_variant else (rise_time + 1 / resolution) / 2
+    sigma = rise_time / 4
+    gauss = np.exp(-((ts - cen) ** 2) / (2 * sigma * sigma))
+    offset = np.exp(-((-1 - cen) ** 2) / (2 * sigma * sigma))
+    risefun = gauss - offset
+    return risefun / np.sum(risefun)
+
+
+def tf_convolve(sig: np.ndarray, resp: np.ndarray) -> np.ndarray:
+    """FFT convolution truncated to the signal length: out[n] = sum_m resp[m] sig[n - m]."""
+    n = len(sig) + len(resp)
+    out = np.fft.ifft(np.fft.fft(sig, n) * np.fft.fft(resp, n))
+    return out[: len(sig)]
+
+
+def tf_convolve_legacy(sig: np.ndarray, resp: np.ndarray) -> np.ndarray:
+    """Legacy variant: out[n] = sum_m resp[m] sig[n - 1 - m]."""
+    s, r = len(sig), len(resp)
+    n = s + 2 * r
+    pad = np.concatenate([np.zeros(r), sig, np.zeros(r)])
+    out = np.fft.ifft(np.fft.fft(pad, n) * np.fft.fft(resp, n))
+    return out[r - 1: s + r - 1]
+
+
+def response(i_sig, q_sig, rise_time: float, resolution: float, fft_variant: bool = False):
+    rf = rise_function(rise_time, resolution, fft_variant)
+    conv = tf_convolve if fft_variant else tf_convolve_legacy
+    return np.real(conv(i_sig, rf)), np.real(conv(q_sig, rf))
+
+
+def mixer(lo_i, lo_q, i_sig, q_sig):
+    return lo_i * i_sig + lo_q * q_sig
+
+
+def flux_tuning(signal, phi: float, phi_0: float, omega_0: float, anhar: float, d: Optional[float]):
+    def factor(p):
+        x = np.pi * p / phi_0
+        if d is not None:
+            return np.sqrt(np.sqrt(np.cos(x) ** 2 + d ** 2 * np.sin(x) ** 2))
+        return np.sqrt(np.abs(np.cos(x)))
+
+    def freq(p):
+        return (omega_0 - anhar) * factor(p) + anhar
+    return freq(phi + signal) - freq(phi)
+
+
+@dataclass
+class ChainSpec:
+    """The standard device chain of one drive line."""
+    sim_res: float = 100e9
+    awg_res: float = 2e9
+    rise_time: float = 0.3e-9
+    response_fft: bool = False          # ResponseFFT instead of the legacy Response
+    v2hz: float = 1e9                   # VoltsToHertz factor (with its 2 pi if the unit says so)
+    flux: Optional[Dict] = None         # FluxTuning parameters instead of VoltsToHertz: phi, phi_0, omega_0, anhar, d
+
+
+def generate_signal(envelopes: Sequence[EnvelopeSpec], omega_lo: float, t_start: float, t_end: float,
+                    chain: ChainSpec, stages: Optional[dict] = None):
+    """One channel of Generator.generate_signals (c3/generator/generator.py:172-229) for the standard chain.
+    Returns (values [N], ts [N]); ``stages`` (if given) receives every intermediate signal."""
+    ts = create_ts(t_start, t_end, chain.sim_res)
+    lo_i, lo_q = lo_signal(ts, omega_lo)
+    ts_awg = create_ts(t_start, t_end, chain.awg_res)
+    awg_i, awg_q = awg_signal(envelopes, ts_awg, t_start)
+    dac_i, dac_q = resize_nearest(awg_i, len(ts)), resize_nearest(awg_q, len(ts))
+    resp_i, resp_q = response(dac_i, dac_q, chain.rise_time, chain.sim_res, chain.response_fft)
+    mixed = mixer(lo_i, lo_q, resp_i, resp_q)
+    if chain.flux is not None:
+        values = flux_tuning(mixed, **chain.flux)
+    else:
+        values = mixed * chain.v2hz
+    if stages is not None:
+        stages.update(lo_i=lo_i, lo_q=lo_q, ts_awg=ts_awg, awg_i=awg_i, awg_q=awg_q, dac_i=dac_i, dac_q=dac_q,
+                      resp_i=resp_i, resp_q=resp_q, mixed=mixed)
+    return values, ts

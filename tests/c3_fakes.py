@@ -1,0 +1,138 @@
+"""Duck-typed stand-ins for the reference objects the mirrored APIs consume (TensorFlow, and with it the
+reference package, cannot be imported here).  Class NAMES match the reference's because the signal-chain
+mirror dispatches on them exactly like a hjson config's ``c3type`` would."""
+import numpy as np
+
+
+class Quantity:
+    """c3/c3objs.py Quantity: value * (2 pi if the unit says so)."""
+
+    def __init__(self, value, unit=""):
+        self.unit = unit
+        self._v = np.asarray(value, dtype=np.float64) * (2 * np.pi if "2pi" in unit else 1.0)
+
+    def get_value(self):
+        return self._v
+
+
+class _Dev:
+    def __init__(self, name="", resolution=0.0, **params):
+        self.name, self.resolution, self.params = name, resolution, params
+
+
+class LO(_Dev):
+    pass
+
+
+class AWG(_Dev):
+    pass
+
+
+class DigitalToAnalog(_Dev):
+    pass
+
+
+class Response(_Dev):
+    pass
+
+
+class ResponseFFT(_Dev):
+    pass
+
+
+class Mixer(_Dev):
+    pass
+
+
+class VoltsToHertz(_Dev):
+    pass
+
+
+class FluxTuning(_Dev):
+    pass
+
+
+class Additive_Noise(_Dev):
+    pass
+
+
+class _Shape:
+    def __init__(self, name):
+        self.__name__ = name
+
+
+class Envelope:
+    def __init__(self, name, shape, params, use_t_before=False):
+        self.name, self.shape, self.params, self.use_t_before = name, _Shape(shape), params, use_t_before
+
+
+class EnvelopeDrag(Envelope):
+    pass
+
+
+class Carrier:
+    def __init__(self, name, params):
+        self.name, self.params = name, params
+
+
+class Instruction:
+    def __init__(self, name, t_start, t_end, channels):
+        self.name, self.t_start, self.t_end = name, t_start, t_end
+        self.comps = {c: {} for c in channels}
+        self._options = {c: {} for c in channels}
+
+    def add_component(self, comp, chan):
+        self.comps[chan][comp.name] = comp
+        self._options[chan][comp.name] = {}
+
+
+def standard_chain(lo="LO", awg="AWG", dac="DigitalToAnalog", resp="Response", mixer="Mixer", out="VoltsToHertz"):
+    chain = {lo: [], awg: [], dac: [awg]}
+    if resp:
+        chain[resp] = [dac]
+        chain[mixer] = [lo, resp]
+    else:
+        chain[mixer] = [lo, dac]
+    chain[out] = [mixer]
+    return chain
+
+
+def reference_generator_setup():
+    """The objects of test/test_generator.py:21-118 of the reference."""
+    sim_res, awg_res = 100e9, 2e9
+    devices = {
+        "LO": LO("lo", sim_res), "AWG": AWG("awg", awg_res), "DigitalToAnalog": DigitalToAnalog("dac", sim_res),
+        "Response": Response("resp", sim_res, rise_time=Quantity(0.3e-9, "s")), "Mixer": Mixer("mixer"),
+        "VoltsToHertz": VoltsToHertz("v_to_hz", V_to_Hz=Quantity(1e9, "Hz/V")),
+    }
+    t_final, sideband = 7e-9, 50e6
+    env = Envelope("gauss", "gaussian_nonorm", {
+        "amp": Quantity(0.5, "V"), "t_final": Quantity(t_final, "s"), "sigma": Quantity(t_final / 4, "s"),
+        "xy_angle": Quantity(0.0, "rad"), "freq_offset": Quantity(-sideband - 3e6, "Hz 2pi"), "delta": Quantity(-1, "")})
+    carr = Carrier("carrier", {"freq": Quantity(5e9 + sideband, "Hz 2pi"), "framechange": Quantity(0.0, "rad")})
+    instr = Instruction("rx90p", 0.0, t_final, ["d1"])
+    instr.add_component(env, "d1")
+    instr.add_component(carr, "d1")
+    return devices, {"d1": standard_chain()}, instr
+
+
+def tunable_coupler_flux_setup():
+    """The flux line ("TC") of test/test_tunable_coupler.py:158-262 (xy_angle already sign-flipped, :279-283)."""
+    sim_res, awg_res, phi_0 = 100e9, 2.4e9, 10.0
+    devices = {
+        "lo": LO("lo", sim_res), "awg": AWG("awg", awg_res), "dac": DigitalToAnalog("dac", sim_res),
+        "resp": Response("resp", sim_res, rise_time=Quantity(0.3e-9, "s")), "mixer": Mixer("mixer"),
+        "fluxbias": FluxTuning("fluxbias", phi_0=Quantity(phi_0, "Wb"), phi=Quantity(phi_0 * 0.23, "Wb"),
+                               omega_0=Quantity(8.1e9, "Hz 2pi"), d=Quantity(0.36, ""), anhar=Quantity(-286e6, "Hz 2pi")),
+    }
+    chain = standard_chain("lo", "awg", "dac", "resp", "mixer", "fluxbias")
+    t = 100e-9
+    env = Envelope("flux", "flattop", {
+        "amp": Quantity(0.1 * phi_0, "V"), "t_final": Quantity(t, "s"), "t_up": Quantity(5e-9, "s"),
+        "t_down": Quantity(t - 5e-9, "s"), "risefall": Quantity(5e-9, "s"), "freq_offset": Quantity(0.0, "Hz 2pi"),
+        "xy_angle": Quantity(0.3590456701578104, "rad")})
+    carr = Carrier("carrier", {"freq": Quantity(829e6, "Hz 2pi"), "framechange": Quantity(0.0, "rad")})
+    instr = Instruction("crzp", 0.0, t, ["TC"])
+    instr.add_component(env, "TC")
+    instr.add_component(carr, "TC")
+    return devices, {"TC": chain}, instr

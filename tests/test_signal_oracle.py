@@ -1,0 +1,91 @@
+"""CPU: the signal-chain oracle (oracle/c3_signal_oracle.py) against the reference's own fixtures, stage by
+stage (test/generator_data.pickle <- test/test_generator.py:118-190; AWG samples and final flux-line field of
+test/tunable_coupler_data.pickle), and the host logic of the Generator mirror (no GPU needed)."""
+import numpy as np
+import pytest
+
+import c3_fakes as fk
+from oracle import c3_signal_oracle as so
+
+TP = 2 * np.pi
+
+
+def _rx90p_env():
+    t_final = 7e-9
+    return so.EnvelopeSpec(shape="gaussian_nonorm", amp=0.5, t_final=t_final, sigma=t_final / 4, xy_angle=0.0,
+                           freq_offset=(-50e6 - 3e6) * TP, delta=-1)
+
+
+def test_generator_chain_stage_by_stage(golden_generator):
+    g = golden_generator
+    st = {}
+    vals, ts = so.generate_signal([_rx90p_env()], (5e9 + 50e6) * TP, 0.0, 7e-9, so.ChainSpec(), st)
+    assert np.array_equal(ts, g["lo_ts"])                                       # test_LO, :118-127
+    assert np.abs(st["lo_i"] - g["lo_I"]).max() < 1e-12 and np.abs(st["lo_q"] - g["lo_Q"]).max() < 1e-12
+    assert np.abs(st["awg_i"] - g["awg_I"]).max() < 1e-14                       # test_AWG, :131-138
+    assert np.abs(st["awg_q"] - g["awg_Q"]).max() < 1e-14
+    assert np.array_equal(so.resize_nearest(g["awg_I"], 700), g["dac_I"])       # test_DAC, :142-151
+    assert np.array_equal(so.resize_nearest(g["awg_Q"], 700), g["dac_Q"])
+    ri, rq = so.response(g["dac_I"], g["dac_Q"], 0.3e-9, 100e9)                 # test_Response, :155-164
+    assert np.abs(ri - g["resp_I"]).max() < 1e-14 and np.abs(rq - g["resp_Q"]).max() < 1e-14
+    assert np.array_equal(so.mixer(g["lo_I"], g["lo_Q"], g["resp_I"], g["resp_Q"]), g["mixer"])   # test_mixer
+    assert np.abs(g["mixer"] * 1e9 - g["v2hz"]).max() < 1e-6                    # test_v2hz
+    scale = np.abs(g["full_values"]).max()
+    assert np.abs(vals - g["full_values"]).max() < 1e-12 * scale                # test_full_signal_chain, :183-190
+
+
+def test_tunable_coupler_flux_line(golden_tunable_coupler):
+    """AWG at 2.4 GS/s (non-integer resampling ratio 41.67: pins the half-pixel nearest-neighbour rule), flattop
+    envelope, FluxTuning output: the 10 000-sample control field of test/test_tunable_coupler.py."""
+    g = golden_tunable_coupler
+    env = so.EnvelopeSpec(shape="flattop", amp=1.0, t_final=100e-9, t_up=5e-9, t_down=95e-9, risefall=5e-9,
+                          xy_angle=0.3590456701578104)
+    chain = so.ChainSpec(awg_res=2.4e9, flux=dict(phi=2.3, phi_0=10.0, omega_0=8.1e9 * TP, anhar=-286e6 * TP, d=0.36))
+    st = {}
+    vals, ts = so.generate_signal([env], 829e6 * TP, 0.0, 100e-9, chain, st)
+    assert np.array_equal(st["ts_awg"], g["tc_awg_ts"]) and np.array_equal(ts, g["tc_ts"])
+    assert np.abs(st["awg_i"] - g["tc_awg_I"]).max() < 1e-14 and np.abs(st["awg_q"] - g["tc_awg_Q"]).max() < 1e-14
+    assert np.abs(vals - g["tc_signal"]).max() < 1e-12 * np.abs(g["tc_signal"]).max()
+
+
+def test_convolutions_are_plain_sums():
+    rng = np.random.default_rng(0)
+    x, r = rng.normal(size=57), rng.normal(size=9)
+    full = np.convolve(x, r)
+    assert np.allclose(so.tf_convolve(x, r).real, full[:57], atol=1e-13)
+    assert np.allclose(so.tf_convolve_legacy(x, r).real, np.concatenate([[0.0], full[:56]]), atol=1e-13)
+
+
+@pytest.mark.parametrize("shape", ["gaussian_nonorm", "gaussian_sigma", "cosine", "flattop"])
+def test_shape_derivatives(shape):
+    e = so.EnvelopeSpec(shape=shape, t_final=8e-9, sigma=1.7e-9, t_up=1e-9, t_down=6.5e-9, risefall=0.8e-9)
+    t = np.linspace(0.2e-9, 7.8e-9, 41)
+    h = 1e-15
+    fd = (so.shape_values(shape, t + h, e) - so.shape_values(shape, t - h, e)) / (2 * h)
+    an = so.shape_derivative(shape, t, e)
+    assert np.abs(fd - an).max() < 1e-4 * np.abs(an).max()
+
+
+def test_generator_mirror_host_logic():
+    from c3_b200.generator import Generator, CHAIN_KEYS
+    devices, chains, instr = fk.reference_generator_setup()
+    gen = Generator(devices, chains)
+    spec = gen._specs["d1"]
+    assert spec["sim_res"] == 100e9 and spec["awg_res"] == 2e9 and spec["resp_kind"] == 1.0 and spec["v2hz"] == 1e9
+    chans, env, shape, flags, lo, chain = gen._tables(instr, {("d1", "gauss", "amp"): [0.1, 0.2, 0.3]})
+    assert chans == ["d1"] and env.shape == (3, 1, 1, 9) and list(env[:, 0, 0, 0]) == [0.1, 0.2, 0.3]
+    assert shape[0, 0] == 2 and flags[0, 0] == 0 and abs(lo[0, 0] - 5.05e9 * TP) < 1 and chain.shape == (1, len(CHAIN_KEYS))
+    assert abs(env[0, 0, 0, 4] - (-53e6 * TP)) < 1e-3
+    d2, c2, i2 = fk.tunable_coupler_flux_setup()
+    s2 = Generator(d2, c2)._specs["TC"]
+    assert s2["out_kind"] == 1.0 and s2["d"] == 0.36 and abs(s2["omega_0"] - 8.1e9 * TP) < 1
+    # unsupported pieces fail loudly (no silent CPU path)
+    bad = dict(devices)
+    bad["Noise"] = fk.Additive_Noise("noise")
+    with pytest.raises(Exception, match="C3:ERROR"):
+        Generator(bad, {"d1": dict(chains["d1"], Noise=["Mixer"])})
+    with pytest.raises(Exception, match="C3:ERROR"):
+        Generator(devices, {"d1": dict(chains["d1"], Mixer=["Response", "LO"])})
+    instr.add_component(fk.Envelope("odd", "slepian_fourier", {}), "d1")
+    with pytest.raises(Exception, match="C3:ERROR"):
+        gen._tables(instr)
