@@ -95,7 +95,14 @@ int pwc_path(int K, int D, int batched_model) {
 size_t cta_smem_bytes(int D) { return (((size_t)D * sizeof(int) + 15) & ~(size_t)15) + (size_t)kCtaSlots * D * D * sizeof(cplx); }
 
 int round8(int D) { return (D + 7) & ~7; }
-size_t gemm_smem_bytes(int D) { return (size_t)kGemmSlots * round8(D) * (round8(D) + 4) * sizeof(cplx); }
+size_t gemm_mats_bytes(int D) { return (size_t)kGemmSlots * round8(D) * (round8(D) + 4) * sizeof(cplx); }
+// the shared-model generators ride along in shared memory when they fit next to the matrix slots
+bool gemm_g_in_smem(int D, int K, int batched_model) {
+    return !batched_model && gemm_mats_bytes(D) + (size_t)(K + 1) * D * D * sizeof(cplx) <= (size_t)220 * 1024;
+}
+size_t gemm_smem_bytes(int D, int K = -1, int batched_model = 1) {
+    return gemm_mats_bytes(D) + ((K >= 0 && gemm_g_in_smem(D, K, batched_model)) ? (size_t)(K + 1) * D * D * sizeof(cplx) : 0);
+}
 
 int cta_grid(int D, long long units) {
     int per_sm = 1;
@@ -328,10 +335,10 @@ int launch_cta_t(const CtaParams& cp, int grid, cudaStream_t st) {
     return C3B_OK;
 }
 
-template <int TM, int TN>
+template <int TM, int TN, int DPT = 0, int KST = 0>
 int launch_gemm_t(const GemmParams& gp, int grid, cudaStream_t st) {
-    auto kern = pwc_t18_cta_kernel<TM, TN>;
-    const size_t smem = gp.c.use_smem ? gemm_smem_bytes(gp.c.D) : 0;
+    auto kern = pwc_t18_cta_kernel<TM, TN, DPT, KST>;
+    const size_t smem = gp.c.use_smem ? gemm_smem_bytes(gp.c.D, gp.g_in_smem ? gp.c.K : -1, gp.g_in_smem ? 0 : 1) : 0;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kCtaThreads, smem, st>>>(gp);
     CUDA_TRY(cudaGetLastError());
@@ -343,7 +350,9 @@ int launch_gemm(const CtaParams& cp, const cplx* TR, int grid, cudaStream_t st) 
     GemmParams gp{};
     gp.c = cp; gp.TR = TR; gp.DP = round8(cp.D);
     gp.LD = cp.use_smem ? gp.DP + 4 : gp.DP;
+    gp.g_in_smem = (cp.use_smem && cp.hlist == nullptr && cp.G != nullptr && gemm_g_in_smem(cp.D, cp.K, cp.model_stride != 0)) ? 1 : 0;
     if (gp.DP <= 16) return launch_gemm_t<1, 1>(gp, grid, st);
+    if (gp.DP == 32 && cp.use_smem) return cp.D <= 28 ? launch_gemm_t<1, 2, 32, 7>(gp, grid, st) : launch_gemm_t<1, 2, 32, 8>(gp, grid, st);
     if (gp.DP <= 48) return launch_gemm_t<1, 2>(gp, grid, st);
     return launch_gemm_t<2, 2>(gp, grid, st);
 }

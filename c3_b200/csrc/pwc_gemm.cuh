@@ -18,10 +18,10 @@
 
 namespace c3b {
 
-constexpr int kGemmSlots = 10;   // S0..S8 scratch + P
+constexpr int kGemmSlots = 8;    // S0..S5 scratch + P + Q (see the slot plan in pwc_t18_cta_kernel)
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a, const double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -32,8 +32,12 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a
 // LD is the leading dimension (>= DP); KP = D rounded up to 4 bounds the k loop (columns/rows beyond D
 // are zero).  In shared memory LD = DP + 4 (= 4 mod 8 in 16-byte units) makes the A-fragment loads
 // bank-conflict free and the B-fragment loads 2-way (with LD = DP = 32 they were 8-way / 4-way).
-template <int TM, int TN>
-__device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP, const int LD, const int KP) {
+template <int TM, int TN, int DPT = 0, int KST = 0>
+__device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP_, const int LD_, const int KP) {
+    // DPT > 0: tile extent and leading dimension are compile-time (DPT, DPT + 4): the k loop unrolls fully and
+    // every fragment address is base + immediate
+    const int DP = DPT > 0 ? DPT : DP_;
+    const int LD = DPT > 0 ? DPT + 4 : LD_;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = kCtaThreads / 32;
     const int nb = DP >> 3;                       // m8n8 blocks per dimension
@@ -52,22 +56,64 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
         for (int i = 0; i < TM; ++i) arow[i] = (min(bi0 + i, nb - 1) * 8 + fr) * LD + fc;
 #pragma unroll
         for (int j = 0; j < TN; ++j) bcol[j] = fc * LD + min(bj0 + j, nb - 1) * 8 + fr;
-#pragma unroll 2
-        for (int k0 = 0; k0 < KP; k0 += 4) {
+        auto kstep = [&](const int k0) {
             cplx a[TM], b[TN];
 #pragma unroll
             for (int i = 0; i < TM; ++i) a[i] = A[arow[i] + k0];
 #pragma unroll
             for (int j = 0; j < TN; ++j) b[j] = B[bcol[j] + k0 * LD];
+            // the two updates of one accumulator are issued TM*TN*2 DMMAs apart (fixed-latency dependency)
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < TN; ++j) {
                     dmma8x8x4(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
                     dmma8x8x4(ci[i][j][0], ci[i][j][1], a[i].x, b[j].y);
+                }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
                     dmma8x8x4(cr[i][j][0], cr[i][j][1], -a[i].y, b[j].y);
                     dmma8x8x4(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
                 }
+        };
+        if (DPT > 0) {
+            // software pipeline by hand: the fragments of k step kk+1 are requested before the DMMAs of step kk are
+            // issued.  ptxas otherwise sinks every LDS right in front of its first use (minimal registers) and both
+            // warps of a scheduler eat the shared-memory latency at every k step; the __syncwarp() is a scheduling
+            // fence that loads may not sink below.
+            constexpr int KS = KST > 0 ? KST : (DPT > 0 ? DPT / 4 : 1);   // k steps: ceil(D / 4), compile-time
+            cplx af[KS][TM], bf[KS][TN];
+            auto fetch = [&](const int kk) {
+#pragma unroll
+                for (int i = 0; i < TM; ++i) af[kk][i] = A[arow[i] + kk * 4];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) bf[kk][j] = B[bcol[j] + kk * 4 * LD];
+            };
+            fetch(0);
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+                if (kk + 1 < KS) fetch(kk + 1);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) {
+                        dmma8x8x4(cr[i][j][0], cr[i][j][1], af[kk][i].x, bf[kk][j].x);
+                        dmma8x8x4(ci[i][j][0], ci[i][j][1], af[kk][i].x, bf[kk][j].y);
+                    }
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) {
+                        dmma8x8x4(cr[i][j][0], cr[i][j][1], -af[kk][i].y, bf[kk][j].y);
+                        dmma8x8x4(ci[i][j][0], ci[i][j][1], af[kk][i].y, bf[kk][j].x);
+                    }
+            }
+        } else {
+#pragma unroll 2
+            for (int k0 = 0; k0 < KP; k0 += 4) kstep(k0);
         }
 #pragma unroll
         for (int i = 0; i < TM; ++i)
@@ -82,12 +128,18 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
     }
 }
 
-// exact 1-norm over the D x D part of a DP-strided matrix
-__device__ __forceinline__ double cta_norm1_ld(const cplx* A, const int D, const int DP, double* red) {
+// inf-norm (largest row sum of |a_ij|) over the D x D part of an LD-strided matrix, all threads busy:
+// 8 threads per row, shuffle-reduced.  Any subordinate norm bounds the Taylor truncation error the same way.
+__device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, const int LD, double* red) {
+    const int part = threadIdx.x & 7;
     double best = 0.0;
-    for (int c = threadIdx.x; c < D; c += kCtaThreads) {
+    for (int r = threadIdx.x >> 3; r < ((D + 31) & ~31); r += kCtaThreads / 8) {
         double s = 0.0;
-        for (int i = 0; i < D; ++i) s += cabs1(A[i * DP + c]);
+        if (r < D)
+            for (int j = part; j < D; j += 8) s += cabs1(A[r * LD + j]);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
         best = fmax(best, s);
     }
     best = warp_max(best);
@@ -105,27 +157,48 @@ struct GemmParams {
     const cplx* TR;    // [(Bm), K+1] trace shifts already subtracted from G's diagonals, or null
     int DP;            // D rounded up to a multiple of 8 (tile extent)
     int LD;            // leading dimension of every workspace matrix (DP, or DP + 4 in shared memory)
+    int g_in_smem;     // the (shared) generators are staged in shared memory after the matrix slots
 };
 
-template <int TM, int TN>
+// Slot plan (8 matrices of DP x LD): the Taylor combinations overwrite the powers they are formed from
+//   S0: A -> B1 -> (B3+A9) A9 -> T18 (squaring ping)   S1: A2 -> B5 (squaring pong)   S2: A3 -> B4
+//   S3: A6 -> B3 -> B3 + A9                           S4: B2                         S5: B1 B5 -> A9
+//   P, Q: running product and its update (pointers swap, no copy)
+template <int TM, int TN, int DPT = 0, int KST = 0>
 __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[kCtaThreads / 32];
     const CtaParams& p = gp.c;
-    const int D = p.D, K = p.K, DP = gp.DP, LD = gp.LD;
+    const int D = p.D, K = p.K;
+    const int DP = DPT > 0 ? DPT : gp.DP;
+    const int LD = DPT > 0 ? DPT + 4 : gp.LD;
     const int KP = (D + 3) & ~3;
     const int PP = DP * LD;
+    const int RL = D * LD;                          // rows >= D are padding: zeroed once, never written non-zero
     const int tid = threadIdx.x;
 
-    cplx* mats = p.use_smem ? reinterpret_cast<cplx*>(smem_raw) : p.ws + (size_t)blockIdx.x * kGemmSlots * PP;
-    cplx* S[kGemmSlots];
-#pragma unroll
-    for (int i = 0; i < kGemmSlots; ++i) S[i] = mats + (size_t)i * PP;
-    cplx* const P = S[9];
+    // DPT > 0 is only launched with shared-memory matrices: keeping the pointer provably shared lets ptxas emit
+    // LDS/STS instead of generic loads
+    cplx* mats = (DPT > 0) ? reinterpret_cast<cplx*>(smem_raw)
+                           : (p.use_smem ? reinterpret_cast<cplx*>(smem_raw) : p.ws + (size_t)blockIdx.x * kGemmSlots * PP);
+    cplx* const S0 = mats;
+    cplx* const S1 = mats + (size_t)1 * PP;
+    cplx* const S2 = mats + (size_t)2 * PP;
+    cplx* const S3 = mats + (size_t)3 * PP;
+    cplx* const S4 = mats + (size_t)4 * PP;
+    cplx* const S5 = mats + (size_t)5 * PP;
+    cplx* P = mats + (size_t)6 * PP;
+    cplx* Q = mats + (size_t)7 * PP;
     const bool shifted = gp.TR != nullptr && p.hlist == nullptr;
 
     // zero everything once: the padding rows/columns stay zero through every product
     for (int e = tid; e < kGemmSlots * PP; e += kCtaThreads) mats[e] = cmake(0.0, 0.0);
+    const cplx* Gs = nullptr;                       // generators staged in shared memory (shared model only)
+    if (gp.g_in_smem) {
+        cplx* g = reinterpret_cast<cplx*>(smem_raw) + (size_t)kGemmSlots * PP;
+        for (int e = tid; e < (K + 1) * D * D; e += kCtaThreads) g[e] = p.G[e];
+        Gs = g;
+    }
     __syncthreads();
 
     const long long units = (long long)p.B * p.S;
@@ -134,18 +207,18 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
         const int sidx = (int)(unit - (long long)b * p.S);
         const int n_begin = sidx * p.seg_len;
         const int n_end = min(p.N, n_begin + p.seg_len);
-        const cplx* Gb = p.G ? p.G + (size_t)b * p.model_stride : nullptr;
+        const cplx* Gb = Gs ? Gs : (p.G ? p.G + (size_t)b * p.model_stride : nullptr);
         const cplx* TRb = shifted ? gp.TR + (size_t)b * (p.model_stride ? (K + 1) : 0) : nullptr;
         const double* sig_b = p.signals ? p.signals + (size_t)b * K * p.N : nullptr;
         const cplx hs = cmake(p.hscale_re, p.hscale_im);
         cplx mu_acc = cmake(0.0, 0.0);
 
         for (int n = n_begin; n < n_end; ++n) {
-            cplx* A = S[0];
+            cplx* A = S0;
             // ---- assemble (D x D part; padding stays zero) ---------------------------------------
             if (p.hlist == nullptr) {
-                for (int e = tid; e < D * D; e += kCtaThreads) {
-                    const int i = e / D, j = e - i * D;
+                auto element = [&](const int i, const int j) {
+                    const int e = i * D + j;
                     cplx v = Gb[e];
                     for (int k = 0; k < K; ++k) {
                         const double c = __ldg(sig_b + (size_t)k * p.N + n);
@@ -154,6 +227,14 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                         v.y = fma(c, gk.y, v.y);
                     }
                     A[i * LD + j] = v;
+                };
+                if (DPT > 0) {                                   // DPT lanes walk one row: no integer division
+                    constexpr int W = DPT > 0 ? DPT : 1;
+                    const int j = tid % W;
+                    if (j < D)
+                        for (int i = tid / W; i < D; i += kCtaThreads / W) element(i, j);
+                } else {
+                    for (int e = tid; e < D * D; e += kCtaThreads) element(e / D, e % D);
                 }
                 if (shifted) {
                     cplx mu = TRb[0];
@@ -172,53 +253,53 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                 }
             }
             __syncthreads();
-            const double nrm = cta_norm1_ld(A, D, LD, red);
+            const double nrm = cta_norm_inf_ld(A, D, LD, red);
             const int s = squarings_for(nrm, C3B_THETA18);
             if (s > 0) {
                 const double sc = pow2neg(s);
-                for (int e = tid; e < PP; e += kCtaThreads) { A[e].x *= sc; A[e].y *= sc; }
+                for (int e = tid; e < RL; e += kCtaThreads) { A[e].x *= sc; A[e].y *= sc; }
                 __syncthreads();
             }
             // ---- T18: A2 = S1, A3 = S2, A6 = S3 -----------------------------------------------------
-            cta_zgemm<TM, TN>(S[1], A, A, DP, LD, KP);
+            cta_zgemm<TM, TN, DPT, KST>(S1, A, A, DP, LD, KP);
             __syncthreads();
-            cta_zgemm<TM, TN>(S[2], S[1], A, DP, LD, KP);
+            cta_zgemm<TM, TN, DPT, KST>(S2, S1, A, DP, LD, KP);
             __syncthreads();
-            cta_zgemm<TM, TN>(S[3], S[2], S[2], DP, LD, KP);
+            cta_zgemm<TM, TN, DPT, KST>(S3, S2, S2, DP, LD, KP);
             __syncthreads();
-            // B1 -> S4, B5 -> S5, B4 -> S6, B3 -> S7, B2 -> S8
-            for (int e = tid; e < PP; e += kCtaThreads) {
+            // in place: B1 -> S0, B5 -> S1, B4 -> S2, B3 -> S3, B2 -> S4
+            for (int e = tid; e < RL; e += kCtaThreads) {
                 const int i = e / LD, j = e - i * LD;
-                const double dg = (i == j && i < D) ? 1.0 : 0.0;
-                const cplx x1 = A[e], x2 = S[1][e], x3 = S[2][e], x6 = S[3][e];
-                S[4][e] = cmake(C3B_T18_A11 * x1.x + C3B_T18_A21 * x2.x + C3B_T18_A31 * x3.x,
-                                C3B_T18_A11 * x1.y + C3B_T18_A21 * x2.y + C3B_T18_A31 * x3.y);
-                S[5][e] = cmake(C3B_T18_B24 * x2.x + C3B_T18_B34 * x3.x + C3B_T18_B64 * x6.x,
-                                C3B_T18_B24 * x2.y + C3B_T18_B34 * x3.y + C3B_T18_B64 * x6.y);
-                S[6][e] = cmake(C3B_T18_B03 * dg + C3B_T18_B13 * x1.x + C3B_T18_B23 * x2.x + C3B_T18_B33 * x3.x + C3B_T18_B63 * x6.x,
-                                C3B_T18_B13 * x1.y + C3B_T18_B23 * x2.y + C3B_T18_B33 * x3.y + C3B_T18_B63 * x6.y);
-                S[7][e] = cmake(C3B_T18_B02 * dg + C3B_T18_B12 * x1.x + C3B_T18_B22 * x2.x + C3B_T18_B32 * x3.x + C3B_T18_B62 * x6.x,
-                                C3B_T18_B12 * x1.y + C3B_T18_B22 * x2.y + C3B_T18_B32 * x3.y + C3B_T18_B62 * x6.y);
-                S[8][e] = cmake(C3B_T18_B11 * x1.x + C3B_T18_B21 * x2.x + C3B_T18_B31 * x3.x + C3B_T18_B61 * x6.x,
-                                C3B_T18_B11 * x1.y + C3B_T18_B21 * x2.y + C3B_T18_B31 * x3.y + C3B_T18_B61 * x6.y);
+                const double dg = (i == j) ? 1.0 : 0.0;
+                const cplx x1 = S0[e], x2 = S1[e], x3 = S2[e], x6 = S3[e];
+                S0[e] = cmake(C3B_T18_A11 * x1.x + C3B_T18_A21 * x2.x + C3B_T18_A31 * x3.x,
+                              C3B_T18_A11 * x1.y + C3B_T18_A21 * x2.y + C3B_T18_A31 * x3.y);
+                S1[e] = cmake(C3B_T18_B24 * x2.x + C3B_T18_B34 * x3.x + C3B_T18_B64 * x6.x,
+                              C3B_T18_B24 * x2.y + C3B_T18_B34 * x3.y + C3B_T18_B64 * x6.y);
+                S2[e] = cmake(C3B_T18_B03 * dg + C3B_T18_B13 * x1.x + C3B_T18_B23 * x2.x + C3B_T18_B33 * x3.x + C3B_T18_B63 * x6.x,
+                              C3B_T18_B13 * x1.y + C3B_T18_B23 * x2.y + C3B_T18_B33 * x3.y + C3B_T18_B63 * x6.y);
+                S3[e] = cmake(C3B_T18_B02 * dg + C3B_T18_B12 * x1.x + C3B_T18_B22 * x2.x + C3B_T18_B32 * x3.x + C3B_T18_B62 * x6.x,
+                              C3B_T18_B12 * x1.y + C3B_T18_B22 * x2.y + C3B_T18_B32 * x3.y + C3B_T18_B62 * x6.y);
+                S4[e] = cmake(C3B_T18_B11 * x1.x + C3B_T18_B21 * x2.x + C3B_T18_B31 * x3.x + C3B_T18_B61 * x6.x,
+                              C3B_T18_B11 * x1.y + C3B_T18_B21 * x2.y + C3B_T18_B31 * x3.y + C3B_T18_B61 * x6.y);
             }
             __syncthreads();
-            cta_zgemm<TM, TN>(S[1], S[4], S[5], DP, LD, KP);      // B1 B5
+            cta_zgemm<TM, TN, DPT, KST>(S5, S0, S1, DP, LD, KP);        // B1 B5
             __syncthreads();
-            for (int e = tid; e < PP; e += kCtaThreads) {  // A9 -> S2, B3 + A9 -> S3
-                const cplx a9 = cmake(S[1][e].x + S[6][e].x, S[1][e].y + S[6][e].y);
-                S[2][e] = a9;
-                S[3][e] = cmake(S[7][e].x + a9.x, S[7][e].y + a9.y);
+            for (int e = tid; e < RL; e += kCtaThreads) {          // A9 -> S5, B3 + A9 -> S3
+                const cplx a9 = cmake(S5[e].x + S2[e].x, S5[e].y + S2[e].y);
+                S5[e] = a9;
+                S3[e] = cmake(S3[e].x + a9.x, S3[e].y + a9.y);
             }
             __syncthreads();
-            cta_zgemm<TM, TN>(S[1], S[3], S[2], DP, LD, KP);      // (B3 + A9) A9
+            cta_zgemm<TM, TN, DPT, KST>(S0, S3, S5, DP, LD, KP);        // (B3 + A9) A9
             __syncthreads();
-            cplx* X = S[4];
-            for (int e = tid; e < PP; e += kCtaThreads) X[e] = cmake(S[1][e].x + S[8][e].x, S[1][e].y + S[8][e].y);
+            cplx* X = S0;
+            for (int e = tid; e < RL; e += kCtaThreads) X[e] = cmake(S0[e].x + S4[e].x, S0[e].y + S4[e].y);
             __syncthreads();
-            for (int i = 0; i < s; ++i) {                  // undo the scaling
-                cplx* nxt = (X == S[4]) ? S[5] : S[4];
-                cta_zgemm<TM, TN>(nxt, X, X, DP, LD, KP);
+            for (int i = 0; i < s; ++i) {                          // undo the scaling
+                cplx* nxt = (X == S0) ? S1 : S0;
+                cta_zgemm<TM, TN, DPT, KST>(nxt, X, X, DP, LD, KP);
                 __syncthreads();
                 X = nxt;
             }
@@ -240,13 +321,13 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                 }
             }
             if (n == n_begin) {
-                for (int e = tid; e < PP; e += kCtaThreads) P[e] = X[e];
-            } else {
-                cta_zgemm<TM, TN>(S[6], X, P, DP, LD, KP);
+                for (int e = tid; e < RL; e += kCtaThreads) P[e] = X[e];
                 __syncthreads();
-                for (int e = tid; e < PP; e += kCtaThreads) P[e] = S[6][e];
+            } else {
+                cta_zgemm<TM, TN, DPT, KST>(Q, X, P, DP, LD, KP);
+                __syncthreads();
+                cplx* t = P; P = Q; Q = t;
             }
-            __syncthreads();
         }
         cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * D * D) : (p.seg_out + ((size_t)b * p.S + sidx) * D * D);
         if (n_end > n_begin) {
