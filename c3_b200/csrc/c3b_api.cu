@@ -48,6 +48,7 @@ bool g_ev_valid = false;
 long long g_target_units = 32768;  // rows kernel: aim for this many warp work units per launch
 long long g_force_cta = 0;         // route everything to the CTA kernel (testing)
 long long g_cta_variant = getenv("C3B_CTA_VARIANT") ? atoll(getenv("C3B_CTA_VARIANT")) : 1;  // 0: Pade + pivoted Gauss-Jordan, 1: Taylor-18 on DMMA tiles
+long long g_cta_threads = getenv("C3B_CTA_THREADS") ? atoll(getenv("C3B_CTA_THREADS")) : 512;   // DMMA CTA kernel, DP = 32: 256 or 512 threads
 long long g_min_chunk = getenv("C3B_MIN_CHUNK") ? atoll(getenv("C3B_MIN_CHUNK")) : 8;         // rows kernel: minimum slices per lane group
 // 1: rows v2 (one row per lane, Pade) | 4-6: rows v3 (experimental) | 7-12: block layout, Pade + Gauss-Jordan (d=9)
 // 13 (default): block layout, degree-18 Taylor, trace shift, all d <= 12
@@ -335,12 +336,12 @@ int launch_cta_t(const CtaParams& cp, int grid, cudaStream_t st) {
     return C3B_OK;
 }
 
-template <int TM, int TN, int DPT = 0, int KST = 0>
+template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
 int launch_gemm_t(const GemmParams& gp, int grid, cudaStream_t st) {
-    auto kern = pwc_t18_cta_kernel<TM, TN, DPT, KST>;
+    auto kern = pwc_t18_cta_kernel<TM, TN, DPT, KST, NT>;
     const size_t smem = gp.c.use_smem ? gemm_smem_bytes(gp.c.D, gp.g_in_smem ? gp.c.K : -1, gp.g_in_smem ? 0 : 1) : 0;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kCtaThreads, smem, st>>>(gp);
+    kern<<<grid, NT, smem, st>>>(gp);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;
@@ -352,7 +353,10 @@ int launch_gemm(const CtaParams& cp, const cplx* TR, int grid, cudaStream_t st) 
     gp.LD = cp.use_smem ? gp.DP + 4 : gp.DP;
     gp.g_in_smem = (cp.use_smem && cp.hlist == nullptr && cp.G != nullptr && gemm_g_in_smem(cp.D, cp.K, cp.model_stride != 0)) ? 1 : 0;
     if (gp.DP <= 16) return launch_gemm_t<1, 1>(gp, grid, st);
-    if (gp.DP == 32 && cp.use_smem) return cp.D <= 28 ? launch_gemm_t<1, 2, 32, 7>(gp, grid, st) : launch_gemm_t<1, 2, 32, 8>(gp, grid, st);
+    if (gp.DP == 32 && cp.use_smem) {
+        if (g_cta_threads == 512) return cp.D <= 28 ? launch_gemm_t<1, 1, 32, 7, 512>(gp, grid, st) : launch_gemm_t<1, 1, 32, 8, 512>(gp, grid, st);
+        return cp.D <= 28 ? launch_gemm_t<1, 2, 32, 7>(gp, grid, st) : launch_gemm_t<1, 2, 32, 8>(gp, grid, st);
+    }
     if (gp.DP <= 48) return launch_gemm_t<1, 2>(gp, grid, st);
     return launch_gemm_t<2, 2>(gp, grid, st);
 }
@@ -451,6 +455,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (!strcmp(key, "target_units")) { g_target_units = value < 1 ? 1 : value; return C3B_OK; }
     if (!strcmp(key, "force_cta")) { g_force_cta = value; return C3B_OK; }
     if (!strcmp(key, "cta_variant")) { g_cta_variant = value; return C3B_OK; }
+    if (!strcmp(key, "cta_threads")) { g_cta_threads = value; return C3B_OK; }
     if (!strcmp(key, "profile")) { g_profile = value; return C3B_OK; }
     if (!strcmp(key, "rows_variant")) { g_rows_variant = value; return C3B_OK; }
     if (!strcmp(key, "min_chunk")) { g_min_chunk = value < 1 ? 1 : value; return C3B_OK; }

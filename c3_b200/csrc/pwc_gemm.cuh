@@ -32,14 +32,14 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a
 // LD is the leading dimension (>= DP); KP = D rounded up to 4 bounds the k loop (columns/rows beyond D
 // are zero).  In shared memory LD = DP + 4 (= 4 mod 8 in 16-byte units) makes the A-fragment loads
 // bank-conflict free and the B-fragment loads 2-way (with LD = DP = 32 they were 8-way / 4-way).
-template <int TM, int TN, int DPT = 0, int KST = 0>
+template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
 __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP_, const int LD_, const int KP) {
     // DPT > 0: tile extent and leading dimension are compile-time (DPT, DPT + 4): the k loop unrolls fully and
     // every fragment address is base + immediate
     const int DP = DPT > 0 ? DPT : DP_;
     const int LD = DPT > 0 ? DPT + 4 : LD_;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int NW = kCtaThreads / 32;
+    constexpr int NW = NT / 32;
     const int nb = DP >> 3;                       // m8n8 blocks per dimension
     const int mt_r = (nb + TM - 1) / TM, mt_c = (nb + TN - 1) / TN;
     const int fr = lane >> 2, fc = lane & 3;      // fragment coordinates
@@ -130,10 +130,11 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
 
 // inf-norm (largest row sum of |a_ij|) over the D x D part of an LD-strided matrix, all threads busy:
 // 8 threads per row, shuffle-reduced.  Any subordinate norm bounds the Taylor truncation error the same way.
+template <int NT>
 __device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, const int LD, double* red) {
     const int part = threadIdx.x & 7;
     double best = 0.0;
-    for (int r = threadIdx.x >> 3; r < ((D + 31) & ~31); r += kCtaThreads / 8) {
+    for (int r = threadIdx.x >> 3; r < ((D + 31) & ~31); r += NT / 8) {
         double s = 0.0;
         if (r < D)
             for (int j = part; j < D; j += 8) s += cabs1(A[r * LD + j]);
@@ -147,7 +148,7 @@ __device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, co
     __syncthreads();
     double v = red[0];
 #pragma unroll
-    for (int w = 1; w < kCtaThreads / 32; ++w) v = fmax(v, red[w]);
+    for (int w = 1; w < NT / 32; ++w) v = fmax(v, red[w]);
     __syncthreads();
     return v;
 }
@@ -164,10 +165,10 @@ struct GemmParams {
 //   S0: A -> B1 -> (B3+A9) A9 -> T18 (squaring ping)   S1: A2 -> B5 (squaring pong)   S2: A3 -> B4
 //   S3: A6 -> B3 -> B3 + A9                           S4: B2                         S5: B1 B5 -> A9
 //   P, Q: running product and its update (pointers swap, no copy)
-template <int TM, int TN, int DPT = 0, int KST = 0>
-__global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmParams gp) {
+template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
+__global__ void __launch_bounds__(NT) pwc_t18_cta_kernel(const GemmParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[kCtaThreads / 32];
+    __shared__ double red[NT / 32];
     const CtaParams& p = gp.c;
     const int D = p.D, K = p.K;
     const int DP = DPT > 0 ? DPT : gp.DP;
@@ -192,11 +193,11 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
     const bool shifted = gp.TR != nullptr && p.hlist == nullptr;
 
     // zero everything once: the padding rows/columns stay zero through every product
-    for (int e = tid; e < kGemmSlots * PP; e += kCtaThreads) mats[e] = cmake(0.0, 0.0);
+    for (int e = tid; e < kGemmSlots * PP; e += NT) mats[e] = cmake(0.0, 0.0);
     const cplx* Gs = nullptr;                       // generators staged in shared memory (shared model only)
     if (gp.g_in_smem) {
         cplx* g = reinterpret_cast<cplx*>(smem_raw) + (size_t)kGemmSlots * PP;
-        for (int e = tid; e < (K + 1) * D * D; e += kCtaThreads) g[e] = p.G[e];
+        for (int e = tid; e < (K + 1) * D * D; e += NT) g[e] = p.G[e];
         Gs = g;
     }
     __syncthreads();
@@ -232,9 +233,9 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                     constexpr int W = DPT > 0 ? DPT : 1;
                     const int j = tid % W;
                     if (j < D)
-                        for (int i = tid / W; i < D; i += kCtaThreads / W) element(i, j);
+                        for (int i = tid / W; i < D; i += NT / W) element(i, j);
                 } else {
-                    for (int e = tid; e < D * D; e += kCtaThreads) element(e / D, e % D);
+                    for (int e = tid; e < D * D; e += NT) element(e / D, e % D);
                 }
                 if (shifted) {
                     cplx mu = TRb[0];
@@ -247,28 +248,28 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                 }
             } else {
                 const cplx* H = p.hlist + ((size_t)b * p.N + n) * D * D;
-                for (int e = tid; e < D * D; e += kCtaThreads) {
+                for (int e = tid; e < D * D; e += NT) {
                     const int i = e / D, j = e - i * D;
                     A[i * LD + j] = cmul(hs, H[e]);
                 }
             }
             __syncthreads();
-            const double nrm = cta_norm_inf_ld(A, D, LD, red);
+            const double nrm = cta_norm_inf_ld<NT>(A, D, LD, red);
             const int s = squarings_for(nrm, C3B_THETA18);
             if (s > 0) {
                 const double sc = pow2neg(s);
-                for (int e = tid; e < RL; e += kCtaThreads) { A[e].x *= sc; A[e].y *= sc; }
+                for (int e = tid; e < RL; e += NT) { A[e].x *= sc; A[e].y *= sc; }
                 __syncthreads();
             }
             // ---- T18: A2 = S1, A3 = S2, A6 = S3 -----------------------------------------------------
-            cta_zgemm<TM, TN, DPT, KST>(S1, A, A, DP, LD, KP);
+            cta_zgemm<TM, TN, DPT, KST, NT>(S1, A, A, DP, LD, KP);
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST>(S2, S1, A, DP, LD, KP);
+            cta_zgemm<TM, TN, DPT, KST, NT>(S2, S1, A, DP, LD, KP);
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST>(S3, S2, S2, DP, LD, KP);
+            cta_zgemm<TM, TN, DPT, KST, NT>(S3, S2, S2, DP, LD, KP);
             __syncthreads();
             // in place: B1 -> S0, B5 -> S1, B4 -> S2, B3 -> S3, B2 -> S4
-            for (int e = tid; e < RL; e += kCtaThreads) {
+            for (int e = tid; e < RL; e += NT) {
                 const int i = e / LD, j = e - i * LD;
                 const double dg = (i == j) ? 1.0 : 0.0;
                 const cplx x1 = S0[e], x2 = S1[e], x3 = S2[e], x6 = S3[e];
@@ -284,22 +285,22 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                               C3B_T18_B11 * x1.y + C3B_T18_B21 * x2.y + C3B_T18_B31 * x3.y + C3B_T18_B61 * x6.y);
             }
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST>(S5, S0, S1, DP, LD, KP);        // B1 B5
+            cta_zgemm<TM, TN, DPT, KST, NT>(S5, S0, S1, DP, LD, KP);        // B1 B5
             __syncthreads();
-            for (int e = tid; e < RL; e += kCtaThreads) {          // A9 -> S5, B3 + A9 -> S3
+            for (int e = tid; e < RL; e += NT) {          // A9 -> S5, B3 + A9 -> S3
                 const cplx a9 = cmake(S5[e].x + S2[e].x, S5[e].y + S2[e].y);
                 S5[e] = a9;
                 S3[e] = cmake(S3[e].x + a9.x, S3[e].y + a9.y);
             }
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST>(S0, S3, S5, DP, LD, KP);        // (B3 + A9) A9
+            cta_zgemm<TM, TN, DPT, KST, NT>(S0, S3, S5, DP, LD, KP);        // (B3 + A9) A9
             __syncthreads();
             cplx* X = S0;
-            for (int e = tid; e < RL; e += kCtaThreads) X[e] = cmake(S0[e].x + S4[e].x, S0[e].y + S4[e].y);
+            for (int e = tid; e < RL; e += NT) X[e] = cmake(S0[e].x + S4[e].x, S0[e].y + S4[e].y);
             __syncthreads();
             for (int i = 0; i < s; ++i) {                          // undo the scaling
                 cplx* nxt = (X == S0) ? S1 : S0;
-                cta_zgemm<TM, TN, DPT, KST>(nxt, X, X, DP, LD, KP);
+                cta_zgemm<TM, TN, DPT, KST, NT>(nxt, X, X, DP, LD, KP);
                 __syncthreads();
                 X = nxt;
             }
@@ -315,16 +316,16 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
                     }
                     phn = cexp_(mu);
                 }
-                for (int e = tid; e < D * D; e += kCtaThreads) {
+                for (int e = tid; e < D * D; e += NT) {
                     const int i = e / D, j = e - i * D;
                     o[e] = cmul(phn, X[i * LD + j]);
                 }
             }
             if (n == n_begin) {
-                for (int e = tid; e < RL; e += kCtaThreads) P[e] = X[e];
+                for (int e = tid; e < RL; e += NT) P[e] = X[e];
                 __syncthreads();
             } else {
-                cta_zgemm<TM, TN, DPT, KST>(Q, X, P, DP, LD, KP);
+                cta_zgemm<TM, TN, DPT, KST, NT>(Q, X, P, DP, LD, KP);
                 __syncthreads();
                 cplx* t = P; P = Q; Q = t;
             }
@@ -332,12 +333,12 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_t18_cta_kernel(const GemmPara
         cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * D * D) : (p.seg_out + ((size_t)b * p.S + sidx) * D * D);
         if (n_end > n_begin) {
             const cplx phu = shifted ? cexp_(mu_acc) : cmake(1.0, 0.0);
-            for (int e = tid; e < D * D; e += kCtaThreads) {
+            for (int e = tid; e < D * D; e += NT) {
                 const int i = e / D, j = e - i * D;
                 o[e] = cmul(phu, P[i * LD + j]);
             }
         } else {
-            for (int e = tid; e < D * D; e += kCtaThreads) o[e] = cmake((e / D) == (e % D) ? 1.0 : 0.0, 0.0);
+            for (int e = tid; e < D * D; e += NT) o[e] = cmake((e / D) == (e % D) ? 1.0 : 0.0, 0.0);
         }
         __syncthreads();
     }
