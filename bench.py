@@ -292,13 +292,52 @@ def run_engine(args):
     torch.cuda.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
+
+    # ---- end to end from pulse PARAMETERS: the control fields are generated on the device (f-2) --------
+    # same gate length / slice count, one DRAG Gaussian per line, per-sample amplitude, angle and detuning
+    rng = np.random.default_rng(4321 + rank)
+    T = N * DT
+    envp = np.zeros((B, K, 1, 9))
+    envp[..., 0, 0] = rng.uniform(0.2, 0.5, (B, K))              # amp
+    envp[..., 0, 1] = T                                          # t_final
+    envp[..., 0, 2] = T / 4                                      # sigma
+    envp[..., 0, 3] = rng.uniform(0, 2 * np.pi, (B, K))          # xy_angle
+    envp[..., 0, 4] = -2 * np.pi * 53e6                          # freq_offset
+    envp[..., 0, 5] = -1.0                                       # delta
+    envp[..., 0, 8] = 1.0
+    env_host = torch.as_tensor(envp).pin_memory()
+    lo_host = torch.as_tensor(np.broadcast_to(2 * np.pi * np.array([5.05e9, 5.65e9]), (B, K)).copy()).pin_memory()
+    shape_t = torch.full((K, 1), 2, dtype=torch.int32, device=dev)         # gaussian_nonorm
+    flags_t = torch.ones((K, 1), dtype=torch.int32, device=dev)            # DRAG quadrature
+    chain_t = torch.as_tensor(np.tile([1.0 / DT, 2e9, 0.3e-9, 1, 0, 1e9, 0, 1, 0, 0, np.nan], (K, 1)), device=dev)
+    sig_buf = torch.empty((B, K, N), dtype=torch.float64, device=dev)
+
+    def params_step(i):
+        sig = engine.generate_signals(env_host, shape_t, flags_t, lo_host, chain_t, 0.0, T, out=sig_buf)   # H2D of the parameters inside
+        U = engine.pwc_closed(h0, hks, sig, DT)
+        if world > 1:
+            U = all_gather_unitaries(U)[rank * B:(rank + 1) * B]
+        U_host.copy_(U, non_blocking=True)
+        torch.cuda.synchronize()
+        return U_host
+
+    for i in range(2):
+        params_step(i)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        params_step(i)
+    torch.cuda.synchronize()
+    barrier()
+    par_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
     if world > 1:
-        t = torch.tensor([ms_total, e2e_s * 1e3, kernel_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_s * 1e3, kernel_ms, par_s * 1e3], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms, kernel_ms = [float(x) for x in t.tolist()]
-        e2e_s = e2e_ms * 1e-3
+        ms_total, e2e_ms, kernel_ms, par_ms = [float(x) for x in t.tolist()]
+        e2e_s, par_s = e2e_ms * 1e-3, par_ms * 1e-3
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
@@ -332,6 +371,11 @@ def run_engine(args):
                        "kernel": "pwc_blk_t18_kernel<9,3> (fused assemble + degree-18 Taylor expm in 5 products + ordered product, 3x3 lane blocks)"},
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": B * K * N * 8,
                     "d2h_bytes_per_step": B * D * D * 16, "api": "c3_b200.propagation.pwc_batch(host signals) -> U.cpu()"},
+            "e2e_from_params": {"value": n_gpus * B * N * args.steps / par_s, "unit": "slices/s",
+                                "h2d_bytes_per_step": int(env_host.numel() * 8 + lo_host.numel() * 8),
+                                "d2h_bytes_per_step": B * D * D * 16,
+                                "api": "engine.generate_signals(host pulse parameters) -> engine.pwc_closed -> U.cpu(): "
+                                       "control fields generated on the device (SURVEY 8f row f-2)"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / dfma_peak, "traffic": traffic, "traffic_unit": "bytes per launch",

@@ -37,6 +37,9 @@ def _worker(rank, world, port, B, results):
         lo, hi = shard_bounds(B, world, rank)
         U2 = all_gather_unitaries(want[lo:hi].clone(), B)
         ok = ok and torch.equal(U2, want)
+        # fused-fidelity variant: the gather carries one float64 per batch element
+        fid = propagate_sharded(lambda s_, c: _fake_propagate(s_, c).diagonal(dim1=1, dim2=2).real.sum(-1), signals, 2.0)
+        ok = ok and fid.shape == (B,) and torch.allclose(fid, want.diagonal(dim1=1, dim2=2).real.sum(-1))
         results[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
