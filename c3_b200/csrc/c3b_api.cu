@@ -785,6 +785,30 @@ int c3b_generate_signals(const double* env_params, const int32_t* env_shape, con
     return C3B_OK;
 }
 
+int c3b_generate_signals_grad(const double* env_params, const int32_t* env_shape, const int32_t* env_flags,
+                              const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
+                              int B, int K, int E, int N, int n_awg_max, const double* gsignals, double* grad_env,
+                              double* grad_lo, double* grad_v2hz, void* stream) {
+    if (B <= 0 || K <= 0 || E <= 0 || N <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d E=%d N=%d)", B, K, E, N);
+    if (!env_params || !env_shape || !env_flags || !lo_freq || !chain || !gsignals || !grad_env || !grad_lo)
+        return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    SignalGradParams gp{};
+    SignalParams& sp = gp.f;
+    sp.env = env_params; sp.shape = env_shape; sp.flags = env_flags; sp.lo_freq = lo_freq; sp.chain = chain;
+    sp.chain_batched = chain_batched; sp.t_start = t_start; sp.t_end = t_end;
+    sp.B = B; sp.K = K; sp.E = E; sp.N = N; sp.out = nullptr;
+    sp.max_awg = (n_awg_max > 0 && n_awg_max <= N) ? n_awg_max : N + 1;
+    sp.max_taps = 1024;
+    gp.gsig = gsignals; gp.genv = grad_env; gp.glo = grad_lo; gp.gv2hz = grad_v2hz;
+    const size_t smem = ((size_t)4 * sp.max_awg + sp.max_taps + (size_t)2 * N) * sizeof(double);
+    if (smem > 200 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gate too long for the on-chip signal-chain gradient (N=%d)", N);
+    CUDA_TRY(cudaFuncSetAttribute(signal_chain_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    signal_chain_grad_kernel<<<B * K, 128, smem, static_cast<cudaStream_t>(stream)>>>(gp);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return C3B_OK;
+}
+
 long long c3b_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 double c3b_last_kernel_ms(void) {

@@ -33,49 +33,96 @@ struct SignalParams {
     double* out;             // [B, K, N]
 };
 
-__device__ __forceinline__ double sigmoid_(double x) { return 1.0 / (1.0 + exp(-x)); }
+// ---- forward-mode dual numbers: the SAME envelope formulas give values (T = double) and parameter derivatives
+// (T = Dual, seeded on one of the 9 envelope parameters) -- the reference differentiates them with tf.GradientTape
+struct Dual {
+    double v, d;
+    __device__ __forceinline__ Dual() : v(0.0), d(0.0) {}
+    __device__ __forceinline__ Dual(double v_) : v(v_), d(0.0) {}
+    __device__ __forceinline__ Dual(double v_, double d_) : v(v_), d(d_) {}
+};
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
+__device__ __forceinline__ Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) { return Dual(a.v / b.v, (a.d * b.v - a.v * b.d) / (b.v * b.v)); }
+__device__ __forceinline__ double t_val(double x) { return x; }
+__device__ __forceinline__ double t_val(Dual x) { return x.v; }
+__device__ __forceinline__ double t_exp(double x) { return exp(x); }
+__device__ __forceinline__ Dual t_exp(Dual x) { const double e = exp(x.v); return Dual(e, e * x.d); }
+__device__ __forceinline__ double t_erf(double x) { return erf(x); }
+__device__ __forceinline__ Dual t_erf(Dual x) { return Dual(erf(x.v), 1.1283791670955126 * exp(-x.v * x.v) * x.d); }
+__device__ __forceinline__ double t_cos(double x) { return cos(x); }
+__device__ __forceinline__ Dual t_cos(Dual x) { return Dual(cos(x.v), -sin(x.v) * x.d); }
+__device__ __forceinline__ double t_sin(double x) { return sin(x); }
+__device__ __forceinline__ Dual t_sin(Dual x) { return Dual(sin(x.v), cos(x.v) * x.d); }
+__device__ __forceinline__ double t_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ Dual t_sqrt(Dual x) { const double r = sqrt(x.v); return Dual(r, 0.5 * x.d / r); }
+__device__ __forceinline__ double t_sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }
+__device__ __forceinline__ Dual t_sigmoid(Dual x) { const double s = 1.0 / (1.0 + exp(-x.v)); return Dual(s, s * (1.0 - s) * x.d); }
 
-__device__ __forceinline__ double shape_value(int id, double t, const double* e) {
+template <typename T>
+__device__ __forceinline__ T shape_value(int id, T t, const T* e) {
     switch (id) {
-        case SHAPE_RECT: return 1.0;
+        case SHAPE_RECT: return T(1.0);
         case SHAPE_GAUSSIAN_NONORM: {
-            const double u = t - e[ENV_TFINAL] / 2, s = e[ENV_SIGMA];
-            return exp(-(u * u) / (2 * s * s));
+            const T u = t - e[ENV_TFINAL] / T(2.0), s = e[ENV_SIGMA];
+            return t_exp(-(u * u) / (T(2.0) * s * s));
         }
         case SHAPE_GAUSSIAN_SIGMA: {
-            const double tf = e[ENV_TFINAL], s = e[ENV_SIGMA], u = t - tf / 2;
-            const double gauss = exp(-(u * u) / (2 * s * s));
-            const double offset = exp(-(tf * tf) / (8 * s * s));
-            const double norm = sqrt(2 * M_PI * s * s) * erf(tf / (sqrt(8.0) * s)) - tf * offset;
+            const T tf = e[ENV_TFINAL], s = e[ENV_SIGMA], u = t - tf / T(2.0);
+            const T gauss = t_exp(-(u * u) / (T(2.0) * s * s));
+            const T offset = t_exp(-(tf * tf) / (T(8.0) * s * s));
+            const T norm = t_sqrt(T(2 * M_PI) * s * s) * t_erf(tf / (T(sqrt(8.0)) * s)) - tf * offset;
             return (gauss - offset) / norm;
         }
-        case SHAPE_COSINE: return 0.5 * (1 - cos(2 * M_PI * t / e[ENV_TFINAL]));
+        case SHAPE_COSINE: return T(0.5) * (T(1.0) - t_cos(T(2 * M_PI) * t / e[ENV_TFINAL]));
         case SHAPE_FLATTOP:
-            return (1 + erf((t - e[ENV_TUP]) / e[ENV_RISEFALL])) / 2 * (1 + erf((-t + e[ENV_TDOWN]) / e[ENV_RISEFALL])) / 2;
-        default: return 0.0;
+            return (T(1.0) + t_erf((t - e[ENV_TUP]) / e[ENV_RISEFALL])) / T(2.0) *
+                   (T(1.0) + t_erf((-t + e[ENV_TDOWN]) / e[ENV_RISEFALL])) / T(2.0);
+        default: return T(0.0);
     }
 }
 
-__device__ __forceinline__ double shape_deriv(int id, double t, const double* e) {
+template <typename T>
+__device__ __forceinline__ T shape_deriv(int id, T t, const T* e) {
     switch (id) {
         case SHAPE_GAUSSIAN_NONORM:
         case SHAPE_GAUSSIAN_SIGMA: {
-            const double tf = e[ENV_TFINAL], s = e[ENV_SIGMA], u = t - tf / 2;
-            double g = exp(-(u * u) / (2 * s * s)) * (-u / (s * s));
+            const T tf = e[ENV_TFINAL], s = e[ENV_SIGMA], u = t - tf / T(2.0);
+            T g = t_exp(-(u * u) / (T(2.0) * s * s)) * (-u / (s * s));
             if (id == SHAPE_GAUSSIAN_SIGMA) {
-                const double offset = exp(-(tf * tf) / (8 * s * s));
-                g /= sqrt(2 * M_PI * s * s) * erf(tf / (sqrt(8.0) * s)) - tf * offset;
+                const T offset = t_exp(-(tf * tf) / (T(8.0) * s * s));
+                g = g / (t_sqrt(T(2 * M_PI) * s * s) * t_erf(tf / (T(sqrt(8.0)) * s)) - tf * offset);
             }
             return g;
         }
-        case SHAPE_COSINE: return 0.5 * sin(2 * M_PI * t / e[ENV_TFINAL]) * 2 * M_PI / e[ENV_TFINAL];
+        case SHAPE_COSINE: return T(0.5) * t_sin(T(2 * M_PI) * t / e[ENV_TFINAL]) * T(2 * M_PI) / e[ENV_TFINAL];
         case SHAPE_FLATTOP: {
-            const double rf = e[ENV_RISEFALL], up = (t - e[ENV_TUP]) / rf, dn = (-t + e[ENV_TDOWN]) / rf;
-            const double c = 2 / sqrt(M_PI) / rf;
-            return (c * exp(-up * up) * (1 + erf(dn)) - (1 + erf(up)) * c * exp(-dn * dn)) / 4;
+            const T rf = e[ENV_RISEFALL], up = (t - e[ENV_TUP]) / rf, dn = (-t + e[ENV_TDOWN]) / rf;
+            const T c = T(2 / sqrt(M_PI)) / rf;
+            return (c * t_exp(-(up * up)) * (T(1.0) + t_erf(dn)) - (T(1.0) + t_erf(up)) * c * t_exp(-(dn * dn))) / T(4.0);
         }
-        default: return 0.0;
+        default: return T(0.0);
     }
+}
+
+// One envelope's contribution to the AWG sample at time t (offset from the instruction start):
+// amp * (mask * shape [- value one sample before the start] - i * delta * mask * shape' * dt) * exp(i (xy - w_off t))
+// (c3/signal/gates.py:341-370, c3/signal/pulse.py:93-180).  off0 / off1 are the first two grid offsets.
+template <typename T>
+__device__ __forceinline__ void awg_term(int id, int fl, double t, const T* ev, double off0, double off1, T& re, T& im) {
+    const double dts = off1 - off0;
+    const T tt(t);
+    const T mask = t_sigmoid(T((t / dts + 0.001) * 1e6)) * t_sigmoid((T(0.999) * ev[ENV_TFINAL] - tt) / T(dts) * T(1e6));
+    T sv = shape_value<T>(id, tt, ev);
+    if (fl & 2) sv = sv - shape_value<T>(id, T(2 * off0 - off1), ev);
+    const T env_re = mask * sv;
+    const T env_im = (fl & 1) ? -(mask * shape_deriv<T>(id, tt, ev) * T(dts)) * ev[ENV_DELTA] : T(0.0);
+    const T ph = ev[ENV_XY] - ev[ENV_FREQ_OFFSET] * tt;
+    const T cs = t_cos(ph), sn = t_sin(ph);
+    re = ev[ENV_AMP] * (env_re * cs - env_im * sn);
+    im = ev[ENV_AMP] * (env_re * sn + env_im * cs);
 }
 
 // numpy.linspace(start, stop, num)[i]
@@ -91,6 +138,104 @@ __device__ __forceinline__ double flux_factor(double p, double phi0, double d, b
     return has_d ? sqrt(sqrt(c * c + d * d * s * s)) : sqrt(fabs(c));
 }
 
+// per-(sample, line) view of the chain: grids, resampling ratio, response variant
+struct ChainCtx {
+    const double* ch;
+    double sim_res, awg_res, rise, a0, a1, off0, off1, s0, s1, ratio, w_lo;
+    int resp_kind, out_kind, n_awg, N, shift, taps;
+    bool has_d;
+};
+
+__device__ __forceinline__ ChainCtx chain_ctx(const SignalParams& p, const int bk, const int k) {
+    ChainCtx c;
+    c.ch = p.chain + (p.chain_batched ? (size_t)bk : (size_t)k) * CH_NPAR;
+    c.sim_res = c.ch[CH_SIM_RES]; c.awg_res = c.ch[CH_AWG_RES]; c.rise = c.ch[CH_RISE_TIME];
+    c.resp_kind = (int)c.ch[CH_RESP_KIND]; c.out_kind = (int)c.ch[CH_OUT_KIND];
+    const double span = fabs(p.t_start - p.t_end);
+    c.n_awg = (int)(span * c.awg_res);
+    c.N = p.N;
+    const double dt_awg = 1.0 / c.awg_res, dt_sim = 1.0 / c.sim_res;
+    c.a0 = p.t_start + dt_awg / 2; c.a1 = p.t_end - dt_awg / 2;
+    c.off0 = linspace_at(c.a0, c.a1, c.n_awg, 0) - p.t_start;
+    c.off1 = c.n_awg > 1 ? linspace_at(c.a0, c.a1, c.n_awg, 1) - p.t_start : c.off0 + dt_awg;
+    c.s0 = p.t_start + dt_sim / 2; c.s1 = p.t_end - dt_sim / 2;
+    c.ratio = (double)c.n_awg / (double)c.N;
+    c.w_lo = p.lo_freq[bk];
+    c.shift = (c.resp_kind == 1) ? 1 : 0;
+    c.taps = (c.resp_kind != 0) ? (int)floor(c.rise * c.sim_res) : 0;
+    c.has_d = c.ch[CH_D] == c.ch[CH_D];                  // NaN: symmetric SQUID
+    return c;
+}
+
+// AWG samples: sum of the line's envelopes on the AWG time grid -> sI, sQ [n_awg]
+__device__ __forceinline__ void fill_awg(const SignalParams& p, const ChainCtx& c, const int b, const int k, double* sI, double* sQ) {
+    for (int j = threadIdx.x; j < c.n_awg; j += blockDim.x) {
+        const double t = linspace_at(c.a0, c.a1, c.n_awg, j) - p.t_start;
+        double re = 0.0, im = 0.0;
+        for (int e = 0; e < p.E; ++e) {
+            const int id = p.shape[k * p.E + e];
+            if (id < 0) continue;
+            const double* ev = p.env + (((size_t)b * p.K + k) * p.E + e) * ENV_NPAR;
+            double tr, ti;
+            awg_term<double>(id, p.flags[k * p.E + e], t, ev, c.off0, c.off1, tr, ti);
+            re += tr;
+            im += ti;
+        }
+        sI[j] = re;
+        sQ[j] = im;
+    }
+}
+
+// normalised Gaussian rise function of the Response device -> sR [taps]; contains CTA barriers
+__device__ __forceinline__ void fill_taps(const ChainCtx& c, double* sR, double* s_norm) {
+    if (c.resp_kind != 0) {
+        const double cen = (c.resp_kind == 2) ? (c.rise - 1 / c.sim_res) / 2 : (c.rise + 1 / c.sim_res) / 2;
+        const double sg = c.rise / 4;
+        const double offset = exp(-((-1 - cen) * (-1 - cen)) / (2 * sg * sg));
+        for (int m = threadIdx.x; m < c.taps; m += blockDim.x) {
+            const double tr = linspace_at(0.0, c.rise, c.taps, m);
+            sR[m] = exp(-((tr - cen) * (tr - cen)) / (2 * sg * sg)) - offset;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int m = 0; m < c.taps; ++m) s += sR[m];
+            *s_norm = s;
+        }
+        __syncthreads();
+        for (int m = threadIdx.x; m < c.taps; m += blockDim.x) sR[m] = sR[m] / *s_norm;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int awg_index(const ChainCtx& c, const int j) {   // DigitalToAnalog, half-pixel nearest
+    const int idx = (int)floor((j + 0.5) * c.ratio);
+    return idx < c.n_awg - 1 ? idx : c.n_awg - 1;
+}
+
+// band-limited I/Q at simulation sample n: resample + direct convolution with the rise function
+__device__ __forceinline__ void iq_at(const ChainCtx& c, const double* sI, const double* sQ, const double* sR, const int n,
+                                      double& vi, double& vq) {
+    if (c.resp_kind == 0) {
+        const int idx = awg_index(c, n);
+        vi = sI[idx];
+        vq = sQ[idx];
+        return;
+    }
+    vi = 0.0; vq = 0.0;
+    for (int m = 0; m < c.taps; ++m) {
+        const int j = n - c.shift - m;
+        if (j < 0) break;
+        const int idx = awg_index(c, j);
+        vi = fma(sR[m], sI[idx], vi);
+        vq = fma(sR[m], sQ[idx], vq);
+    }
+}
+
+__device__ __forceinline__ double flux_freq(const ChainCtx& c, const double phi) {
+    return (c.ch[CH_OMEGA0] - c.ch[CH_ANHAR]) * flux_factor(phi, c.ch[CH_PHI0], c.ch[CH_D], c.has_d) + c.ch[CH_ANHAR];
+}
+
 __global__ void __launch_bounds__(128) signal_chain_kernel(const SignalParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sI = reinterpret_cast<double*>(smem_raw);    // [max_awg]
@@ -100,106 +245,158 @@ __global__ void __launch_bounds__(128) signal_chain_kernel(const SignalParams p)
 
     const int bk = blockIdx.x;
     const int b = bk / p.K, k = bk - b * p.K;
-    const double* ch = p.chain + (p.chain_batched ? (size_t)bk : (size_t)k) * CH_NPAR;
-    const double sim_res = ch[CH_SIM_RES], awg_res = ch[CH_AWG_RES], rise = ch[CH_RISE_TIME];
-    const int resp_kind = (int)ch[CH_RESP_KIND], out_kind = (int)ch[CH_OUT_KIND];
-    const double span = fabs(p.t_start - p.t_end);
-    const int n_awg = (int)(span * awg_res);
-    const int N = p.N;
-    const double dt_awg = 1.0 / awg_res, dt_sim = 1.0 / sim_res;
-    const double a0 = p.t_start + dt_awg / 2, a1 = p.t_end - dt_awg / 2;
+    const ChainCtx c = chain_ctx(p, bk, k);
+    fill_awg(p, c, b, k, sI, sQ);
+    fill_taps(c, sR, &s_norm);
 
-    // ---- AWG samples: sum of the line's envelopes on the AWG time grid -------------------------------------
-    const double step = n_awg > 1 ? linspace_at(a0, a1, n_awg, 1) - linspace_at(a0, a1, n_awg, 0) : dt_awg;  // ts[1] - ts[0]
-    const double off0 = linspace_at(a0, a1, n_awg, 0) - p.t_start;
-    const double off1 = n_awg > 1 ? linspace_at(a0, a1, n_awg, 1) - p.t_start : off0 + dt_awg;
-    const double dts = off1 - off0;                      // ts_off[1] - ts_off[0]
-    for (int j = threadIdx.x; j < n_awg; j += blockDim.x) {
-        const double t = linspace_at(a0, a1, n_awg, j) - p.t_start;
-        double re = 0.0, im = 0.0;
-        for (int e = 0; e < p.E; ++e) {
-            const int id = p.shape[k * p.E + e];
-            if (id < 0) continue;
-            const int fl = p.flags[k * p.E + e];
-            const double* ev = p.env + (((size_t)b * p.K + k) * p.E + e) * ENV_NPAR;
-            const double tfin = ev[ENV_TFINAL];
-            const double mask = sigmoid_((t / dts + 0.001) * 1e6) * sigmoid_((0.999 * tfin - t) / dts * 1e6);
-            double sv = shape_value(id, t, ev);
-            if (fl & 2) sv -= shape_value(id, 2 * off0 - off1, ev);
-            const double env_re = mask * sv;
-            const double env_im = (fl & 1) ? -(mask * shape_deriv(id, t, ev) * dts) * ev[ENV_DELTA] : 0.0;
-            double sn, cs;
-            sincos(ev[ENV_XY] - ev[ENV_FREQ_OFFSET] * t, &sn, &cs);
-            const double amp = ev[ENV_AMP];
-            re += amp * (env_re * cs - env_im * sn);
-            im += amp * (env_re * sn + env_im * cs);
-        }
-        sI[j] = re;
-        sQ[j] = im;
+    // ---- simulation grid: resample, convolve, mix with the LO, convert ------------------------------------------
+    const double f_ref = (c.out_kind == 1) ? flux_freq(c, c.ch[CH_PHI]) : 0.0;
+    double* out = p.out + (size_t)bk * c.N;
+    for (int n = threadIdx.x; n < c.N; n += blockDim.x) {
+        double vi, vq;
+        iq_at(c, sI, sQ, sR, n, vi, vq);
+        const double t = linspace_at(c.s0, c.s1, c.N, n);
+        double sn, cs;
+        sincos(c.w_lo * t, &sn, &cs);
+        const double mixed = cs * vi + sn * vq;
+        out[n] = (c.out_kind == 1) ? flux_freq(c, c.ch[CH_PHI] + mixed) - f_ref : mixed * c.ch[CH_V2HZ];
     }
-    (void)step;
+}
 
-    // ---- Gaussian rise function of the Response device ---------------------------------------------------------
-    int taps = 0;
-    if (resp_kind != 0) {
-        taps = (int)floor(rise * sim_res);
-        const double cen = (resp_kind == 2) ? (rise - 1 / sim_res) / 2 : (rise + 1 / sim_res) / 2;
-        const double sg = rise / 4;
-        const double offset = exp(-((-1 - cen) * (-1 - cen)) / (2 * sg * sg));
-        for (int m = threadIdx.x; m < taps; m += blockDim.x) {
-            const double tr = linspace_at(0.0, rise, taps, m);
-            sR[m] = exp(-((tr - cen) * (tr - cen)) / (2 * sg * sg)) - offset;
+// ---- reverse mode: dL/d(pulse parameters) from dL/d(signals) --------------------------------------------------------
+// The chain is linear from the AWG samples to the mixer output, so its adjoint is exact and cheap:
+//   h[n]   = gsig[n] * d out / d mixed * (cos, sin)(w t_n)
+//   a[j]   = sum over the simulation samples j' resampled from AWG sample j of sum_m r[m] h[j' + shift + m]
+//   dL/dp  = sum_j a_I[j] dI_j/dp + a_Q[j] dQ_j/dp, with dI/dp, dQ/dp from the dual-number envelope evaluation
+// plus the direct terms for the carrier frequency and V_to_Hz.  Replaces tf.GradientTape through
+// Generator.generate_signals (the reference's gradient-based optimal control of pulse parameters,
+// c3/optimizers/optimalcontrol.py:200-228).
+struct SignalGradParams {
+    SignalParams f;          // forward description (f.out unused)
+    const double* gsig;      // [B, K, N]
+    double* genv;            // [B, K, E, ENV_NPAR]
+    double* glo;             // [B, K]
+    double* gv2hz;           // [B, K] or null
+};
+
+__device__ __forceinline__ double block_sum_128(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+}
+
+__global__ void __launch_bounds__(128) signal_chain_grad_kernel(const SignalGradParams g) {
+    const SignalParams& p = g.f;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sI = reinterpret_cast<double*>(smem_raw);    // [max_awg] forward AWG samples
+    double* sQ = sI + p.max_awg;
+    double* aI = sQ + p.max_awg;                         // [max_awg] adjoint of the AWG samples
+    double* aQ = aI + p.max_awg;
+    double* sR = aQ + p.max_awg;                         // [max_taps]
+    double* hI = sR + p.max_taps;                        // [N]
+    double* hQ = hI + p.N;
+    __shared__ double s_norm;
+    __shared__ double red[4];
+
+    const int bk = blockIdx.x;
+    const int b = bk / p.K, k = bk - b * p.K;
+    const ChainCtx c = chain_ctx(p, bk, k);
+    fill_awg(p, c, b, k, sI, sQ);
+    fill_taps(c, sR, &s_norm);
+
+    // ---- pass 1 over the simulation grid: direct terms and h -------------------------------------------------------
+    const double* gs = g.gsig + (size_t)bk * c.N;
+    double acc_lo = 0.0, acc_v = 0.0;
+    for (int n = threadIdx.x; n < c.N; n += blockDim.x) {
+        double vi, vq;
+        iq_at(c, sI, sQ, sR, n, vi, vq);
+        const double t = linspace_at(c.s0, c.s1, c.N, n);
+        double sn, cs;
+        sincos(c.w_lo * t, &sn, &cs);
+        const double mixed = cs * vi + sn * vq;
+        double dout;                                      // d out / d mixed
+        if (c.out_kind == 1) {
+            const double x = M_PI * (c.ch[CH_PHI] + mixed) / c.ch[CH_PHI0];
+            const double cx = cos(x), sx = sin(x);
+            double dfac;
+            if (c.has_d) {
+                const double d2 = c.ch[CH_D] * c.ch[CH_D];
+                const double q = cx * cx + d2 * sx * sx;
+                dfac = 0.5 * (d2 - 1.0) * sx * cx / (sqrt(sqrt(q)) * sqrt(q));
+            } else {
+                dfac = -0.5 * sx * (cx >= 0 ? 1.0 : -1.0) / sqrt(fabs(cx));
+            }
+            dout = (c.ch[CH_OMEGA0] - c.ch[CH_ANHAR]) * dfac * M_PI / c.ch[CH_PHI0];
+        } else {
+            dout = c.ch[CH_V2HZ];
+            acc_v += gs[n] * mixed;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double s = 0.0;
-            for (int m = 0; m < taps; ++m) s += sR[m];
-            s_norm = s;
-        }
-        __syncthreads();
-        for (int m = threadIdx.x; m < taps; m += blockDim.x) sR[m] = sR[m] / s_norm;
+        const double gg = gs[n] * dout;
+        hI[n] = gg * cs;
+        hQ[n] = gg * sn;
+        acc_lo += gg * t * (-sn * vi + cs * vq);
+    }
+    const double tot_lo = block_sum_128(acc_lo, red);
+    const double tot_v = block_sum_128(acc_v, red);
+    if (threadIdx.x == 0) {
+        g.glo[bk] = tot_lo;
+        if (g.gv2hz) g.gv2hz[bk] = tot_v;
     }
     __syncthreads();
 
-    // ---- simulation grid: resample, convolve, mix with the LO, convert ------------------------------------------
-    const double s0 = p.t_start + dt_sim / 2, s1 = p.t_end - dt_sim / 2;
-    const double ratio = (double)n_awg / (double)N;
-    const double w_lo = p.lo_freq[bk];
-    const int shift = (resp_kind == 1) ? 1 : 0;
-    const bool has_d = ch[CH_D] == ch[CH_D];             // NaN: symmetric SQUID
-    double f_ref = 0.0;
-    if (out_kind == 1) f_ref = (ch[CH_OMEGA0] - ch[CH_ANHAR]) * flux_factor(ch[CH_PHI], ch[CH_PHI0], ch[CH_D], has_d) + ch[CH_ANHAR];
-    double* out = p.out + (size_t)bk * N;
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        double vi, vq;
-        if (resp_kind == 0) {
-            int idx = (int)floor((n + 0.5) * ratio);
-            idx = idx < n_awg - 1 ? idx : n_awg - 1;
-            vi = sI[idx];
-            vq = sQ[idx];
-        } else {
-            vi = 0.0; vq = 0.0;
-            for (int m = 0; m < taps; ++m) {
-                const int j = n - shift - m;
-                if (j < 0) break;
-                int idx = (int)floor((j + 0.5) * ratio);
-                idx = idx < n_awg - 1 ? idx : n_awg - 1;
-                const double r = sR[m];
-                vi = fma(r, sI[idx], vi);
-                vq = fma(r, sQ[idx], vq);
+    // ---- pass 2: adjoint of convolution + resampling, one AWG sample per thread (deterministic order) ---------------
+    for (int j = threadIdx.x; j < c.n_awg; j += blockDim.x) {
+        // simulation samples [lo, hi) that the DigitalToAnalog maps to AWG sample j (the map is monotone)
+        int lo = (int)ceil(j / c.ratio - 0.5) - 1;
+        if (lo < 0) lo = 0;
+        while (lo < c.N && awg_index(c, lo) < j) ++lo;
+        while (lo > 0 && awg_index(c, lo - 1) >= j) --lo;
+        double ai = 0.0, aq = 0.0;
+        for (int jp = lo; jp < c.N && awg_index(c, jp) == j; ++jp) {
+            if (c.resp_kind == 0) {
+                ai += hI[jp];
+                aq += hQ[jp];
+            } else {
+                for (int m = 0; m < c.taps; ++m) {
+                    const int n = jp + c.shift + m;
+                    if (n >= c.N) break;
+                    ai = fma(sR[m], hI[n], ai);
+                    aq = fma(sR[m], hQ[n], aq);
+                }
             }
         }
-        const double t = linspace_at(s0, s1, N, n);
-        double sn, cs;
-        sincos(w_lo * t, &sn, &cs);
-        const double mixed = cs * vi + sn * vq;
-        double v;
-        if (out_kind == 1) {
-            v = (ch[CH_OMEGA0] - ch[CH_ANHAR]) * flux_factor(ch[CH_PHI] + mixed, ch[CH_PHI0], ch[CH_D], has_d) + ch[CH_ANHAR] - f_ref;
-        } else {
-            v = mixed * ch[CH_V2HZ];
+        aI[j] = ai;
+        aQ[j] = aq;
+    }
+    __syncthreads();
+
+    // ---- pass 3: envelope parameter derivatives by dual numbers --------------------------------------------------------
+    for (int e = 0; e < p.E; ++e) {
+        const int id = p.shape[k * p.E + e];
+        double* out = g.genv + (((size_t)b * p.K + k) * p.E + e) * ENV_NPAR;
+        if (id < 0) {
+            if (threadIdx.x < ENV_NPAR) out[threadIdx.x] = 0.0;
+            continue;
         }
-        out[n] = v;
+        const int fl = p.flags[k * p.E + e];
+        const double* ev = p.env + (((size_t)b * p.K + k) * p.E + e) * ENV_NPAR;
+        for (int q = 0; q < ENV_NPAR; ++q) {
+            Dual dv[ENV_NPAR];
+#pragma unroll
+            for (int i = 0; i < ENV_NPAR; ++i) dv[i] = Dual(ev[i], i == q ? 1.0 : 0.0);
+            double acc = 0.0;
+            for (int j = threadIdx.x; j < c.n_awg; j += blockDim.x) {
+                const double t = linspace_at(c.a0, c.a1, c.n_awg, j) - p.t_start;
+                Dual re, im;
+                awg_term<Dual>(id, fl, t, dv, c.off0, c.off1, re, im);
+                acc += aI[j] * re.d + aQ[j] * im.d;
+            }
+            const double tot = block_sum_128(acc, red);
+            if (threadIdx.x == 0) out[q] = tot;
+        }
     }
 }
 

@@ -373,6 +373,61 @@ def generate_signals(env_params, env_shape, env_flags, lo_freq, chain, t_start: 
     return out
 
 
+def generate_signals_grad(env_params, env_shape, env_flags, lo_freq, chain, t_start: float, t_end: float, gsignals,
+                          device=None):
+    """(grad_env [B,K,E,9], grad_lo [B,K], grad_v2hz [B,K]) from dL/dsignals [B,K,N] (c3b_generate_signals_grad)."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        env_params = _as(env_params, torch.float64, device)
+        B, K, E, _ = env_params.shape
+        env_shape = _as(env_shape, torch.int32, device)
+        env_flags = _as(env_flags, torch.int32, device)
+        lo_freq = _as(lo_freq, torch.float64, device)
+        chain = _as(chain, torch.float64, device)
+        gsignals = _as(gsignals, torch.float64, device)
+        batched = chain.dim() == 3
+        N = gsignals.shape[-1]
+        if tuple(gsignals.shape) != (B, K, N):
+            raise ValueError("C3:ERROR: gsignals must be [B,K,N]")
+        ch = chain.reshape(-1, 11)
+        n_awg_max = int((abs(float(t_start) - float(t_end)) * ch[:, 1]).max().item()) + 1
+        genv = torch.empty((B, K, E, 9), dtype=torch.float64, device=device)
+        glo = torch.empty((B, K), dtype=torch.float64, device=device)
+        gv = torch.empty((B, K), dtype=torch.float64, device=device)
+        _lib.check(lib.c3b_generate_signals_grad(_ptr(env_params), _ptr(env_shape), _ptr(env_flags), _ptr(lo_freq),
+                                                 _ptr(chain), int(batched), float(t_start), float(t_end), B, K, E, N,
+                                                 n_awg_max, _ptr(gsignals), _ptr(genv), _ptr(glo), _ptr(gv), _stream()))
+    return genv, glo, gv
+
+
+class _SignalChainFn(torch.autograd.Function):
+    """signals = chain(env_params, lo_freq), differentiable w.r.t. both."""
+
+    @staticmethod
+    def forward(ctx, env_params, lo_freq, env_shape, env_flags, chain, t_start, t_end):
+        sig = generate_signals(env_params.detach(), env_shape, env_flags, lo_freq.detach(), chain, t_start, t_end)
+        ctx.save_for_backward(env_params.detach(), lo_freq.detach())
+        ctx.static = (env_shape, env_flags, chain, t_start, t_end)
+        return sig
+
+    @staticmethod
+    def backward(ctx, gsig):
+        env_params, lo_freq = ctx.saved_tensors
+        env_shape, env_flags, chain, t_start, t_end = ctx.static
+        genv, glo, _ = generate_signals_grad(env_params, env_shape, env_flags, lo_freq, chain, t_start, t_end, gsig.contiguous())
+        return genv, glo, None, None, None, None, None
+
+
+def generate_signals_autograd(env_params: torch.Tensor, lo_freq: torch.Tensor, env_shape, env_flags, chain,
+                              t_start: float, t_end: float) -> torch.Tensor:
+    """Differentiable control fields [B,K,N]: gradients of any loss flow back to the pulse parameters
+    ``env_params [B,K,E,9]`` and the carrier frequencies ``lo_freq [B,K]`` (CUDA float64 tensors)."""
+    if not (env_params.is_cuda and lo_freq.is_cuda):
+        raise ValueError("C3:ERROR: generate_signals_autograd needs CUDA tensors")
+    return _SignalChainFn.apply(env_params, lo_freq, env_shape, env_flags, chain, float(t_start), float(t_end))
+
+
 def kron(A, B, device=None) -> torch.Tensor:
     """(Batched) Kronecker product with the row-major convention of tf_kron."""
     lib = _lib.load()

@@ -138,6 +138,18 @@ int c3b_generate_signals(const double* env_params, const int32_t* env_shape, con
                          const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
                          int B, int K, int E, int N, double* signals_out, void* stream);
 
+/* Reverse mode of c3b_generate_signals: from dL/d signals [B,K,N] (e.g. the output of c3b_pwc_closed_grad) to the
+ * gradient with respect to the pulse parameters -- what tf.GradientTape propagates through
+ * Generator.generate_signals in the reference's gradient-based optimal control (c3/optimizers/optimalcontrol.py:200-228).
+ *   grad_env  [B,K,E,9]  dL / d(amp, t_final, sigma, xy_angle, freq_offset, delta, t_up, t_down, risefall)
+ *   grad_lo   [B,K]      dL / d(carrier frequency)
+ *   grad_v2hz [B,K]      dL / d(V_to_Hz) (VoltsToHertz lines; 0 for FluxTuning lines), or NULL
+ *   n_awg_max            largest AWG sample count of any line (bounds shared memory); <= 0: N + 1 */
+int c3b_generate_signals_grad(const double* env_params, const int32_t* env_shape, const int32_t* env_flags,
+                              const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
+                              int B, int K, int E, int N, int n_awg_max, const double* gsignals, double* grad_env,
+                              double* grad_lo, double* grad_v2hz, void* stream);
+
 /* Ordered product of M matrices per batch row: out[b] = mats[b,M-1] ... mats[b,0].
  *   replaces tf_matmul_left (c3/utils/tf_utils.py:120-129) and tf_matmul_n (:144-193).
  *   mats [B,M,D,D], out [B,D,D]. */

@@ -132,3 +132,157 @@ def test_parameters_to_propagators_on_device(gen_mod):
         assert _rel(sig[b].cpu().numpy(), want_sig) < RTOL
         want_U = orc.propagate_batch(m.h0, m.hks, want_sig[None], dt)[0]
         assert np.linalg.norm(U[b].cpu().numpy() - want_U) / np.linalg.norm(want_U) < 1e-10
+
+
+def _oracle_signals(env, sid, flags, lo, chain, shapes, t_start, t_end, resp_kind):
+    """Oracle control fields [B,K,N] for the flat parameter tables the C ABI takes."""
+    B, K, E, _ = env.shape
+    out = []
+    for b in range(B):
+        rows = []
+        for k in range(K):
+            specs = []
+            for e in range(E):
+                if sid[k, e] < 0:
+                    continue
+                v = env[b, k, e]
+                specs.append(so.EnvelopeSpec(shape=shapes[k][e], amp=v[0], t_final=v[1], sigma=v[2], xy_angle=v[3],
+                                             freq_offset=v[4], delta=v[5], t_up=v[6], t_down=v[7], risefall=v[8],
+                                             drag=bool(flags[k][e] & 1), use_t_before=bool(flags[k][e] & 2)))
+            c = chain[k] if chain.ndim == 2 else chain[b, k]
+            cs = so.ChainSpec(sim_res=c[0], awg_res=c[1], rise_time=c[2], response_fft=(resp_kind == 2), v2hz=c[5],
+                              flux=None if c[4] == 0 else dict(phi=c[6], phi_0=c[7], omega_0=c[8], anhar=c[9],
+                                                               d=None if np.isnan(c[10]) else c[10]))
+            if resp_kind == 0:
+                st = {}
+                so.generate_signal(specs, lo[b, k], t_start, t_end, cs, st)
+                mixed = so.mixer(st["lo_i"], st["lo_q"], st["dac_i"], st["dac_q"])
+                rows.append(mixed * cs.v2hz if cs.flux is None else so.flux_tuning(mixed, **cs.flux))
+            else:
+                rows.append(so.generate_signal(specs, lo[b, k], t_start, t_end, cs)[0])
+        out.append(np.stack(rows))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("resp_kind", [0, 1, 2])
+def test_signal_chain_gradient_vs_oracle_finite_differences(gen_mod, resp_kind):
+    """Reverse mode of the chain (c3b_generate_signals_grad) against central finite differences of the ORACLE for
+    every envelope parameter, the carrier frequency and V_to_Hz; L = sum w * signals with random weights."""
+    from c3_b200 import engine
+    rng = np.random.default_rng(5 + resp_kind)
+    B, K, E = 2, 3, 2
+    t_start, t_end = 0.0, 9.7e-9
+    shapes = [["gaussian_nonorm", "flattop"], ["cosine", "gaussian_sigma"], ["gaussian_nonorm", None]]
+    flags = np.array([[1, 2], [1 | 2, 0], [1, 0]], dtype=np.int32)
+    env = np.zeros((B, K, E, 9))
+    sid = -np.ones((K, E), dtype=np.int32)
+    for k in range(K):
+        for e in range(E):
+            if shapes[k][e] is None:
+                continue
+            sid[k, e] = gen_mod.SHAPE_IDS[shapes[k][e]]
+            # fixed pulse lengths: a random t_final can put an AWG sample inside the (dt * 1e-6 wide) edge of the
+            # reference's sigmoid mask, where a finite difference sees a jump
+            tf_ = 8.3e-9 + 0.23e-9 * (np.arange(B) + 2 * e + 0.5 * k)
+            env[:, k, e] = np.stack([rng.uniform(0.1, 0.6, B), tf_, tf_ / rng.uniform(3, 5, B), rng.uniform(-3, 3, B),
+                                     rng.uniform(-80e6, 80e6, B) * TP, rng.uniform(-2, 2, B), rng.uniform(1e-9, 2e-9, B),
+                                     tf_ - rng.uniform(1e-9, 2e-9, B), rng.uniform(0.5e-9, 1.5e-9, B)], axis=1)
+    ts_awg = so.create_ts(t_start, t_end, 1.7e9)
+    assert np.abs(ts_awg[None, :] - 0.999 * env[..., 1].reshape(-1, 1)).min() > 1e-12
+    env[:, 1, 1, 0] *= 2e-9          # gaussian_sigma has unit AREA (values ~ 1/sigma): keep the line O(1) V
+    lo = rng.uniform(4e9, 6e9, (B, K)) * TP
+    chain = np.zeros((K, 11))
+    for k in range(K):
+        chain[k] = [100e9, 1.7e9, 0.37e-9, resp_kind, 0, 1e9 * (1 + 0.1 * k), 0, 1, 0, 0, np.nan]
+    chain[2, 4:] = [1, 0, 2.3, 10.0, 8.1e9 * TP, -286e6 * TP, 0.36 if resp_kind else np.nan]
+    N = engine.signal_slice_num(t_start, t_end, 100e9)      # int(9.7e-9 * 100e9) = 969 in floating point
+    w = rng.normal(size=(B, K, N))
+    genv, glo, gv = engine.generate_signals_grad(env, sid, flags, lo, chain, t_start, t_end, w)
+    genv, glo, gv = genv.cpu().numpy(), glo.cpu().numpy(), gv.cpu().numpy()
+
+    def loss(env_, lo_, chain_, b=None, k=None):
+        """sum w * signals restricted to one (sample, line) when given: the finite difference of a parameter of
+        that line is then not drowned in the rounding noise of the other lines' sums"""
+        if b is None:
+            return float(np.sum(w * _oracle_signals(env_, sid, flags, lo_, chain_, shapes, t_start, t_end, resp_kind)))
+        sig = _oracle_signals(env_[b:b + 1, k:k + 1], sid[k:k + 1], flags[k:k + 1], lo_[b:b + 1, k:k + 1],
+                              chain_[k:k + 1], shapes[k:k + 1], t_start, t_end, resp_kind)
+        return float(np.sum(w[b, k] * sig[0, 0]))
+
+    def fd(x, index, rel):
+        h = abs(x[index]) * rel if x[index] != 0 else rel
+        xp, xm = x.copy(), x.copy()
+        xp[index] += h
+        xm[index] -= h
+        return xp, xm, 2 * h
+
+    checked = 0
+    for b in range(B):
+        for k in range(K):
+            for e in range(E):
+                if sid[k, e] < 0:
+                    assert np.all(genv[b, k, e] == 0)
+                    continue
+                for q in range(9):
+                    xp, xm, h2 = fd(env, (b, k, e, q), 1e-6)
+                    want = (loss(xp, lo, chain, b, k) - loss(xm, lo, chain, b, k)) / h2
+                    tol = 2e-5 * max(abs(want), abs(genv[b, k, e, q])) + 1e-7 * np.abs(genv[b, k, :, q]).max()
+                    assert abs(genv[b, k, e, q] - want) <= tol, (b, k, e, q, genv[b, k, e, q], want)
+                    checked += 1
+            xp, xm, h2 = fd(lo, (b, k), 1e-9)
+            want = (loss(env, xp, chain, b, k) - loss(env, xm, chain, b, k)) / h2
+            assert abs(glo[b, k] - want) < 1e-4 * abs(want) + 1e-6 * np.abs(glo).max(), (b, k, glo[b, k], want)
+    for k in range(K):
+        if chain[k, 4] == 0:
+            xp, xm, h2 = fd(chain, (k, 5), 1e-6)
+            want = (loss(env, lo, xp) - loss(env, lo, xm)) / h2
+            assert abs(gv[:, k].sum() - want) < 1e-6 * abs(want)
+        else:
+            assert np.all(gv[:, k] == 0)
+    assert checked == 2 * 5 * 9
+
+
+def test_pulse_parameter_gradient_through_the_whole_pipeline(gen_mod):
+    """parameters -> fields (f-2) -> propagators (a1-a11) -> infidelity (f-3) -> backward (f-3, f-1, f-2) on the
+    device: dL/d(pulse parameters) against central finite differences of the same device pipeline."""
+    from c3_b200 import engine, fidelities as fid, propagation as prop, synth
+    from oracle import c3_fid_oracle as fo
+    m = synth.two_transmon()
+    B, K = 3, 2
+    T, N = 7e-9, 700
+    rng = np.random.default_rng(9)
+    env = np.zeros((B, K, 1, 9))
+    env[..., 0, 0] = rng.uniform(0.3, 0.5, (B, K))
+    env[..., 0, 1] = T
+    env[..., 0, 2] = T / 4
+    env[..., 0, 3] = rng.uniform(0, 1, (B, K))
+    env[..., 0, 4] = -53e6 * TP
+    env[..., 0, 5] = -1.0
+    env[..., 0, 8] = 1.0
+    lo = np.broadcast_to(np.array([5.05e9, 5.65e9]) * TP, (B, K)).copy()
+    sid = np.full((K, 1), 2, dtype=np.int32)
+    flags = np.ones((K, 1), dtype=np.int32)
+    chain = np.tile([100e9, 2e9, 0.3e-9, 1, 0, 1e9, 0, 1, 0, 0, np.nan], (K, 1))
+    G = np.kron(fo.GATES["rx90p"], fo.GATES["id"])
+
+    def pipeline(env_t, lo_t):
+        sig = engine.generate_signals_autograd(env_t, lo_t, sid, flags, chain, 0.0, T)
+        U = prop.pwc_batch_autograd(m.h0, m.hks, sig, 1e-11)
+        return fid.unitary_infid_autograd(G, U, [0, 1], [3, 3]).mean()
+
+    env_t = torch.tensor(env, device="cuda", requires_grad=True)
+    lo_t = torch.tensor(lo, device="cuda", requires_grad=True)
+    L = pipeline(env_t, lo_t)
+    L.backward()
+    g = env_t.grad.cpu().numpy()
+    for (b, k, q, rel) in [(0, 0, 0, 1e-5), (1, 1, 0, 1e-5), (2, 0, 3, 1e-5), (0, 1, 5, 1e-4), (1, 0, 4, 1e-6), (2, 1, 2, 1e-5)]:
+        h = abs(env[b, k, 0, q]) * rel
+        ep, em = env.copy(), env.copy()
+        ep[b, k, 0, q] += h
+        em[b, k, 0, q] -= h
+        with torch.no_grad():
+            lp = float(pipeline(torch.tensor(ep, device="cuda"), torch.tensor(lo, device="cuda")))
+            lm = float(pipeline(torch.tensor(em, device="cuda"), torch.tensor(lo, device="cuda")))
+        want = (lp - lm) / (2 * h)
+        assert abs(g[b, k, 0, q] - want) < 2e-4 * abs(want) + 1e-9 * np.abs(g[..., q]).max(), (b, k, q, g[b, k, 0, q], want)
+    assert lo_t.grad is not None and torch.isfinite(lo_t.grad).all()
