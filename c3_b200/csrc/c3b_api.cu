@@ -49,6 +49,7 @@ long long g_target_units = 32768;  // rows kernel: aim for this many warp work u
 long long g_force_cta = 0;         // route everything to the CTA kernel (testing)
 long long g_cta_variant = getenv("C3B_CTA_VARIANT") ? atoll(getenv("C3B_CTA_VARIANT")) : 1;  // 0: Pade + pivoted Gauss-Jordan, 1: Taylor-18 on DMMA tiles
 long long g_cta_threads = getenv("C3B_CTA_THREADS") ? atoll(getenv("C3B_CTA_THREADS")) : 512;   // DMMA CTA kernel, DP = 32: 256 or 512 threads
+long long g_grad_variant = getenv("C3B_GRAD_VARIANT") ? atoll(getenv("C3B_GRAD_VARIANT")) : 1;   // 1: Frechet of the Taylor scheme (d <= 16), 0: augmented exponential
 long long g_min_chunk = getenv("C3B_MIN_CHUNK") ? atoll(getenv("C3B_MIN_CHUNK")) : 8;         // rows kernel: minimum slices per lane group
 // 1: rows v2 (one row per lane, Pade) | 4-6: rows v3 (experimental) | 7-12: block layout, Pade + Gauss-Jordan (d=9)
 // 13 (default): block layout, degree-18 Taylor, trace shift, all d <= 12
@@ -456,6 +457,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (!strcmp(key, "force_cta")) { g_force_cta = value; return C3B_OK; }
     if (!strcmp(key, "cta_variant")) { g_cta_variant = value; return C3B_OK; }
     if (!strcmp(key, "cta_threads")) { g_cta_threads = value; return C3B_OK; }
+    if (!strcmp(key, "grad_variant")) { g_grad_variant = value; return C3B_OK; }
     if (!strcmp(key, "profile")) { g_profile = value; return C3B_OK; }
     if (!strcmp(key, "rows_variant")) { g_rows_variant = value; return C3B_OK; }
     if (!strcmp(key, "min_chunk")) { g_min_chunk = value < 1 ? 1 : value; return C3B_OK; }
@@ -637,18 +639,23 @@ double c3b_measure_fp64_peak(int kind, int device, double seconds) {
 }
 
 // ---- gradient -------------------------------------------------------------
+// variant 1 (default, d <= 16): Frechet derivative of the Taylor scheme on (X, dX) pairs, fused contraction
+// variant 0: augmented 2d x 2d exponential through the forward kernels (any d <= 32)
+static int grad_variant_for(int d) { return (g_grad_variant == 1 && d <= 16) ? 1 : 0; }
+
 static size_t grad_chunk_bytes(int Bc, int K, int N, int d, size_t* off /*[9]*/) {
     const size_t dd = (size_t)d * d * sizeof(cplx), dd2 = 4 * dd;
+    const bool aug = grad_variant_for(d) == 0;
     size_t o = 0;
     off[0] = o; o += align_up(c3b_pwc_workspace_bytes(Bc, K, N, d, 0, 0));          // forward workspace
-    off[1] = o; o += align_up(c3b_pwc_workspace_bytes(Bc, 0, N, 2 * d, 0, 0));      // augmented H-list workspace
+    off[1] = o; if (aug) o += align_up(c3b_pwc_workspace_bytes(Bc, 0, N, 2 * d, 0, 0));   // augmented H-list workspace
     off[2] = o; o += align_up((size_t)Bc * dd);                                    // U (forward)
     off[3] = o; o += align_up((size_t)Bc * N * dd);                                // dUs
-    off[4] = o; o += align_up((size_t)Bc * N * dd);                                // Psi
+    off[4] = o; o += align_up((size_t)Bc * N * dd);                                // Psi, then M (in place)
     off[5] = o; o += align_up((size_t)Bc * sizeof(double));                        // alpha
-    off[6] = o; o += align_up((size_t)Bc * N * dd2);                               // Haug
-    off[7] = o; o += align_up((size_t)Bc * N * dd2);                               // exp(hscale Haug)
-    off[8] = o; o += align_up((size_t)Bc * dd2);                                   // product of the augmented slices (unused)
+    off[6] = o; if (aug) o += align_up((size_t)Bc * N * dd2);                      // Haug
+    off[7] = o; if (aug) o += align_up((size_t)Bc * N * dd2);                      // exp(hscale Haug)
+    off[8] = o; if (aug) o += align_up((size_t)Bc * dd2);                          // product of the augmented slices (unused)
     return o;
 }
 
@@ -672,6 +679,7 @@ int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(workspace);
     const size_t dd = (size_t)d * d;
+    const int variant = grad_variant_for(d);
     cplx* Utmp = reinterpret_cast<cplx*>(ws + off[2]);
     cplx* dUs = reinterpret_cast<cplx*>(ws + off[3]);
     cplx* Psi = reinterpret_cast<cplx*>(ws + off[4]);
@@ -679,7 +687,15 @@ int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, 
     cplx* Haug = reinterpret_cast<cplx*>(ws + off[6]);
     cplx* Eaug = reinterpret_cast<cplx*>(ws + off[7]);
     cplx* Uaug = reinterpret_cast<cplx*>(ws + off[8]);
-    const int wpb = 4;
+    // sweep kernels: one warp per batch row with 3-4 matrices in shared memory; d = 32 needs 64 KB per warp
+    int wpb = (int)((size_t)192 * 1024 / ((size_t)4 * dd * sizeof(cplx)));
+    if (wpb > 4) wpb = 4;
+    if (wpb < 1) wpb = 1;
+    const int sweep_smem = (int)((size_t)wpb * 4 * dd * sizeof(cplx));
+    CUDA_TRY(cudaFuncSetAttribute(grad_suffix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
+    CUDA_TRY(cudaFuncSetAttribute(grad_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
+    CUDA_TRY(cudaFuncSetAttribute(grad_suffix2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
+    CUDA_TRY(cudaFuncSetAttribute(grad_prefix2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
     for (int b0 = 0; b0 < B; b0 += Bc) {
         const int nb = (B - b0 < Bc) ? (B - b0) : Bc;
         const double* sig = signals + (size_t)b0 * K * N;
@@ -687,8 +703,39 @@ int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, 
         int rc = c3b_pwc_closed(h0, hks, sig, dt, nb, K, N, d, 0, Udst, dUs, ws + off[0], off[1] - off[0], stream);
         if (rc) return rc;
         const int blocks = (nb + wpb - 1) / wpb;
-        grad_suffix_kernel<<<blocks, wpb * 32, (size_t)wpb * 3 * dd * sizeof(cplx), st>>>(
-            dUs, static_cast<const cplx*>(Ubar) + (size_t)b0 * dd, Psi, alpha, nb, N, d);
+        const cplx* ub = static_cast<const cplx*>(Ubar) + (size_t)b0 * dd;
+        if (variant == 1) {
+            grad_suffix2_kernel<<<blocks, wpb * 32, (size_t)wpb * 3 * dd * sizeof(cplx), st>>>(dUs, ub, Psi, alpha, nb, N, d);
+            CUDA_TRY(cudaGetLastError());
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            grad_prefix2_kernel<<<blocks, wpb * 32, (size_t)wpb * 4 * dd * sizeof(cplx), st>>>(dUs, Psi, nb, N, d);
+            CUDA_TRY(cudaGetLastError());
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            // generators, row sums and trace shifts as the forward call left them in its workspace
+            const Plan pl = make_plan(nb, K, N, d, 0, false);
+            char* fws = ws + off[0];
+            const cplx* G = reinterpret_cast<const cplx*>(fws + pl.off_G);
+            const double* RS = reinterpret_cast<const double*>(fws + pl.off_RS);
+            const bool shifted = (pl.path == 1 && rows_kernel_takes_shift(d)) || (pl.path != 1 && g_cta_variant == 1);
+            const cplx* TR = shifted ? reinterpret_cast<const cplx*>(fws + pl.off_TR) : nullptr;
+            const size_t per_warp = (size_t)kFrechetBufs * dd * sizeof(cplx);
+            int fw = (int)((size_t)96 * 1024 / per_warp);
+            if (fw < 1) fw = 1;
+            if (fw > 4) fw = 4;
+            const size_t smem = fw * per_warp;
+            CUDA_TRY(cudaFuncSetAttribute(grad_frechet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
+            if (per_sm < 1) per_sm = 1;
+            long long grid = (long long)num_sms() * per_sm;
+            const long long needb = ((long long)nb * N + fw - 1) / fw;
+            if (grid > needb) grid = needb;
+            grad_frechet_kernel<<<(int)grid, fw * 32, smem, st>>>(G, RS, TR, sig, Psi, static_cast<const cplx*>(hks), alpha,
+                                                                grad_out + (size_t)b0 * K * N, dt, nb, K, N, d);
+            CUDA_TRY(cudaGetLastError());
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            continue;
+        }
+        grad_suffix_kernel<<<blocks, wpb * 32, (size_t)wpb * 3 * dd * sizeof(cplx), st>>>(dUs, ub, Psi, alpha, nb, N, d);
         CUDA_TRY(cudaGetLastError());
         g_launches.fetch_add(1, std::memory_order_relaxed);
         grad_prefix_kernel<<<blocks, wpb * 32, (size_t)wpb * 4 * dd * sizeof(cplx), st>>>(

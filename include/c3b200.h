@@ -80,7 +80,8 @@ int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C
  *   Ubar     [B,d,d]  cotangent of U with dL = Re tr(Ubar^dag dU)  (torch's grad_output for U)
  *   grad_out [B,K,N]  float64, dL/d signals[b,k,n]
  *   U_out    [B,d,d]  or NULL: the forward result is produced on the way
- *   chunk    batch rows processed per pass (bounds the workspace: ~10 N d^2 16 bytes per row); <= 0: all
+ *   chunk    batch rows processed per pass (bounds the workspace: ~2 N d^2 16 bytes per row for d <= 16,
+ *            ~10 N d^2 16 above); <= 0: all
  * Shared model only (h0 [d,d], hks [K,d,d]), d <= 32. */
 size_t c3b_pwc_grad_workspace_bytes(int B, int K, int N, int d, int chunk);
 int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,

@@ -424,6 +424,31 @@ def test_gradient_matches_autograd_oracle(eng, levels, N, B):
     assert rel_fro(g, g_ref) < 1e-8
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("scale,d", [(1.0, 9), (6.0, 9), (40.0, 9), (3.0, 5), (1.0, 12), (1.0, 16)])
+def test_gradient_variants_and_squarings(eng, variant, scale, d):
+    """Both gradient implementations (0: augmented exponential, 1: Frechet derivative of the Taylor scheme with the
+    fused contraction) against torch-CPU autograd, including slices that need 1 .. 6 squarings and every
+    chunk width of the shared-memory product (d divisible by 3, by 2, by neither)."""
+    from oracle import c3_grad_oracle as gorc
+    rng = np.random.default_rng(int(scale) + d)
+    K, B, N = 2, 3, 17
+    h0, hks = _rand_model(rng, d, K, 0.9 * scale)
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    q = np.stack([np.linalg.qr(rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d)))[0] for _ in range(B)])
+    L_ref, g_ref, U_ref = gorc.loss_and_grad(h0, hks, sig, 1.0, q)
+    Uc = torch.tensor(U_ref, requires_grad=True)
+    T = torch.as_tensor(q)
+    ((1.0 - (torch.einsum("bij,bij->b", T.conj(), Uc).abs() ** 2) / d ** 2).sum()).backward()
+    eng.set_tuning("grad_variant", variant)
+    try:
+        U, g = eng.pwc_closed_grad(h0, hks, sig, 1.0, Uc.grad.numpy())
+    finally:
+        eng.set_tuning("grad_variant", 1)
+    assert rel_fro(U.cpu().numpy(), U_ref) < TOL
+    assert rel_fro(g.cpu().numpy(), g_ref) < 1e-8
+
+
 def test_gradient_chunking_and_finite_difference(eng):
     """Chunked passes give the same gradient; a central finite difference agrees to 1e-6."""
     from c3_b200 import synth
