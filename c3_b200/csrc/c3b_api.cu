@@ -643,12 +643,14 @@ double c3b_measure_fp64_peak(int kind, int device, double seconds) {
 // variant 0: augmented 2d x 2d exponential through the forward kernels (any d <= 32)
 static int grad_variant_for(int d) { return (g_grad_variant == 1 && d <= 16) ? 1 : 0; }
 
-static size_t grad_chunk_bytes(int Bc, int K, int N, int d, size_t* off /*[9]*/) {
-    const size_t dd = (size_t)d * d * sizeof(cplx), dd2 = 4 * dd;
-    const bool aug = grad_variant_for(d) == 0;
+// D: matrix dimension of the propagators (d, or d^2 for Lindblad); dh: Hilbert dimension passed to the workspace query
+static size_t grad_chunk_bytes(int Bc, int K, int N, int dh, int lindblad, size_t* off /*[9]*/) {
+    const int D = lindblad ? dh * dh : dh;
+    const size_t dd = (size_t)D * D * sizeof(cplx), dd2 = 4 * dd;
+    const bool aug = grad_variant_for(D) == 0;
     size_t o = 0;
-    off[0] = o; o += align_up(c3b_pwc_workspace_bytes(Bc, K, N, d, 0, 0));          // forward workspace
-    off[1] = o; if (aug) o += align_up(c3b_pwc_workspace_bytes(Bc, 0, N, 2 * d, 0, 0));   // augmented H-list workspace
+    off[0] = o; o += align_up(c3b_pwc_workspace_bytes(Bc, K, N, dh, lindblad, 0));       // forward workspace
+    off[1] = o; if (aug) o += align_up(c3b_pwc_workspace_bytes(Bc, 0, N, 2 * D, 0, 0));   // augmented H-list workspace
     off[2] = o; o += align_up((size_t)Bc * dd);                                    // U (forward)
     off[3] = o; o += align_up((size_t)Bc * N * dd);                                // dUs
     off[4] = o; o += align_up((size_t)Bc * N * dd);                                // Psi, then M (in place)
@@ -663,23 +665,33 @@ size_t c3b_pwc_grad_workspace_bytes(int B, int K, int N, int d, int chunk) {
     if (B <= 0 || N <= 0 || d <= 0 || K <= 0) return 0;
     const int Bc = (chunk > 0 && chunk < B) ? chunk : B;
     size_t off[9];
-    return grad_chunk_bytes(Bc, K, N, d, off);
+    return grad_chunk_bytes(Bc, K, N, d, 0, off);
 }
 
-int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
-                        const void* Ubar, double* grad_out, void* U_out, int chunk, void* workspace,
-                        size_t workspace_bytes, void* stream) {
-    if (B <= 0 || N <= 0 || d <= 0 || K <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d N=%d d=%d)", B, K, N, d);
-    if (!h0 || !hks || !signals || !Ubar || !grad_out || !workspace) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
-    if (d > 32) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gradient path supports d <= 32 (got %d)", d);
+size_t c3b_pwc_lindblad_grad_workspace_bytes(int B, int K, int N, int d, int chunk) {
+    if (B <= 0 || N <= 0 || d <= 0 || K <= 0) return 0;
     const int Bc = (chunk > 0 && chunk < B) ? chunk : B;
     size_t off[9];
-    const size_t need = grad_chunk_bytes(Bc, K, N, d, off);
+    return grad_chunk_bytes(Bc, K, N, d, 1, off);
+}
+
+static int pwc_grad_impl(int lindblad, const void* h0, const void* hks, const void* col_ops, int C, const double* signals,
+                         double dt, int B, int K, int N, int dh, const void* Ubar, double* grad_out, void* U_out,
+                         int chunk, void* workspace, size_t workspace_bytes, void* stream) {
+    if (B <= 0 || N <= 0 || dh <= 0 || K <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d N=%d d=%d)", B, K, N, dh);
+    if (!h0 || !hks || !signals || !Ubar || !grad_out || !workspace) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    const int d = lindblad ? dh * dh : dh;                      // dimension of the propagators
+    if (d > 32) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gradient path supports matrix dimension <= 32 (got %d)", d);
+    const int variant = grad_variant_for(d);
+    if (lindblad && variant != 1)
+        return fail(C3B_EUNSUPPORTED, "C3:ERROR: the Lindblad gradient needs d^2 <= 16 and grad_variant 1 (got d=%d)", dh);
+    const int Bc = (chunk > 0 && chunk < B) ? chunk : B;
+    size_t off[9];
+    const size_t need = grad_chunk_bytes(Bc, K, N, dh, lindblad, off);
     if (workspace_bytes < need) return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small: %zu < %zu bytes", workspace_bytes, need);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(workspace);
     const size_t dd = (size_t)d * d;
-    const int variant = grad_variant_for(d);
     cplx* Utmp = reinterpret_cast<cplx*>(ws + off[2]);
     cplx* dUs = reinterpret_cast<cplx*>(ws + off[3]);
     cplx* Psi = reinterpret_cast<cplx*>(ws + off[4]);
@@ -700,7 +712,9 @@ int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, 
         const int nb = (B - b0 < Bc) ? (B - b0) : Bc;
         const double* sig = signals + (size_t)b0 * K * N;
         cplx* Udst = U_out ? static_cast<cplx*>(U_out) + (size_t)b0 * dd : Utmp;
-        int rc = c3b_pwc_closed(h0, hks, sig, dt, nb, K, N, d, 0, Udst, dUs, ws + off[0], off[1] - off[0], stream);
+        int rc = lindblad
+            ? c3b_pwc_lindblad(h0, hks, col_ops, C, sig, dt, nb, K, N, dh, 0, Udst, dUs, ws + off[0], off[1] - off[0], stream)
+            : c3b_pwc_closed(h0, hks, sig, dt, nb, K, N, dh, 0, Udst, dUs, ws + off[0], off[1] - off[0], stream);
         if (rc) return rc;
         const int blocks = (nb + wpb - 1) / wpb;
         const cplx* ub = static_cast<const cplx*>(Ubar) + (size_t)b0 * dd;
@@ -729,8 +743,8 @@ int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, 
             long long grid = (long long)num_sms() * per_sm;
             const long long needb = ((long long)nb * N + fw - 1) / fw;
             if (grid > needb) grid = needb;
-            grad_frechet_kernel<<<(int)grid, fw * 32, smem, st>>>(G, RS, TR, sig, Psi, static_cast<const cplx*>(hks), alpha,
-                                                                grad_out + (size_t)b0 * K * N, dt, nb, K, N, d);
+            grad_frechet_kernel<<<(int)grid, fw * 32, smem, st>>>(G, RS, TR, sig, Psi, alpha, grad_out + (size_t)b0 * K * N,
+                                                                nb, K, N, d);
             CUDA_TRY(cudaGetLastError());
             g_launches.fetch_add(1, std::memory_order_relaxed);
             continue;
@@ -751,6 +765,21 @@ int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, 
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     return C3B_OK;
+}
+
+int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
+                        const void* Ubar, double* grad_out, void* U_out, int chunk, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    return pwc_grad_impl(0, h0, hks, nullptr, 0, signals, dt, B, K, N, d, Ubar, grad_out, U_out, chunk, workspace,
+                         workspace_bytes, stream);
+}
+
+int c3b_pwc_lindblad_grad(const void* h0, const void* hks, const void* col_ops, int C, const double* signals, double dt,
+                          int B, int K, int N, int d, const void* Ubar, double* grad_out, void* U_out, int chunk,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    if (C < 0 || (C > 0 && col_ops == nullptr)) return fail(C3B_EINVAL, "C3:ERROR: C=%d but col_ops is NULL", C);
+    return pwc_grad_impl(1, h0, hks, col_ops, C, signals, dt, B, K, N, d, Ubar, grad_out, U_out, chunk, workspace,
+                         workspace_bytes, stream);
 }
 
 // ---- goal functions on the propagators ------------------------------------

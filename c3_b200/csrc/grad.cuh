@@ -256,14 +256,15 @@ __global__ void grad_prefix2_kernel(const cplx* __restrict__ dUs, cplx* __restri
 constexpr int kFrechetBufs = 16;
 
 // One warp per (b, n): W_n = L(A_n, M_n) by the Taylor-scheme derivative above, then
-//   grad[b,k,n] = (1/alpha_b) Re tr(W_n G_k),  G_k = -i dt h_k.
+//   grad[b,k,n] = (1/alpha_b) Re tr(W_n G_k),  G_k = dA/dc_k  (-i dt h_k for the closed system, the commutator
+//   superoperator -i dt (h_k (x) I - I (x) h_k^T) for Lindblad, where d is the superoperator dimension).
 // G / RS / TR are the trace-shifted generators, their row sums and the shifts of the forward pass (RowsParams
-// conventions); Mn [B,N,d,d] from grad_prefix2_kernel.  Dynamic smem = warps * 16 * d*d * 16 bytes.
+// conventions; the unshifted G_k is G[k+1] + TR[k+1] I); Mn [B,N,d,d] from grad_prefix2_kernel.
+// Dynamic smem = warps * 16 * d*d * 16 bytes.
 __global__ void grad_frechet_kernel(const cplx* __restrict__ G, const double* __restrict__ RS, const cplx* __restrict__ TR,
                                     const double* __restrict__ signals, const cplx* __restrict__ Mn,
-                                    const cplx* __restrict__ hks, const double* __restrict__ alpha,
-                                    double* __restrict__ grad, const double dt, const int B, const int K, const int N,
-                                    const int d) {
+                                    const double* __restrict__ alpha, double* __restrict__ grad, const int B, const int K,
+                                    const int N, const int d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int dd = d * d;
@@ -393,16 +394,18 @@ __global__ void grad_frechet_kernel(const cplx* __restrict__ G, const double* __
         const double a = alpha[b];
         const double inv_a = a > 0.0 ? 1.0 / a : 0.0;
         for (int k = 0; k < K; ++k) {
+            const cplx tk = TR ? TR[k + 1] : cmake(0.0, 0.0);
             double acc = 0.0;
             for (int e = lane; e < dd; e += 32) {
                 const int i = e / d, j = e - i * d;
                 const cplx wv = cmul(ph, dX[e]);
-                const cplx h = hks[(size_t)k * dd + j * d + i];
-                acc = fma(wv.x, h.y, fma(wv.y, h.x, acc));      // Re(w * (-i dt h)) / dt
+                cplx g = G[(size_t)(k + 1) * dd + j * d + i];
+                if (i == j) { g.x += tk.x; g.y += tk.y; }
+                acc = fma(wv.x, g.x, fma(-wv.y, g.y, acc));     // Re(w_ij g_ji)
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) grad[((size_t)b * K + k) * N + n] = acc * dt * inv_a;
+            if (lane == 0) grad[((size_t)b * K + k) * N + n] = acc * inv_a;
         }
         __syncwarp();
     }

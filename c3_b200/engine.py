@@ -189,6 +189,43 @@ def pwc_closed_grad(h0, hks, signals, dt: float, Ubar, max_workspace_bytes: int 
     return U, grad
 
 
+def pwc_lindblad_grad(h0, hks, col_ops, signals, dt: float, Ubar, max_workspace_bytes: int = 6 << 30, device=None):
+    """Forward U [B,D,D] (D = d^2) and the gradient [B,K,N] of a real scalar loss w.r.t. the control fields through the
+    Lindblad superoperator propagators; ``Ubar`` as in :func:`pwc_closed_grad`.  Needs d^2 <= 16."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        signals = _as(signals, torch.float64, device)
+        if signals.dim() == 2:
+            signals = signals.unsqueeze(0)
+        B, K, N = signals.shape
+        h0 = _as(h0, torch.complex128, device)
+        hks = _as(hks, torch.complex128, device)
+        if h0.dim() != 2:
+            raise ValueError("C3:ERROR: the gradient path needs a shared model h0 [d,d]")
+        d = h0.shape[-1]
+        D = d * d
+        if isinstance(col_ops, (list, tuple)):
+            col_ops = torch.stack([_as(c, torch.complex128, device) for c in col_ops]) if len(col_ops) else None
+        C = 0
+        if col_ops is not None:
+            col_ops = _as(col_ops, torch.complex128, device)
+            C = col_ops.shape[-3]
+        Ubar = _as(Ubar, torch.complex128, device)
+        if tuple(Ubar.shape) != (B, D, D):
+            raise ValueError(f"C3:ERROR: Ubar has shape {tuple(Ubar.shape)}, expected {(B, D, D)}")
+        U = torch.empty((B, D, D), dtype=torch.complex128, device=device)
+        grad = torch.empty((B, K, N), dtype=torch.float64, device=device)
+        chunk = B
+        while chunk > 1 and lib.c3b_pwc_lindblad_grad_workspace_bytes(B, K, N, d, chunk) > max_workspace_bytes:
+            chunk = (chunk + 1) // 2
+        nbytes = lib.c3b_pwc_lindblad_grad_workspace_bytes(B, K, N, d, chunk)
+        ws = _workspace(nbytes, device)
+        _lib.check(lib.c3b_pwc_lindblad_grad(_ptr(h0), _ptr(hks), _ptr(col_ops), C, _ptr(signals), float(dt), B, K, N, d,
+                                             _ptr(Ubar), _ptr(grad), _ptr(U), chunk, _ptr(ws), ws.numel(), _stream()))
+    return U, grad
+
+
 def pwc_closed_hlist(Hs, dt: float, return_dUs: bool = False, device=None):
     """Same with explicit Hamiltonians Hs [B,N,d,d] (or [N,d,d]); the reference's
     ``signals is None`` mode (c3/libraries/propagation.py:294-308, 437-438)."""

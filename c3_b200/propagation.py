@@ -165,16 +165,37 @@ class _PwcClosedFn(torch.autograd.Function):
         return g.to(signals.dtype).reshape(signals.shape), None, None, None
 
 
-def pwc_batch_autograd(h0, hks, signals: torch.Tensor, dt) -> torch.Tensor:
+class _PwcLindbladFn(torch.autograd.Function):
+    """U = pwc_batch(..., lindbladian=True), differentiable w.r.t. ``signals`` (d^2 <= 16)."""
+
+    @staticmethod
+    def forward(ctx, signals, h0, hks, col_ops, dt):
+        U = engine.pwc_lindblad(h0, hks, col_ops, signals.detach(), dt)
+        ctx.save_for_backward(signals.detach())
+        ctx.h0, ctx.hks, ctx.col_ops, ctx.dt = h0, hks, col_ops, dt
+        return U
+
+    @staticmethod
+    def backward(ctx, grad_U):
+        (signals,) = ctx.saved_tensors
+        _, g = engine.pwc_lindblad_grad(ctx.h0, ctx.hks, ctx.col_ops, signals, ctx.dt, grad_U.contiguous())
+        return g.to(signals.dtype).reshape(signals.shape), None, None, None, None
+
+
+def pwc_batch_autograd(h0, hks, signals: torch.Tensor, dt, col_ops=None, lindbladian: bool = False) -> torch.Tensor:
     """Differentiable batched propagators: ``signals`` is a CUDA float64 tensor [B,K,N] with
     ``requires_grad``; gradients of any real loss of U flow back to it (what the reference gets from
-    tf.GradientTape, c3/optimizers/optimizer.py:210-215).  Closed system, shared model."""
+    tf.GradientTape, c3/optimizers/optimizer.py:210-215).  Shared model; closed system (d <= 32) or, with
+    ``lindbladian=True`` and ``col_ops``, the Lindblad superoperator propagators (d^2 <= 16)."""
     if not (isinstance(signals, torch.Tensor) and signals.is_cuda):
         raise ValueError("C3:ERROR: pwc_batch_autograd needs a CUDA tensor for `signals`")
     dev = signals.device
     h0_t = torch.as_tensor(_host(h0), dtype=torch.complex128).to(dev) if not isinstance(h0, torch.Tensor) else h0.to(dev)
     hks_t = torch.as_tensor(_host(hks), dtype=torch.complex128).to(dev) if not isinstance(hks, torch.Tensor) else hks.to(dev)
     sig = signals if signals.dim() == 3 else signals.unsqueeze(0)
+    if lindbladian:
+        cols = torch.stack([torch.as_tensor(_host(c), dtype=torch.complex128) for c in col_ops]).to(dev)
+        return _PwcLindbladFn.apply(sig, h0_t, hks_t, cols, float(np.real(dt)))
     return _PwcClosedFn.apply(sig, h0_t, hks_t, float(np.real(dt)))
 
 

@@ -151,6 +151,13 @@ int c3b_generate_signals_grad(const double* env_params, const int32_t* env_shape
                               int B, int K, int E, int N, int n_awg_max, const double* gsignals, double* grad_env,
                               double* grad_lo, double* grad_v2hz, void* stream);
 
+/* Same for the Lindblad superoperator propagators (Ubar, U_out [B,D,D], D = d*d): the generators dA/dc_k are the
+ * commutator superoperators -i dt (h_k (x) I - I (x) h_k^T).  Needs D <= 16 (d <= 4: one qutrit, two qubits). */
+size_t c3b_pwc_lindblad_grad_workspace_bytes(int B, int K, int N, int d, int chunk);
+int c3b_pwc_lindblad_grad(const void* h0, const void* hks, const void* col_ops, int C, const double* signals, double dt,
+                          int B, int K, int N, int d, const void* Ubar, double* grad_out, void* U_out, int chunk,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Ordered product of M matrices per batch row: out[b] = mats[b,M-1] ... mats[b,0].
  *   replaces tf_matmul_left (c3/utils/tf_utils.py:120-129) and tf_matmul_n (:144-193).
  *   mats [B,M,D,D], out [B,D,D]. */

@@ -32,3 +32,30 @@ def loss_and_grad(h0, hks, signals_np, dt, target):
     L = (1.0 - (ov.abs() ** 2) / d ** 2).sum()
     L.backward()
     return float(L), sig.grad.numpy(), U.detach().numpy()
+
+
+def propagate_lindblad_torch(h0, hks, col_ops, signals, dt):
+    """Lindblad superoperator propagators [B,D,D] on torch-CPU (autograd-able in ``signals``): the operator of
+    c3/libraries/propagation.py:563-582 (row-major Kronecker convention of tf_kron), matrix_exp per slice,
+    later slices on the left."""
+    h0 = torch.as_tensor(h0, dtype=torch.complex128)
+    hks = torch.as_tensor(hks, dtype=torch.complex128)
+    cols = torch.as_tensor(np.asarray(col_ops), dtype=torch.complex128)
+    d = h0.shape[-1]
+    eye = torch.eye(d, dtype=torch.complex128)
+    c = signals.to(torch.complex128)
+    H = h0[None, None] + torch.einsum("bkn,kij->bnij", c, hks)
+
+    def kron(a, b):
+        return torch.einsum("...ij,...kl->...ikjl", a, b).reshape(a.shape[:-2] + (d * d, d * d))
+
+    lind = -1j * (kron(H, eye.expand_as(H)) - kron(eye.expand_as(H), H.transpose(-1, -2)))
+    diss = torch.zeros((d * d, d * d), dtype=torch.complex128)
+    for L in cols:
+        m = L.conj().T @ L
+        diss = diss + kron(L, L.conj()) - 0.5 * kron(m, eye) - 0.5 * kron(eye, m.T)
+    dU = torch.linalg.matrix_exp((lind + diss) * dt)
+    U = dU[:, 0]
+    for n in range(1, dU.shape[1]):
+        U = dU[:, n] @ U
+    return U

@@ -449,6 +449,34 @@ def test_gradient_variants_and_squarings(eng, variant, scale, d):
     assert rel_fro(g.cpu().numpy(), g_ref) < 1e-8
 
 
+@pytest.mark.parametrize("levels", [2, 3])
+def test_lindblad_gradient_matches_autograd_oracle(eng, levels):
+    """Open-system gradient: dL/dsignals through the Lindblad superoperator propagators (D = 4: one qubit pair would be
+    16; here one/two-level systems of the synthetic chip) vs torch-CPU autograd through the same operator."""
+    from c3_b200 import synth, propagation as prop
+    from oracle import c3_grad_oracle as gorc
+    m = synth.one_qubit(levels=3) if levels == 3 else synth.two_transmon(levels=2)     # D = 9 resp. 16
+    D = m.d * m.d
+    B, N = 3, 25
+    rng = np.random.default_rng(levels)
+    sig = synth.controls(m, B, N)
+    cols = np.asarray(m.col_ops) * 3e3          # strong damping so that the dissipator matters over 25 slices
+    T = rng.normal(size=(B, D, D)) + 1j * rng.normal(size=(B, D, D))
+    s_ref = torch.tensor(sig, dtype=torch.float64, requires_grad=True)
+    U_ref = gorc.propagate_lindblad_torch(m.h0, m.hks, cols, s_ref, 1e-11)
+    L_ref = (torch.einsum("bij,bij->b", torch.as_tensor(T).conj(), U_ref).abs() ** 2).sum()
+    L_ref.backward()
+    want_U = orc.propagate_batch(m.h0, m.hks, sig, 1e-11, col_ops=cols, lindbladian=True)
+    assert rel_fro(U_ref.detach().numpy(), want_U) < 1e-10           # the torch restatement agrees with the oracle
+    s = torch.tensor(sig, device="cuda", requires_grad=True)
+    U = prop.pwc_batch_autograd(m.h0, m.hks, s, 1e-11, col_ops=list(cols), lindbladian=True)
+    L = (torch.einsum("bij,bij->b", torch.as_tensor(T, device="cuda").conj(), U).abs() ** 2).sum()
+    L.backward()
+    assert rel_fro(U.detach().cpu().numpy(), want_U) < TOL
+    assert abs(float(L) - float(L_ref)) < 1e-9 * abs(float(L_ref))
+    assert rel_fro(s.grad.cpu().numpy(), s_ref.grad.numpy()) < 1e-8
+
+
 def test_gradient_chunking_and_finite_difference(eng):
     """Chunked passes give the same gradient; a central finite difference agrees to 1e-6."""
     from c3_b200 import synth
