@@ -16,6 +16,7 @@ SYMBOLS = [
     "c3b_last_kernel_ms", "c3b_pwc_grad_workspace_bytes", "c3b_pwc_closed_grad",
     "c3b_gate_infid", "c3b_gate_infid_grad", "c3b_seq_populations", "c3b_signal_slice_num", "c3b_generate_signals",
     "c3b_generate_signals_grad", "c3b_pwc_lindblad_grad_workspace_bytes", "c3b_pwc_lindblad_grad",
+    "c3b_dress_models",
 ]
 
 _lib = None
@@ -55,6 +56,8 @@ def load() -> C.CDLL:
     lib.c3b_pwc_lindblad_grad_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.c3b_pwc_lindblad_grad.restype = i
     lib.c3b_pwc_lindblad_grad.argtypes = [vp, vp, vp, i, vp, d, i, i, i, i, vp, vp, vp, i, vp, sz, vp]
+    lib.c3b_dress_models.restype = i
+    lib.c3b_dress_models.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp]
     lib.c3b_gate_infid.restype = i
     lib.c3b_gate_infid.argtypes = [vp, i, i, vp, vp, i, i, vp, vp, vp]
     lib.c3b_gate_infid_grad.restype = i

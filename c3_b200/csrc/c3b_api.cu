@@ -17,6 +17,7 @@
 #include "grad.cuh"
 #include "fidelity.cuh"
 #include "signal_chain.cuh"
+#include "dressing.cuh"
 #include "peak.cuh"
 
 using namespace c3b;
@@ -880,6 +881,31 @@ int c3b_generate_signals_grad(const double* env_params, const int32_t* env_shape
     if (smem > 200 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gate too long for the on-chip signal-chain gradient (N=%d)", N);
     CUDA_TRY(cudaFuncSetAttribute(signal_chain_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     signal_chain_grad_kernel<<<B * K, 128, smem, static_cast<cudaStream_t>(stream)>>>(gp);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return C3B_OK;
+}
+
+// ---- batched dressing of model samples --------------------------------------------------
+int c3b_dress_models(const void* drift, const void* ops, int ops_batched, int B, int M, int d, int ordered,
+                     double* eigenframe, void* transform, void* dressed_drift, void* dressed_ops, int32_t* info,
+                     void* stream) {
+    if (B <= 0 || d <= 0 || M < 0) return fail(C3B_EINVAL, "C3:ERROR: bad size (B=%d M=%d d=%d)", B, M, d);
+    if (d > 32) return fail(C3B_EUNSUPPORTED, "C3:ERROR: on-device dressing supports d <= 32 (got %d)", d);
+    if (!drift || !eigenframe || !transform) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (M > 0 && dressed_ops && !ops) return fail(C3B_EINVAL, "C3:ERROR: dressed_ops requested but ops is NULL");
+    DressParams dp{};
+    dp.drift = static_cast<const cplx*>(drift); dp.ops = static_cast<const cplx*>(ops); dp.ops_batched = ops_batched;
+    dp.B = B; dp.M = M; dp.d = d; dp.ordered = ordered;
+    dp.eigenframe = eigenframe; dp.transform = static_cast<cplx*>(transform);
+    dp.dressed_drift = static_cast<cplx*>(dressed_drift); dp.dressed_ops = static_cast<cplx*>(dressed_ops); dp.info = info;
+    const size_t per_warp = (size_t)4 * d * d * sizeof(cplx) + (size_t)4 * d * sizeof(double);
+    int wpb = (int)((size_t)96 * 1024 / per_warp);
+    if (wpb > 4) wpb = 4;
+    if (wpb < 1) wpb = 1;
+    const size_t smem = wpb * per_warp;
+    CUDA_TRY(cudaFuncSetAttribute(dress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dress_kernel<<<(B + wpb - 1) / wpb, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(dp);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return C3B_OK;

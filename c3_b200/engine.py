@@ -465,6 +465,38 @@ def generate_signals_autograd(env_params: torch.Tensor, lo_freq: torch.Tensor, e
     return _SignalChainFn.apply(env_params, lo_freq, env_shape, env_flags, chain, float(t_start), float(t_end))
 
 
+def dress_models(drift, ops=None, ordered: bool = True, device=None):
+    """Dressed frame of every drift Hamiltonian ``drift [B,d,d]`` (or [d,d]) and T^dag X T of ``ops [M,d,d]`` /
+    ``[B,M,d,d]`` (c3/model.py:453-534).  Returns dict(eigenframe [B,d], transform [B,d,d], drift [B,d,d],
+    ops [B,M,d,d] or None, sweeps [B])."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        drift = _as(drift, torch.complex128, device)
+        squeeze = drift.dim() == 2
+        if squeeze:
+            drift = drift.unsqueeze(0)
+        B, d, _ = drift.shape
+        M, batched = 0, False
+        if ops is not None:
+            ops = _as(ops, torch.complex128, device)
+            batched = ops.dim() == 4
+            M = ops.shape[-3]
+            if batched and ops.shape[0] != B:
+                raise ValueError("C3:ERROR: batched operators must have the batch size of the drift")
+        ef = torch.empty((B, d), dtype=torch.float64, device=device)
+        T = torch.empty((B, d, d), dtype=torch.complex128, device=device)
+        dd = torch.empty((B, d, d), dtype=torch.complex128, device=device)
+        dops = torch.empty((B, M, d, d), dtype=torch.complex128, device=device) if M > 0 else None
+        info = torch.empty((B,), dtype=torch.int32, device=device)
+        _lib.check(lib.c3b_dress_models(_ptr(drift), _ptr(ops), int(batched), B, M, d, int(bool(ordered)), _ptr(ef), _ptr(T),
+                                        _ptr(dd), _ptr(dops), _ptr(info), _stream()))
+    out = {"eigenframe": ef, "transform": T, "drift": dd, "ops": dops, "sweeps": info}
+    if squeeze:
+        out = {k: (v[0] if v is not None else None) for k, v in out.items()}
+    return out
+
+
 def kron(A, B, device=None) -> torch.Tensor:
     """(Batched) Kronecker product with the row-major convention of tf_kron."""
     lib = _lib.load()

@@ -158,6 +158,18 @@ int c3b_pwc_lindblad_grad(const void* h0, const void* hks, const void* col_ops, 
                           int B, int K, int N, int d, const void* Ubar, double* grad_out, void* U_out, int chunk,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Dressing of a batch of model samples: eigendecomposition of every drift Hamiltonian,
+ * reordering of the eigenvectors by overlap with the bare states, and T^dag X T of the sample's operators --
+ * Model.update_drift_eigen / reorder_frame / update_dressed (c3/model.py:453-534), once per sample instead of once
+ * per host-side model update.
+ *   drift [B,d,d] Hermitian;  ops [M,d,d] (or [B,M,d,d] if ops_batched) control Hamiltonians / collapse operators, or NULL
+ *   ordered != 0: reorder_frame(ordered=True); 0: ascending eigenvalues, T = eigenvectors
+ *   eigenframe [B,d] float64;  transform [B,d,d];  dressed_drift [B,d,d] or NULL;  dressed_ops [B,M,d,d] or NULL
+ *   info [B] int32 (Jacobi sweeps used, 100 = not converged) or NULL.   d <= 32. */
+int c3b_dress_models(const void* drift, const void* ops, int ops_batched, int B, int M, int d, int ordered,
+                     double* eigenframe, void* transform, void* dressed_drift, void* dressed_ops, int32_t* info,
+                     void* stream);
+
 /* Ordered product of M matrices per batch row: out[b] = mats[b,M-1] ... mats[b,0].
  *   replaces tf_matmul_left (c3/utils/tf_utils.py:120-129) and tf_matmul_n (:144-193).
  *   mats [B,M,D,D], out [B,D,D]. */

@@ -42,17 +42,33 @@ def x_drive(a):              # c3/libraries/hamiltonians.py (x_drive): a^dag + a
     return a.T.conj() + a
 
 
-def dressing_transform(drift: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-    """eigh + reorder by largest overlap + sign fix (c3/model.py:453-502, ordered=True,
-    the ``max_probabilities > 0.5`` branch)."""
-    e, v = np.linalg.eigh(drift)
+def reorder_frame(e: np.ndarray, v: np.ndarray, ordered: bool = True):
+    """c3/model.py:453-492: assign every eigenvector to the bare state it overlaps most with.  If every
+    eigenvector has one component of probability > 0.5 that component decides; otherwise ("overly dressed") the
+    assignment is greedy: repeatedly take the largest remaining |v|^2 and strike out its row and column."""
+    if not ordered:
+        return np.eye(len(e)), np.real(e), v
     v_sq = np.real(v * np.conj(v))
-    if v_sq.max(axis=0).min() <= 0.5:
-        raise RuntimeError("overly dressed states: fallback branch of reorder_frame not restated")
-    reorder = (v_sq > 0.5).astype(np.float64)
+    if v_sq.max(axis=0).min() > 0.5:
+        reorder = (v_sq > 0.5).astype(np.float64)
+    else:
+        vc = v_sq.copy()
+        reorder = np.zeros_like(vc)
+        for _ in range(vc.shape[1]):
+            idx = np.unravel_index(np.argmax(vc), vc.shape)
+            vc[idx[0], :] = 0
+            vc[:, idx[1]] = 0
+            reorder[idx] = 1
     signed = np.sign(np.real(v)) * reorder
     eigenframe = reorder @ np.real(e)
     transform = v @ signed.T
+    return reorder, eigenframe, transform
+
+
+def dressing_transform(drift: np.ndarray, ordered: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """eigh + reorder by largest overlap + sign fix (c3/model.py:453-502)."""
+    e, v = np.linalg.eigh(drift)
+    _, eigenframe, transform = reorder_frame(e, v, ordered)
     return eigenframe, transform.astype(np.complex128)
 
 
@@ -80,6 +96,18 @@ def transmon_factor(phi: float, phi_0: float, d: float) -> float:
     """Flux dependence of a tunable transmon (c3/libraries/chip.py:355-372)."""
     x = np.pi * phi / phi_0
     return float(np.sqrt(np.sqrt(np.cos(x) ** 2 + d ** 2 * np.sin(x) ** 2)))
+
+
+def tunable_coupler_drift(phi: float = 2.3, g1: float = 142e6, g2: float = 116e6):
+    """Bare drift of the three-body chip at coupler flux ``phi`` with coupling strengths g1 (Q1-TC), g2 (Q2-TC) in Hz."""
+    tp = 2 * np.pi
+    a_tc, a_q1, a_q2 = annihilators([3, 3, 3])
+    freq_tc, anhar_tc = 8.1e9 * tp, -235e6 * tp
+    f_tc = (freq_tc - anhar_tc) * transmon_factor(phi, 10.0, 0.36) + anhar_tc
+    drift = f_tc * resonator(a_tc) + anhar_tc * duffing(a_tc)
+    drift = drift + 6.189e9 * tp * resonator(a_q1) + (-286e6 * tp) * duffing(a_q1)
+    drift = drift + 5.089e9 * tp * resonator(a_q2) + (-310e6 * tp) * duffing(a_q2)
+    return drift + g1 * tp * int_XX(a_q1, a_tc) + g2 * tp * int_XX(a_q2, a_tc)
 
 
 def tunable_coupler_model():

@@ -45,3 +45,8 @@ def golden_tunable_coupler():
 @pytest.fixture(scope="session")
 def golden_generator():
     return dict(np.load(os.path.join(GOLDEN, "generator.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_tc_levels():
+    return dict(np.load(os.path.join(GOLDEN, "tunable_coupler_levels.npz")))

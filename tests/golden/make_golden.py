@@ -113,6 +113,15 @@ def tunable_coupler():
     )
 
 
+def tunable_coupler_levels():
+    """test/test_tunable_coupler.py:315-383: eigenframes over 101 coupler flux values, uncoupled (product_basis),
+    dressed and reordered (ordered_basis), dressed ascending (dressed_basis), in GHz."""
+    d = load("tunable_coupler_data.pickle")
+    np.savez_compressed(os.path.join(HERE, "tunable_coupler_levels.npz"),
+                        flux_ratio=np.linspace(-0.10, 0.7, 101, endpoint=True),
+                        product_basis=d["product_basis"], ordered_basis=d["ordered_basis"], dressed_basis=d["dressed_basis"])
+
+
 def generator_chain():
     d = load("generator_data.pickle")
     np.savez_compressed(
@@ -129,6 +138,7 @@ def generator_chain():
 if __name__ == "__main__":
     two_qubit()
     tunable_coupler()
+    tunable_coupler_levels()
     generator_chain()
     transmon_expanded()
     tf_utils()

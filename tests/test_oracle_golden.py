@@ -172,3 +172,37 @@ def test_rebuilt_tunable_coupler_model():
     e = m["eigenframe"]
     assert abs(abs(abs(e[0]) - abs(e[9])) - 45100118139.44866) / 45100118139.44866 < 1e-12
     assert abs(abs(abs(e[9]) - abs(e[18])) - 43784918348.34318) / 43784918348.34318 < 1e-12
+
+
+def _tc_level_sweep(golden, dress):
+    """Replay test/test_tunable_coupler.py:315-383 with ``dress(drift, ordered) -> eigenframe``."""
+    from oracle import c3_model_oracle as mo
+    e0 = dress(mo.tunable_coupler_drift(phi=0.0), True)
+    order = np.argsort(np.abs(e0) / 2 / np.pi / 1e9)
+    prod, ordd, dres, fallback = [], [], [], []
+    for r in golden["flux_ratio"]:
+        phi = r * 10.0
+        drift = mo.tunable_coupler_drift(phi)
+        prod.append(dress(mo.tunable_coupler_drift(phi, 0.0, 0.0), True)[order] / 2 / np.pi / 1e9)
+        ordd.append(dress(drift, True)[order] / 2 / np.pi / 1e9)
+        dres.append(dress(drift, False) / 2 / np.pi / 1e9)
+        v = np.linalg.eigh(drift)[1]
+        fallback.append((np.abs(v) ** 2).max(axis=0).min() <= 0.5)
+    return np.array(prod), np.array(ordd), np.array(dres), np.array(fallback)
+
+
+def test_dressing_oracle_against_pickled_energy_levels(golden_tc_levels):
+    """f-4 oracle (eigh + reorder_frame, c3/model.py:453-502) against the reference's pickled level sweeps (d = 27,
+    101 flux points).  Where every eigenvector has a component above 0.5 (70 points) all three tables are reproduced to
+    1e-11 GHz; of the 31 "overly dressed" points 18 agree as well and at 13 avoided crossings one or two levels swap:
+    the pickle predates the current greedy fallback, and the reference's own test only asks for |diff| < 1 GHz
+    (test_tunable_coupler.py:376-381)."""
+    from oracle import c3_model_oracle as mo
+    g = golden_tc_levels
+    prod, ordd, dres, fallback = _tc_level_sweep(g, lambda h, o: mo.dressing_transform(h, ordered=o)[0])
+    assert np.abs(prod - g["product_basis"]).max() < 1e-12
+    assert np.abs(dres - g["dressed_basis"]).max() < 1e-11
+    assert np.abs(ordd[~fallback] - g["ordered_basis"][~fallback]).max() < 1e-11
+    differs = (np.abs(ordd - g["ordered_basis"]) > 1e-9).sum(axis=1)
+    assert fallback.sum() == 31 and (differs > 0).sum() == 13 and not np.any(differs[~fallback]) and differs.max() <= 2
+    assert np.abs(ordd - g["ordered_basis"]).max() < 1.0
