@@ -1,0 +1,80 @@
+"""Element-major ("block-interleaved") shared layout: addr(blk, e) = e*S + slot[blk]; at a given instruction all lanes
+read the same element e of different blocks, so conflicts depend on (slot[blk] + off_g) mod 8 only.
+Searches slot residues, group offsets, lane->block permutations, shadow lanes for the x-own / both-own products."""
+import random, sys, math
+random.seed(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+MODE = sys.argv[2] if len(sys.argv) > 2 else "xown"
+
+def wf(keys):   # keys: per lane (g, blk) or None
+    tot = 0
+    for q in range(4):
+        slots = {}
+        for k in keys[q*8:(q+1)*8]:
+            if k is None: continue
+            slots.setdefault(k[2], set()).add((k[0], k[1]))
+        tot += max((len(v) for v in slots.values()), default=0)
+    return tot
+
+def patterns(bi, bj, kord):
+    """block read by lane (bi,bj) for every load instruction class"""
+    if MODE == "xown":
+        return [(bj, bj), (bi, (bj+1) % 3), ((bj+1) % 3, bj), (bi, (bj+2) % 3), ((bj+2) % 3, bj)]
+    if bi != bj:
+        k2 = 3 - bi - bj
+        return [(bi, bi), (bj, bj), (bi, k2), (k2, bj)]
+    k1 = (bi + 1 + kord) % 3; k2 = (bi + 2 - kord) % 3
+    return [(bi, k1), (k1, bj), (bi, k2), (k2, bj)]
+
+def cost(st, detail=False):
+    res, offs, perms, shadow, kord = st
+    lanes = []
+    for lane in range(32):
+        src = lane if lane < 27 else shadow[lane - 27]
+        g = src // 9
+        li = perms[g][src % 9]
+        lanes.append((g, li // 3, li % 3, lane < 27, src))
+    npat = 5 if MODE == "xown" else 4
+    ld = 0
+    for pi in range(npat):
+        keys = []
+        for (g, bi, bj, on, src) in lanes:
+            b = patterns(bi, bj, kord[src])[pi]
+            blk = b[0]*3 + b[1]
+            keys.append((g, blk, (res[blk] + offs[g]) & 7))
+        ld += wf(keys)
+    stt = wf([(g, bi*3+bj, (res[bi*3+bj] + offs[g]) & 7) if on else None for (g, bi, bj, on, src) in lanes])
+    # model (generator) loads: all groups read the same buffer -> same (blk) merges across groups
+    mod = wf([(0, bi*3+bj, res[bi*3+bj]) for (g, bi, bj, on, src) in lanes])
+    if detail: return ld / npat, stt, mod
+    return 6 * 9 * ld + 81 * stt + 27 * mod     # wavefronts per slice (6 products, 9 published matrices, 3 generators)
+
+def rand_state():
+    return [[random.randrange(8) for _ in range(9)], [0, random.randrange(8), random.randrange(8)],
+            [random.sample(range(9), 9) for _ in range(3)], [random.randrange(27) for _ in range(5)],
+            [random.randrange(2) for _ in range(27)]]
+
+def mutate(st):
+    res, offs, perms, shadow, kord = st
+    st = [list(res), list(offs), [list(p) for p in perms], list(shadow), list(kord)]
+    m = random.random()
+    if m < 0.25: st[0][random.randrange(9)] = random.randrange(8)
+    elif m < 0.35: st[1][random.randrange(1, 3)] = random.randrange(8)
+    elif m < 0.8:
+        p = st[2][random.randrange(3)]; i, j = random.sample(range(9), 2); p[i], p[j] = p[j], p[i]
+    elif m < 0.9: st[3][random.randrange(5)] = random.randrange(27)
+    else: st[4][random.randrange(27)] ^= 1
+    return st
+
+best = None
+for restart in range(6):
+    cur = rand_state(); cc = cost(cur)
+    T = 60.0
+    for it in range(40000):
+        nx = mutate(cur); nc = cost(nx)
+        if nc <= cc or random.random() < math.exp((cc - nc) / T):
+            cur, cc = nx, nc
+            if best is None or cc < best[0]:
+                best = (cc, cur)
+        T = max(1.0, T * 0.9998)
+    print("restart", restart, "best", best[0], cost(best[1], True), flush=True)
+print(best)
