@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libc3b200.so")
 SOURCES = ["c3b_api.cu"]
-HEADERS = ["c3b_common.cuh", "pwc_rows.cuh", "pwc_blk.cuh", "pwc_cta.cuh", "pwc_gemm.cuh", "grad.cuh", "fidelity.cuh", "signal_chain.cuh", "dressing.cuh", "product.cuh", "peak.cuh",
+HEADERS = ["c3b_common.cuh", "pwc_rows.cuh", "pwc_blk.cuh", "pwc_blk9.cuh", "pwc_cta.cuh", "pwc_gemm.cuh", "grad.cuh", "fidelity.cuh", "signal_chain.cuh", "dressing.cuh", "product.cuh", "peak.cuh",
            os.path.join("..", "..", "include", "c3b200.h")]
 
 NVCC_FLAGS = [

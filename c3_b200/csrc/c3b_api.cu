@@ -12,6 +12,7 @@
 #include "pwc_cta.cuh"
 #include "pwc_rows.cuh"
 #include "pwc_blk.cuh"
+#include "pwc_blk9.cuh"
 #include "product.cuh"
 #include "pwc_gemm.cuh"
 #include "grad.cuh"
@@ -280,6 +281,26 @@ int launch_blk_t18_t(const RowsParams& rp, unsigned int* counter, cudaStream_t s
     return C3B_OK;
 }
 
+template <int WARPS, int MINB, bool NOSEL>
+int launch_blk9_t18_t(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
+    const size_t smem = Blk9T<NOSEL>::smem_bytes(rp.K, WARPS);
+    if (smem > 227 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: too many control lines (K=%d) for the d=%d block kernel", rp.K, rp.d);
+    auto kern = pwc_blk9_t18_kernel<WARPS, MINB, NOSEL>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    const long long units = (long long)rp.B * rp.S;
+    int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > MINB) per_sm = MINB;
+    long long grid = (long long)num_sms() * per_sm;
+    const long long need = (units + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(int)grid, WARPS * 32, smem, st>>>(rp, counter);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return C3B_OK;
+}
+
 // does the kernel that launch_rows() would pick accept trace-shifted generators?
 bool rows_kernel_takes_shift(int d) { return g_rows_variant >= 13 && blk_template_dim(d) != 0; }
 
@@ -291,7 +312,9 @@ int launch_rows(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
             case 4: return launch_blk_t18_t<4, 2, 4, 3>(rp, counter, st);
             case 6: return launch_blk_t18_t<6, 3, 4, 2>(rp, counter, st);
             case 8: return launch_blk_t18_t<8, 2, 4, 3>(rp, counter, st);
-            case 9: return (g_rows_variant == 14) ? launch_blk_t18_t<9, 3, 4, 3>(rp, counter, st)
+            case 9: if (g_rows_variant == 15) return launch_blk9_t18_t<4, 2, false>(rp, counter, st);
+                    if (g_rows_variant == 16) return launch_blk9_t18_t<4, 2, true>(rp, counter, st);
+                    return (g_rows_variant == 14) ? launch_blk_t18_t<9, 3, 4, 3>(rp, counter, st)
                                                   : launch_blk_t18_t<9, 3, 4, 2>(rp, counter, st);
             case 12: return launch_blk_t18_t<12, 3, 4, 2>(rp, counter, st);
         }

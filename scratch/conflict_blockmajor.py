@@ -21,8 +21,10 @@ def patterns(bi, bj, kord):
         return [(bj, bj), (bi, (bj+1) % 3), ((bj+1) % 3, bj), (bi, (bj+2) % 3), ((bj+2) % 3, bj)]
     if bi != bj:
         k2 = 3 - bi - bj
-        return [(bi, bi), (bj, bj), (bi, k2), (k2, bj)]
+        return [(bi, bi), (bj, bj), (bi, k2), (k2, bj)] + ([None] if MODE == "both2" else [])
     k1 = (bi + 1 + kord) % 3; k2 = (bi + 2 - kord) % 3
+    if MODE == "both2":
+        return [(bi, k1), (bi, bi), (bi, k2), (k2, bj), (k1, bi)]
     return [(bi, k1), (k1, bj), (bi, k2), (k2, bj)]
 
 def cost(st, detail=False):
@@ -33,12 +35,13 @@ def cost(st, detail=False):
         g = src // 9
         li = perms[g][src % 9]
         lanes.append((g, li // 3, li % 3, lane < 27, src))
-    npat = 5 if MODE == "xown" else 4
+    npat = 5 if MODE in ("xown", "both2") else 4
     ld = 0
     for pi in range(npat):
         keys = []
         for (g, bi, bj, on, src) in lanes:
             b = patterns(bi, bj, kord[src])[pi]
+            if b is None: keys.append(None); continue
             blk = b[0]*3 + b[1]
             keys.append((g, blk, (res[blk] + offs[g]) & 7))
         ld += wf(keys)
@@ -66,15 +69,15 @@ def mutate(st):
     return st
 
 best = None
-for restart in range(6):
+for restart in range(3):
     cur = rand_state(); cc = cost(cur)
     T = 60.0
-    for it in range(40000):
+    for it in range(150000):
         nx = mutate(cur); nc = cost(nx)
         if nc <= cc or random.random() < math.exp((cc - nc) / T):
             cur, cc = nx, nc
             if best is None or cc < best[0]:
                 best = (cc, cur)
-        T = max(1.0, T * 0.9998)
+        T = max(1.0, T * 0.99995)
     print("restart", restart, "best", best[0], cost(best[1], True), flush=True)
 print(best)
