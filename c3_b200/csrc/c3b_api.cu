@@ -55,7 +55,7 @@ long long g_grad_variant = getenv("C3B_GRAD_VARIANT") ? atoll(getenv("C3B_GRAD_V
 long long g_min_chunk = getenv("C3B_MIN_CHUNK") ? atoll(getenv("C3B_MIN_CHUNK")) : 8;         // rows kernel: minimum slices per lane group
 // 1: rows v2 (one row per lane, Pade) | 4-6: rows v3 (experimental) | 7-12: block layout, Pade + Gauss-Jordan (d=9)
 // 13 (default): block layout, degree-18 Taylor, trace shift, all d <= 12
-long long g_rows_variant = getenv("C3B_ROWS_VARIANT") ? atoll(getenv("C3B_ROWS_VARIANT")) : 13;      // 0: v1 kernel, 1: v2 (255 regs), 2: v2 V-in-smem (168 regs), 3: v2 (168 regs)
+long long g_rows_variant = getenv("C3B_ROWS_VARIANT") ? atoll(getenv("C3B_ROWS_VARIANT")) : 16;      // 0: v1 kernel, 1: v2 (255 regs), 2: v2 V-in-smem (168 regs), 3: v2 (168 regs)
 
 int num_sms() {
     static int cached = 0;

@@ -32,8 +32,8 @@ struct Blk9T {
     static constexpr int BUF = 9 * S;              // one 9x9 matrix
     static constexpr int NBUF = 5;                 // A/B3, A2/B1/.., A3/B5/A9, P, B2 per lane group
     // group bases (mod 8) as searched with the tables below; warp stride = 0 (mod 8)
-    static constexpr int G1 = NOSEL ? 411 : 410;
-    static constexpr int G2 = NOSEL ? 820 : 822;
+    static constexpr int G1 = NOSEL ? 409 : 410;
+    static constexpr int G2 = NOSEL ? 821 : 822;
     static constexpr int WARP_ELEMS = NOSEL ? 1232 : 1232;
     static_assert(G1 >= NBUF * BUF && G2 >= G1 + NBUF * BUF && WARP_ELEMS >= G2 + NBUF * BUF && WARP_ELEMS % 8 == 0, "layout");
     __host__ __device__ static constexpr int group_off(int g) { return g == 0 ? 0 : (g == 1 ? G1 : G2); }
@@ -46,18 +46,18 @@ struct Blk9 { static constexpr int S = 9; static constexpr int BUF = 81; };
 
 // block (bi*3+bj) -> slot inside an element row (slots 0 and 8 share a bank)
 __constant__ signed char kB9Slot[9] = {4, 0, 2, 1, 8, 6, 3, 7, 5};
-// lane (0..26) -> block owned, per group of 9 lanes
-__constant__ signed char kB9Perm[27] = {5, 1, 6, 2, 8, 0, 3, 7, 4,   2, 6, 3, 0, 1, 7, 8, 5, 4,   8, 6, 4, 3, 5, 7, 1, 0, 2};
+// lane (0..26) -> 9 * group + block owned
+__constant__ signed char kB9Perm[27] = {5, 1, 6, 2, 8, 0, 3, 7, 4,   11, 15, 12, 9, 10, 16, 17, 14, 13,   26, 24, 22, 21, 23, 25, 19, 18, 20};
 // lanes 27..31 shadow these lanes (same addresses, never store)
 __constant__ signed char kB9Shadow[5] = {12, 9, 14, 13, 12};
 // diagonal lanes: 0 -> (k1, k2) = (bi+1, bi+2), 1 -> (bi+2, bi+1)
 __constant__ signed char kB9Kord[27] = {0, 0, 0, 0, 0, 1, 0, 0, 1,   1, 1, 0, 1, 1, 1, 0, 1, 0,   1, 0, 0, 0, 1, 0, 1, 1, 1};
 
 // second table set: layout searched for the select-free product (NOSEL), see mm_own9
-__constant__ signed char kB9nSlot[9] = {0, 5, 8, 3, 2, 1, 4, 7, 6};
-__constant__ signed char kB9nPerm[27] = {1, 7, 4, 6, 3, 8, 0, 5, 2,   3, 8, 2, 7, 4, 5, 6, 1, 0,   8, 1, 4, 3, 0, 5, 7, 6, 2};
-__constant__ signed char kB9nShadow[5] = {26, 15, 24, 14, 24};
-__constant__ signed char kB9nKord[27] = {0, 1, 0, 0, 0, 0, 0, 1, 0,   1, 0, 0, 1, 1, 0, 1, 1, 0,   1, 1, 0, 0, 0, 0, 1, 1, 0};
+__constant__ signed char kB9nSlot[9] = {2, 6, 1, 5, 4, 0, 7, 3, 8};
+__constant__ signed char kB9nPerm[27] = {6, 9, 16, 11, 12, 13, 15, 17, 1,   4, 10, 0, 3, 2, 7, 8, 22, 26,   20, 21, 19, 18, 25, 24, 23, 14, 5};
+__constant__ signed char kB9nShadow[5] = {0, 8, 25, 8, 25};
+__constant__ signed char kB9nKord[27] = {0, 0, 0, 0, 0, 1, 1, 1, 0,   1, 0, 1, 1, 0, 0, 0, 1, 0,   0, 0, 0, 0, 0, 1, 0, 0, 1};
 template <bool NOSEL> struct Blk9Tab {
     __device__ static __forceinline__ int slot(int i) { return NOSEL ? kB9nSlot[i] : kB9Slot[i]; }
     __device__ static __forceinline__ int perm(int i) { return NOSEL ? kB9nPerm[i] : kB9Perm[i]; }
@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
 
     const bool lane_on = lane < 27;
     const int src = lane_on ? lane : TB::shadow(lane - 27);
-    const int g = src / 9;
-    const int li = TB::perm(src);
+    const int g = TB::perm(src) / 9;           // lane group = the slice chunk this lane works on
+    const int li = TB::perm(src) - g * 9;      // block owned
     const int bi = li / 3, bj = li - bi * 3;
     const int r0 = bi * 3, c0 = bj * 3;
     Blk9Lane L;
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
     if (hmode) {
 #pragma unroll
         for (int q = 0; q < 3; ++q)
-            for (int j = 0; j < 9; ++j)
-                if (TB::perm(g * 9 + j) == bi * 3 + q) rowlane[q] = g * 9 + j;
+            for (int j = 0; j < 27; ++j)
+                if (TB::perm(j) == g * 9 + bi * 3 + q) rowlane[q] = j;
     }
 
     cplx* gbase = sWarps + (size_t)warp * LY::WARP_ELEMS + LY::group_off(g);

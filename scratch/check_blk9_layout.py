@@ -18,11 +18,11 @@ for nosel in (0, 1):
     slot, perm, shadow, kord = tab(pre + 'Slot'), tab(pre + 'Perm'), tab(pre + 'Shadow'), tab(pre + 'Kord')
     g1 = int(re.search(r"G1 = NOSEL \? (\d+) : (\d+)", src).group(1 if nosel else 2)); g2 = int(re.search(r"G2 = NOSEL \? (\d+) : (\d+)", src).group(1 if nosel else 2))
     goff = [0, g1, g2]
-    assert sorted(slot) == list(range(9)) and all(sorted(perm[i*9:(i+1)*9]) == list(range(9)) for i in range(3))
+    assert sorted(slot) == list(range(9)) and sorted(perm) == list(range(27))
     lanes = []
     for lane in range(32):
         s = lane if lane < 27 else shadow[lane-27]
-        g = s // 9; li = perm[s]; bi, bj = li // 3, li % 3
+        g = perm[s] // 9; li = perm[s] % 9; bi, bj = li // 3, li % 3
         yd = None
         if bi != bj: kx1, ky1, k2 = bi, bj, 3 - bi - bj
         else:

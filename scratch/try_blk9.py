@@ -36,5 +36,5 @@ for v in VS + VS:
         U = engine.pwc_closed(m.h0, m.hks, sig, 1e-11)
         torch.cuda.synchronize(); ts.append(engine.last_kernel_ms())
     print("variant", v, "kernel ms", ts, "slices/s %.3e" % (B * N / min(ts) * 1e3))
-    if v == 13: U13 = U.clone()
+    if v == VS[0]: U13 = U.clone()
     else: print(v, "vs 13", rel(U.cpu().numpy(), U13.cpu().numpy()))

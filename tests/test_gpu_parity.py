@@ -228,10 +228,14 @@ def test_cta_kernels_pade_and_taylor(eng, d, cta_variant):
     assert rel_fro(U.cpu().numpy(), wantU) < TOL
 
 
-@pytest.mark.parametrize("variant", [1, 8, 13])
+DEFAULT_ROWS_VARIANT = 16
+
+
+@pytest.mark.parametrize("variant", [1, 8, 13, 15, 16])
 def test_register_kernel_variants_d9(eng, variant):
-    """The three generations of the small-d kernel on the headline shape: rows/Pade (1),
-    blocks/Pade + Gauss-Jordan (8), blocks/Taylor-18 + trace shift (13, default)."""
+    """The generations of the small-d kernel on the headline shape: rows/Pade (1), blocks/Pade + Gauss-Jordan (8),
+    blocks/Taylor-18 + trace shift (13), own-block products in the element-major layout with register selects (15)
+    and select-free (16, default for d = 9)."""
     from c3_b200 import synth
     m = synth.two_transmon()
     sig = synth.controls(m, 3, 203)
@@ -239,10 +243,32 @@ def test_register_kernel_variants_d9(eng, variant):
     try:
         U, dUs = eng.pwc_closed(m.h0, m.hks, sig, 1e-11, return_dUs=True)
     finally:
-        eng.set_tuning("rows_variant", 13)
+        eng.set_tuning("rows_variant", DEFAULT_ROWS_VARIANT)
     wantU, want_dUs = orc.propagate_batch(m.h0, m.hks, sig, 1e-11, return_dUs=True)
     assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
     assert rel_fro(U.cpu().numpy(), wantU) < TOL
+
+
+@pytest.mark.parametrize("variant", [13, 15, 16])
+@pytest.mark.parametrize("scale,N,B", [(6.0, 37, 2), (30.0, 20, 3), (0.5, 1, 2), (2.0, 1000, 5)])
+def test_d9_kernel_generations_random_models(eng, variant, scale, N, B):
+    """d = 9 kernels on random complex Hermitian models: squarings (norm up to ~30), a single slice, ragged segments
+    (B * N forces several segments per batch element), the H-list entry and the partial propagators."""
+    rng = np.random.default_rng(int(scale * 10) + N)
+    d, K = 9, 2
+    h0, hks = _rand_model(rng, d, K, scale)
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    eng.set_tuning("rows_variant", variant)
+    try:
+        U, dUs = eng.pwc_closed(h0, hks, sig, 1.0, return_dUs=True)
+        Hs = h0[None, None] + np.einsum("bkn,kij->bnij", sig, hks)
+        U2 = eng.pwc_closed_hlist(Hs, 1.0)
+    finally:
+        eng.set_tuning("rows_variant", DEFAULT_ROWS_VARIANT)
+    wantU, want_dUs = orc.propagate_batch(h0, hks, sig, 1.0, return_dUs=True)
+    assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
+    assert rel_fro(U.cpu().numpy(), wantU) < TOL
+    assert rel_fro(U2.cpu().numpy(), wantU) < TOL
 
 
 def test_lindblad_config3_shape(eng):
