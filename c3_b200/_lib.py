@@ -16,7 +16,7 @@ SYMBOLS = [
     "c3b_last_kernel_ms", "c3b_pwc_grad_workspace_bytes", "c3b_pwc_closed_grad",
     "c3b_gate_infid", "c3b_gate_infid_grad", "c3b_seq_populations", "c3b_signal_slice_num", "c3b_generate_signals",
     "c3b_generate_signals_grad", "c3b_pwc_lindblad_grad_workspace_bytes", "c3b_pwc_lindblad_grad",
-    "c3b_dress_models",
+    "c3b_dress_models", "c3b_pwc_closed_gated", "c3b_pwc_gated_supported",
 ]
 
 _lib = None
@@ -44,6 +44,10 @@ def load() -> C.CDLL:
     lib.c3b_pwc_workspace_bytes.argtypes = [i, i, i, i, i, i]
     lib.c3b_pwc_closed.restype = i
     lib.c3b_pwc_closed.argtypes = [vp, vp, vp, d, i, i, i, i, i, vp, vp, vp, sz, vp]
+    lib.c3b_pwc_closed_gated.restype = i
+    lib.c3b_pwc_closed_gated.argtypes = [vp, vp, vp, d, i, i, i, i, vp, vp, vp, sz, vp]
+    lib.c3b_pwc_gated_supported.restype = i
+    lib.c3b_pwc_gated_supported.argtypes = [i]
     lib.c3b_pwc_closed_hlist.restype = i
     lib.c3b_pwc_closed_hlist.argtypes = [vp, d, i, i, i, vp, vp, vp, sz, vp]
     lib.c3b_pwc_lindblad.restype = i

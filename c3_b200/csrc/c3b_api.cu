@@ -281,11 +281,11 @@ int launch_blk_t18_t(const RowsParams& rp, unsigned int* counter, cudaStream_t s
     return C3B_OK;
 }
 
-template <int WARPS, int MINB, bool NOSEL>
+template <int WARPS, int MINB, bool NOSEL, bool GATED = false>
 int launch_blk9_t18_t(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
     const size_t smem = Blk9T<NOSEL>::smem_bytes(rp.K, WARPS);
     if (smem > 227 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: too many control lines (K=%d) for the d=%d block kernel", rp.K, rp.d);
-    auto kern = pwc_blk9_t18_kernel<WARPS, MINB, NOSEL>;
+    auto kern = pwc_blk9_t18_kernel<WARPS, MINB, NOSEL, GATED>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     const long long units = (long long)rp.B * rp.S;
@@ -313,7 +313,8 @@ int launch_rows(const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
             case 6: return launch_blk_t18_t<6, 3, 4, 2>(rp, counter, st);
             case 8: return launch_blk_t18_t<8, 2, 4, 3>(rp, counter, st);
             case 9: if (g_rows_variant == 15) return launch_blk9_t18_t<4, 2, false>(rp, counter, st);
-                    if (g_rows_variant == 16) return launch_blk9_t18_t<4, 2, true>(rp, counter, st);
+                    if (g_rows_variant == 16) return rp.rows_ready ? launch_blk9_t18_t<4, 2, true, true>(rp, counter, st)
+                                                                   : launch_blk9_t18_t<4, 2, true>(rp, counter, st);
                     return (g_rows_variant == 14) ? launch_blk_t18_t<9, 3, 4, 3>(rp, counter, st)
                                                   : launch_blk_t18_t<9, 3, 4, 2>(rp, counter, st);
             case 12: return launch_blk_t18_t<12, 3, 4, 2>(rp, counter, st);
@@ -418,6 +419,8 @@ int launch_product(ProductParams pp, cudaStream_t st) {
     return launch_product_t<32, 4, 3>(pp, (int)g, st);
 }
 
+thread_local const unsigned int* t_rows_ready = nullptr;   // set by c3b_pwc_closed_gated around its call of c3b_pwc_closed
+
 // common tail of the three pwc entry points once G (or the H list) is in place
 int run_pwc(const Plan& pl, const cplx* G, const double* RS, const cplx* TR, const double* signals, const cplx* hlist, double dt,
             int B, int K, int N, int D, int batched_model, cplx* U_out, cplx* dUs_out, char* ws, cudaStream_t st) {
@@ -433,9 +436,13 @@ int run_pwc(const Plan& pl, const cplx* G, const double* RS, const cplx* TR, con
         rp.model_stride = 0;
         rp.B = B; rp.K = K; rp.N = N; rp.d = D; rp.S = pl.S; rp.seg_len = pl.seg_len;
         rp.U_out = U_out; rp.seg_out = seg; rp.dUs_out = dUs_out;
+        rp.rows_ready = t_rows_ready;
+        if (t_rows_ready != nullptr && !(g_rows_variant == 16 && D == 9))
+            return fail(C3B_EUNSUPPORTED, "C3:ERROR: gated launch is built for the d = 9 kernel only");
         int rc = launch_rows(rp, reinterpret_cast<unsigned int*>(ws + pl.off_counter), st);
         if (rc) return rc;
     } else {
+        if (t_rows_ready != nullptr) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gated launch is built for the d = 9 kernel only");
         CtaParams cp{};
         cp.G = G; cp.signals = signals; cp.hlist = hlist;
         cp.hscale_re = 0.0; cp.hscale_im = -dt;
@@ -531,6 +538,18 @@ int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, doubl
     return run_pwc(pl, G, RS, TR, signals, nullptr, dt, B, K, N, d, batched_model, static_cast<cplx*>(U_out),
                    static_cast<cplx*>(dUs_out), ws, st);
 }
+
+int c3b_pwc_closed_gated(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
+                         void* U_out, const uint32_t* rows_ready, void* workspace, size_t workspace_bytes, void* stream) {
+    if (rows_ready == nullptr) return fail(C3B_EINVAL, "C3:ERROR: rows_ready is NULL");
+    if (K <= 0) return fail(C3B_EINVAL, "C3:ERROR: gated launch needs control fields (K > 0)");
+    t_rows_ready = rows_ready;
+    const int rc = c3b_pwc_closed(h0, hks, signals, dt, B, K, N, d, 0, U_out, nullptr, workspace, workspace_bytes, stream);
+    t_rows_ready = nullptr;
+    return rc;
+}
+
+int c3b_pwc_gated_supported(int d) { return (g_rows_variant == 16 && d == 9 && g_force_cta == 0) ? 1 : 0; }
 
 int c3b_pwc_closed_hlist(const void* Hs, double dt, int B, int N, int d, void* U_out, void* dUs_out,
                          void* workspace, size_t workspace_bytes, void* stream) {

@@ -154,7 +154,7 @@ __device__ __forceinline__ void store_own9(cplx* __restrict__ M, const int sown,
     }
 }
 
-template <int WARPS, int MINB, bool NOSEL>
+template <int WARPS, int MINB, bool NOSEL, bool GATED>
 __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const RowsParams p, unsigned int* __restrict__ counter) {
     using LY = Blk9T<NOSEL>;
     using TB = Blk9Tab<NOSEL>;
@@ -246,6 +246,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
         const int my_begin = n_begin + g * cl;
         const int my_end = min(n_end, my_begin + cl);
         const double* sig_b = p.signals ? p.signals + (size_t)b * K * p.N : nullptr;
+        if constexpr (GATED) {
+            if (!wait_rows_ready(p.rows_ready, b, lane)) {       // the row never arrived: fail loudly, do not hang
+                cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * d * d) : (p.seg_out + ((size_t)b * p.S + sidx) * d * d);
+                for (int e = lane; e < d * d; e += 32) o[e] = cmake(__longlong_as_double(0x7ff8000000000000LL), 0.0);
+                continue;
+            }
+        }
         cplx mu_acc = cmake(0.0, 0.0);
 
 #pragma unroll 1
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
                 }
                 if (shifted && on) mu = p.TR[0];
                 for (int k = 0; k < K; ++k) {
-                    const double cs = on ? __ldg(sig_b + (size_t)k * p.N + n) : 0.0;
+                    const double cs = on ? load_signal(sig_b + (size_t)k * p.N + n, GATED) : 0.0;
                     const cplx* gk = sG + (k + 1) * BUF + L.sown;
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {

@@ -103,11 +103,16 @@ def pwc_closed(h0, hks, signals, dt: float, return_dUs: bool = False, device=Non
     return (U, dUs) if return_dUs else U
 
 
-def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, device=None):
-    """Closed-system propagators for HOST-resident signals [B,K,N] (numpy or CPU tensor, ideally
-    pinned): the batch is cut into chunks and the host->device copy of chunk i+1 overlaps the kernel
-    of chunk i (two CUDA streams), so PCIe time hides behind compute.  Returns U [B,d,d] on the
-    device, ordered on the caller's current stream."""
+def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, first_chunk: int = 256, device=None):
+    """Closed-system propagators for HOST-resident signals [B,K,N] (numpy or CPU tensor, ideally pinned).
+
+    d = 9 (the headline kernel): ONE persistent launch over the whole batch, gated by a device counter.  The host
+    enqueues the chunked host->device copies on a copy stream, each followed by a 4-byte copy that raises the counter
+    to the number of batch rows that have landed; the kernel starts once the first (small) chunk is in and its warps,
+    which take batch rows in order, wait only if they overtake the copy engine (``c3b_pwc_closed_gated``).
+    Other d: the batch is cut into chunks and the copy of chunk i+1 overlaps the kernel of chunk i (two streams).
+    Returns U [B,d,d] on the device, ordered on the caller's current stream."""
+    lib = _lib.load()
     device = torch.device(device) if device is not None else default_device()
     if not isinstance(signals_host, torch.Tensor):
         signals_host = torch.as_tensor(signals_host)
@@ -122,12 +127,40 @@ def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, de
         hks = _as(hks, torch.complex128, device) if K > 0 else None
         d = h0.shape[-1]
         U = torch.empty((B, d, d), dtype=torch.complex128, device=device)
-        if B <= chunk or h0.dim() == 3:
+        if B <= chunk or h0.dim() == 3 or K == 0:
             return pwc_closed(h0, hks, signals_host.to(device, non_blocking=True), dt, device=device, out=U)
         main = torch.cuda.current_stream()
         streams = _side_streams(device)
         start = torch.cuda.Event()
         start.record(main)
+        if lib.c3b_pwc_gated_supported(int(d)):
+            if tuple(hks.shape) != (K, d, d):
+                raise ValueError(f"C3:ERROR: hks has shape {tuple(hks.shape)}, expected {(K, d, d)}")
+            bounds = [0, min(B, max(1, int(first_chunk)))]
+            while bounds[-1] < B:
+                bounds.append(min(B, bounds[-1] + chunk))
+            sig = torch.empty((B, K, N), dtype=torch.float64, device=device)
+            ready = torch.empty((1,), dtype=torch.int32, device=device)
+            marks = torch.tensor(bounds[1:], dtype=torch.int32).pin_memory()
+            cs = streams[0]
+            cs.wait_event(start)
+            first = torch.cuda.Event()
+            with torch.cuda.stream(cs):
+                ready.zero_()
+                for i in range(len(bounds) - 1):
+                    sig[bounds[i]:bounds[i + 1]].copy_(signals_host[bounds[i]:bounds[i + 1]], non_blocking=True)
+                    ready.copy_(marks[i:i + 1], non_blocking=True)
+                    if i == 0:
+                        first.record(cs)
+            sig.record_stream(cs)
+            ready.record_stream(cs)
+            _keepalive(device, marks, cs)
+            main.wait_event(first)          # every copy is already enqueued: the kernel can only wait on the copy engine
+            nbytes = lib.c3b_pwc_workspace_bytes(B, K, N, d, 0, 0)
+            ws = _workspace(nbytes, device)
+            _lib.check(lib.c3b_pwc_closed_gated(_ptr(h0), _ptr(hks), _ptr(sig), float(dt), B, K, N, d, _ptr(U), _ptr(ready),
+                                                _ptr(ws), ws.numel(), _stream()))
+            return U
         done = []
         for i, b0 in enumerate(range(0, B, chunk)):
             b1 = min(B, b0 + chunk)
@@ -144,6 +177,19 @@ def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, de
             main.wait_event(ev)
         U.record_stream(main)
     return U
+
+
+_pinned_in_flight = {}
+
+
+def _keepalive(device, host_tensor, stream):
+    """Keep a pinned staging tensor alive until the copies that read it have run (dropped on a later call)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    q = _pinned_in_flight.setdefault(key, [])
+    q[:] = [(e, t) for (e, t) in q if not e.query()]
+    q.append((ev, host_tensor))
 
 
 _side = {}

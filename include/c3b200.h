@@ -60,6 +60,17 @@ int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, doubl
                    int batched_model, void* U_out, void* dUs_out, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* Gated variant of c3b_pwc_closed for HOST-resident control fields (shared model, no dUs, d = 9: the headline kernel): the caller enqueues
+ * the host->device copies of `signals` in batch order on a copy stream, each chunk followed by a 4-byte copy that
+ * raises *rows_ready (device memory, zero before the first chunk) to the number of batch rows that have landed, and
+ * launches this ONE call on another stream as soon as the first chunk is in.  Warps take batch rows in order and wait
+ * on *rows_ready only if they overtake the copy engine, so PCIe time hides behind the whole-batch kernel instead of
+ * cutting it into per-chunk launches.  A row that does not arrive within ~4 s is returned as NaN (no GPU hang).
+ * c3b_pwc_gated_supported(d) != 0 says whether the dimension takes this path. */
+int c3b_pwc_closed_gated(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
+                         void* U_out, const uint32_t* rows_ready, void* workspace, size_t workspace_bytes, void* stream);
+int c3b_pwc_gated_supported(int d);
+
 /* Same with explicit per-slice Hamiltonians (the reference's `signals is None` branch,
  * c3/libraries/propagation.py:294-308, 491-499, 437-438):  Hs [B,N,d,d]. */
 int c3b_pwc_closed_hlist(const void* Hs, double dt, int B, int N, int d, void* U_out, void* dUs_out,

@@ -410,6 +410,26 @@ def test_host_pipelined_path_matches_device_path(eng):
     assert rel_fro(U_host[[0, 1023, 1024, 2499]].cpu().numpy(), want) < TOL
 
 
+@pytest.mark.parametrize("d,chunk,first", [(9, 3, 1), (9, 64, 256), (6, 5, 2), (27, 4, 1)])
+def test_gated_single_launch_host_path(eng, d, chunk, first):
+    """Host-resident control fields through the gated single launch (c3b_pwc_closed_gated: d = 9) and through the
+    chunked two-stream fallback (d = 6, 27): many small chunks, repeated calls on reused buffers, bit-identical to the
+    device-resident call."""
+    rng = np.random.default_rng(d)
+    K, B, N = 2, 23, 40
+    h0, hks = _rand_model(rng, d, K, 1.5)
+    for rep in range(3):
+        sig = rng.uniform(-1, 1, size=(B, K, N))
+        host = torch.as_tensor(sig).pin_memory()
+        U_host = eng.pwc_closed_from_host(h0, hks, host, 1.0, chunk=chunk, first_chunk=first)
+        U_dev = eng.pwc_closed(h0, hks, torch.as_tensor(sig).cuda(), 1.0)
+        torch.cuda.synchronize()
+        assert not torch.isnan(U_host.real).any()
+        assert rel_fro(U_host.cpu().numpy(), U_dev.cpu().numpy()) < 1e-13
+    want = orc.propagate_batch(h0, hks, sig, 1.0)
+    assert rel_fro(U_host.cpu().numpy(), want) < TOL
+
+
 def test_error_reporting(eng):
     from c3_b200 import _lib
     lib = _lib.load()
