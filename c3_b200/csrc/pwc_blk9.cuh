@@ -238,6 +238,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
         const long long unit = unit_u;
         if (unit >= total_units) break;
         const int b = (int)(unit / p.S);
+        if constexpr (GATED) {
+            // gated launch: wait (all lanes, uniform code) until this unit's batch row has landed; rows arrive in order.
+            // A row that never arrives ends this warp's work like an exhausted counter: the caller pre-fills U with NaN,
+            // so the failure is loud and the GPU does not hang.
+            if (!wait_rows_ready(p.rows_ready, b)) break;
+        }
         const int sidx = (int)(unit - (long long)b * p.S);
         const int n_begin = sidx * p.seg_len;
         const int n_end = min(p.N, n_begin + p.seg_len);
@@ -246,13 +252,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
         const int my_begin = n_begin + g * cl;
         const int my_end = min(n_end, my_begin + cl);
         const double* sig_b = p.signals ? p.signals + (size_t)b * K * p.N : nullptr;
-        if constexpr (GATED) {
-            if (!wait_rows_ready(p.rows_ready, b, lane)) {       // the row never arrived: fail loudly, do not hang
-                cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * d * d) : (p.seg_out + ((size_t)b * p.S + sidx) * d * d);
-                for (int e = lane; e < d * d; e += 32) o[e] = cmake(__longlong_as_double(0x7ff8000000000000LL), 0.0);
-                continue;
-            }
-        }
         cplx mu_acc = cmake(0.0, 0.0);
 
 #pragma unroll 1

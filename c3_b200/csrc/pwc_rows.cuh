@@ -45,23 +45,18 @@ struct RowsParams {
     const unsigned int* rows_ready;   // gated launch (host-resident signals): batch rows [0, *rows_ready) have landed in `signals`; or null
 };
 
-// Gated launch: wait until batch row b of the control fields has arrived.  The host enqueues the chunked host->device
-// copies of `signals` on a copy stream, each followed by a 4-byte copy that raises *rows_ready, and launches ONE
-// persistent kernel; warps pull units in batch order and spin here only if they overtake the copy engine.  Returns
-// false after ~4 s without progress (the caller then poisons its output with NaN instead of hanging the GPU).
-__device__ __forceinline__ bool wait_rows_ready(const unsigned int* rows_ready, const int b, const int lane) {
-    int ok = 1;
-    if (lane == 0) {
-        unsigned int spins = 0, v;
-        for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(rows_ready) : "memory");
-            if (v > (unsigned int)b) break;
-            __nanosleep(256);
-            if (++spins > (1u << 24)) { ok = 0; break; }
-        }
+// Gated launch: wait until batch row b of the control fields has arrived (warp-uniform: every lane polls).  The host enqueues the
+// chunked host->device copies of `signals` on a copy stream, each followed by a 4-byte copy that raises *rows_ready, and
+// launches ONE persistent kernel; warps pull units in batch order and spin here only if they overtake the copy engine.
+// Returns false after ~4 s without progress.
+__device__ __forceinline__ bool wait_rows_ready(const unsigned int* rows_ready, const int b) {
+    unsigned int spins = 0, v;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(rows_ready) : "memory");
+        if (v > (unsigned int)b) return true;
+        __nanosleep(256);
+        if (++spins > (1u << 24)) return false;
     }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    return ok != 0;
 }
 // control-field sample.  Also in a gated launch the read-only path is safe: no thread touches a row's addresses before
 // the acquire load of *rows_ready has seen it (the asm's memory clobber keeps the compiler from hoisting), and L1 holds

@@ -139,6 +139,7 @@ def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, fi
             bounds = [0, min(B, max(1, int(first_chunk)))]
             while bounds[-1] < B:
                 bounds.append(min(B, bounds[-1] + chunk))
+            U.fill_(float("nan"))            # rows the kernel never gets to see (copy failure) stay NaN: loud, not a hang
             sig = torch.empty((B, K, N), dtype=torch.float64, device=device)
             ready = torch.empty((1,), dtype=torch.int32, device=device)
             marks = torch.tensor(bounds[1:], dtype=torch.int32).pin_memory()

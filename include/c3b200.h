@@ -65,7 +65,7 @@ int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, doubl
  * raises *rows_ready (device memory, zero before the first chunk) to the number of batch rows that have landed, and
  * launches this ONE call on another stream as soon as the first chunk is in.  Warps take batch rows in order and wait
  * on *rows_ready only if they overtake the copy engine, so PCIe time hides behind the whole-batch kernel instead of
- * cutting it into per-chunk launches.  A row that does not arrive within ~4 s is returned as NaN (no GPU hang).
+ * cutting it into per-chunk launches.  If a row does not arrive within ~4 s the kernel stops taking work (no GPU hang): pre-fill U_out with NaN to see it.
  * c3b_pwc_gated_supported(d) != 0 says whether the dimension takes this path. */
 int c3b_pwc_closed_gated(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
                          void* U_out, const uint32_t* rows_ready, void* workspace, size_t workspace_bytes, void* stream);

@@ -26,7 +26,10 @@ for chunk in (512, 1024, 2048):
             U = engine.pwc_closed_from_host(m.h0, m.hks, host, 1e-11, chunk=chunk)
             Uh.copy_(U, non_blocking=True); torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / 5
-    print(f"chunk {chunk}: e2e {dt*1e3:.3f} ms/step  ({B*N/dt:.3e}/s)")
+    engine.set_tuning("profile", 1)
+    U = engine.pwc_closed_from_host(m.h0, m.hks, host, 1e-11, chunk=chunk); torch.cuda.synchronize()
+    print(f"chunk {chunk}: e2e {dt*1e3:.3f} ms/step  ({B*N/dt:.3e}/s); gated kernel {engine.last_kernel_ms():.3f} ms")
+    engine.set_tuning("profile", 0)
 # raw copies
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(5): d = host.to("cuda", non_blocking=True); torch.cuda.synchronize()
