@@ -48,6 +48,7 @@ bool g_ev_valid = false;
 
 // ---- tuning (process-wide) -------------------------------------------------------------------
 long long g_target_units = 32768;  // rows kernel: aim for this many warp work units per launch
+long long g_gemm_big = getenv("C3B_GEMM_BIG") ? atoll(getenv("C3B_GEMM_BIG")) : 0;   // DMMA CTA kernel, DP = 88 (D = 81): macro-tile shape
 long long g_force_cta = 0;         // route everything to the CTA kernel (testing)
 long long g_cta_variant = getenv("C3B_CTA_VARIANT") ? atoll(getenv("C3B_CTA_VARIANT")) : 1;  // 0: Pade + pivoted Gauss-Jordan, 1: Taylor-18 on DMMA tiles
 long long g_cta_threads = getenv("C3B_CTA_THREADS") ? atoll(getenv("C3B_CTA_THREADS")) : 512;   // DMMA CTA kernel, DP = 32: 256 or 512 threads
@@ -384,6 +385,9 @@ int launch_gemm(const CtaParams& cp, const cplx* TR, int grid, cudaStream_t st) 
         return cp.D <= 28 ? launch_gemm_t<1, 2, 32, 7>(gp, grid, st) : launch_gemm_t<1, 2, 32, 8>(gp, grid, st);
     }
     if (gp.DP <= 48) return launch_gemm_t<1, 2>(gp, grid, st);
+    // 11 x 11 blocks at D = 81: 3 x 2 macro tiles give 24 tiles = 3 full rounds of the 8 warps (144 block slots for 121
+    // blocks) where 2 x 2 gives 36 tiles = 5 rounds (160 slots): 20.5 -> 19.9 ms on the 296 x 40 probe (2 x 3: 20.5, 3 x 3: 23.9)
+    if (gp.DP == 88 && g_gemm_big == 0) return launch_gemm_t<3, 2>(gp, grid, st);
     return launch_gemm_t<2, 2>(gp, grid, st);
 }
 
@@ -486,6 +490,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (key == nullptr) return fail(C3B_EINVAL, "C3:ERROR: null tuning key");
     if (!strcmp(key, "target_units")) { g_target_units = value < 1 ? 1 : value; return C3B_OK; }
     if (!strcmp(key, "force_cta")) { g_force_cta = value; return C3B_OK; }
+    if (!strcmp(key, "gemm_big")) { g_gemm_big = value; return C3B_OK; }
     if (!strcmp(key, "cta_variant")) { g_cta_variant = value; return C3B_OK; }
     if (!strcmp(key, "cta_threads")) { g_cta_threads = value; return C3B_OK; }
     if (!strcmp(key, "grad_variant")) { g_grad_variant = value; return C3B_OK; }
