@@ -49,6 +49,7 @@ bool g_ev_valid = false;
 // ---- tuning (process-wide) -------------------------------------------------------------------
 long long g_target_units = 32768;  // rows kernel: aim for this many warp work units per launch
 long long g_gemm_big = getenv("C3B_GEMM_BIG") ? atoll(getenv("C3B_GEMM_BIG")) : 0;   // DMMA CTA kernel, DP = 88 (D = 81): macro-tile shape
+long long g_seq_variant = 1;       // evaluate_sequences: 1 = lane-group kernel for small d, 0 = CTA-per-sequence product kernel
 long long g_force_cta = 0;         // route everything to the CTA kernel (testing)
 long long g_cta_variant = getenv("C3B_CTA_VARIANT") ? atoll(getenv("C3B_CTA_VARIANT")) : 1;  // 0: Pade + pivoted Gauss-Jordan, 1: Taylor-18 on DMMA tiles
 long long g_cta_threads = getenv("C3B_CTA_THREADS") ? atoll(getenv("C3B_CTA_THREADS")) : 512;   // DMMA CTA kernel, DP = 32: 256 or 512 threads
@@ -470,6 +471,41 @@ int run_pwc(const Plan& pl, const cplx* G, const double* RS, const cplx* TR, con
     return C3B_OK;
 }
 
+template <int D, int BS>
+int launch_seq_blk_t(const cplx* gates, int Gn, const int* idx, const int* lens, int S, int Lmax, int d, cplx* out, cudaStream_t st) {
+    using L = BlkLayout<D, BS>;
+    constexpr int WARPS = 4;
+    const size_t smem = ((size_t)Gn * L::BUF + (size_t)WARPS * L::WARP_ELEMS) * sizeof(cplx);
+    auto kern = seq_product_blk_kernel<D, BS, WARPS>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long wunits = ((long long)S + L::MPW - 1) / L::MPW;
+    long long grid = (wunits + WARPS - 1) / WARPS;
+    const long long cap = (long long)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<(int)grid, WARPS * 32, smem, st>>>(gates, Gn, idx, lens, S, Lmax, d, out);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return C3B_OK;
+}
+
+// lane-group kernel for small dimensions when the zero-padded gate table fits in shared memory; -1 = not applicable
+int launch_seq_blk(const cplx* gates, int Gn, const int* idx, const int* lens, int S, int Lmax, int d, cplx* out, cudaStream_t st) {
+    const int TD = blk_template_dim(d);
+    if (TD == 0 || g_seq_variant == 0 || Lmax <= 0) return -1;
+    if ((size_t)Gn * (TD + 2) * TD * sizeof(cplx) > (size_t)96 * 1024) return -1;
+    switch (TD) {
+        case 2: return launch_seq_blk_t<2, 2>(gates, Gn, idx, lens, S, Lmax, d, out, st);
+        case 3: return launch_seq_blk_t<3, 3>(gates, Gn, idx, lens, S, Lmax, d, out, st);
+        case 4: return launch_seq_blk_t<4, 2>(gates, Gn, idx, lens, S, Lmax, d, out, st);
+        case 6: return launch_seq_blk_t<6, 3>(gates, Gn, idx, lens, S, Lmax, d, out, st);
+        case 8: return launch_seq_blk_t<8, 2>(gates, Gn, idx, lens, S, Lmax, d, out, st);
+        case 9: return launch_seq_blk_t<9, 3>(gates, Gn, idx, lens, S, Lmax, d, out, st);
+        case 12: return launch_seq_blk_t<12, 3>(gates, Gn, idx, lens, S, Lmax, d, out, st);
+    }
+    return -1;
+}
+
 int check_common(int B, int K, int N, int d, const void* U_out, const void* ws) {
     if (B <= 0 || N <= 0 || d <= 0 || K < 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d N=%d d=%d)", B, K, N, d);
     if (U_out == nullptr) return fail(C3B_EINVAL, "C3:ERROR: U_out is NULL");
@@ -490,6 +526,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (key == nullptr) return fail(C3B_EINVAL, "C3:ERROR: null tuning key");
     if (!strcmp(key, "target_units")) { g_target_units = value < 1 ? 1 : value; return C3B_OK; }
     if (!strcmp(key, "force_cta")) { g_force_cta = value; return C3B_OK; }
+    if (!strcmp(key, "seq_variant")) { g_seq_variant = value; return C3B_OK; }
     if (!strcmp(key, "gemm_big")) { g_gemm_big = value; return C3B_OK; }
     if (!strcmp(key, "cta_variant")) { g_cta_variant = value; return C3B_OK; }
     if (!strcmp(key, "cta_threads")) { g_cta_threads = value; return C3B_OK; }
@@ -656,6 +693,11 @@ int c3b_seq_product(const void* gates, int Gn, const int32_t* seq_idx, const int
         return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
     if (D > 64 && (workspace == nullptr || workspace_bytes < product_scratch_bytes(D)))
         return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small");
+    {
+        const int rc = launch_seq_blk(static_cast<const cplx*>(gates), Gn, seq_idx, seq_len, S, Lmax, D, static_cast<cplx*>(out),
+                                      static_cast<cudaStream_t>(stream));
+        if (rc >= 0) return rc;
+    }
     ProductParams pp{};
     pp.mats = static_cast<const cplx*>(gates); pp.idx = seq_idx; pp.lens = seq_len;
     pp.B = S; pp.M = Lmax; pp.D = D; pp.S = 1; pp.seg_len = Lmax > 0 ? Lmax : 1;

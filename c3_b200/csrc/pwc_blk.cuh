@@ -672,4 +672,80 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_t18_kernel(const Row
     }
 }
 
+// =============================================================================================
+// evaluate_sequences for small dimensions (c3/libraries/propagation.py:588-627): U_seq = G[i_{L-1}] ... G[i_1] G[i_0],
+// empty sequence -> identity.  The CTA-per-sequence product_kernel pays a __syncthreads round per factor (4096 sequences
+// of ~45 gates at d = 9: 0.45 ms, all latency); here a lane group of NB x NB lanes owns one sequence (MPW sequences per
+// warp), the gate table sits zero-padded in shared memory, the running product ping-pongs between two per-group buffers
+// and only __syncwarp separates the factors.
+// =============================================================================================
+template <int D, int BS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) seq_product_blk_kernel(const cplx* __restrict__ gates, const int Gn,
+                                                                     const int* __restrict__ idx, const int* __restrict__ lens,
+                                                                     const int S, const int Lmax, const int d,
+                                                                     cplx* __restrict__ out) {
+    using L = BlkLayout<D, BS>;
+    constexpr int NB = L::NB, LPM = L::LPM, MPW = L::MPW, LD = L::LD;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* sGates = reinterpret_cast<cplx*>(smem_raw);                       // [Gn, D, LD] zero padded
+    cplx* sWarps = sGates + (size_t)Gn * L::BUF;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < Gn * L::BUF; e += WARPS * 32) {
+        const int gi = e / L::BUF, rem = e - gi * L::BUF;
+        const int r = rem / LD, j = rem - r * LD;
+        sGates[e] = (r < d && j < d) ? gates[(size_t)gi * d * d + r * d + j] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    const int g_raw = lane / LPM;
+    const bool lane_on = g_raw < MPW;
+    const int g = lane_on ? g_raw : MPW - 1;
+    const int li = ((lane_on ? (lane - g_raw * LPM) : LPM - 1) + L::rot(g)) % LPM;
+    const int bi = li / NB, bj = li - bi * NB;
+    const int r0 = bi * BS, c0 = bj * BS;
+    const int rc_off = r0 * LD + c0;
+    cplx* gbase = sWarps + (size_t)warp * L::WARP_ELEMS + L::group_off(g);
+    const long long nwarp_units = ((long long)S + MPW - 1) / MPW;
+    for (long long wu = (long long)blockIdx.x * WARPS + warp; wu < nwarp_units; wu += (long long)gridDim.x * WARPS) {
+        const long long seq = wu * MPW + g;
+        const bool have = lane_on && seq < S;
+        const int len = have ? min(lens[seq], Lmax) : 0;
+        int maxlen = len;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+        cplx* P = gbase;                 // running product
+        cplx* T = gbase + L::BUF;
+        cplx C[BS][BS];
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+#pragma unroll
+            for (int c = 0; c < BS; ++c) C[a][c] = cmake((bi == bj && a == c && r0 + a < d) ? 1.0 : 0.0, 0.0);
+        store_blk<D, BS, LD>(P + rc_off, C, lane_on);
+        __syncwarp();
+        const int* my_idx = idx + (size_t)(have ? seq : 0) * Lmax;
+        for (int m = 0; m < maxlen; ++m) {
+            const bool active = m < len;
+            int gi = active ? __ldg(my_idx + m) : 0;
+            gi = min(max(gi, 0), Gn - 1);
+            mm_blk<D, BS, LD>(sGates + (size_t)gi * L::BUF + r0 * LD, P + c0, C);
+            if (active) {                // group-uniform: the group's buffers swap roles
+                store_blk<D, BS, LD>(T + rc_off, C, lane_on);
+                cplx* t = P; P = T; T = t;
+            }
+            __syncwarp();
+        }
+        if (have) {
+#pragma unroll
+            for (int a = 0; a < BS; ++a) {
+                const int row = r0 + a;
+                if (row < d) {
+#pragma unroll
+                    for (int c = 0; c < BS; ++c)
+                        if (c0 + c < d) out[(size_t)seq * d * d + row * d + c0 + c] = P[rc_off + a * LD + c];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace c3b

@@ -348,21 +348,26 @@ def test_ordered_product(eng, D, M):
         assert rel_fro(tu.tf_matmul_right(x).cpu().numpy(), orc.tf_matmul_right(x)) < 1e-11
 
 
-def test_evaluate_sequences(eng):
-    """c3/libraries/propagation.py:588-627 incl. the empty-sequence identity."""
+@pytest.mark.parametrize("d,seq_variant", [(9, 1), (9, 0), (3, 1), (4, 1), (7, 1), (12, 1), (27, 1)])
+def test_evaluate_sequences(eng, d, seq_variant):
+    """c3/libraries/propagation.py:588-627 incl. the empty-sequence identity: the lane-group kernel (small d, gate table
+    in shared memory; d = 7 zero-padded to 8) and the CTA-per-sequence kernel (seq_variant 0, and any d > 12)."""
     from c3_b200 import propagation as prop
-    rng = np.random.default_rng(5)
-    d = 9
+    rng = np.random.default_rng(5 + d)
     names = ["rx90p[0]", "ry90p[0]", "rx90m[0]", "ry90m[0]", "id[0]"]
     gates = {}
     for n in names:
         q, _ = np.linalg.qr(rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d)))
         gates[n] = q
     seqs = [[], ["id[0]"], ["rx90p[0]", "ry90p[0]"]]
-    for _ in range(40):
+    for _ in range(47):
         L = int(rng.integers(1, 60))
         seqs.append([names[i] for i in rng.integers(0, len(names), size=L)])
-    got = prop.evaluate_sequences({k: torch.as_tensor(v) for k, v in gates.items()}, seqs)
+    eng.set_tuning("seq_variant", seq_variant)
+    try:
+        got = prop.evaluate_sequences({k: torch.as_tensor(v) for k, v in gates.items()}, seqs)
+    finally:
+        eng.set_tuning("seq_variant", 1)
     want = orc.evaluate_sequences(gates, seqs)
     assert len(got) == len(want)
     for a, b in zip(got, want):
