@@ -411,8 +411,38 @@ int launch_product_t(const ProductParams& pp, int grid, cudaStream_t st) {
     return C3B_OK;
 }
 
+template <int D, int BS>
+int launch_fold_blk_t(const ProductParams& pp, cudaStream_t st) {
+    using L = BlkLayout<D, BS>;
+    constexpr int WARPS = 4;
+    const size_t smem = (size_t)WARPS * L::WARP_ELEMS * sizeof(cplx);
+    auto kern = fold_blk_kernel<D, BS, WARPS>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long wunits = ((long long)pp.B + L::MPW - 1) / L::MPW;
+    long long grid = (wunits + WARPS - 1) / WARPS;
+    const long long cap = (long long)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<(int)grid, WARPS * 32, smem, st>>>(pp.mats, pp.B, pp.M, pp.D, pp.out);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return C3B_OK;
+}
+
 int launch_product(ProductParams pp, cudaStream_t st) {
     const int D = pp.D;
+    if (g_seq_variant != 0 && pp.idx == nullptr && pp.lens == nullptr && pp.S == 1 && pp.seg_len >= pp.M && pp.M >= 1 &&
+        (long long)pp.B * 2 >= num_sms()) {      // lane-group fold for small d (a few rows only: the CTA kernel has less latency)
+        switch (blk_template_dim(D)) {
+            case 2: return launch_fold_blk_t<2, 2>(pp, st);
+            case 3: return launch_fold_blk_t<3, 3>(pp, st);
+            case 4: return launch_fold_blk_t<4, 2>(pp, st);
+            case 6: return launch_fold_blk_t<6, 3>(pp, st);
+            case 8: return launch_fold_blk_t<8, 2>(pp, st);
+            case 9: return launch_fold_blk_t<9, 3>(pp, st);
+            case 12: return launch_fold_blk_t<12, 3>(pp, st);
+        }
+    }
     pp.use_smem = D <= 64;
     const long long units = (long long)pp.B * pp.S;
     long long g = pp.use_smem ? (long long)num_sms() * 4 : cta_grid(D, pp.B);

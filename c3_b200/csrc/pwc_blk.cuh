@@ -748,4 +748,67 @@ __global__ void __launch_bounds__(WARPS * 32) seq_product_blk_kernel(const cplx*
     }
 }
 
+// Ordered product of M matrices per batch row for small dimensions, out[b] = mats[b,M-1] ... mats[b,0]
+// (tf_matmul_left / tf_matmul_n, c3/utils/tf_utils.py:120-193; also the fold of the fused kernels' segment products):
+// a lane group per batch row, the next factor's own block is fetched from global memory while the current product runs.
+template <int D, int BS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) fold_blk_kernel(const cplx* __restrict__ mats, const int B, const int M, const int d,
+                                                              cplx* __restrict__ out) {
+    using L = BlkLayout<D, BS>;
+    constexpr int NB = L::NB, LPM = L::LPM, MPW = L::MPW, LD = L::LD;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* sWarps = reinterpret_cast<cplx*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g_raw = lane / LPM;
+    const bool lane_on = g_raw < MPW;
+    const int g = lane_on ? g_raw : MPW - 1;
+    const int li = ((lane_on ? (lane - g_raw * LPM) : LPM - 1) + L::rot(g)) % LPM;
+    const int bi = li / NB, bj = li - bi * NB;
+    const int r0 = bi * BS, c0 = bj * BS;
+    const int rc_off = r0 * LD + c0;
+    cplx* gbase = sWarps + (size_t)warp * L::WARP_ELEMS + L::group_off(g);
+    cplx* bufX = gbase + 2 * L::BUF;
+    const long long nwu = ((long long)B + MPW - 1) / MPW;
+    auto fetch = [&](const cplx* src, cplx (&x)[BS][BS], const bool pred) {
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+#pragma unroll
+            for (int c = 0; c < BS; ++c)
+                x[a][c] = (pred && r0 + a < d && c0 + c < d) ? src[(r0 + a) * d + c0 + c] : cmake(0.0, 0.0);
+    };
+    for (long long wu = (long long)blockIdx.x * WARPS + warp; wu < nwu; wu += (long long)gridDim.x * WARPS) {
+        const long long b = wu * MPW + g;
+        const bool have = lane_on && b < B;
+        const cplx* base = mats + (size_t)(have ? b : 0) * M * d * d;
+        cplx* P = gbase;
+        cplx* T = gbase + L::BUF;
+        cplx X[BS][BS], C[BS][BS];
+        fetch(base, X, have);
+        store_blk<D, BS, LD>(P + rc_off, X, lane_on);
+        if (M > 1) fetch(base + (size_t)d * d, X, have);
+        __syncwarp();
+        for (int m = 1; m < M; ++m) {
+            store_blk<D, BS, LD>(bufX + rc_off, X, lane_on);
+            __syncwarp();
+            if (m + 1 < M) fetch(base + (size_t)(m + 1) * d * d, X, have);      // in flight during the product
+            mm_blk<D, BS, LD>(bufX + r0 * LD, P + c0, C);
+            store_blk<D, BS, LD>(T + rc_off, C, lane_on);
+            cplx* t = P; P = T; T = t;
+            __syncwarp();
+        }
+        if (have) {
+#pragma unroll
+            for (int a = 0; a < BS; ++a) {
+                const int row = r0 + a;
+                if (row < d) {
+#pragma unroll
+                    for (int c = 0; c < BS; ++c)
+                        if (c0 + c < d) out[(size_t)b * d * d + row * d + c0 + c] = P[rc_off + a * LD + c];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace c3b
