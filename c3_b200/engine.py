@@ -142,7 +142,7 @@ def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, fi
             U.fill_(float("nan"))            # rows the kernel never gets to see (copy failure) stay NaN: loud, not a hang
             sig = torch.empty((B, K, N), dtype=torch.float64, device=device)
             ready = torch.empty((1,), dtype=torch.int32, device=device)
-            marks = torch.tensor(bounds[1:], dtype=torch.int32).pin_memory()
+            marks = _gate_marks(tuple(bounds[1:]))
             cs = streams[0]
             cs.wait_event(start)
             first = torch.cuda.Event()
@@ -155,7 +155,6 @@ def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, fi
                         first.record(cs)
             sig.record_stream(cs)
             ready.record_stream(cs)
-            _keepalive(device, marks, cs)
             main.wait_event(first)          # every copy is already enqueued: the kernel can only wait on the copy engine
             nbytes = lib.c3b_pwc_workspace_bytes(B, K, N, d, 0, 0)
             ws = _workspace(nbytes, device)
@@ -178,6 +177,20 @@ def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, fi
             main.wait_event(ev)
         U.record_stream(main)
     return U
+
+
+_marks_cache = {}
+
+
+def _gate_marks(bounds) -> torch.Tensor:
+    """Pinned int32 row counts of the gated launch (cached: pinning costs a cudaHostAlloc, and the contents never change)."""
+    t = _marks_cache.get(bounds)
+    if t is None:
+        if len(_marks_cache) > 64:
+            _marks_cache.clear()
+        t = torch.tensor(bounds, dtype=torch.int32).pin_memory()
+        _marks_cache[bounds] = t
+    return t
 
 
 _pinned_in_flight = {}
