@@ -166,7 +166,7 @@ struct GemmParams {
 //   S3: A6 -> B3 -> B3 + A9                           S4: B2                         S5: B1 B5 -> A9
 //   P, Q: running product and its update (pointers swap, no copy)
 template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
-__global__ void __launch_bounds__(NT) pwc_t18_cta_kernel(const GemmParams gp) {
+__global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_cta_kernel(const GemmParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[NT / 32];
     const CtaParams& p = gp.c;
@@ -235,7 +235,38 @@ __global__ void __launch_bounds__(NT) pwc_t18_cta_kernel(const GemmParams gp) {
                     if (j < D)
                         for (int i = tid / W; i < D; i += NT / W) element(i, j);
                 } else {
-                    for (int e = tid; e < D * D; e += NT) element(e / D, e % D);
+                    if (K <= 3) {                                  // batches of 4 elements, loads first (operands in L2)
+                        constexpr int AU = 4;
+                        double cs[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (k < K) cs[k] = __ldg(sig_b + (size_t)k * p.N + n);
+                        const int DD = D * D;
+                        for (int e0 = tid; e0 < DD; e0 += AU * NT) {
+                            cplx g0[AU], g1[AU], g2[AU], g3[AU];
+#pragma unroll
+                            for (int u = 0; u < AU; ++u) {
+                                const int e = min(e0 + u * NT, DD - 1);
+                                g0[u] = Gb[e];
+                                g1[u] = K > 0 ? Gb[(size_t)DD + e] : cmake(0.0, 0.0);
+                                g2[u] = K > 1 ? Gb[(size_t)2 * DD + e] : cmake(0.0, 0.0);
+                                g3[u] = K > 2 ? Gb[(size_t)3 * DD + e] : cmake(0.0, 0.0);
+                            }
+#pragma unroll
+                            for (int u = 0; u < AU; ++u) {
+                                const int e = e0 + u * NT;
+                                if (e < DD) {
+                                    cplx v = g0[u];
+                                    v.x = fma(cs[0], g1[u].x, v.x); v.y = fma(cs[0], g1[u].y, v.y);
+                                    v.x = fma(cs[1], g2[u].x, v.x); v.y = fma(cs[1], g2[u].y, v.y);
+                                    v.x = fma(cs[2], g3[u].x, v.x); v.y = fma(cs[2], g3[u].y, v.y);
+                                    A[(e / D) * LD + (e % D)] = v;
+                                }
+                            }
+                        }
+                    } else {
+                        for (int e = tid; e < D * D; e += NT) element(e / D, e % D);
+                    }
                 }
                 if (shifted) {
                     cplx mu = TRb[0];
@@ -269,34 +300,72 @@ __global__ void __launch_bounds__(NT) pwc_t18_cta_kernel(const GemmParams gp) {
             cta_zgemm<TM, TN, DPT, KST, NT>(S3, S2, S2, DP, LD, KP);
             __syncthreads();
             // in place: B1 -> S0, B5 -> S1, B4 -> S2, B3 -> S3, B2 -> S4
-            for (int e = tid; e < RL; e += NT) {
-                const int i = e / LD, j = e - i * LD;
-                const double dg = (i == j) ? 1.0 : 0.0;
-                const cplx x1 = S0[e], x2 = S1[e], x3 = S2[e], x6 = S3[e];
-                S0[e] = cmake(C3B_T18_A11 * x1.x + C3B_T18_A21 * x2.x + C3B_T18_A31 * x3.x,
-                              C3B_T18_A11 * x1.y + C3B_T18_A21 * x2.y + C3B_T18_A31 * x3.y);
-                S1[e] = cmake(C3B_T18_B24 * x2.x + C3B_T18_B34 * x3.x + C3B_T18_B64 * x6.x,
-                              C3B_T18_B24 * x2.y + C3B_T18_B34 * x3.y + C3B_T18_B64 * x6.y);
-                S2[e] = cmake(C3B_T18_B03 * dg + C3B_T18_B13 * x1.x + C3B_T18_B23 * x2.x + C3B_T18_B33 * x3.x + C3B_T18_B63 * x6.x,
-                              C3B_T18_B13 * x1.y + C3B_T18_B23 * x2.y + C3B_T18_B33 * x3.y + C3B_T18_B63 * x6.y);
-                S3[e] = cmake(C3B_T18_B02 * dg + C3B_T18_B12 * x1.x + C3B_T18_B22 * x2.x + C3B_T18_B32 * x3.x + C3B_T18_B62 * x6.x,
-                              C3B_T18_B12 * x1.y + C3B_T18_B22 * x2.y + C3B_T18_B32 * x3.y + C3B_T18_B62 * x6.y);
-                S4[e] = cmake(C3B_T18_B11 * x1.x + C3B_T18_B21 * x2.x + C3B_T18_B31 * x3.x + C3B_T18_B61 * x6.x,
-                              C3B_T18_B11 * x1.y + C3B_T18_B21 * x2.y + C3B_T18_B31 * x3.y + C3B_T18_B61 * x6.y);
+            // element-wise passes in batches of EU elements per thread, loads first: the compiler may not hoist a load over
+            // the previous element's stores (same buffers), and at D = 81 the operands come from L2
+            constexpr int EU = (DPT > 0) ? 2 : 4;      // shared-memory matrices (d = 27): 2 is enough and 4 costs registers
+            for (int e0 = tid; e0 < RL; e0 += EU * NT) {
+                cplx x1[EU], x2[EU], x3[EU], x6[EU];
+#pragma unroll
+                for (int u = 0; u < EU; ++u) {
+                    const int e = min(e0 + u * NT, RL - 1);
+                    x1[u] = S0[e]; x2[u] = S1[e]; x3[u] = S2[e]; x6[u] = S3[e];
+                }
+#pragma unroll
+                for (int u = 0; u < EU; ++u) {
+                    const int e = e0 + u * NT;
+                    if (e < RL) {
+                        const int i = e / LD, j = e - i * LD;
+                        const double dg = (i == j) ? 1.0 : 0.0;
+                        S0[e] = cmake(C3B_T18_A11 * x1[u].x + C3B_T18_A21 * x2[u].x + C3B_T18_A31 * x3[u].x,
+                                      C3B_T18_A11 * x1[u].y + C3B_T18_A21 * x2[u].y + C3B_T18_A31 * x3[u].y);
+                        S1[e] = cmake(C3B_T18_B24 * x2[u].x + C3B_T18_B34 * x3[u].x + C3B_T18_B64 * x6[u].x,
+                                      C3B_T18_B24 * x2[u].y + C3B_T18_B34 * x3[u].y + C3B_T18_B64 * x6[u].y);
+                        S2[e] = cmake(C3B_T18_B03 * dg + C3B_T18_B13 * x1[u].x + C3B_T18_B23 * x2[u].x + C3B_T18_B33 * x3[u].x + C3B_T18_B63 * x6[u].x,
+                                      C3B_T18_B13 * x1[u].y + C3B_T18_B23 * x2[u].y + C3B_T18_B33 * x3[u].y + C3B_T18_B63 * x6[u].y);
+                        S3[e] = cmake(C3B_T18_B02 * dg + C3B_T18_B12 * x1[u].x + C3B_T18_B22 * x2[u].x + C3B_T18_B32 * x3[u].x + C3B_T18_B62 * x6[u].x,
+                                      C3B_T18_B12 * x1[u].y + C3B_T18_B22 * x2[u].y + C3B_T18_B32 * x3[u].y + C3B_T18_B62 * x6[u].y);
+                        S4[e] = cmake(C3B_T18_B11 * x1[u].x + C3B_T18_B21 * x2[u].x + C3B_T18_B31 * x3[u].x + C3B_T18_B61 * x6[u].x,
+                                      C3B_T18_B11 * x1[u].y + C3B_T18_B21 * x2[u].y + C3B_T18_B31 * x3[u].y + C3B_T18_B61 * x6[u].y);
+                    }
+                }
             }
             __syncthreads();
             cta_zgemm<TM, TN, DPT, KST, NT>(S5, S0, S1, DP, LD, KP);        // B1 B5
             __syncthreads();
-            for (int e = tid; e < RL; e += NT) {          // A9 -> S5, B3 + A9 -> S3
-                const cplx a9 = cmake(S5[e].x + S2[e].x, S5[e].y + S2[e].y);
-                S5[e] = a9;
-                S3[e] = cmake(S3[e].x + a9.x, S3[e].y + a9.y);
+            for (int e0 = tid; e0 < RL; e0 += EU * NT) {   // A9 -> S5, B3 + A9 -> S3
+                cplx p5[EU], b4[EU], b3[EU];
+#pragma unroll
+                for (int u = 0; u < EU; ++u) {
+                    const int e = min(e0 + u * NT, RL - 1);
+                    p5[u] = S5[e]; b4[u] = S2[e]; b3[u] = S3[e];
+                }
+#pragma unroll
+                for (int u = 0; u < EU; ++u) {
+                    const int e = e0 + u * NT;
+                    if (e < RL) {
+                        const cplx a9 = cmake(p5[u].x + b4[u].x, p5[u].y + b4[u].y);
+                        S5[e] = a9;
+                        S3[e] = cmake(b3[u].x + a9.x, b3[u].y + a9.y);
+                    }
+                }
             }
             __syncthreads();
             cta_zgemm<TM, TN, DPT, KST, NT>(S0, S3, S5, DP, LD, KP);        // (B3 + A9) A9
             __syncthreads();
             cplx* X = S0;
-            for (int e = tid; e < RL; e += NT) X[e] = cmake(S0[e].x + S4[e].x, S0[e].y + S4[e].y);
+            for (int e0 = tid; e0 < RL; e0 += EU * NT) {
+                cplx t0[EU], t4[EU];
+#pragma unroll
+                for (int u = 0; u < EU; ++u) {
+                    const int e = min(e0 + u * NT, RL - 1);
+                    t0[u] = S0[e]; t4[u] = S4[e];
+                }
+#pragma unroll
+                for (int u = 0; u < EU; ++u) {
+                    const int e = e0 + u * NT;
+                    if (e < RL) X[e] = cmake(t0[u].x + t4[u].x, t0[u].y + t4[u].y);
+                }
+            }
             __syncthreads();
             for (int i = 0; i < s; ++i) {                          // undo the scaling
                 cplx* nxt = (X == S0) ? S1 : S0;
