@@ -50,6 +50,7 @@ bool g_ev_valid = false;
 long long g_target_units = 32768;  // rows kernel: aim for this many warp work units per launch
 long long g_gemm_big = getenv("C3B_GEMM_BIG") ? atoll(getenv("C3B_GEMM_BIG")) : 0;   // DMMA CTA kernel, DP = 88 (D = 81): macro-tile shape
 long long g_seq_variant = 1;       // evaluate_sequences: 1 = lane-group kernel for small d, 0 = CTA-per-sequence product kernel
+long long g_norm_bound = 1;        // DMMA CTA kernel: scaling from the row-sum bound (1) or from the exact inf-norm of every slice (0)
 long long g_force_cta = 0;         // route everything to the CTA kernel (testing)
 long long g_cta_variant = getenv("C3B_CTA_VARIANT") ? atoll(getenv("C3B_CTA_VARIANT")) : 1;  // 0: Pade + pivoted Gauss-Jordan, 1: Taylor-18 on DMMA tiles
 long long g_cta_threads = getenv("C3B_CTA_THREADS") ? atoll(getenv("C3B_CTA_THREADS")) : 512;   // DMMA CTA kernel, DP = 32: 256 or 512 threads
@@ -375,9 +376,10 @@ int launch_gemm_t(const GemmParams& gp, int grid, cudaStream_t st) {
     return C3B_OK;
 }
 
-int launch_gemm(const CtaParams& cp, const cplx* TR, int grid, cudaStream_t st) {
+int launch_gemm(const CtaParams& cp, const cplx* TR, const double* RS, int grid, cudaStream_t st) {
     GemmParams gp{};
     gp.c = cp; gp.TR = TR; gp.DP = round8(cp.D);
+    gp.RS = (g_norm_bound && TR != nullptr) ? RS : nullptr;   // RS are the row sums of the SHIFTED generators
     gp.LD = cp.use_smem ? gp.DP + 4 : gp.DP;
     gp.g_in_smem = (cp.use_smem && cp.hlist == nullptr && cp.G != nullptr && gemm_g_in_smem(cp.D, cp.K, cp.model_stride != 0)) ? 1 : 0;
     if (gp.DP <= 16) return launch_gemm_t<1, 1>(gp, grid, st);
@@ -486,7 +488,7 @@ int run_pwc(const Plan& pl, const cplx* G, const double* RS, const cplx* TR, con
         cp.U_out = U_out; cp.seg_out = seg; cp.dUs_out = dUs_out;
         cp.ws = reinterpret_cast<cplx*>(ws + pl.off_cta);
         cp.use_smem = pl.path == 2;
-        int rc = (g_cta_variant == 1) ? launch_gemm(cp, TR, pl.grid, st) : launch_cta(cp, pl.grid, st);
+        int rc = (g_cta_variant == 1) ? launch_gemm(cp, TR, RS, pl.grid, st) : launch_cta(cp, pl.grid, st);
         if (rc) return rc;
     }
     if (g_profile) { CUDA_TRY(cudaEventRecord(g_ev1, st)); g_ev_valid = true; }
@@ -556,6 +558,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (key == nullptr) return fail(C3B_EINVAL, "C3:ERROR: null tuning key");
     if (!strcmp(key, "target_units")) { g_target_units = value < 1 ? 1 : value; return C3B_OK; }
     if (!strcmp(key, "force_cta")) { g_force_cta = value; return C3B_OK; }
+    if (!strcmp(key, "norm_bound")) { g_norm_bound = value; return C3B_OK; }
     if (!strcmp(key, "seq_variant")) { g_seq_variant = value; return C3B_OK; }
     if (!strcmp(key, "gemm_big")) { g_gemm_big = value; return C3B_OK; }
     if (!strcmp(key, "cta_variant")) { g_cta_variant = value; return C3B_OK; }

@@ -156,6 +156,7 @@ __device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, co
 struct GemmParams {
     CtaParams c;       // same fields as the Pade CTA kernel (G, signals, hlist, sizes, outputs, ws, use_smem)
     const cplx* TR;    // [(Bm), K+1] trace shifts already subtracted from G's diagonals, or null
+    const double* RS;  // [(Bm), K+1, D] row sums of |G_k| (after the shift): inf-norm bound without a pass over the slice, or null
     int DP;            // D rounded up to a multiple of 8 (tile extent)
     int LD;            // leading dimension of every workspace matrix (DP, or DP + 4 in shared memory)
     int g_in_smem;     // the (shared) generators are staged in shared memory after the matrix slots
@@ -214,8 +215,25 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
         const cplx hs = cmake(p.hscale_re, p.hscale_im);
         cplx mu_acc = cmake(0.0, 0.0);
 
+        const double* RSb = (gp.RS != nullptr && p.hlist == nullptr) ? gp.RS + (size_t)b * (p.model_stride ? (size_t)(K + 1) * D : 0) : nullptr;
         for (int n = n_begin; n < n_end; ++n) {
             cplx* A = S0;
+            // ---- scaling from the row-sum bound  ||A_n||_inf <= max_r ( rs_0[r] + sum_k |c_k[n]| rs_k[r] ):  known BEFORE the
+            //      slice is assembled (every warp computes it, no barrier), so the 2^-s factor is folded into the assembly and
+            //      the norm pass over the slice (two barriers, D^2 square roots) disappears.  The bound is exact when the
+            //      generators have disjoint supports (diagonal drift + off-diagonal drives), never below the true norm.
+            int s_pre = -1;
+            double asc = 1.0;
+            if (RSb != nullptr) {
+                double v = 0.0;
+                for (int r = tid & 31; r < D; r += 32) {
+                    double t = RSb[r];
+                    for (int k = 0; k < K; ++k) t = fma(fabs(__ldg(sig_b + (size_t)k * p.N + n)), RSb[(size_t)(k + 1) * D + r], t);
+                    v = fmax(v, t);
+                }
+                s_pre = squarings_for(warp_max(v), C3B_THETA18);
+                asc = pow2neg(s_pre);
+            }
             // ---- assemble (D x D part; padding stays zero) ---------------------------------------
             if (p.hlist == nullptr) {
                 auto element = [&](const int i, const int j) {
@@ -227,7 +245,7 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
                         v.x = fma(c, gk.x, v.x);
                         v.y = fma(c, gk.y, v.y);
                     }
-                    A[i * LD + j] = v;
+                    A[i * LD + j] = cmake(v.x * asc, v.y * asc);
                 };
                 if (DPT > 0) {                                   // DPT lanes walk one row: no integer division
                     constexpr int W = DPT > 0 ? DPT : 1;
@@ -260,7 +278,7 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
                                     v.x = fma(cs[0], g1[u].x, v.x); v.y = fma(cs[0], g1[u].y, v.y);
                                     v.x = fma(cs[1], g2[u].x, v.x); v.y = fma(cs[1], g2[u].y, v.y);
                                     v.x = fma(cs[2], g3[u].x, v.x); v.y = fma(cs[2], g3[u].y, v.y);
-                                    A[(e / D) * LD + (e % D)] = v;
+                                    A[(e / D) * LD + (e % D)] = cmake(v.x * asc, v.y * asc);
                                 }
                             }
                         }
@@ -285,12 +303,15 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
                 }
             }
             __syncthreads();
-            const double nrm = cta_norm_inf_ld<NT>(A, D, LD, red);
-            const int s = squarings_for(nrm, C3B_THETA18);
-            if (s > 0) {
-                const double sc = pow2neg(s);
-                for (int e = tid; e < RL; e += NT) { A[e].x *= sc; A[e].y *= sc; }
-                __syncthreads();
+            int s = s_pre;
+            if (s_pre < 0) {                                   // explicit slices (H list): exact inf-norm of the slice
+                const double nrm = cta_norm_inf_ld<NT>(A, D, LD, red);
+                s = squarings_for(nrm, C3B_THETA18);
+                if (s > 0) {
+                    const double sc = pow2neg(s);
+                    for (int e = tid; e < RL; e += NT) { A[e].x *= sc; A[e].y *= sc; }
+                    __syncthreads();
+                }
             }
             // ---- T18: A2 = S1, A3 = S2, A6 = S3 -----------------------------------------------------
             cta_zgemm<TM, TN, DPT, KST, NT>(S1, A, A, DP, LD, KP);

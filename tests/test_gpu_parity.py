@@ -271,6 +271,29 @@ def test_d9_kernel_generations_random_models(eng, variant, scale, N, B):
     assert rel_fro(U2.cpu().numpy(), wantU) < TOL
 
 
+@pytest.mark.parametrize("norm_bound", [0, 1])
+@pytest.mark.parametrize("d,scale", [(14, 0.8), (27, 2.5), (27, 20.0), (33, 6.0)])
+def test_cta_kernel_scaling_from_row_sum_bound(eng, d, scale, norm_bound):
+    """DMMA CTA kernel: squarings chosen from the row-sum bound of the generators (default) or from the exact inf-norm of
+    every assembled slice; shared and per-sample models."""
+    rng = np.random.default_rng(d + int(scale * 10))
+    K, B, N = 2, 3, 7
+    h0, hks = _rand_model(rng, d, K, scale)
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    eng.set_tuning("norm_bound", norm_bound)
+    try:
+        U, dUs = eng.pwc_closed(h0, hks, sig, 1.0, return_dUs=True)
+        Ub = eng.pwc_closed(np.stack([h0 * (1 + 0.1 * b) for b in range(B)]), np.stack([hks] * B), sig, 1.0)
+    finally:
+        eng.set_tuning("norm_bound", 1)
+    wantU, want_dUs = orc.propagate_batch(h0, hks, sig, 1.0, return_dUs=True)
+    assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
+    assert rel_fro(U.cpu().numpy(), wantU) < TOL
+    for b in range(B):
+        want = orc.propagate_batch(h0 * (1 + 0.1 * b), hks, sig[b:b + 1], 1.0)[0]
+        assert rel_fro(Ub[b].cpu().numpy(), want) < TOL
+
+
 def test_lindblad_config3_shape(eng):
     """BASELINE config 3 shape (two 3-level transmons, D=81) on a small batch / few slices."""
     from c3_b200 import synth
