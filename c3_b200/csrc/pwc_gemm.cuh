@@ -32,8 +32,12 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a
 // LD is the leading dimension (>= DP); KP = D rounded up to 4 bounds the k loop (columns/rows beyond D
 // are zero).  In shared memory LD = DP + 4 (= 4 mod 8 in 16-byte units) makes the A-fragment loads
 // bank-conflict free and the B-fragment loads 2-way (with LD = DP = 32 they were 8-way / 4-way).
-template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
-__device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP_, const int LD_, const int KP) {
+// EPI fuses the element-wise step that follows two of the scheme's products into the epilogue (the accumulators are still in
+// registers): 1: C = A B + E1 (= A9), E2 += C (= B3 + A9);  2: C = A B + E1 (= T18).  Padding rows / columns are zero in every
+// operand, so they stay zero.
+template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads, int EPI = 0>
+__device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP_, const int LD_, const int KP,
+                                          const cplx* E1 = nullptr, cplx* E2 = nullptr) {
     // DPT > 0: tile extent and leading dimension are compile-time (DPT, DPT + 4): the k loop unrolls fully and
     // every fragment address is base + immediate
     const int DP = DPT > 0 ? DPT : DP_;
@@ -120,9 +124,19 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 if (bi0 + i < nb && bj0 + j < nb) {
-                    cplx* o = C + ((bi0 + i) * 8 + fr) * LD + (bj0 + j) * 8 + 2 * fc;
-                    o[0] = cmake(cr[i][j][0], ci[i][j][0]);
-                    o[1] = cmake(cr[i][j][1], ci[i][j][1]);
+                    const int idx = ((bi0 + i) * 8 + fr) * LD + (bj0 + j) * 8 + 2 * fc;
+                    cplx c0 = cmake(cr[i][j][0], ci[i][j][0]), c1 = cmake(cr[i][j][1], ci[i][j][1]);
+                    if constexpr (EPI != 0) {
+                        const cplx e0 = E1[idx], e1 = E1[idx + 1];
+                        c0.x += e0.x; c0.y += e0.y; c1.x += e1.x; c1.y += e1.y;
+                    }
+                    if constexpr (EPI == 1) {
+                        const cplx f0 = E2[idx], f1 = E2[idx + 1];
+                        E2[idx] = cmake(f0.x + c0.x, f0.y + c0.y);
+                        E2[idx + 1] = cmake(f1.x + c1.x, f1.y + c1.y);
+                    }
+                    C[idx] = c0;
+                    C[idx + 1] = c1;
                 }
             }
     }
@@ -351,43 +365,11 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
                 }
             }
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT>(S5, S0, S1, DP, LD, KP);        // B1 B5
+            cta_zgemm<TM, TN, DPT, KST, NT, 1>(S5, S0, S1, DP, LD, KP, S2, S3);   // A9 = B4 + B1 B5 -> S5;  B3 + A9 -> S3 (epilogue)
             __syncthreads();
-            for (int e0 = tid; e0 < RL; e0 += EU * NT) {   // A9 -> S5, B3 + A9 -> S3
-                cplx p5[EU], b4[EU], b3[EU];
-#pragma unroll
-                for (int u = 0; u < EU; ++u) {
-                    const int e = min(e0 + u * NT, RL - 1);
-                    p5[u] = S5[e]; b4[u] = S2[e]; b3[u] = S3[e];
-                }
-#pragma unroll
-                for (int u = 0; u < EU; ++u) {
-                    const int e = e0 + u * NT;
-                    if (e < RL) {
-                        const cplx a9 = cmake(p5[u].x + b4[u].x, p5[u].y + b4[u].y);
-                        S5[e] = a9;
-                        S3[e] = cmake(b3[u].x + a9.x, b3[u].y + a9.y);
-                    }
-                }
-            }
-            __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT>(S0, S3, S5, DP, LD, KP);        // (B3 + A9) A9
+            cta_zgemm<TM, TN, DPT, KST, NT, 2>(S0, S3, S5, DP, LD, KP, S4);       // T18 = B2 + (B3 + A9) A9 (epilogue)
             __syncthreads();
             cplx* X = S0;
-            for (int e0 = tid; e0 < RL; e0 += EU * NT) {
-                cplx t0[EU], t4[EU];
-#pragma unroll
-                for (int u = 0; u < EU; ++u) {
-                    const int e = min(e0 + u * NT, RL - 1);
-                    t0[u] = S0[e]; t4[u] = S4[e];
-                }
-#pragma unroll
-                for (int u = 0; u < EU; ++u) {
-                    const int e = e0 + u * NT;
-                    if (e < RL) X[e] = cmake(t0[u].x + t4[u].x, t0[u].y + t4[u].y);
-                }
-            }
-            __syncthreads();
             for (int i = 0; i < s; ++i) {                          // undo the scaling
                 cplx* nxt = (X == S0) ? S1 : S0;
                 cta_zgemm<TM, TN, DPT, KST, NT>(nxt, X, X, DP, LD, KP);
