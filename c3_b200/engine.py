@@ -127,6 +127,7 @@ def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, fi
         hks = _as(hks, torch.complex128, device) if K > 0 else None
         d = h0.shape[-1]
         U = torch.empty((B, d, d), dtype=torch.complex128, device=device)
+        chunk = max(1, int(chunk))
         if B <= chunk or h0.dim() == 3 or K == 0:
             return pwc_closed(h0, hks, signals_host.to(device, non_blocking=True), dt, device=device, out=U)
         main = torch.cuda.current_stream()
