@@ -474,6 +474,8 @@ int run_pwc(const Plan& pl, const cplx* G, const double* RS, const cplx* TR, con
         rp.B = B; rp.K = K; rp.N = N; rp.d = D; rp.S = pl.S; rp.seg_len = pl.seg_len;
         rp.U_out = U_out; rp.seg_out = seg; rp.dUs_out = dUs_out;
         rp.rows_ready = t_rows_ready;
+        if (t_rows_ready != nullptr && seg != nullptr)     // a row that never arrives must surface as NaN after the fold, too
+            CUDA_TRY(cudaMemsetAsync(seg, 0xff, (size_t)B * pl.S * D * D * sizeof(cplx), st));
         if (t_rows_ready != nullptr && !(g_rows_variant == 16 && D == 9))
             return fail(C3B_EUNSUPPORTED, "C3:ERROR: gated launch is built for the d = 9 kernel only");
         int rc = launch_rows(rp, reinterpret_cast<unsigned int*>(ws + pl.off_counter), st);
