@@ -12,11 +12,12 @@ LIB_PATH = os.path.join(HERE, "libc3b200.so")
 SYMBOLS = [
     "c3b_version", "c3b_last_error", "c3b_pwc_workspace_bytes", "c3b_pwc_closed", "c3b_pwc_closed_hlist",
     "c3b_pwc_lindblad", "c3b_product_workspace_bytes", "c3b_ordered_product", "c3b_seq_product", "c3b_kron",
-    "c3b_set_tuning", "c3b_pwc_path", "c3b_measure_fp64_peak", "c3b_microbench", "c3b_launch_count",
+    "c3b_set_tuning", "c3b_pwc_path", "c3b_measure_fp64_peak", "c3b_launch_count",
     "c3b_last_kernel_ms", "c3b_pwc_grad_workspace_bytes", "c3b_pwc_closed_grad",
     "c3b_gate_infid", "c3b_gate_infid_grad", "c3b_seq_populations", "c3b_signal_slice_num", "c3b_generate_signals",
     "c3b_generate_signals_grad", "c3b_pwc_lindblad_grad_workspace_bytes", "c3b_pwc_lindblad_grad",
     "c3b_dress_models", "c3b_pwc_closed_gated", "c3b_pwc_gated_supported",
+    "c3b_model_bytes", "c3b_model_prepare", "c3b_pwc_prepared_workspace_bytes", "c3b_pwc_prepared",
 ]
 
 _lib = None
@@ -90,8 +91,14 @@ def load() -> C.CDLL:
     lib.c3b_measure_fp64_peak.argtypes = [i, i, d]
     lib.c3b_launch_count.restype = C.c_longlong
     lib.c3b_last_kernel_ms.restype = d
-    lib.c3b_microbench.restype = d
-    lib.c3b_microbench.argtypes = [i, i, i]
+    lib.c3b_model_bytes.restype = sz
+    lib.c3b_model_bytes.argtypes = [i, i, i, i]
+    lib.c3b_model_prepare.restype = i
+    lib.c3b_model_prepare.argtypes = [vp, vp, vp, i, d, i, i, i, i, vp, sz, vp]
+    lib.c3b_pwc_prepared_workspace_bytes.restype = sz
+    lib.c3b_pwc_prepared_workspace_bytes.argtypes = [i, i, i, i, i]
+    lib.c3b_pwc_prepared.restype = i
+    lib.c3b_pwc_prepared.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp, vp, sz, vp]
     _lib = lib
     return lib
 

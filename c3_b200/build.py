@@ -1,21 +1,26 @@
-"""Build libc3b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a."""
+"""Build libc3b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+One object file per kernel family (c3_b200/csrc/*.cu), compiled in parallel and linked into
+c3_b200/libc3b200.so; objects are cached under c3_b200/csrc/_obj (git-ignored) and rebuilt when the
+source or any header changes."""
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libc3b200.so")
-SOURCES = ["c3b_api.cu"]
-HEADERS = ["c3b_common.cuh", "pwc_rows.cuh", "pwc_blk.cuh", "pwc_blk9.cuh", "pwc_cta.cuh", "pwc_gemm.cuh", "grad.cuh", "fidelity.cuh", "signal_chain.cuh", "dressing.cuh", "product.cuh", "peak.cuh",
-           os.path.join("..", "..", "include", "c3b200.h")]
+PUBLIC_HEADER = os.path.normpath(os.path.join(HERE, "..", "include", "c3b200.h"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -26,26 +31,60 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libc3b200.so")
 
 
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _headers():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [PUBLIC_HEADER]
+
+
+def _obj_path(src: str) -> str:
+    return os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+
+
+def _stale_objects(force: bool):
+    hdr_time = max(os.path.getmtime(h) for h in _headers())
+    out = []
+    for src in sources():
+        obj = _obj_path(src)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            out.append(src)
+    return out
+
+
 def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return any(os.path.getmtime(p) > t for p in sources() + _headers())
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile c3_b200/csrc/*.cu into c3_b200/libc3b200.so.  Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def compile_one(src):
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", src, "-o", _obj_path(src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, res
+
+    todo = _stale_objects(force)
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(todo)))) as pool:
+        for src, res in pool.map(compile_one, todo):
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {os.path.basename(src)}:\n" + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB + ".tmp"] + [_obj_path(s) for s in sources()]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     os.replace(LIB + ".tmp", LIB)
-    if verbose:
-        print(res.stderr)
     return LIB
 
 

@@ -1,0 +1,42 @@
+// d = 9 (and zero-padded d = 7): the headline lane-group kernels.
+#include "c3b_host.cuh"
+#include "pwc_blk.cuh"
+#include "pwc_blk9.cuh"
+
+namespace c3b {
+
+namespace {
+
+template <typename Kern>
+int launch_persistent(Kern kern, size_t smem, int warps, int minb, const RowsParams& rp, unsigned int* counter, cudaStream_t st) {
+    if (smem > 227 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: too many control lines (K=%d) for the d=%d lane-group kernel", rp.K, rp.d);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    const long long units = (long long)rp.B * rp.S;
+    int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > minb) per_sm = minb;
+    long long grid = (long long)num_sms() * per_sm;
+    const long long need = (units + warps - 1) / warps;
+    if (grid > need) grid = need;
+    kern<<<(int)grid, warps * 32, smem, st>>>(rp, counter);
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return C3B_OK;
+}
+
+}  // namespace
+
+bool d9_gated_supported(int variant) { return variant == 1; }
+
+int launch_d9(const RowsParams& rp, unsigned int* counter, int variant, cudaStream_t st) {
+    if (rp.gate != nullptr && !d9_gated_supported(variant))
+        return fail(C3B_EUNSUPPORTED, "C3:ERROR: gated launch is not built for d9_variant %d", variant);
+    if (variant == 0)
+        return launch_persistent(pwc_blk_t18_kernel<9, 3, 4, 2>, BlkLayout<9, 3>::smem_bytes(rp.K, 4), 4, 2, rp, counter, st);
+    const size_t smem = Blk9T<true>::smem_bytes(rp.K, 4);
+    if (rp.gate != nullptr) return launch_persistent(pwc_blk9_t18_kernel<4, 2, true, true>, smem, 4, 2, rp, counter, st);
+    return launch_persistent(pwc_blk9_t18_kernel<4, 2, true, false>, smem, 4, 2, rp, counter, st);
+}
+
+}  // namespace c3b

@@ -1,0 +1,42 @@
+// Taylor-18 PWC propagators on fp64 tensor-core (DMMA) tiles, one CTA per (batch row, segment): d > 12, Lindblad
+// superoperators (D = d^2), per-sample models.
+#include "c3b_host.cuh"
+#include "pwc_gemm.cuh"
+
+namespace c3b {
+
+namespace {
+
+template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
+int launch_gemm_t(const GemmParams& gp, int grid, cudaStream_t st) {
+    auto kern = pwc_t18_cta_kernel<TM, TN, DPT, KST, NT>;
+    const size_t smem = gp.c.use_smem ? gemm_smem_bytes(gp.c.D, gp.g_in_smem ? gp.c.K : -1, gp.g_in_smem ? 0 : 1) : 0;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NT, smem, st>>>(gp);
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return C3B_OK;
+}
+
+}  // namespace
+
+int launch_gemm(const CtaParams& cp, const cplx* TR, const double* RS, int grid, cudaStream_t st) {
+    const Tuning& tn = tuning();
+    GemmParams gp{};
+    gp.c = cp; gp.TR = TR; gp.DP = round8(cp.D);
+    gp.RS = (tn.norm_bound && TR != nullptr) ? RS : nullptr;   // RS are the row sums of the SHIFTED generators
+    gp.LD = cp.use_smem ? gp.DP + 4 : gp.DP;
+    gp.g_in_smem = (cp.use_smem && cp.hlist == nullptr && cp.G != nullptr && gemm_g_in_smem(cp.D, cp.K, cp.model_stride != 0)) ? 1 : 0;
+    if (gp.DP <= 16) return launch_gemm_t<1, 1>(gp, grid, st);
+    if (gp.DP == 32 && cp.use_smem) {
+        if (tn.cta_threads == 512) return cp.D <= 28 ? launch_gemm_t<1, 1, 32, 7, 512>(gp, grid, st) : launch_gemm_t<1, 1, 32, 8, 512>(gp, grid, st);
+        return cp.D <= 28 ? launch_gemm_t<1, 2, 32, 7>(gp, grid, st) : launch_gemm_t<1, 2, 32, 8>(gp, grid, st);
+    }
+    if (gp.DP <= 48) return launch_gemm_t<1, 2>(gp, grid, st);
+    // 11 x 11 blocks at D = 81: 3 x 2 macro tiles give 24 tiles = 3 full rounds of the 8 warps (144 block slots for 121
+    // blocks) where 2 x 2 gives 36 tiles = 5 rounds (160 slots): 20.5 -> 19.9 ms on the 296 x 40 probe (2 x 3: 20.5, 3 x 3: 23.9)
+    if (gp.DP == 88 && tn.gemm_big == 0) return launch_gemm_t<3, 2>(gp, grid, st);
+    return launch_gemm_t<2, 2>(gp, grid, st);
+}
+
+}  // namespace c3b

@@ -12,16 +12,6 @@
 
 namespace c3b {
 
-struct ProductParams {
-    const cplx* mats;    // [B, M, D, D]  or the gate table [Gn, D, D] when idx != null
-    const int* idx;      // [B, M] gate indices or null
-    const int* lens;     // [B] valid length per batch row or null (= M)
-    int B, M, D;
-    int S, seg_len;      // segments per batch row
-    cplx* out;           // [B, S, D, D]
-    cplx* ws;            // gridDim.x * 2 * D * D when !use_smem
-    int use_smem;
-};
 
 template <int CT, int TR, int TC>
 __global__ void __launch_bounds__(kCtaThreads) product_kernel(const ProductParams p) {

@@ -16,7 +16,7 @@
 // c3b_common.cuh).  Orders m in {3,5,7,9}; powers A^2, A^4, A^6 = A^4 A^2, A^8 = A^4 A^4.
 #pragma once
 #include "c3b_common.cuh"
-#include "pwc_rows.cuh"   // RowsParams
+#include "c3b_params.cuh"
 
 namespace c3b {
 
@@ -83,296 +83,6 @@ __device__ __forceinline__ cplx shfl_c(const cplx v, const int src) {
     r.x = __shfl_sync(0xffffffffu, v.x, src);
     r.y = __shfl_sync(0xffffffffu, v.y, src);
     return r;
-}
-
-template <int D, int BS, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_kernel(const RowsParams p, unsigned int* __restrict__ counter) {
-    using L = BlkLayout<D, BS>;
-    constexpr int NB = L::NB, LPM = L::LPM, MPW = L::MPW, LD = L::LD;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int K = p.K;
-    const int d = p.d;
-    cplx* sG = reinterpret_cast<cplx*>(smem_raw);                 // [(K+1), D, LD] zero padded
-    double* sRS = reinterpret_cast<double*>(sG + (K + 1) * D * LD);  // [(K+1), D]
-    cplx* sWarps = reinterpret_cast<cplx*>(sRS + (((K + 1) * D + 1) & ~1));
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const bool hmode = p.hlist != nullptr;
-
-    if (!hmode) {
-        for (int idx = tid; idx < (K + 1) * D * D; idx += WARPS * 32) {
-            const int k = idx / (D * D);
-            const int rem = idx - k * D * D;
-            const int r = rem / D, j = rem - r * D;
-            cplx v = cmake(0.0, 0.0);
-            if (r < d && j < d) v = p.G[(size_t)k * d * d + r * d + j];
-            sG[(k * D + r) * LD + j] = v;
-        }
-        for (int idx = tid; idx < (K + 1) * D; idx += WARPS * 32) {
-            const int k = idx / D, r = idx - k * D;
-            sRS[idx] = (r < d) ? p.RS[k * d + r] : 0.0;
-        }
-    }
-    __syncthreads();   // the only CTA-wide barrier
-
-    const int g_raw = lane / LPM;
-    const bool lane_on = g_raw < MPW;
-    // leftover lanes shadow the LAST lane of the LAST group (same addresses as their quarter-warp
-    // neighbours: no extra bank conflicts) and never store
-    const int g = lane_on ? g_raw : MPW - 1;
-    const int li = ((lane_on ? (lane - g_raw * LPM) : LPM - 1) + L::rot(g)) % LPM;   // block index owned by this lane
-    const int bi = li / NB, bj = li - bi * NB;
-    const int r0 = bi * BS, c0 = bj * BS;
-    const int gbase_lane = g * LPM;
-    const int grot = L::rot(g);
-    auto lane_of = [&](int blk) { return gbase_lane + (blk - grot + LPM) % LPM; };   // lane holding block index blk
-    const bool on_diag = (bi == bj);
-
-    cplx* gbase = sWarps + (size_t)warp * L::WARP_ELEMS + L::group_off(g);
-    cplx* bufA = gbase;
-    cplx* bufA2 = gbase + L::BUF;
-    cplx* bufX = gbase + 2 * L::BUF;
-    cplx* bufP = gbase + 3 * L::BUF;
-    const int rc_off = r0 * LD + c0;                   // this lane's block inside a per-matrix buffer
-    const int mg_off = r0 * LD + c0;                   // ... and inside a model matrix (same padded stride)
-    const cplx hs = cmake(p.hscale_re, p.hscale_im);
-    const long long total_units = (long long)p.B * p.S;
-
-    for (;;) {
-        unsigned int unit_u = 0;
-        if (lane == 0) unit_u = atomicAdd(counter, 1u);
-        unit_u = __shfl_sync(0xffffffffu, unit_u, 0);
-        const long long unit = unit_u;
-        if (unit >= total_units) break;
-        const int b = (int)(unit / p.S);
-        const int sidx = (int)(unit - (long long)b * p.S);
-        const int n_begin = sidx * p.seg_len;
-        const int n_end = min(p.N, n_begin + p.seg_len);
-        const int len = n_end - n_begin;
-        const int cl = (len + MPW - 1) / MPW;
-        const int my_begin = n_begin + g * cl;
-        const int my_end = min(n_end, my_begin + cl);
-        const double* sig_b = p.signals ? p.signals + (size_t)b * K * p.N : nullptr;
-
-#pragma unroll 1
-        for (int it = 0; it < cl; ++it) {
-            const int n = my_begin + it;
-            const bool on = lane_on && (n < my_end);
-
-            // ---- assemble this lane's block of A_n and the inf-norm bound of its rows -----------
-            cplx C[BS][BS];
-            double nb = 0.0;
-            if (!hmode) {
-                double nba[BS];
-#pragma unroll
-                for (int a = 0; a < BS; ++a) {
-                    nba[a] = on ? sRS[r0 + a] : 0.0;
-#pragma unroll
-                    for (int c = 0; c < BS; ++c) C[a][c] = on ? sG[mg_off + a * LD + c] : cmake(0.0, 0.0);
-                }
-                for (int k = 0; k < K; ++k) {
-                    const double cs = on ? __ldg(sig_b + (size_t)k * p.N + n) : 0.0;
-                    const cplx* gk = sG + (k + 1) * D * LD + mg_off;
-#pragma unroll
-                    for (int a = 0; a < BS; ++a) {
-#pragma unroll
-                        for (int c = 0; c < BS; ++c) {
-                            const cplx gv = gk[a * LD + c];
-                            C[a][c].x = fma(cs, gv.x, C[a][c].x);
-                            C[a][c].y = fma(cs, gv.y, C[a][c].y);
-                        }
-                        nba[a] = fma(fabs(cs), sRS[(k + 1) * D + r0 + a], nba[a]);
-                    }
-                }
-#pragma unroll
-                for (int a = 0; a < BS; ++a) nb = fmax(nb, nba[a]);
-            } else {
-                // explicit Hamiltonians: partial row sums of this block, summed over the NB lanes of the block-row
-#pragma unroll
-                for (int a = 0; a < BS; ++a) {
-                    const int row = r0 + a;
-                    double rs = 0.0;
-#pragma unroll
-                    for (int c = 0; c < BS; ++c) {
-                        cplx h = cmake(0.0, 0.0);
-                        if (on && row < d && c0 + c < d)
-                            h = p.hlist[((size_t)b * p.N + n) * d * d + (size_t)row * d + c0 + c];
-                        C[a][c] = cmul(hs, h);
-                        rs += cabs1(C[a][c]);
-                    }
-                    double tot = 0.0;
-#pragma unroll
-                    for (int q = 0; q < NB; ++q) tot += __shfl_sync(0xffffffffu, rs, lane_of(bi * NB + q));
-                    nb = fmax(nb, tot);
-                }
-            }
-            nb = warp_max(nb);
-
-            const int s = squarings_for(nb, C3B_NOPIVOT_LIMIT);
-            const double ns = nb * pow2neg(s);
-            const int mi = ns < C3B_THETA3 ? 0 : (ns < C3B_THETA5 ? 1 : (ns < C3B_THETA7 ? 2 : 3));  // m = 2 mi + 3
-            if (s > 0) {
-                const double sc = pow2neg(s);
-#pragma unroll
-                for (int a = 0; a < BS; ++a)
-#pragma unroll
-                    for (int c = 0; c < BS; ++c) { C[a][c].x *= sc; C[a][c].y *= sc; }
-            }
-            store_blk<D, BS, LD>(bufA + rc_off, C, lane_on);
-            __syncwarp();
-
-            const double* cf = kPade[mi];
-            cplx W[BS][BS], V[BS][BS];
-            // phases: 0..mi powers | mi+1: U = W A | then s squarings | then the running product
-            const int ph_solve = mi + 1;
-            const int ph_lastsq = mi + 1 + s;
-            const int ph_last = ph_lastsq + (it > 0 ? 1 : 0);
-            const cplx* Xr = bufA + r0 * LD;
-            const cplx* Yc = bufA + c0;
-
-#pragma unroll 1
-            for (int ph = 0; ph <= ph_last; ++ph) {
-                mm_blk<D, BS, LD>(Xr, Yc, C);
-                if (ph < ph_solve) {
-                    // C = A^(2 ph + 2)
-                    const double cw = cf[2 * ph + 3], cv = cf[2 * ph + 2];
-                    if (ph == 0) {
-                        const double c1 = cf[1], c0c = cf[0];
-#pragma unroll
-                        for (int a = 0; a < BS; ++a)
-#pragma unroll
-                            for (int c = 0; c < BS; ++c) {
-                                const bool dg = on_diag && (a == c);
-                                W[a][c] = cmake(cw * C[a][c].x + (dg ? c1 : 0.0), cw * C[a][c].y);
-                                V[a][c] = cmake(cv * C[a][c].x + (dg ? c0c : 0.0), cv * C[a][c].y);
-                            }
-                        if (mi > 0) store_blk<D, BS, LD>(bufA2 + rc_off, C, lane_on);       // A^2: operand of A^4, A^6
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < BS; ++a)
-#pragma unroll
-                            for (int c = 0; c < BS; ++c) {
-                                W[a][c].x = fma(cw, C[a][c].x, W[a][c].x);
-                                W[a][c].y = fma(cw, C[a][c].y, W[a][c].y);
-                                V[a][c].x = fma(cv, C[a][c].x, V[a][c].x);
-                                V[a][c].y = fma(cv, C[a][c].y, V[a][c].y);
-                            }
-                        if (ph == 1 && mi > 1) store_blk<D, BS, LD>(bufX + rc_off, C, lane_on);  // A^4: operand of A^6, A^8
-                    }
-                    if (ph < mi) {
-                        __syncwarp();
-                        if (ph == 0) { Xr = bufA2 + r0 * LD; Yc = bufA2 + c0; }          // A^4 = A^2 A^2
-                        else if (ph == 1) { Xr = bufX + r0 * LD; Yc = bufA2 + c0; }      // A^6 = A^4 A^2
-                        else { Xr = bufX + r0 * LD; Yc = bufX + c0; }                    // A^8 = A^4 A^4
-                    } else {
-                        // all powers done: publish W as the left operand of U = W A
-                        __syncwarp();                                                   // bufX (A^4) no longer read
-                        store_blk<D, BS, LD>(bufX + rc_off, W, lane_on);
-                        __syncwarp();
-                        Xr = bufX + r0 * LD;
-                        Yc = bufA + c0;
-                    }
-                } else if (ph == ph_solve) {
-                    // C = U.  W <- Q = V - U,  C <- R = V + U;  then C <- Q^{-1} C
-#pragma unroll
-                    for (int a = 0; a < BS; ++a)
-#pragma unroll
-                        for (int c = 0; c < BS; ++c) {
-                            const cplx v = V[a][c], u = C[a][c];
-                            W[a][c] = cmake(v.x - u.x, v.y - u.y);
-                            C[a][c] = cmake(v.x + u.x, v.y + u.y);
-                        }
-#pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        const int bk = k / BS, kc = k % BS;   // compile-time after unrolling
-                        const cplx pk = shfl_c(W[kc][kc], lane_of(bk * NB + bk));
-                        cplx qa[BS], pq[BS], pr[BS];
-#pragma unroll
-                        for (int a = 0; a < BS; ++a) qa[a] = shfl_c(W[a][kc], lane_of(bi * NB + bk));
-#pragma unroll
-                        for (int c = 0; c < BS; ++c) {
-                            pq[c] = shfl_c(W[kc][c], lane_of(bk * NB + bj));
-                            pr[c] = shfl_c(C[kc][c], lane_of(bk * NB + bj));
-                        }
-                        const cplx inv = crcp(pk);
-                        cplx f[BS];
-#pragma unroll
-                        for (int a = 0; a < BS; ++a) f[a] = cmul(qa[a], inv);
-                        if (bi == bk) f[kc] = cmake(1.0 - inv.x, -inv.y);   // pivot row: row <- row * inv
-#pragma unroll
-                        for (int a = 0; a < BS; ++a)
-#pragma unroll
-                            for (int c = 0; c < BS; ++c) {
-                                cfms(W[a][c], f[a], pq[c]);
-                                cfms(C[a][c], f[a], pr[c]);
-                            }
-                    }
-                    // C = dU (scaled).  Publish it as the next left operand.
-                    store_blk<D, BS, LD>(bufX + rc_off, C, lane_on);
-                    __syncwarp();
-                    Xr = bufX + r0 * LD;
-                    Yc = (s > 0) ? (bufX + c0) : (bufP + c0);
-                } else if (ph <= ph_lastsq) {
-                    // C = (previous)^2
-                    __syncwarp();
-                    store_blk<D, BS, LD>(bufX + rc_off, C, lane_on);
-                    __syncwarp();
-                    Xr = bufX + r0 * LD;
-                    Yc = (ph < ph_lastsq) ? (bufX + c0) : (bufP + c0);
-                } else {
-                    // C = dU_n * P
-                    __syncwarp();
-                    store_blk<D, BS, LD>(bufP + rc_off, C, lane_on);
-                }
-                if (ph == ph_lastsq) {                 // C holds dU_n
-                    if (p.dUs_out != nullptr && on) {
-#pragma unroll
-                        for (int a = 0; a < BS; ++a) {
-                            const int row = r0 + a;
-                            if (row < d) {
-                                cplx* o = p.dUs_out + ((size_t)b * p.N + n) * d * d + (size_t)row * d + c0;
-#pragma unroll
-                                for (int c = 0; c < BS; ++c)
-                                    if (c0 + c < d) o[c] = C[a][c];
-                            }
-                        }
-                    }
-                    if (it == 0) store_blk<D, BS, LD>(bufP + rc_off, C, lane_on);
-                }
-            }
-        }
-        __syncwarp();
-
-        // ---- fold the group products: P_{MPW-1} ... P_1 P_0 (every group computes it; group 0 writes) ----
-        cplx* wbase = sWarps + (size_t)warp * L::WARP_ELEMS;
-        const cplx* cur = wbase + L::group_off(MPW - 1) + 3 * L::BUF;
-        int flip = 0;
-#pragma unroll 1
-        for (int gg = MPW - 2; gg >= 0; --gg) {
-            cplx T[BS][BS];
-            mm_blk<D, BS, LD>(cur + r0 * LD, wbase + L::group_off(gg) + 3 * L::BUF + c0, T);
-            cplx* dst = flip ? bufA : bufX;
-            store_blk<D, BS, LD>(dst + rc_off, T, lane_on);
-            __syncwarp();
-            cur = dst;
-            flip ^= 1;
-        }
-        if (lane_on && g == 0) {
-            cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * d * d) : (p.seg_out + ((size_t)b * p.S + sidx) * d * d);
-#pragma unroll
-            for (int a = 0; a < BS; ++a) {
-                const int row = r0 + a;
-                if (row < d) {
-#pragma unroll
-                    for (int c = 0; c < BS; ++c)
-                        if (c0 + c < d) o[row * d + c0 + c] = cur[(r0 + a) * LD + c0 + c];
-                }
-            }
-        }
-        __syncwarp();
-    }
 }
 
 // =============================================================================================

@@ -22,7 +22,7 @@
 // (scratch/conflict_blockmajor.py): 4.0 wavefronts per load, 5 per store / generator load.
 #pragma once
 #include "c3b_common.cuh"
-#include "pwc_rows.cuh"   // RowsParams
+#include "c3b_params.cuh"
 
 namespace c3b {
 
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
             // gated launch: wait (all lanes, uniform code) until this unit's batch row has landed; rows arrive in order.
             // A row that never arrives ends this warp's work like an exhausted counter: the caller pre-fills U with NaN,
             // so the failure is loud and the GPU does not hang.
-            if (!wait_rows_ready(p.rows_ready, b)) break;
+            if (!wait_rows_ready(p.gate, b)) break;
         }
         const int sidx = (int)(unit - (long long)b * p.S);
         const int n_begin = sidx * p.seg_len;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
                 }
                 if (shifted && on) mu = p.TR[0];
                 for (int k = 0; k < K; ++k) {
-                    const double cs = on ? load_signal(sig_b + (size_t)k * p.N + n, GATED) : 0.0;
+                    const double cs = on ? load_signal<GATED>(sig_b + (size_t)k * p.N + n) : 0.0;
                     const cplx* gk = sG + (k + 1) * BUF + L.sown;
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {

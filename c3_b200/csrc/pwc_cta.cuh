@@ -8,27 +8,10 @@
 // 1-norm (thresholds theta_3..theta_9, else 13 with s = ceil(log2(norm/theta_13))) and a
 // Gauss-Jordan solve WITH partial pivoting (row permutation kept in shared memory).
 #pragma once
-#include "c3b_common.cuh"
+#include "c3b_params.cuh"
 
 namespace c3b {
 
-struct CtaParams {
-    const cplx* G;          // [(Bm), K+1, D, D] pre-scaled generators
-    const double* signals;  // [B, K, N]
-    const cplx* hlist;      // [B, N, D, D] or null
-    double hscale_re, hscale_im;
-    long long model_stride;  // elements between batch models in G (0 = shared)
-    int B, K, N, D;
-    int S, seg_len;
-    cplx* U_out;    // [B, D, D]
-    cplx* seg_out;  // [B, S, D, D]
-    cplx* dUs_out;  // [B, N, D, D] or null
-    cplx* ws;       // global workspace, gridDim.x * kCtaSlots * D * D (only when matrices do not fit smem)
-    int use_smem;   // 1: matrices in dynamic shared memory
-};
-
-constexpr int kCtaThreads = 256;
-constexpr int kCtaSlots = 9;  // M0..M7 scratch + P
 
 // ---- C = A * B (+ optional linear epilogue handled by callers) -----------------------------
 // (No __restrict__: the operands may live in the global workspace written earlier by this
@@ -192,11 +175,17 @@ __global__ void __launch_bounds__(kCtaThreads) pwc_cta_kernel(const CtaParams p)
             cplx* A = M[0];
             // ---- assemble ------------------------------------------------------------------
             if (p.hlist == nullptr) {
+                // prepared models carry TRACE-SHIFTED generators (c3b_model_prepare); this literal restatement works on
+                // the unshifted matrix, so the shift mu_n = t_0 + sum_k c_k t_k goes back onto the diagonal here
+                const cplx* TRb = p.unshift ? p.unshift + (p.model_stride ? (size_t)b * (K + 1) : 0) : nullptr;
                 for (int e = tid; e < DD; e += kCtaThreads) {
                     cplx v = Gb[e];
+                    const bool dg = TRb != nullptr && (e / D == e % D);
+                    if (dg) { v.x += TRb[0].x; v.y += TRb[0].y; }
                     for (int k = 0; k < K; ++k) {
                         const double c = __ldg(sig_b + (size_t)k * p.N + n);
-                        const cplx gk = Gb[(size_t)(k + 1) * DD + e];
+                        cplx gk = Gb[(size_t)(k + 1) * DD + e];
+                        if (dg) { gk.x += TRb[k + 1].x; gk.y += TRb[k + 1].y; }
                         v.x = fma(c, gk.x, v.x);
                         v.y = fma(c, gk.y, v.y);
                     }

@@ -18,7 +18,6 @@
 
 namespace c3b {
 
-constexpr int kGemmSlots = 8;    // S0..S5 scratch + P + Q (see the slot plan in pwc_t18_cta_kernel)
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a, const double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -167,14 +166,6 @@ __device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, co
     return v;
 }
 
-struct GemmParams {
-    CtaParams c;       // same fields as the Pade CTA kernel (G, signals, hlist, sizes, outputs, ws, use_smem)
-    const cplx* TR;    // [(Bm), K+1] trace shifts already subtracted from G's diagonals, or null
-    const double* RS;  // [(Bm), K+1, D] row sums of |G_k| (after the shift): inf-norm bound without a pass over the slice, or null
-    int DP;            // D rounded up to a multiple of 8 (tile extent)
-    int LD;            // leading dimension of every workspace matrix (DP, or DP + 4 in shared memory)
-    int g_in_smem;     // the (shared) generators are staged in shared memory after the matrix slots
-};
 
 // Slot plan (8 matrices of DP x LD): the Taylor combinations overwrite the powers they are formed from
 //   S0: A -> B1 -> (B3+A9) A9 -> T18 (squaring ping)   S1: A2 -> B5 (squaring pong)   S2: A3 -> B4

@@ -50,6 +50,15 @@ def propagate_sharded(fn, signals: torch.Tensor, *args, **kwargs) -> torch.Tenso
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return fn(signals, *args, **kwargs)
     B = signals.shape[0]
-    lo, hi = shard_bounds(B, dist.get_world_size(), dist.get_rank())
-    U_local = fn(signals[lo:hi], *args, **kwargs)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lo, hi = shard_bounds(B, world, rank)
+    U_local = fn(signals[lo:hi], *args, **kwargs) if hi > lo else None
+    if B < world:
+        # more ranks than batch rows: the ranks without work skip the kernel (it rejects B = 0) but still take part in the
+        # gather, with an empty shard shaped like rank 0's result (rank 0 always owns a row)
+        meta = [(tuple(U_local.shape[1:]), U_local.dtype) if rank == 0 else None]
+        dist.broadcast_object_list(meta, src=0)
+        if U_local is None:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            U_local = torch.empty((0,) + meta[0][0], dtype=meta[0][1], device=dev)
     return all_gather_unitaries(U_local, B)

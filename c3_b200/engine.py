@@ -140,27 +140,28 @@ def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, fi
             bounds = [0, min(B, max(1, int(first_chunk)))]
             while bounds[-1] < B:
                 bounds.append(min(B, bounds[-1] + chunk))
-            U.fill_(float("nan"))            # rows the kernel never gets to see (copy failure) stay NaN: loud, not a hang
+            U.fill_(float("nan"))            # rows the kernel never gets to see (copy failure) stay NaN
             sig = torch.empty((B, K, N), dtype=torch.float64, device=device)
-            ready = torch.empty((1,), dtype=torch.int32, device=device)
+            gate = torch.empty((2,), dtype=torch.int32, device=device)     # [rows landed, timeout flag]
             marks = _gate_marks(tuple(bounds[1:]))
             cs = streams[0]
             cs.wait_event(start)
             first = torch.cuda.Event()
             with torch.cuda.stream(cs):
-                ready.zero_()
+                gate.zero_()
                 for i in range(len(bounds) - 1):
                     sig[bounds[i]:bounds[i + 1]].copy_(signals_host[bounds[i]:bounds[i + 1]], non_blocking=True)
-                    ready.copy_(marks[i:i + 1], non_blocking=True)
+                    gate[0:1].copy_(marks[i:i + 1], non_blocking=True)
                     if i == 0:
                         first.record(cs)
             sig.record_stream(cs)
-            ready.record_stream(cs)
+            gate.record_stream(cs)
             main.wait_event(first)          # every copy is already enqueued: the kernel can only wait on the copy engine
             nbytes = lib.c3b_pwc_workspace_bytes(B, K, N, d, 0, 0)
             ws = _workspace(nbytes, device)
-            _lib.check(lib.c3b_pwc_closed_gated(_ptr(h0), _ptr(hks), _ptr(sig), float(dt), B, K, N, d, _ptr(U), _ptr(ready),
+            _lib.check(lib.c3b_pwc_closed_gated(_ptr(h0), _ptr(hks), _ptr(sig), float(dt), B, K, N, d, _ptr(U), _ptr(gate),
                                                 _ptr(ws), ws.numel(), _stream()))
+            _watch_gate(gate, main)
             return U
         done = []
         for i, b0 in enumerate(range(0, B, chunk)):
@@ -194,17 +195,34 @@ def _gate_marks(bounds) -> torch.Tensor:
     return t
 
 
-_pinned_in_flight = {}
+_gates_in_flight = []
 
 
-def _keepalive(device, host_tensor, stream):
-    """Keep a pinned staging tensor alive until the copies that read it have run (dropped on a later call)."""
-    key = device.index if device.index is not None else torch.cuda.current_device()
+def _watch_gate(gate: torch.Tensor, stream) -> None:
+    """Remember the status word of a gated launch; it is read once the launch has finished (see check_gated_launches)."""
     ev = torch.cuda.Event()
     ev.record(stream)
-    q = _pinned_in_flight.setdefault(key, [])
-    q[:] = [(e, t) for (e, t) in q if not e.query()]
-    q.append((ev, host_tensor))
+    _gates_in_flight.append((ev, gate))
+    check_gated_launches(wait=False)
+
+
+def check_gated_launches(wait: bool = True) -> None:
+    """Raise if a gated launch (pwc_closed_from_host) gave up on a batch row that never arrived from the host: the
+    kernel sets gate[1] and leaves the affected rows of U as NaN instead of hanging the GPU.  ``wait=False`` (what every
+    later gated call does on entry) only looks at launches that have already finished; ``wait=True`` synchronises on the
+    outstanding ones first -- call it wherever the result is consumed on the host."""
+    keep = []
+    failed = False
+    for ev, gate in _gates_in_flight:
+        if wait:
+            ev.synchronize()
+        if ev.query():
+            failed = failed or bool(gate[1].item() != 0)
+        else:
+            keep.append((ev, gate))
+    _gates_in_flight[:] = keep
+    if failed:
+        raise _lib.C3BError("C3:ERROR: gated launch timed out waiting for host control fields; the affected rows of U are NaN")
 
 
 _side = {}
@@ -266,12 +284,7 @@ def pwc_lindblad_grad(h0, hks, col_ops, signals, dt: float, Ubar, max_workspace_
             raise ValueError("C3:ERROR: the gradient path needs a shared model h0 [d,d]")
         d = h0.shape[-1]
         D = d * d
-        if isinstance(col_ops, (list, tuple)):
-            col_ops = torch.stack([_as(c, torch.complex128, device) for c in col_ops]) if len(col_ops) else None
-        C = 0
-        if col_ops is not None:
-            col_ops = _as(col_ops, torch.complex128, device)
-            C = col_ops.shape[-3]
+        col_ops, C = _collapse_ops(col_ops, 0, d, device)
         Ubar = _as(Ubar, torch.complex128, device)
         if tuple(Ubar.shape) != (B, D, D):
             raise ValueError(f"C3:ERROR: Ubar has shape {tuple(Ubar.shape)}, expected {(B, D, D)}")
@@ -306,6 +319,32 @@ def pwc_closed_hlist(Hs, dt: float, return_dUs: bool = False, device=None):
     return (U, dUs) if return_dUs else U
 
 
+def _collapse_ops(col_ops, n_models: int, d: int, device):
+    """Collapse operators in the layout the C ABI reads: [C,d,d] for a shared model (``n_models == 0``), [B,C,d,d] for
+    per-sample models.  Accepts a list of [d,d] (or, per sample, of [B,d,d]) or a stacked tensor; operators shared by all
+    samples of a batched model are expanded."""
+    if col_ops is None or (isinstance(col_ops, (list, tuple)) and len(col_ops) == 0):
+        return None, 0
+    if isinstance(col_ops, (list, tuple)):
+        ops = [_as(c, torch.complex128, device) for c in col_ops]
+        col_ops = torch.stack(ops, dim=1 if ops[0].dim() == 3 else 0)
+    else:
+        col_ops = _as(col_ops, torch.complex128, device)
+    if col_ops.dim() == 2:
+        col_ops = col_ops.unsqueeze(0)
+    if col_ops.shape[-2:] != (d, d):
+        raise ValueError(f"C3:ERROR: collapse operators have shape {tuple(col_ops.shape)}, expected [..., {d}, {d}]")
+    C = col_ops.shape[-3]
+    if n_models:
+        if col_ops.dim() == 3:
+            col_ops = col_ops.unsqueeze(0).expand(n_models, C, d, d)
+        if tuple(col_ops.shape) != (n_models, C, d, d):
+            raise ValueError(f"C3:ERROR: collapse operators have shape {tuple(col_ops.shape)}, expected {(n_models, C, d, d)}")
+    elif col_ops.dim() != 3:
+        raise ValueError(f"C3:ERROR: collapse operators have shape {tuple(col_ops.shape)}, expected {(C, d, d)} for a shared model")
+    return col_ops.contiguous(), C
+
+
 def pwc_lindblad(h0, hks, col_ops, signals, dt: float, return_dUs: bool = False, device=None):
     """Lindblad superoperator propagators U [B,d^2,d^2] (c3/libraries/propagation.py:551-585)."""
     lib = _lib.load()
@@ -318,14 +357,16 @@ def pwc_lindblad(h0, hks, col_ops, signals, dt: float, return_dUs: bool = False,
         h0 = _as(h0, torch.complex128, device)
         batched = h0.dim() == 3
         d = h0.shape[-1]
-        hks = _as(hks, torch.complex128, device) if K > 0 else None
-        if isinstance(col_ops, (list, tuple)):
-            col_ops = torch.stack([_as(c, torch.complex128, device) for c in col_ops]) if len(col_ops) else None
-        if col_ops is not None:
-            col_ops = _as(col_ops, torch.complex128, device)
-            C = col_ops.shape[-3]
+        if batched and h0.shape[0] != B:
+            raise ValueError("C3:ERROR: batched h0 must have the batch size of signals")
+        if K > 0:
+            hks = _as(hks, torch.complex128, device)
+            want = (B, K, d, d) if batched else (K, d, d)
+            if tuple(hks.shape) != want:
+                raise ValueError(f"C3:ERROR: hks has shape {tuple(hks.shape)}, expected {want}")
         else:
-            C = 0
+            hks = None
+        col_ops, C = _collapse_ops(col_ops, B if batched else 0, d, device)
         D = d * d
         U = torch.empty((B, D, D), dtype=torch.complex128, device=device)
         dUs = torch.empty((B, N, D, D), dtype=torch.complex128, device=device) if return_dUs else None
@@ -334,6 +375,126 @@ def pwc_lindblad(h0, hks, col_ops, signals, dt: float, return_dUs: bool = False,
         _lib.check(lib.c3b_pwc_lindblad(_ptr(h0), _ptr(hks), _ptr(col_ops), C, _ptr(signals), float(dt), B, K, N, d,
                                         int(batched), _ptr(U), _ptr(dUs), _ptr(ws), ws.numel(), _stream()))
     return (U, dUs) if return_dUs else U
+
+
+class PreparedModel:
+    """Device-resident generators of one model (or of B per-sample models): what ``c3b_model_prepare`` builds once per model
+    update so that every later propagation is one fused launch (the reference rebuilds them inside every
+    tf_propagation_* call, c3/libraries/propagation.py:426-440, 551-585)."""
+
+    def __init__(self, blob: torch.Tensor, K: int, d: int, dt: float, lindblad: bool, n_models: int):
+        self.blob, self.K, self.d, self.dt, self.lindblad, self.n_models = blob, K, d, dt, lindblad, n_models
+
+    @property
+    def D(self) -> int:
+        return self.d * self.d if self.lindblad else self.d
+
+    @property
+    def device(self) -> torch.device:
+        return self.blob.device
+
+
+def prepare_model(h0, hks, dt: float, col_ops=None, lindblad: bool = False, device=None) -> PreparedModel:
+    """Generators for ``h0 [d,d]`` / ``hks [K,d,d]`` (or [B,d,d] / [B,K,d,d] for per-sample models) and slice length ``dt``;
+    with ``lindblad`` the superoperator generators of ``col_ops``."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        h0 = _as(h0, torch.complex128, device)
+        batched = h0.dim() == 3
+        d = h0.shape[-1]
+        n_models = h0.shape[0] if batched else 1
+        K = 0
+        if hks is not None:
+            hks = _as(hks, torch.complex128, device)
+            K = hks.shape[-3] if hks.numel() else 0
+        if K > 0:
+            want = (n_models, K, d, d) if batched else (K, d, d)
+            if tuple(hks.shape) != want:
+                raise ValueError(f"C3:ERROR: hks has shape {tuple(hks.shape)}, expected {want}")
+        else:
+            hks = None
+        C = 0
+        if lindblad:
+            col_ops, C = _collapse_ops(col_ops, n_models if batched else 0, d, device)
+        else:
+            col_ops = None
+        nbytes = lib.c3b_model_bytes(K, d, int(lindblad), n_models)
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.check(lib.c3b_model_prepare(_ptr(h0), _ptr(hks), _ptr(col_ops), C, float(dt), K, d, int(lindblad), n_models,
+                                         _ptr(blob), nbytes, _stream()))
+    return PreparedModel(blob, K, d, float(dt), bool(lindblad), n_models)
+
+
+def pwc_prepared(model: PreparedModel, signals, return_dUs: bool = False, out=None, dUs_out=None):
+    """U [B,D,D] (and dUs [B,N,D,D]) for ``signals [B,K,N]`` with a prepared model: one fused launch (+ one fold launch when
+    the time axis is segmented), no setup kernels."""
+    lib = _lib.load()
+    device = model.device
+    with torch.cuda.device(device):
+        signals = _as(signals, torch.float64, device)
+        if signals.dim() == 2:
+            signals = signals.unsqueeze(0)
+        B, K, N = signals.shape
+        if K != model.K:
+            raise ValueError(f"C3:ERROR: signals have {K} control lines, the prepared model has {model.K}")
+        if model.n_models not in (1, B):
+            raise ValueError("C3:ERROR: a per-sample prepared model needs one signal row per model")
+        D = model.D
+        U = out if out is not None else torch.empty((B, D, D), dtype=torch.complex128, device=device)
+        if tuple(U.shape) != (B, D, D) or U.dtype != torch.complex128 or not U.is_contiguous():
+            raise ValueError("C3:ERROR: `out` must be a contiguous complex128 [B,D,D] tensor")
+        dUs = None
+        if return_dUs:
+            dUs = dUs_out if dUs_out is not None else torch.empty((B, N, D, D), dtype=torch.complex128, device=device)
+        nbytes = lib.c3b_pwc_prepared_workspace_bytes(B, N, model.d, int(model.lindblad), model.n_models)
+        ws = _workspace(nbytes, device)
+        _lib.check(lib.c3b_pwc_prepared(_ptr(model.blob), _ptr(signals), B, K, N, model.d, int(model.lindblad), model.n_models,
+                                        _ptr(U), _ptr(dUs), _ptr(ws), ws.numel(), _stream()))
+    return (U, dUs) if return_dUs else U
+
+
+class GraphedPwc:
+    """A prepared-model propagation of fixed shape captured in a CUDA graph: one graph launch per call, for the
+    latency-bound small-batch calls of a per-gate optimiser loop (B = 1 ... a gate set).
+
+    ``run(signals)`` copies the control fields into the graph's static input buffer (device-to-device, or from pinned
+    host memory) and replays; the returned tensors are the graph's static outputs, valid until the next ``run``."""
+
+    def __init__(self, model: PreparedModel, B: int, N: int, return_dUs: bool = False):
+        self.model, self.B, self.N, self.return_dUs = model, int(B), int(N), bool(return_dUs)
+        dev = model.device
+        D = model.D
+        with torch.cuda.device(dev):
+            self.signals = torch.zeros((self.B, model.K, self.N), dtype=torch.float64, device=dev)
+            self.U = torch.empty((self.B, D, D), dtype=torch.complex128, device=dev)
+            self.dUs = torch.empty((self.B, self.N, D, D), dtype=torch.complex128, device=dev) if return_dUs else None
+            # a private workspace: the shared per-stream one may be regrown (freed) by other calls between replays
+            nbytes = _lib.load().c3b_pwc_prepared_workspace_bytes(self.B, self.N, model.d, int(model.lindblad), model.n_models)
+            self._ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._launch()                       # warm-up outside capture (cudaFuncSetAttribute, lazy module load)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._launch()
+
+    def _launch(self):
+        lib = _lib.load()
+        m = self.model
+        _lib.check(lib.c3b_pwc_prepared(_ptr(m.blob), _ptr(self.signals), self.B, m.K, self.N, m.d, int(m.lindblad), m.n_models,
+                                        _ptr(self.U), _ptr(self.dUs), _ptr(self._ws), self._ws.numel(), _stream()))
+
+    def run(self, signals=None):
+        if signals is not None:
+            if not isinstance(signals, torch.Tensor):
+                signals = torch.as_tensor(signals)
+            self.signals.copy_(signals.reshape(self.signals.shape), non_blocking=True)
+        self.graph.replay()
+        return (self.U, self.dUs) if self.return_dUs else self.U
 
 
 def ordered_product(mats, device=None) -> torch.Tensor:

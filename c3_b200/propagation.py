@@ -90,10 +90,22 @@ def _real_signals(signals):
 # array-level API
 # --------------------------------------------------------------------------------------------
 
+def _slice_hamiltonians(h0, hks, cflds_t) -> torch.Tensor:
+    """H_n = h0[n] + sum_k c_k[n] hks[k] for a per-slice drift ``h0 [N,d,d]`` (host-side staging of an H list)."""
+    h = torch.as_tensor(_host(h0), dtype=torch.complex128)
+    hk = torch.as_tensor(_host(hks), dtype=torch.complex128)
+    c = torch.as_tensor(_host(_real_signals(cflds_t)), dtype=torch.complex128)
+    if h.shape[0] != c.shape[-1]:
+        raise ValueError(f"C3:ERROR: {h.shape[0]} drift slices for {c.shape[-1]} signal samples")
+    return h + torch.einsum("kn,kij->nij", c, hk)
+
 def tf_propagation_vectorized(h0, hks, cflds_t, dt):
     """dU_n = expm(-i (h0 + sum_k c_k[n] hks[k]) dt) for every slice -> [n,d,d]
     (propagation.py:426-440).  With ``hks is None`` ``h0`` is the list of Hamiltonians [n,d,d]."""
     if hks is not None and cflds_t is not None:
+        if _np(h0).ndim == 3:
+            _, dUs = engine.pwc_closed_hlist(_slice_hamiltonians(h0, hks, cflds_t), float(np.real(dt)), return_dUs=True)
+            return dUs[0]
         _, dUs = engine.pwc_closed(_np(h0), _np(hks), _real_signals(cflds_t), float(np.real(dt)), return_dUs=True)
     else:
         _, dUs = engine.pwc_closed_hlist(_np(h0), float(np.real(dt)), return_dUs=True)
@@ -124,6 +136,10 @@ def tf_batch_propagate(hamiltonian, hks, signals, dt, batch_size, col_ops=None, 
         if lindbladian:
             _, dUs = engine.pwc_lindblad(_np(hamiltonian), _np(hks), [_np(c) for c in col_ops], sig,
                                          float(np.real(dt)), return_dUs=True)
+        elif _np(hamiltonian).ndim == 3 and not batched:
+            # a per-slice drift [N,d,d] next to the control terms (the reference's `len(h0.shape) < 3` test,
+            # propagation.py:430-436): assemble the slice Hamiltonians and take the H-list entry
+            _, dUs = engine.pwc_closed_hlist(_slice_hamiltonians(hamiltonian, hks, sig), float(np.real(dt)), return_dUs=True)
         else:
             _, dUs = engine.pwc_closed(_np(hamiltonian), _np(hks), sig, float(np.real(dt)), return_dUs=True)
         return dUs if batched else dUs[0]
@@ -203,6 +219,66 @@ def pwc_batch_autograd(h0, hks, signals: torch.Tensor, dt, col_ops=None, lindbla
 # gate-level API (duck-typed Model / Generator / Instruction exactly as the reference uses them)
 # --------------------------------------------------------------------------------------------
 
+class GateInputs:
+    """What one gate hands to the engine, gathered from the duck-typed Model / Generator / Instruction exactly as the
+    reference's ``pwc`` gathers it (propagation.py:282-321): either control fields + control Hamiltonians
+    (``signals [K,N]``, ``hks [K,d,d]``) or, with ``model.controllability`` off, the list of slice Hamiltonians
+    (``hlist [N,d,d]``); collapse operators when the model is Lindbladian; the excitation cutter if one is set."""
+
+    __slots__ = ("h0", "hks", "signals", "hlist", "col_ops", "ts", "dt", "cutter", "channels")
+
+    def __init__(self):
+        self.h0 = self.hks = self.signals = self.hlist = self.col_ops = self.ts = self.cutter = None
+        self.dt = 0.0
+        self.channels = ()
+
+    @property
+    def n_slices(self) -> int:
+        return int(self.signals.shape[-1] if self.signals is not None else self.hlist.shape[0])
+
+
+def gather_gate(model, gen, instr) -> GateInputs:
+    """Signals, Hamiltonians, time grid and collapse operators of one instruction (propagation.py:282-321)."""
+    g = GateInputs()
+    signal = gen.generate_signals(instr)
+    g.channels = tuple(signal.keys())
+    if model.controllability:
+        h0, hctrls = model.get_Hamiltonians()
+        g.h0 = _np(h0)
+        # channel order = iteration order of the signal dictionary (propagation.py:289-292)
+        g.signals = _stack_fields([signal[key]["values"] for key in g.channels])
+        g.hks = np.stack([_host(hctrls[key]) for key in g.channels])
+        g.ts = signal[g.channels[-1]]["ts"]
+        ts_np = _host(g.ts)
+    else:
+        g.hlist = _np(model.get_Hamiltonian(signal))
+        ts_all = np.asarray([_host(sig["ts"])[1:] for sig in signal.values()])
+        ts_np = ts_all.mean(axis=0)
+        g.ts = ts_np
+        step = ts_np[1] - ts_np[0]
+        # all lines on one grid, and that grid uniform (propagation.py:301-308)
+        if not np.all(ts_all.var(axis=0) < 1e-5 * step) or not np.all(np.var(np.diff(ts_np)) < 1e-5 * step):
+            raise Exception("C3Error:Something with the times happend.")
+    g.dt = float(ts_np[1] - ts_np[0])
+    if model.max_excitations:
+        g.cutter = _host(model.ex_cutter)
+    if model.lindbladian:
+        if g.signals is None:
+            raise Exception("C3:ERROR: Lindblad propagation needs control Hamiltonians and signals.")
+        cols = [_host(c) for c in model.get_Lindbladians()]
+        if g.cutter is not None:
+            cols = [g.cutter @ c @ g.cutter.T for c in cols]
+        g.col_ops = cols
+    return g
+
+
+def _stack_fields(values):
+    """[K,N] float64 control fields from per-line arrays; stays on the device when the generator produced CUDA tensors."""
+    if all(isinstance(v, torch.Tensor) for v in values):
+        return _real_signals(torch.stack([v.reshape(-1) for v in values]))
+    return _real_signals(np.stack([_host(v) for v in values]))
+
+
 @unitary_deco
 def pwc(model, gen, instr, folding_stack: list, batch_size=None) -> Dict:
     """Solve the equation of motion (Lindblad or Schroedinger) for one gate
@@ -212,53 +288,19 @@ def pwc(model, gen, instr, folding_stack: list, batch_size=None) -> Dict:
     Returns ``{"U": [D,D], "dUs": [N,D,D], "ts": [N]}`` (torch CUDA tensors, ``ts`` as given).
     """
     del folding_stack, batch_size
-    signal = gen.generate_signals(instr)
-    ts = []
-    if model.controllability:
-        h0, hctrls = model.get_Hamiltonians()
-        signals = []
-        hks = []
-        for key in signal:
-            signals.append(_host(signal[key]["values"]))
-            ts = signal[key]["ts"]
-            hks.append(_host(hctrls[key]))
-        signals = np.stack(signals)
-        hks = np.stack(hks)
-        ts_np = _host(ts)
+    g = gather_gate(model, gen, instr)
+    if g.col_ops is not None:
+        U, dUs = engine.pwc_lindblad(g.h0, g.hks, g.col_ops, g.signals, g.dt, return_dUs=True)
+    elif g.signals is not None:
+        U, dUs = engine.pwc_closed(g.h0, g.hks, g.signals, g.dt, return_dUs=True)
     else:
-        h0 = model.get_Hamiltonian(signal)
-        ts_list = np.asarray([_host(sig["ts"])[1:] for sig in signal.values()])
-        ts_np = ts_list.mean(axis=0)
-        ts = ts_np
-        hks = None
-        signals = None
-        if not np.all(ts_list.var(axis=0) < 1e-5 * (ts_np[1] - ts_np[0])):
-            raise Exception("C3Error:Something with the times happend.")
-        if not np.all(np.var(ts_np[1:] - ts_np[:-1]) < 1e-5 * (ts_np[1] - ts_np[0])):
-            raise Exception("C3Error:Something with the times happend.")
-
-    dt = float(ts_np[1] - ts_np[0])
-
-    cutter = _host(model.ex_cutter) if model.max_excitations else None
-
-    if model.lindbladian:
-        col_ops = [_host(c) for c in model.get_Lindbladians()]
-        if cutter is not None:
-            col_ops = [cutter @ c @ cutter.T for c in col_ops]
-        if signals is None:
-            raise Exception("C3:ERROR: Lindblad propagation needs control Hamiltonians and signals.")
-        U, dUs = engine.pwc_lindblad(_np(h0), hks, col_ops, _real_signals(signals), dt, return_dUs=True)
-    elif signals is not None:
-        U, dUs = engine.pwc_closed(_np(h0), hks, _real_signals(signals), dt, return_dUs=True)
-    else:
-        U, dUs = engine.pwc_closed_hlist(_np(h0), dt, return_dUs=True)
+        U, dUs = engine.pwc_closed_hlist(g.hlist, g.dt, return_dUs=True)
     U, dUs = U[0], dUs[0]
-
-    if cutter is not None:
+    if g.cutter is not None:
         # blow-up P^T A P is a scatter of the cut matrix into the full space (c3/model.py:222-224)
-        U = blowup_excitations(cutter, U)
-        dUs = blowup_excitations(cutter, dUs)
-    return {"U": U, "dUs": dUs, "ts": ts}
+        U = blowup_excitations(g.cutter, U)
+        dUs = blowup_excitations(g.cutter, dUs)
+    return {"U": U, "dUs": dUs, "ts": g.ts}
 
 
 def blowup_excitations(cutter, op: torch.Tensor) -> torch.Tensor:

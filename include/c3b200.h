@@ -12,7 +12,9 @@
  *   - complex128 is interleaved (re, im) doubles, matrices are row-major, exactly the
  *     memory image of a contiguous numpy/torch complex128 tensor;
  *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing
- *     synchronises, calls are re-entrant (one thread per GPU is the intended use);
+ *     synchronises; the library keeps no process-wide mutable state except an atomic launch
+ *     counter (error message, tuning knobs and profile events are per calling thread), so calls
+ *     are re-entrant: one thread per GPU is the intended use;
  *   - return value 0 = success, otherwise a negative C3B_E* code; c3b_last_error() gives the
  *     message of the last failure on the calling thread;
  *   - ordered products put LATER slices on the LEFT: U = dU_{N-1} ... dU_1 dU_0
@@ -60,16 +62,39 @@ int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, doubl
                    int batched_model, void* U_out, void* dUs_out, void* workspace, size_t workspace_bytes,
                    void* stream);
 
-/* Gated variant of c3b_pwc_closed for HOST-resident control fields (shared model, no dUs, d = 9: the headline kernel): the caller enqueues
- * the host->device copies of `signals` in batch order on a copy stream, each chunk followed by a 4-byte copy that
- * raises *rows_ready (device memory, zero before the first chunk) to the number of batch rows that have landed, and
- * launches this ONE call on another stream as soon as the first chunk is in.  Warps take batch rows in order and wait
- * on *rows_ready only if they overtake the copy engine, so PCIe time hides behind the whole-batch kernel instead of
- * cutting it into per-chunk launches.  If a row does not arrive within ~4 s the kernel stops taking work (no GPU hang): pre-fill U_out with NaN to see it.
- * c3b_pwc_gated_supported(d) != 0 says whether the dimension takes this path. */
+/* Gated variant of c3b_pwc_closed for HOST-resident control fields (shared model, no dUs, d = 9: the headline
+ * kernel).  The caller enqueues the host->device copies of `signals` in batch order on a copy stream, each chunk
+ * followed by a 4-byte copy that raises gate[0] to the number of batch rows that have landed, and launches this ONE call
+ * on another stream as soon as the first chunk is in.  Warps take batch rows in order and wait on gate[0] only if they
+ * overtake the copy engine, so PCIe time hides behind the whole-batch kernel instead of cutting it into per-chunk
+ * launches.  In-flight rows are read past L1 (ld.global.cg), never through the read-only path.
+ *   gate [2] uint32, device memory, both words zero before the first chunk:
+ *        gate[0]  rows landed (written by the caller's copy stream, read with acquire loads by the kernel)
+ *        gate[1]  set to 1 by the kernel if some row did not arrive within ~4 s WITHOUT copy progress: the warp that
+ *                 waited stops taking work (no GPU hang) and the rows it never computed stay as the caller pre-filled
+ *                 them (fill U_out with NaN).  The caller reads gate[1] at its next synchronisation point and turns a
+ *                 non-zero value into an error -- the call itself returns before the kernel has run.
+ * c3b_pwc_gated_supported(d) != 0 says whether the dimension takes this path (with the calling thread's tuning). */
 int c3b_pwc_closed_gated(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
-                         void* U_out, const uint32_t* rows_ready, void* workspace, size_t workspace_bytes, void* stream);
+                         void* U_out, uint32_t* gate, void* workspace, size_t workspace_bytes, void* stream);
 int c3b_pwc_gated_supported(int d);
+
+/* Prepared models: everything of a launch that depends on the MODEL only -- the generators G_0 = -i dt h0,
+ * G_k = -i dt h_k (closed system) or the Lindblad superoperator generators (c3/libraries/propagation.py:563-582),
+ * trace-shifted, with their row sums -- built once per model update instead of once per call.  The reference
+ * rebuilds these inside every tf_propagation_* call (propagation.py:426-440, 551-585); an optimiser that only changes
+ * pulse parameters calls c3b_model_prepare once and c3b_pwc_prepared per evaluation (one fused launch, plus one fold
+ * launch when the time axis is segmented).
+ *   h0 [n_models,d,d], hks [n_models,K,d,d], col_ops [n_models,C,d,d] (n_models = 1: shared model; = B: one per row)
+ *   model_out: caller-owned device buffer of c3b_model_bytes(K, d, lindblad, n_models) bytes, 16-byte aligned.
+ * c3b_pwc_prepared: same outputs as c3b_pwc_closed / c3b_pwc_lindblad (U_out [B,D,D], dUs_out [B,N,D,D] or NULL,
+ * D = d or d*d); workspace of c3b_pwc_prepared_workspace_bytes(B, N, d, lindblad, n_models) bytes. */
+size_t c3b_model_bytes(int K, int d, int lindblad, int n_models);
+int c3b_model_prepare(const void* h0, const void* hks, const void* col_ops, int C, double dt, int K, int d, int lindblad,
+                      int n_models, void* model_out, size_t model_bytes, void* stream);
+size_t c3b_pwc_prepared_workspace_bytes(int B, int N, int d, int lindblad, int n_models);
+int c3b_pwc_prepared(const void* model, const double* signals, int B, int K, int N, int d, int lindblad, int n_models,
+                     void* U_out, void* dUs_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Same with explicit per-slice Hamiltonians (the reference's `signals is None` branch,
  * c3/libraries/propagation.py:294-308, 491-499, 437-438):  Hs [B,N,d,d]. */
@@ -201,12 +226,15 @@ int c3b_seq_product(const void* gates, int Gn, const int32_t* seq_idx, const int
 int c3b_kron(const void* A, const void* Bm, void* out, int batch, int ra, int ca, int rb, int cb, int a_batched,
              int b_batched, void* stream);
 
-/* Tuning knobs (process-wide; for experiments).  key: "target_units", "min_chunk", "force_cta",
- * "rows_variant", "profile".  Returns C3B_EINVAL for an unknown key. */
+/* Tuning knobs of the CALLING THREAD (thread-local: one thread per GPU is the intended use, and a thread that flips a
+ * knob for an experiment cannot disturb another thread's launches).  Keys: "target_units", "min_chunk" (segmentation of
+ * the time axis), "d9_variant" (0 generic 3x3-block kernel, 1 own-block shared-memory kernel, 2 shuffle-exchange kernel),
+ * "force_cta", "cta_variant" (0 literal Higham cross-check, 1 Taylor-18 on DMMA tiles), "cta_threads", "gemm_big",
+ * "norm_bound", "seq_variant", "grad_variant", "profile".  Returns C3B_EINVAL for an unknown key. */
 int c3b_set_tuning(const char* key, long long value);
 
-/* Which kernel c3b_pwc_* would pick for this shape: 1 = register-resident rows kernel,
- * 2 = CTA kernel with shared-memory matrices, 3 = CTA kernel with global workspace. */
+/* Which kernel c3b_pwc_* would pick for this shape: 1 = lane-group kernel (d <= 12, shared model),
+ * 2 = DMMA CTA kernel with shared-memory matrices, 3 = DMMA CTA kernel with a global workspace. */
 int c3b_pwc_path(int K, int D, int batched_model);
 
 /* Measured fp64 throughput of this GPU in TFLOP/s (2 flops per FMA) -- the roofline
@@ -218,15 +246,11 @@ double c3b_measure_fp64_peak(int kind, int device, double seconds);
 /* Number of CUDA kernels this library has launched in this process so far. */
 long long c3b_launch_count(void);
 
-/* With tuning key "profile" = 1, every c3b_pwc_* call brackets its main (fused) kernel with
- * CUDA events on the caller's stream; this returns the duration in ms of the last one
- * (synchronises on that event).  Negative on error. */
+/* With tuning key "profile" = 1, every c3b_pwc_* call of this thread brackets its main (fused) kernel with CUDA
+ * events on the caller's stream (events live on that stream's device); this returns the duration in ms of the
+ * thread's last one (synchronises on that event).  Negative on error. */
 double c3b_last_kernel_ms(void);
 
-/* Development micro-benchmarks of kernel building blocks (TFLOP/s of the fp64 pipe).
- * kind 0/1/2: the row-times-shared-matrix primitive for D = 9/4/3 with `a` warps per CTA and
- * `b` CTAs per SM.  Synchronises the device. */
-double c3b_microbench(int kind, int a, int b);
 
 #ifdef __cplusplus
 }

@@ -416,3 +416,82 @@ def propagate_batch(h0, hks, signals_bkn, dt, col_ops=None, lindbladian=False, e
     if return_dUs:
         return np.stack(Us), np.stack(dUs_all)
     return np.stack(Us)
+
+
+# ----------------------------------------------------------------------------------------
+# Frame rotation, dephasing channel and the gate loop around pwc
+# (c3/model.py:536-578, 597-639; c3/experiment.py:440-534)
+# ----------------------------------------------------------------------------------------
+
+def frame_rotation(ann_opers: Sequence[np.ndarray], line_to_index: Dict[str, int], t_final, freqs: Dict, framechanges: Dict,
+                   expm=None) -> np.ndarray:
+    """FR = expm( sum_line 1j a_q^dag a_q (freq_line t_final + framechange_line) )  (c3/model.py:536-578).
+    ``line_to_index[line]`` is the subsystem the line drives (``couplings[line].connected[0]`` in the reference)."""
+    expm = expm or (lambda a: expm_tf(a[None])[0])
+    dim = ann_opers[0].shape[0]
+    exponent = np.zeros((dim, dim), dtype=np.complex128)
+    if len(freqs) == 0:
+        return np.eye(dim, dtype=np.complex128)
+    for line in freqs:
+        a = np.asarray(ann_opers[line_to_index[line]])
+        num = a.T.conj() @ a
+        exponent = exponent + 1.0j * num * (freqs[line] * t_final + framechanges[line])
+    return expm(exponent)
+
+
+def dephasing_channel(ann_opers: Sequence[np.ndarray], line_to_index: Dict[str, int], t_final, amps: Dict,
+                      dephasing_strength: float, expm=None) -> np.ndarray:
+    """prod_line ((1 - p) Id + p Z_line) with the ELEMENTWISE product the reference uses (c3/model.py:597-639;
+    ``deph_ch * (...)`` on tf tensors is elementwise), p = t_final amp strength, Z = super(expm(1j pi a^dag a))."""
+    expm = expm or (lambda a: expm_tf(a[None])[0])
+    dim = ann_opers[0].shape[0]
+    Id = tf_super(np.eye(dim, dtype=np.complex128))
+    ch = Id
+    for line in amps:
+        a = np.asarray(ann_opers[line_to_index[line]])
+        num = a.T.conj() @ a
+        Z = tf_super(expm(1.0j * num * np.pi))
+        p = t_final * amps[line] * dephasing_strength
+        if np.real(p) > 1 or np.real(p) < 0:
+            raise ValueError(f"Dephasing channel strength {p} is outside [0,1] range")
+        ch = ch * ((1 - p) * Id + p * Z)
+    return ch
+
+
+def compute_propagators(model, generator, instructions: Dict, sim_res: float, gate_ids=None, batch_size=None,
+                        use_control_fields: bool = True, expm=expm_tf):
+    """The gate loop of Experiment.compute_propagators (c3/experiment.py:440-534): pwc per gate, then FR U (or SFR U for
+    Lindbladian models) and the dephasing channel from the left.  Returns (propagators, partial_propagators)."""
+    propagators, partial = {}, {}
+    for gate in (gate_ids if gate_ids is not None else instructions.keys()):
+        if gate not in instructions:
+            raise Exception(f"C3:Error: Gate '{gate}' is not defined. Available gates are:\n {list(instructions.keys())}.")
+        instr = instructions[gate]
+        model.controllability = use_control_fields
+        steps = int((instr.t_end - instr.t_start) * sim_res)
+        res = pwc(model, generator, instr, compute_folding_stack(steps), batch_size, expm=expm)
+        U, dUs = res["U"], res["dUs"]
+        if model.use_FR:
+            freqs, framechanges = {}, {}
+            for line, ctrls in instr.comps.items():
+                offset = 0.0
+                for ctrl in ctrls.values():
+                    if "freq_offset" in ctrl.params.keys():
+                        if np.asarray(ctrl.params["amp"].get_value()) != 0.0:
+                            offset = float(np.asarray(ctrl.params["freq_offset"].get_value()))
+                freqs[line] = complex(float(np.asarray(ctrls["carrier"].params["freq"].get_value())) + offset)
+                framechanges[line] = complex(float(np.asarray(ctrls["carrier"].params["framechange"].get_value())))
+            t_final = complex(instr.t_end - instr.t_start)
+            FR = np.asarray(model.get_Frame_Rotation(t_final, freqs, framechanges))
+            U = (tf_super(FR) if model.lindbladian else FR) @ U
+        if model.dephasing_strength != 0.0:
+            if not model.lindbladian:
+                raise ValueError("Dephasing can only be added when lindblad is on.")
+            amps = {}
+            for line in instr.comps:
+                amp, _ = generator.devices["awg"].get_average_amp()
+                amps[line] = complex(float(np.asarray(amp)))
+            U = np.asarray(model.get_dephasing_channel(complex(instr.t_end - instr.t_start), amps)) @ U
+        propagators[gate] = U
+        partial[gate] = dUs
+    return propagators, partial

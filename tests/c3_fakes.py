@@ -136,3 +136,86 @@ def tunable_coupler_flux_setup():
     instr.add_component(env, "TC")
     instr.add_component(carr, "TC")
     return devices, {"TC": chain}, instr
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Model / Generator / ParameterMap stand-ins for the propagator path (what c3/libraries/propagation.py:282-321 and
+# c3/experiment.py:440-534 touch), built from arrays
+# ---------------------------------------------------------------------------------------------------------------------
+
+class FakeAWG:
+    def __init__(self, amp=0.0):
+        self.amp = amp
+
+    def get_average_amp(self):
+        return self.amp, self.amp
+
+
+class TableGenerator:
+    """generate_signals(instr) looks the instruction's fields up in a table: {instr.name: {chan: {"values","ts"}}}."""
+
+    def __init__(self, table, avg_amp=0.0):
+        self.table = table
+        self.devices = {"awg": FakeAWG(avg_amp)}
+        self.calls = 0
+
+    def generate_signals(self, instr):
+        self.calls += 1
+        return self.table[instr.name]
+
+
+class ArrayModel:
+    """Model stand-in: drift / control Hamiltonians (dict by channel), collapse operators, optional excitation cutter,
+    optional explicit Hamiltonian list, frame rotation and dephasing channel from the oracle's restatement."""
+
+    def __init__(self, h0, hks, col_ops=(), dims=None, lindbladian=False, max_excitations=0, hlist=None, use_FR=False,
+                 dephasing_strength=0.0, line_to_index=None):
+        from oracle import c3_oracle as orc
+        from oracle import c3_model_oracle as mo
+        self._orc = orc
+        self.h0, self.hks, self.col_ops = np.asarray(h0), {k: np.asarray(v) for k, v in hks.items()}, [np.asarray(c) for c in col_ops]
+        self.dims = list(dims) if dims is not None else [self.h0.shape[0]]
+        self.tot_dim = int(np.prod(self.dims))
+        self.lindbladian, self.max_excitations = lindbladian, max_excitations
+        self.controllability = True
+        self.use_FR, self.dephasing_strength = use_FR, dephasing_strength
+        self.hlist = hlist
+        self.ex_cutter = orc.make_ex_cutter(self.dims, max_excitations) if max_excitations else None
+        self.ann_opers = mo.annihilators(self.dims)
+        self.line_to_index = line_to_index or {}
+
+    def _cut(self, x):
+        return self._orc.cut_excitations(self.ex_cutter, x) if self.max_excitations else x
+
+    def get_Hamiltonians(self):
+        return self._cut(self.h0), {k: self._cut(v) for k, v in self.hks.items()}
+
+    def get_Hamiltonian(self, signal=None):
+        return np.stack([self._cut(h) for h in self.hlist])
+
+    def get_Lindbladians(self):
+        return list(self.col_ops)
+
+    def get_Frame_Rotation(self, t_final, freqs, framechanges):
+        return self._orc.frame_rotation(self.ann_opers, self.line_to_index, t_final, freqs, framechanges)
+
+    def get_dephasing_channel(self, t_final, amps):
+        return self._orc.dephasing_channel(self.ann_opers, self.line_to_index, t_final, amps, self.dephasing_strength)
+
+
+class PMap:
+    def __init__(self, model, generator, instructions):
+        self.model, self.generator, self.instructions = model, generator, instructions
+
+
+def drive_instruction(name, t_end, lines, freq=5e9, framechange=0.0, amp=0.5, freq_offset=0.0):
+    """An instruction with one envelope + carrier per line (parameters as Quantities, c3/signal/gates.py)."""
+    instr = Instruction(name, 0.0, t_end, list(lines))
+    for i, line in enumerate(lines):
+        f = freq[i] if isinstance(freq, (list, tuple)) else freq
+        fc = framechange[i] if isinstance(framechange, (list, tuple)) else framechange
+        instr.add_component(Envelope("gauss", "gaussian_nonorm", {
+            "amp": Quantity(amp, "V"), "t_final": Quantity(t_end, "s"), "sigma": Quantity(t_end / 4, "s"),
+            "xy_angle": Quantity(0.0, "rad"), "freq_offset": Quantity(freq_offset, "Hz 2pi"), "delta": Quantity(0.0, "")}), line)
+        instr.add_component(Carrier("carrier", {"freq": Quantity(f, "Hz 2pi"), "framechange": Quantity(fc, "rad")}), line)
+    return instr

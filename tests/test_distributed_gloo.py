@@ -60,3 +60,8 @@ def test_sharded_batch_even():
 
 def test_sharded_batch_ragged():
     _run(7)
+
+
+def test_sharded_batch_smaller_than_world():
+    """One batch row on two ranks: the rank without work must still join the gather (no hang, no B = 0 kernel call)."""
+    _run(1)

@@ -228,43 +228,47 @@ def test_cta_kernels_pade_and_taylor(eng, d, cta_variant):
     assert rel_fro(U.cpu().numpy(), wantU) < TOL
 
 
-DEFAULT_ROWS_VARIANT = 16
+D9_VARIANTS = [0, 1]
 
 
-@pytest.mark.parametrize("variant", [1, 8, 13, 15, 16])
-def test_register_kernel_variants_d9(eng, variant):
-    """The generations of the small-d kernel on the headline shape: rows/Pade (1), blocks/Pade + Gauss-Jordan (8),
-    blocks/Taylor-18 + trace shift (13), own-block products in the element-major layout with register selects (15)
-    and select-free (16, default for d = 9)."""
+def _default_d9_variant():
+    import os
+    return int(os.environ.get("C3B_D9_VARIANT", 1))
+
+
+@pytest.mark.parametrize("variant", D9_VARIANTS)
+def test_d9_kernel_variants_headline_model(eng, variant):
+    """The d = 9 kernels on the headline model: generic 3x3-block kernel (0), own-block products from the annealed
+    shared-memory layout (1), shuffle-exchange kernel (2)."""
     from c3_b200 import synth
     m = synth.two_transmon()
     sig = synth.controls(m, 3, 203)
-    eng.set_tuning("rows_variant", variant)
+    eng.set_tuning("d9_variant", variant)
     try:
         U, dUs = eng.pwc_closed(m.h0, m.hks, sig, 1e-11, return_dUs=True)
     finally:
-        eng.set_tuning("rows_variant", DEFAULT_ROWS_VARIANT)
+        eng.set_tuning("d9_variant", _default_d9_variant())
     wantU, want_dUs = orc.propagate_batch(m.h0, m.hks, sig, 1e-11, return_dUs=True)
     assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
     assert rel_fro(U.cpu().numpy(), wantU) < TOL
 
 
-@pytest.mark.parametrize("variant", [13, 15, 16])
-@pytest.mark.parametrize("scale,N,B", [(6.0, 37, 2), (30.0, 20, 3), (0.5, 1, 2), (2.0, 1000, 5)])
-def test_d9_kernel_generations_random_models(eng, variant, scale, N, B):
-    """d = 9 kernels on random complex Hermitian models: squarings (norm up to ~30), a single slice, ragged segments
-    (B * N forces several segments per batch element), the H-list entry and the partial propagators."""
+@pytest.mark.parametrize("variant", D9_VARIANTS)
+@pytest.mark.parametrize("scale,N,B,d", [(6.0, 37, 2, 9), (30.0, 20, 3, 9), (0.5, 1, 2, 9), (2.0, 1000, 5, 9), (3.0, 29, 4, 7)])
+def test_d9_kernel_variants_random_models(eng, variant, scale, N, B, d):
+    """d = 9 kernels (and zero-padded d = 7) on random complex Hermitian models: squarings (norm up to ~30), a single
+    slice, ragged segments (B * N forces several segments per batch element), the H-list entry and the partial propagators."""
     rng = np.random.default_rng(int(scale * 10) + N)
-    d, K = 9, 2
+    K = 2
     h0, hks = _rand_model(rng, d, K, scale)
     sig = rng.uniform(-1, 1, size=(B, K, N))
-    eng.set_tuning("rows_variant", variant)
+    eng.set_tuning("d9_variant", variant)
     try:
         U, dUs = eng.pwc_closed(h0, hks, sig, 1.0, return_dUs=True)
         Hs = h0[None, None] + np.einsum("bkn,kij->bnij", sig, hks)
         U2 = eng.pwc_closed_hlist(Hs, 1.0)
     finally:
-        eng.set_tuning("rows_variant", DEFAULT_ROWS_VARIANT)
+        eng.set_tuning("d9_variant", _default_d9_variant())
     wantU, want_dUs = orc.propagate_batch(h0, hks, sig, 1.0, return_dUs=True)
     assert rel_fro(dUs.cpu().numpy(), want_dUs) < TOL
     assert rel_fro(U.cpu().numpy(), wantU) < TOL
@@ -438,24 +442,56 @@ def test_host_pipelined_path_matches_device_path(eng):
     assert rel_fro(U_host[[0, 1023, 1024, 2499]].cpu().numpy(), want) < TOL
 
 
-@pytest.mark.parametrize("d,chunk,first", [(9, 3, 1), (9, 64, 256), (6, 5, 2), (27, 4, 1)])
-def test_gated_single_launch_host_path(eng, d, chunk, first):
+@pytest.mark.parametrize("d,K,N,chunk,first", [(9, 2, 40, 3, 1), (9, 2, 40, 64, 256), (6, 2, 40, 5, 2), (27, 2, 40, 4, 1),
+                                               (9, 1, 37, 1, 1), (9, 2, 37, 2, 1), (9, 1, 37, 3, 2), (9, 3, 13, 1, 3), (7, 1, 5, 2, 1)])
+def test_gated_single_launch_host_path(eng, d, K, N, chunk, first):
     """Host-resident control fields through the gated single launch (c3b_pwc_closed_gated: d = 9) and through the
     chunked two-stream fallback (d = 6, 27): many small chunks, repeated calls on reused buffers, bit-identical to the
-    device-resident call."""
-    rng = np.random.default_rng(d)
-    K, B, N = 2, 23, 40
+    device-resident call.  K * N not a multiple of 4 makes batch rows share 32-byte sectors with their neighbours: the
+    rows in flight must not be read through the non-coherent path."""
+    rng = np.random.default_rng(d + N)
+    B = 23
     h0, hks = _rand_model(rng, d, K, 1.5)
-    for rep in range(3):
+    for rep in range(4):
         sig = rng.uniform(-1, 1, size=(B, K, N))
         host = torch.as_tensor(sig).pin_memory()
         U_host = eng.pwc_closed_from_host(h0, hks, host, 1.0, chunk=chunk, first_chunk=first)
         U_dev = eng.pwc_closed(h0, hks, torch.as_tensor(sig).cuda(), 1.0)
         torch.cuda.synchronize()
+        eng.check_gated_launches()
         assert not torch.isnan(U_host.real).any()
         assert rel_fro(U_host.cpu().numpy(), U_dev.cpu().numpy()) < 1e-13
     want = orc.propagate_batch(h0, hks, sig, 1.0)
     assert rel_fro(U_host.cpu().numpy(), want) < TOL
+
+
+def test_gated_launch_reports_rows_that_never_arrive(eng):
+    """A gate that stops at row 3 of 8: the kernel gives up after its patience runs out (no hang), raises gate[1], leaves
+    the rows it never saw as NaN, and the host turns the flag into an error at its next check."""
+    from c3_b200 import _lib, synth
+    lib = _lib.load()
+    if not lib.c3b_pwc_gated_supported(9):
+        pytest.skip("the selected d = 9 kernel has no gated entry")
+    m = synth.two_transmon()
+    B, K, N = 8, 2, 16
+    dev = eng.default_device()
+    sig = torch.as_tensor(synth.controls(m, B, N)).to(dev)
+    h0 = torch.as_tensor(m.h0).to(dev)
+    hks = torch.as_tensor(m.hks).to(dev)
+    U = torch.full((B, 9, 9), float("nan"), dtype=torch.complex128, device=dev)
+    gate = torch.tensor([3, 0], dtype=torch.int32, device=dev)
+    ws = torch.empty(lib.c3b_pwc_workspace_bytes(B, K, N, 9, 0, 0), dtype=torch.uint8, device=dev)
+    rc = lib.c3b_pwc_closed_gated(h0.data_ptr(), hks.data_ptr(), sig.data_ptr(), 1e-11, B, K, N, 9, U.data_ptr(),
+                                  gate.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    eng._watch_gate(gate, torch.cuda.current_stream())
+    with pytest.raises(_lib.C3BError, match="gated launch timed out"):
+        eng.check_gated_launches()
+    assert int(gate[1].item()) == 1
+    done = ~torch.isnan(U.real).any(dim=(1, 2))
+    assert done[:3].all() and not done[3:].any()
+    want = orc.propagate_batch(m.h0, m.hks, sig[:3].cpu().numpy(), 1e-11)
+    assert rel_fro(U[:3].cpu().numpy(), want) < TOL
 
 
 def test_error_reporting(eng):
