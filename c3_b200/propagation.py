@@ -306,6 +306,10 @@ def pwc(model, gen, instr, folding_stack: list, batch_size=None) -> Dict:
 def blowup_excitations(cutter, op: torch.Tensor) -> torch.Tensor:
     """P^T op P for a 0/1 row-selection matrix P [d_cut, d] as an index scatter."""
     c = _host(cutter)
+    if op.shape[-1] != c.shape[0] or op.shape[-2] != c.shape[0]:
+        # e.g. a Lindblad superoperator of the cut space: P^T S P is not defined for it, and the reference's
+        # model.blowup_excitations (c3/model.py:222-224) fails on the same shapes
+        raise Exception(f"C3:ERROR: cannot blow up a {tuple(op.shape[-2:])} operator with a {tuple(c.shape)} excitation cutter.")
     keep = torch.as_tensor(np.argmax(np.real(c), axis=1), device=op.device)
     d_full = c.shape[1]
     out = torch.zeros(op.shape[:-2] + (d_full, d_full), dtype=op.dtype, device=op.device)
