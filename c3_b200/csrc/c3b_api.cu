@@ -218,6 +218,7 @@ int run_pwc(const Plan& pl, const char* blob, const double* signals, const cplx*
         rp.B = B; rp.K = K; rp.N = N; rp.d = D; rp.S = pl.S; rp.seg_len = pl.seg_len;
         rp.U_out = U_out; rp.seg_out = seg; rp.dUs_out = dUs_out;
         rp.gate = gate;
+        rp.skew = (int)tn.d9_skew;
         unsigned int* counter = reinterpret_cast<unsigned int*>(ws + pl.off_counter);
         int rc = (blk_template_dim(D) == 9) ? launch_d9(rp, counter, (int)tn.d9_variant, st) : launch_small(rp, counter, st);
         if (rc) return rc;
@@ -281,6 +282,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (!strcmp(key, "target_units")) { t.target_units = value < 1 ? 1 : value; return C3B_OK; }
     if (!strcmp(key, "min_chunk")) { t.min_chunk = value < 1 ? 1 : value; return C3B_OK; }
     if (!strcmp(key, "d9_variant")) { t.d9_variant = value; return C3B_OK; }
+    if (!strcmp(key, "d9_skew")) { t.d9_skew = value < 0 ? 0 : value; return C3B_OK; }
     if (!strcmp(key, "force_cta")) { t.force_cta = value; return C3B_OK; }
     if (!strcmp(key, "cta_variant")) { t.cta_variant = value; return C3B_OK; }
     if (!strcmp(key, "cta_threads")) { t.cta_threads = value; return C3B_OK; }

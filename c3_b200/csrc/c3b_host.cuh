@@ -36,6 +36,7 @@ struct Tuning {
     long long target_units = 32768;  // lane-group kernels: aim for this many warp work units per launch
     long long min_chunk = 8;         // lane-group kernels: minimum slices per lane group
     long long d9_variant = 1;        // d = 9: 0 generic 3x3-block kernel, 1 own-block shared-memory kernel, 2 shuffle-exchange kernel
+    long long d9_skew = 120;         // shuffle kernel: clocks between the early and the late half of a CTA's warps
     long long force_cta = 0;         // route everything to the CTA kernels (testing)
     long long cta_variant = 1;       // 0: literal Higham (Pade + pivoted Gauss-Jordan) cross-check, 1: Taylor-18 on DMMA tiles
     long long cta_threads = 512;     // DMMA CTA kernel, DP = 32: 256 or 512 threads

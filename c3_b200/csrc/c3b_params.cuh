@@ -27,6 +27,7 @@ struct RowsParams {
     // gated launch (host-resident signals): gate[0] = number of batch rows [0, gate[0]) that have landed in `signals`
     // (raised by the host's copy stream), gate[1] = set to 1 by the kernel if a row did not arrive in time; or null
     unsigned int* gate;
+    int skew;                     // shuffle kernel: clocks by which the late half of a CTA's warps trails the early half
 };
 
 struct CtaParams {

@@ -2,6 +2,7 @@
 #include "c3b_host.cuh"
 #include "pwc_blk.cuh"
 #include "pwc_blk9.cuh"
+#include "pwc_shfl9.cuh"
 
 namespace c3b {
 
@@ -27,13 +28,18 @@ int launch_persistent(Kern kern, size_t smem, int warps, int minb, const RowsPar
 
 }  // namespace
 
-bool d9_gated_supported(int variant) { return variant == 1; }
+bool d9_gated_supported(int variant) { return variant == 1 || variant == 2; }
 
 int launch_d9(const RowsParams& rp, unsigned int* counter, int variant, cudaStream_t st) {
     if (rp.gate != nullptr && !d9_gated_supported(variant))
         return fail(C3B_EUNSUPPORTED, "C3:ERROR: gated launch is not built for d9_variant %d", variant);
     if (variant == 0)
         return launch_persistent(pwc_blk_t18_kernel<9, 3, 4, 2>, BlkLayout<9, 3>::smem_bytes(rp.K, 4), 4, 2, rp, counter, st);
+    if (variant == 2) {
+        const size_t smem8 = Shfl9::smem_bytes(rp.K, 8);
+        if (rp.gate != nullptr) return launch_persistent(pwc_shfl9_kernel<8, 1, true>, smem8, 8, 1, rp, counter, st);
+        return launch_persistent(pwc_shfl9_kernel<8, 1, false>, smem8, 8, 1, rp, counter, st);
+    }
     const size_t smem = Blk9T<true>::smem_bytes(rp.K, 4);
     if (rp.gate != nullptr) return launch_persistent(pwc_blk9_t18_kernel<4, 2, true, true>, smem, 4, 2, rp, counter, st);
     return launch_persistent(pwc_blk9_t18_kernel<4, 2, true, false>, smem, 4, 2, rp, counter, st);
