@@ -109,7 +109,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "each step is a bounded sample of the workload on host cores"},
+        "config": {"workload": WORKLOAD, "d": D, "K": K, "N": N, "B_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * max(args.gpus, 1),
+                   "dt": DT, "sampled": f"{cores * per_proc} of the {B_PER_GPU} signal sets per step (rate-normalised)",
+                   "parallelism": f"{cores} host processes"},
         "cpu_baseline": {"value": value, "unit": "slices/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reference_note": "TensorFlow (the reference's arithmetic backend) is not installable in this image; "
@@ -171,6 +173,166 @@ class ClockSampler:
             out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
                    "samples": len(sm), "power_w_max": max(power) if power else None}
         return out
+
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations and the strong-scaling point (measured AFTER the headline region)
+# ------------------------------------------------------------------------------------------------
+
+def _timed(fn, reps, torch, dist, world):
+    """Device time of `reps` calls of fn() in ms per call, max over ranks (barrier + synchronize on both sides)."""
+    fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        t = torch.tensor([ms], device=torch.device("cuda", torch.cuda.current_device()), dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms, out
+
+
+def run_configs(engine, synth, dev, rank, world, dfma_peak, all_gather, check):
+    """configs[cfgN] = throughput, roofline fraction and sampled parity of every BASELINE.json configuration at its stated
+    size; `strong` = the headline batch (4096 signal sets in TOTAL) split over the ranks.  Multi-GPU configs (cfg3, cfg4,
+    cfg5) shard their batch over the ranks with one all-gather of the result, as BASELINE.json words them; cfg1 / cfg2 are
+    single-GPU cases and run on every rank's own GPU (rank 0's number is reported)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import scipy.linalg
+    from c3_b200 import flops
+    from c3_b200.distributed import shard_bounds
+
+    def expm_each(a):
+        return np.stack([scipy.linalg.expm(x) for x in a])
+
+    def rel(a, b):
+        return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+    def gather(U, total):
+        return all_gather(U, total) if world > 1 else U
+
+    out = {}
+    orc = None
+    if check:
+        from oracle import c3_oracle as orc            # checker only: sampled rows, never inside a timed region
+
+    # ---- cfg1: single-qubit 3-level, batch 1: latency of one call (prepared model, captured graph) -----------------
+    m1 = synth.one_qubit()
+    pm1 = engine.prepare_model(m1.h0, m1.hks, DT)
+    c1 = {}
+    for n1 in (50, 800):
+        sig = torch.as_tensor(synth.controls(m1, 1, n1)).to(dev)
+        gp = engine.GraphedPwc(pm1, 1, n1)
+        ms_graph, U = _timed(lambda: gp.run(), 200, torch, dist, 1)
+        ms_call, _ = _timed(lambda: engine.pwc_prepared(pm1, sig), 200, torch, dist, 1)
+        ms_cold, _ = _timed(lambda: engine.pwc_closed(m1.h0, m1.hks, sig, DT), 50, torch, dist, 1)
+        gp.run(sig)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(200):
+            gp.run()
+        torch.cuda.synchronize()
+        host_us = (time.perf_counter() - t0) / 200 * 1e6
+        c1[f"N{n1}"] = {"us_per_call_graph_replay": ms_graph * 1e3, "us_per_call_graph_replay_host_clock": host_us,
+                        "us_per_call_prepared": ms_call * 1e3, "us_per_call_unprepared": ms_cold * 1e3,
+                        "slices_per_s": n1 / (ms_graph * 1e-3)}
+        if check:
+            c1[f"N{n1}"]["parity_rel_fro_max"] = rel(gp.run(sig).cpu().numpy(), orc.propagate_batch(m1.h0, m1.hks, sig.cpu().numpy(), DT))
+    out["cfg1"] = {"workload": "single-qubit 3-level rx90p, batch = 1, N = 50 (BASELINE) and N = 800 (what test/one_qubit.hjson yields)",
+                   "launches_per_call": {"unprepared": 5, "prepared": 2, "graph": 1}, **c1}
+
+    # ---- cfg2: two-qubit d = 9, 1000 slices, batch 256 on one GPU -----------------------------------------------------
+    m2 = synth.two_transmon()
+    sig2_h = synth.controls_fast(m2, 256, N, DT, seed=99)
+    sig2 = torch.as_tensor(sig2_h).to(dev)
+    pm2 = engine.prepare_model(m2.h0, m2.hks, DT)
+    ms, U = _timed(lambda: engine.pwc_prepared(pm2, sig2), 20, torch, dist, 1)
+    f2 = flops.flops_per_slice_closed(m2.h0, m2.hks, sig2_h[:4], DT)
+    out["cfg2"] = {"workload": "two-qubit d = 9, N = 1000, batch = 256, one GPU", "ms": ms, "slices_per_s": 256 * N / (ms * 1e-3),
+                   "roofline": {"bound": "fp64", "achieved": 256 * N * f2 / (ms * 1e-3) / 1e12, "peak": dfma_peak, "unit": "TFLOP/s",
+                                "frac": 256 * N * f2 / (ms * 1e-3) / 1e12 / dfma_peak, "flops_per_slice": f2}}
+    if check:
+        rows = [0, 100, 255]
+        want = orc.propagate_batch(m2.h0, m2.hks, sig2_h[rows], DT)
+        out["cfg2"]["parity_rel_fro_max"] = max(rel(U[r].cpu().numpy(), want[i]) for i, r in enumerate(rows))
+
+    # ---- cfg3: Lindblad D = 81, 1000 slices, batch 1024 (sharded over the ranks) ------------------------------------
+    B3 = 1024
+    lo, hi = shard_bounds(B3, world, rank)
+    sig3_h = synth.controls_fast(m2, B3, N, DT, seed=7)
+    sig3 = torch.as_tensor(sig3_h[lo:hi]).to(dev)
+    pm3 = engine.prepare_model(m2.h0, m2.hks, DT, col_ops=m2.col_ops, lindblad=True)
+    ms, U3 = _timed(lambda: gather(engine.pwc_prepared(pm3, sig3), B3), 2, torch, dist, world)
+    H = m2.h0[None] + np.einsum("kn,kij->nij", sig3_h[0, :, ::50], m2.hks)
+    n1 = 2.0 * np.abs(H * DT).sum(axis=-2).max(axis=-1).max()            # superoperator norm ~ 2 x closed (SURVEY 8a)
+    f3 = flops.flops_lindblad(9, *flops.higham_order(float(n1)))
+    out["cfg3"] = {"workload": "two-qubit Lindblad, D = d^2 = 81, N = 1000, batch = 1024" + (f", sharded x{world}" if world > 1 else ""),
+                   "ms": ms, "slices_per_s": B3 * N / (ms * 1e-3),
+                   "roofline": {"bound": "fp64 (DMMA)", "achieved": (hi - lo) * N * f3 / (ms * 1e-3) / 1e12, "peak": dfma_peak,
+                                "unit": "TFLOP/s per GPU", "frac": (hi - lo) * N * f3 / (ms * 1e-3) / 1e12 / dfma_peak, "flops_per_slice": f3}}
+    if check:
+        rows = [0, B3 - 1]
+        want = orc.propagate_batch(m2.h0, m2.hks, sig3_h[rows], DT, col_ops=m2.col_ops, lindbladian=True, expm=expm_each)
+        out["cfg3"]["parity_rel_fro_max"] = max(rel(U3[r].cpu().numpy(), want[i]) for i, r in enumerate(rows))
+        out["cfg3"]["parity_rows"] = len(rows)
+    del U3, sig3
+
+    # ---- cfg4: ORBIT, 4096 random Clifford sequences x 20 Cliffords, d = 9 (sharded over the ranks) ---------------------
+    S4 = 4096
+    gates = engine.pwc_prepared(pm2, torch.as_tensor(synth.controls(m2, 5, 70)).to(dev))
+    idx, lens = synth.rb_sequences(S4, 20, 5, seed=0)
+    lo, hi = shard_bounds(S4, world, rank)
+    idx_d, lens_d = torch.as_tensor(idx[lo:hi]).to(dev), torch.as_tensor(lens[lo:hi]).to(dev)
+    ms, U4 = _timed(lambda: gather(engine.seq_product(gates, idx_d, lens_d), S4), 50, torch, dist, world)
+    out["cfg4"] = {"workload": "ORBIT: 4096 sequences x 20 Cliffords (mean 45 native gates), d = 9" + (f", sharded x{world}" if world > 1 else ""),
+                   "ms": ms, "sequences_per_s": S4 / (ms * 1e-3), "gate_products_per_s": float(lens.sum()) / (ms * 1e-3),
+                   "roofline": {"bound": "latency (1 Gflop in total)", "achieved": float(lens.sum()) * 8 * 729 / (ms * 1e-3) / 1e12,
+                                "peak": dfma_peak, "unit": "TFLOP/s", "frac": float(lens.sum()) * 8 * 729 / (ms * 1e-3) / 1e12 / dfma_peak}}
+    if check:
+        gh = gates.cpu().numpy()
+        names = [f"g{i}" for i in range(5)]
+        rows = [0, 1, S4 // 2, S4 - 1]
+        want = orc.evaluate_sequences({n: gh[i] for i, n in enumerate(names)}, [[names[j] for j in idx[r, :lens[r]]] for r in rows])
+        out["cfg4"]["parity_rel_fro_max"] = max(rel(U4[r].cpu().numpy(), want[i]) for i, r in enumerate(rows))
+
+    # ---- cfg5: tunable coupler d = 27, K = 3, 2000 slices, 8192 samples (sharded over the ranks) ------------------------
+    m5 = synth.tunable_coupler()
+    B5, N5 = 8192, 2000
+    lo, hi = shard_bounds(B5, world, rank)
+    sig5_h = synth.controls_fast(m5, hi - lo, N5, DT, seed=5, b_offset=rank * 1000003)
+    sig5 = torch.as_tensor(sig5_h).to(dev)
+    pm5 = engine.prepare_model(m5.h0, m5.hks, DT)
+    ms, U5 = _timed(lambda: gather(engine.pwc_prepared(pm5, sig5), B5), 2, torch, dist, world)
+    f5 = flops.flops_per_slice_closed(m5.h0, m5.hks, sig5_h[:2, :, ::20], DT)
+    out["cfg5"] = {"workload": "tunable coupler d = 27, K = 3, N = 2000, 8192 parameter samples" + (f", sharded x{world}" if world > 1 else ""),
+                   "ms": ms, "slices_per_s": B5 * N5 / (ms * 1e-3),
+                   "roofline": {"bound": "fp64 (DMMA)", "achieved": (hi - lo) * N5 * f5 / (ms * 1e-3) / 1e12, "peak": dfma_peak,
+                                "unit": "TFLOP/s per GPU", "frac": (hi - lo) * N5 * f5 / (ms * 1e-3) / 1e12 / dfma_peak, "flops_per_slice": f5}}
+    if check:
+        rows = [0, hi - lo - 1]                        # rank 0's shard sits at the head of the gathered batch
+        want = orc.propagate_batch(m5.h0, m5.hks, sig5_h[rows], DT, expm=expm_each)
+        out["cfg5"]["parity_rel_fro_max"] = max(rel(U5[r].cpu().numpy(), want[i]) for i, r in enumerate(rows))
+    del U5, sig5
+
+    # ---- strong scaling: the headline batch of 4096 signal sets in TOTAL, split over the ranks --------------------------
+    lo, hi = shard_bounds(B_PER_GPU, world, rank)
+    sig_s = torch.as_tensor(synth.controls_fast(m2, B_PER_GPU, N, DT, seed=4242)[lo:hi]).to(dev)
+    ms, _ = _timed(lambda: gather(engine.pwc_prepared(pm2, sig_s), B_PER_GPU), 10, torch, dist, world)
+    strong = {"B_total": B_PER_GPU, "B_per_gpu": hi - lo, "n_gpus": world, "ms_per_step": ms, "slices_per_s": B_PER_GPU * N / (ms * 1e-3),
+              "note": "same d = 9, N = 1000 workload with the batch FIXED at 4096; 4 waves of 1184 warp units at 1 GPU shrink to "
+                      "half a wave at 8, so the tail of the persistent kernel and the launch + all-gather latency show"}
+    return out, strong
 
 
 # ------------------------------------------------------------------------------------------------
@@ -240,6 +402,7 @@ def run_engine(args):
 
     # ---- fp64 peak (roofline denominator), measured live -----------------------------------
     dfma_peak = engine.measure_fp64_peak("dfma", 0.5, device=local_rank)
+    dmma_peak = engine.measure_fp64_peak("dmma", 0.3, device=local_rank)
 
     for i in range(max(args.warmup, 3)):  # never fewer than 3 warm-up steps
         step(i)
@@ -333,6 +496,11 @@ def run_engine(args):
     par_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
+    configs, strong = None, None
+    if not args.no_configs:
+        configs, strong = run_configs(engine, synth, dev, rank, world, dfma_peak, all_gather_unitaries,
+                                      check=(rank == 0 and not args.no_parity))
+
     if world > 1:
         t = torch.tensor([ms_total, e2e_s * 1e3, kernel_ms, par_s * 1e3], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -356,7 +524,7 @@ def run_engine(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         traffic, traffic_src = None, None
         try:   # DRAM bytes per launch of the fused kernel from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_s3.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01_traffic_s3.json")))
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
             traffic_src = tj["source"]
         except Exception:
@@ -383,9 +551,14 @@ def run_engine(args):
                          "flops_per_slice": fl, "kernel_ms": kernel_ms,
                          "peak_source": "DFMA micro-benchmark in this process (c3b_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no fp64 entry",
+                         "peak_detail": {"dfma_tflops": dfma_peak, "dmma_m8n8k4_tflops": dmma_peak,
+                                         "theory_tflops": 148 * 64 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12,
+                                         "theory": "148 SMs x 64 DFMA/clk x 2 flop x max SM clock"},
                          "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+            "configs": configs,
+            "strong": strong,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "parity_rel_fro_max": parity,
@@ -424,6 +597,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline only: skip the other BASELINE configs and the strong-scaling point")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
