@@ -352,20 +352,31 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_t18_kernel(const Row
             __syncwarp();
         }
 
-        // ---- fold the group products: P_{MPW-1} ... P_1 P_0 (every group computes it; group 0 writes) ----
+        // ---- fold the group products P_{MPW-1} ... P_1 P_0 as a pairwise tree: at stride s group g (g % 2s == 0)
+        // forms P_{g+s} P_g -- log2(MPW) dependent products instead of MPW - 1 (d <= 3: 5 instead of 31, which was most
+        // of a latency-bound B = 1 call).  Levels ping-pong between the group's P / X / A buffers.
         cplx* wbase = sWarps + (size_t)warp * L::WARP_ELEMS;
-        const cplx* cur = wbase + L::group_off(MPW - 1) + 3 * L::BUF;
-        int flip = 0;
+        int src_slot = 3;
 #pragma unroll 1
-        for (int gg = MPW - 2; gg >= 0; --gg) {
-            cplx T[BS][BS];
-            mm_blk<D, BS, LD>(cur + r0 * LD, wbase + L::group_off(gg) + 3 * L::BUF + c0, T);
-            cplx* dst = flip ? bufA : bufX;
-            store_blk<D, BS, LD>(dst + rc_off, T, lane_on);
+        for (int stride = 1; stride < MPW; stride <<= 1) {
+            const int dst_slot = (src_slot == 2) ? 0 : 2;
+            if (lane_on && (g % (2 * stride)) == 0) {
+                const cplx* own = gbase + src_slot * L::BUF;
+                cplx T[BS][BS];
+                if (g + stride < MPW) {
+                    mm_blk<D, BS, LD>(wbase + L::group_off(g + stride) + src_slot * L::BUF + r0 * LD, own + c0, T);
+                } else {
+#pragma unroll
+                    for (int a = 0; a < BS; ++a)
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) T[a][c] = own[rc_off + a * LD + c];
+                }
+                store_blk<D, BS, LD>(gbase + dst_slot * L::BUF + rc_off, T, true);
+            }
             __syncwarp();
-            cur = dst;
-            flip ^= 1;
+            src_slot = dst_slot;
         }
+        const cplx* cur = wbase + L::group_off(0) + src_slot * L::BUF;
         if (lane_on && g == 0) {
             cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * d * d) : (p.seg_out + ((size_t)b * p.S + sidx) * d * d);
 #pragma unroll

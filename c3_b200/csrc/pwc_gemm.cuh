@@ -5,7 +5,7 @@
 // products (c3b_common.cuh) -> s squarings -> running ordered product.  Every O(D^3) step is ONE
 // routine, cta_zgemm: C = A B on zero-padded DP x DP complex matrices (DP = D rounded up to 8), each
 // warp owning 2x2 (or 1x2) m8n8 tiles and issuing mma.sync.m8n8k4.f64 (DMMA): a complex tile step is
-// 4 real DMMAs (Cr += Ar Br - Ai Bi, Ci += Ar Bi + Ai Br) on fragments loaded straight from the
+// 3 real DMMAs (the 3M product: Ar Br, Ai Bi, (Ar + Ai)(Br + Bi)) on fragments loaded straight from the
 // interleaved complex storage (one 16-byte load = re and im of a fragment element).  One operand
 // load feeds 8 complex MACs per lane (vs 1-1.5 in the register kernels), so the D^2 x D^2 Lindblad
 // superoperator is a genuinely dense contraction on the fp64 pipe, as BASELINE.json's north_star
@@ -48,11 +48,13 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
     const int fr = lane >> 2, fc = lane & 3;      // fragment coordinates
     for (int mt = warp; mt < mt_r * mt_c; mt += NW) {
         const int bi0 = (mt / mt_c) * TM, bj0 = (mt % mt_c) * TN;
-        double cr[TM][TN][2], ci[TM][TN][2];
+        // 3M complex product: P1 = Ar Br, P2 = Ai Bi, P3 = (Ar + Ai)(Br + Bi); Cr = P1 - P2, Ci = P3 - P1 - P2 -- three real
+        // DMMAs per tile step instead of four (the operand sums cost one DADD per loaded fragment element)
+        double p1[TM][TN][2], p2[TM][TN][2], p3[TM][TN][2];
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
-            for (int j = 0; j < TN; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
+            for (int j = 0; j < TN; ++j) { p1[i][j][0] = p1[i][j][1] = p2[i][j][0] = p2[i][j][1] = p3[i][j][0] = p3[i][j][1] = 0.0; }
         // clamp block indices of partial macro tiles (results of clamped duplicates are not stored)
         int arow[TM], bcol[TN];
 #pragma unroll
@@ -65,20 +67,18 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
             for (int i = 0; i < TM; ++i) a[i] = A[arow[i] + k0];
 #pragma unroll
             for (int j = 0; j < TN; ++j) b[j] = B[bcol[j] + k0 * LD];
-            // the two updates of one accumulator are issued TM*TN*2 DMMAs apart (fixed-latency dependency)
+            double as[TM], bs[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) as[i] = a[i].x + a[i].y;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bs[j] = b[j].x + b[j].y;
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < TN; ++j) {
-                    dmma8x8x4(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
-                    dmma8x8x4(ci[i][j][0], ci[i][j][1], a[i].x, b[j].y);
-                }
-#pragma unroll
-            for (int i = 0; i < TM; ++i)
-#pragma unroll
-                for (int j = 0; j < TN; ++j) {
-                    dmma8x8x4(cr[i][j][0], cr[i][j][1], -a[i].y, b[j].y);
-                    dmma8x8x4(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
+                    dmma8x8x4(p1[i][j][0], p1[i][j][1], a[i].x, b[j].x);
+                    dmma8x8x4(p2[i][j][0], p2[i][j][1], a[i].y, b[j].y);
+                    dmma8x8x4(p3[i][j][0], p3[i][j][1], as[i], bs[j]);
                 }
         };
         if (DPT > 0) {
@@ -99,19 +99,18 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
             for (int kk = 0; kk < KS; ++kk) {
                 if (kk + 1 < KS) fetch(kk + 1);
                 __syncwarp();
+                double as[TM], bs[TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) as[i] = af[kk][i].x + af[kk][i].y;
+#pragma unroll
+                for (int j = 0; j < TN; ++j) bs[j] = bf[kk][j].x + bf[kk][j].y;
 #pragma unroll
                 for (int i = 0; i < TM; ++i)
 #pragma unroll
                     for (int j = 0; j < TN; ++j) {
-                        dmma8x8x4(cr[i][j][0], cr[i][j][1], af[kk][i].x, bf[kk][j].x);
-                        dmma8x8x4(ci[i][j][0], ci[i][j][1], af[kk][i].x, bf[kk][j].y);
-                    }
-#pragma unroll
-                for (int i = 0; i < TM; ++i)
-#pragma unroll
-                    for (int j = 0; j < TN; ++j) {
-                        dmma8x8x4(cr[i][j][0], cr[i][j][1], -af[kk][i].y, bf[kk][j].y);
-                        dmma8x8x4(ci[i][j][0], ci[i][j][1], af[kk][i].y, bf[kk][j].x);
+                        dmma8x8x4(p1[i][j][0], p1[i][j][1], af[kk][i].x, bf[kk][j].x);
+                        dmma8x8x4(p2[i][j][0], p2[i][j][1], af[kk][i].y, bf[kk][j].y);
+                        dmma8x8x4(p3[i][j][0], p3[i][j][1], as[i], bs[j]);
                     }
             }
         } else {
@@ -124,7 +123,8 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
             for (int j = 0; j < TN; ++j) {
                 if (bi0 + i < nb && bj0 + j < nb) {
                     const int idx = ((bi0 + i) * 8 + fr) * LD + (bj0 + j) * 8 + 2 * fc;
-                    cplx c0 = cmake(cr[i][j][0], ci[i][j][0]), c1 = cmake(cr[i][j][1], ci[i][j][1]);
+                    cplx c0 = cmake(p1[i][j][0] - p2[i][j][0], p3[i][j][0] - p1[i][j][0] - p2[i][j][0]);
+                    cplx c1 = cmake(p1[i][j][1] - p2[i][j][1], p3[i][j][1] - p1[i][j][1] - p2[i][j][1]);
                     if constexpr (EPI != 0) {
                         const cplx e0 = E1[idx], e1 = E1[idx + 1];
                         c0.x += e0.x; c0.y += e0.y; c1.x += e1.x; c1.y += e1.y;
