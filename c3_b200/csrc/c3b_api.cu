@@ -84,10 +84,14 @@ int num_sms() {
 int cta_grid(int D, long long units) {
     int per_sm = 2;
     if (D <= 32) {
-        const size_t sm = tuning().cta_variant == 1 ? gemm_smem_bytes(D) : cta_smem_bytes(D);
-        per_sm = (int)((size_t)220 * 1024 / (sm + 1024));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 4) per_sm = 4;
+        if (tuning().cta_variant == 1) {
+            per_sm = gemm_ctas_per_sm(D);
+            if (round8(D) == 32 && tuning().cta_threads == 512) per_sm = 1;      // 512-thread CTAs: one per SM (registers)
+        } else {
+            per_sm = (int)((size_t)220 * 1024 / (cta_smem_bytes(D) + 1024));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 4) per_sm = 4;
+        }
     }
     long long g = (long long)num_sms() * per_sm;
     if (g > units) g = units;

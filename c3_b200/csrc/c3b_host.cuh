@@ -39,7 +39,7 @@ struct Tuning {
     long long d9_skew = 120;         // shuffle kernel: clocks between the early and the late half of a CTA's warps
     long long force_cta = 0;         // route everything to the CTA kernels (testing)
     long long cta_variant = 1;       // 0: literal Higham (Pade + pivoted Gauss-Jordan) cross-check, 1: Taylor-18 on DMMA tiles
-    long long cta_threads = 512;     // DMMA CTA kernel, DP = 32: 256 or 512 threads
+    long long cta_threads = 256;     // DMMA CTA kernel, DP = 32: 256 threads (two CTAs per SM) or 512 (one)
     long long gemm_big = 0;          // DMMA CTA kernel, DP = 88 (D = 81): macro-tile shape (0: 3 x 2, 1: 2 x 2)
     long long norm_bound = 1;        // DMMA CTA kernel: scaling from the row-sum bound (1) or the exact inf-norm of every slice (0)
     long long seq_variant = 1;       // evaluate_sequences: 1 lane-group kernel for small d, 0 CTA-per-sequence product kernel
@@ -67,10 +67,20 @@ inline int blk_groups_per_warp(int d) {
 }
 inline int round8(int D) { return (D + 7) & ~7; }
 inline size_t cta_smem_bytes(int D) { return (((size_t)D * sizeof(int) + 15) & ~(size_t)15) + (size_t)kCtaSlots * D * D * sizeof(cplx); }
-inline size_t gemm_mats_bytes(int D) { return (size_t)kGemmSlots * round8(D) * (round8(D) + 4) * sizeof(cplx); }
-// the shared-model generators ride along in shared memory when they fit next to the matrix slots
+// leading dimension of the shared-memory matrices: DP + 4 (bank padding), except DP = 32 (XOR-swizzled, LD = 32)
+inline int gemm_ld_smem(int D) { return round8(D) == 32 ? 32 : round8(D) + 4; }
+inline size_t gemm_mats_bytes(int D) { return (size_t)kGemmSlots * round8(D) * gemm_ld_smem(D) * sizeof(cplx); }
+// CTAs per SM of the shared-memory DMMA kernel (matrix slots only; 4 at most)
+inline int gemm_ctas_per_sm(int D) {
+    int n = (int)((size_t)220 * 1024 / (gemm_mats_bytes(D) + 1024));
+    return n < 1 ? 1 : (n > 4 ? 4 : n);
+}
+// the shared-model generators ride along in shared memory when they fit next to the matrix slots WITHOUT costing a
+// resident CTA (two CTAs per SM overlap one's element-wise phases with the other's products; the generators are then read
+// through L1)
 inline bool gemm_g_in_smem(int D, int K, int batched_model) {
-    return !batched_model && gemm_mats_bytes(D) + (size_t)(K + 1) * D * D * sizeof(cplx) <= (size_t)220 * 1024;
+    return !batched_model &&
+           (size_t)gemm_ctas_per_sm(D) * (gemm_mats_bytes(D) + (size_t)(K + 1) * D * D * sizeof(cplx) + 1024) <= (size_t)220 * 1024;
 }
 inline size_t gemm_smem_bytes(int D, int K = -1, int batched_model = 1) {
     return gemm_mats_bytes(D) + ((K >= 0 && gemm_g_in_smem(D, K, batched_model)) ? (size_t)(K + 1) * D * D * sizeof(cplx) : 0);

@@ -25,7 +25,7 @@ int launch_gemm(const CtaParams& cp, const cplx* TR, const double* RS, int grid,
     GemmParams gp{};
     gp.c = cp; gp.TR = TR; gp.DP = round8(cp.D);
     gp.RS = (tn.norm_bound && TR != nullptr) ? RS : nullptr;   // RS are the row sums of the SHIFTED generators
-    gp.LD = cp.use_smem ? gp.DP + 4 : gp.DP;
+    gp.LD = cp.use_smem ? gemm_ld_smem(cp.D) : gp.DP;
     gp.g_in_smem = (cp.use_smem && cp.hlist == nullptr && cp.G != nullptr && gemm_g_in_smem(cp.D, cp.K, cp.model_stride != 0)) ? 1 : 0;
     if (gp.DP <= 16) return launch_gemm_t<1, 1>(gp, grid, st);
     if (gp.DP == 32 && cp.use_smem) {

@@ -19,6 +19,18 @@
 namespace c3b {
 
 
+// XOR swizzle of the shared-memory matrices of the DP = 32 kernels (leading dimension exactly 32, 16-byte columns):
+// element (i, j) lives at i * 32 + (j ^ swz_of_row(i)).  With f(i) = 4 (i & 1) | 2 ((i >> 1) & 1) the 8 lanes of a quarter-warp
+// hit 8 distinct 16-byte bank slots for BOTH fragment patterns of mma.m8n8k4 (A: 2 rows x 4 consecutive k, B: 4 consecutive k
+// x 2 columns); the padded layout LD = 36 left the B-fragment loads 2-way conflicted (ncu: 32 % of all shared wavefronts,
+// the MIO pipe at 80 % with the tensor pipe at 49 %, profiles/r02_prof_d27_3m.txt).
+__device__ __forceinline__ int swz_of_row(const int i) { return ((i & 1) << 2) | (i & 2); }
+template <bool SWZ>
+__device__ __forceinline__ int mat_idx(const int i, const int j, const int LD) {
+    if constexpr (SWZ) return i * 32 + (j ^ swz_of_row(i));
+    else return i * LD + j;
+}
+
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a, const double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
@@ -39,8 +51,9 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
                                           const cplx* E1 = nullptr, cplx* E2 = nullptr) {
     // DPT > 0: tile extent and leading dimension are compile-time (DPT, DPT + 4): the k loop unrolls fully and
     // every fragment address is base + immediate
+    constexpr bool SWZ = (DPT == 32);
     const int DP = DPT > 0 ? DPT : DP_;
-    const int LD = DPT > 0 ? DPT + 4 : LD_;
+    const int LD = DPT > 0 ? (SWZ ? DPT : DPT + 4) : LD_;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = NT / 32;
     const int nb = DP >> 3;                       // m8n8 blocks per dimension
@@ -56,11 +69,26 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
 #pragma unroll
             for (int j = 0; j < TN; ++j) { p1[i][j][0] = p1[i][j][1] = p2[i][j][0] = p2[i][j][1] = p3[i][j][0] = p3[i][j][1] = 0.0; }
         // clamp block indices of partial macro tiles (results of clamped duplicates are not stored)
-        int arow[TM], bcol[TN];
+        // arow: address of A(row, fc) for even k steps, arow_odd for odd ones (swizzled: (4 kk + fc) ^ f(row) =
+        // 4 kk + (fc ^ (f & 2)) +- (f & 4), the sign alternating with the parity of kk); bcol: address of B(fc, col)
+        int arow[TM], arow_odd[TM], bcol[TN];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) arow[i] = (min(bi0 + i, nb - 1) * 8 + fr) * LD + fc;
+        for (int i = 0; i < TM; ++i) {
+            const int row = min(bi0 + i, nb - 1) * 8 + fr;
+            if constexpr (SWZ) {
+                const int f = swz_of_row(row);
+                arow[i] = row * 32 + (fc ^ (f & 2)) + (f & 4);
+                arow_odd[i] = row * 32 + (fc ^ (f & 2)) - (f & 4);
+            } else {
+                arow[i] = row * LD + fc;
+                arow_odd[i] = arow[i];
+            }
+        }
 #pragma unroll
-        for (int j = 0; j < TN; ++j) bcol[j] = fc * LD + min(bj0 + j, nb - 1) * 8 + fr;
+        for (int j = 0; j < TN; ++j) {
+            if constexpr (SWZ) bcol[j] = fc * 32 + min(bj0 + j, nb - 1) * 8 + (fr ^ swz_of_row(fc));
+            else bcol[j] = fc * LD + min(bj0 + j, nb - 1) * 8 + fr;
+        }
         auto kstep = [&](const int k0) {
             cplx a[TM], b[TN];
 #pragma unroll
@@ -90,7 +118,7 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
             cplx af[KS][TM], bf[KS][TN];
             auto fetch = [&](const int kk) {
 #pragma unroll
-                for (int i = 0; i < TM; ++i) af[kk][i] = A[arow[i] + kk * 4];
+                for (int i = 0; i < TM; ++i) af[kk][i] = A[((kk & 1) ? arow_odd[i] : arow[i]) + kk * 4];
 #pragma unroll
                 for (int j = 0; j < TN; ++j) bf[kk][j] = B[bcol[j] + kk * 4 * LD];
             };
@@ -122,7 +150,7 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 if (bi0 + i < nb && bj0 + j < nb) {
-                    const int idx = ((bi0 + i) * 8 + fr) * LD + (bj0 + j) * 8 + 2 * fc;
+                    const int idx = mat_idx<SWZ>((bi0 + i) * 8 + fr, (bj0 + j) * 8 + 2 * fc, LD);   // idx + 1: the next column (f is even)
                     cplx c0 = cmake(p1[i][j][0] - p2[i][j][0], p3[i][j][0] - p1[i][j][0] - p2[i][j][0]);
                     cplx c1 = cmake(p1[i][j][1] - p2[i][j][1], p3[i][j][1] - p1[i][j][1] - p2[i][j][1]);
                     if constexpr (EPI != 0) {
@@ -144,13 +172,13 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
 // inf-norm (largest row sum of |a_ij|) over the D x D part of an LD-strided matrix, all threads busy:
 // 8 threads per row, shuffle-reduced.  Any subordinate norm bounds the Taylor truncation error the same way.
 template <int NT>
-__device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, const int LD, double* red) {
+__device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, const int LD, double* red, const int ncols) {
     const int part = threadIdx.x & 7;
     double best = 0.0;
     for (int r = threadIdx.x >> 3; r < ((D + 31) & ~31); r += NT / 8) {
         double s = 0.0;
         if (r < D)
-            for (int j = part; j < D; j += 8) s += cabs1(A[r * LD + j]);
+            for (int j = part; j < ncols; j += 8) s += cabs1(A[r * LD + j]);   // swizzled rows: all LD slots (padding is zero)
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -167,18 +195,20 @@ __device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, co
 }
 
 
-// Slot plan (8 matrices of DP x LD): the Taylor combinations overwrite the powers they are formed from
-//   S0: A -> B1 -> (B3+A9) A9 -> T18 (squaring ping)   S1: A2 -> B5 (squaring pong)   S2: A3 -> B4
-//   S3: A6 -> B3 -> B3 + A9                           S4: B2                         S5: B1 B5 -> A9
-//   P, Q: running product and its update (pointers swap, no copy)
+// Slot plan (6 matrices of DP x LD): the Taylor combinations overwrite the powers they are formed from and the fused
+// epilogues write in place (an epilogue reads E1[idx] and writes C[idx] from the same thread, so C may alias E1)
+//   S0: A -> B1 -> T18 (squaring ping)    S1: A2 -> B5 (squaring pong)    S2: A3 -> B4 -> A9 = B1 B5 + B4 (in place)
+//   S3: A6 -> B3 -> B3 + A9               S4: B2 -> receives the updated running product dU_n P
+//   P:  running product; after each slice P and S4 swap roles (pointers, no copy)
 template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
-__global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_cta_kernel(const GemmParams gp) {
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(const GemmParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[NT / 32];
     const CtaParams& p = gp.c;
     const int D = p.D, K = p.K;
+    constexpr bool SWZ = (DPT == 32);
     const int DP = DPT > 0 ? DPT : gp.DP;
-    const int LD = DPT > 0 ? DPT + 4 : gp.LD;
+    const int LD = DPT > 0 ? (SWZ ? DPT : DPT + 4) : gp.LD;
     const int KP = (D + 3) & ~3;
     const int PP = DP * LD;
     const int RL = D * LD;                          // rows >= D are padding: zeroed once, never written non-zero
@@ -192,10 +222,8 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
     cplx* const S1 = mats + (size_t)1 * PP;
     cplx* const S2 = mats + (size_t)2 * PP;
     cplx* const S3 = mats + (size_t)3 * PP;
-    cplx* const S4 = mats + (size_t)4 * PP;
-    cplx* const S5 = mats + (size_t)5 * PP;
-    cplx* P = mats + (size_t)6 * PP;
-    cplx* Q = mats + (size_t)7 * PP;
+    cplx* S4 = mats + (size_t)4 * PP;
+    cplx* P = mats + (size_t)5 * PP;
     const bool shifted = gp.TR != nullptr && p.hlist == nullptr;
 
     // zero everything once: the padding rows/columns stay zero through every product
@@ -250,7 +278,7 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
                         v.x = fma(c, gk.x, v.x);
                         v.y = fma(c, gk.y, v.y);
                     }
-                    A[i * LD + j] = cmake(v.x * asc, v.y * asc);
+                    A[mat_idx<SWZ>(i, j, LD)] = cmake(v.x * asc, v.y * asc);
                 };
                 if (DPT > 0) {                                   // DPT lanes walk one row: no integer division
                     constexpr int W = DPT > 0 ? DPT : 1;
@@ -304,13 +332,13 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
                 const cplx* H = p.hlist + ((size_t)b * p.N + n) * D * D;
                 for (int e = tid; e < D * D; e += NT) {
                     const int i = e / D, j = e - i * D;
-                    A[i * LD + j] = cmul(hs, H[e]);
+                    A[mat_idx<SWZ>(i, j, LD)] = cmul(hs, H[e]);
                 }
             }
             __syncthreads();
             int s = s_pre;
             if (s_pre < 0) {                                   // explicit slices (H list): exact inf-norm of the slice
-                const double nrm = cta_norm_inf_ld<NT>(A, D, LD, red);
+                const double nrm = cta_norm_inf_ld<NT>(A, D, LD, red, SWZ ? LD : D);
                 s = squarings_for(nrm, C3B_THETA18);
                 if (s > 0) {
                     const double sc = pow2neg(s);
@@ -340,7 +368,7 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
                 for (int u = 0; u < EU; ++u) {
                     const int e = e0 + u * NT;
                     if (e < RL) {
-                        const int i = e / LD, j = e - i * LD;
+                        const int i = e / LD, j = SWZ ? ((e - i * LD) ^ swz_of_row(i)) : (e - i * LD);
                         const double dg = (i == j) ? 1.0 : 0.0;
                         S0[e] = cmake(C3B_T18_A11 * x1[u].x + C3B_T18_A21 * x2[u].x + C3B_T18_A31 * x3[u].x,
                                       C3B_T18_A11 * x1[u].y + C3B_T18_A21 * x2[u].y + C3B_T18_A31 * x3[u].y);
@@ -356,9 +384,9 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
                 }
             }
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT, 1>(S5, S0, S1, DP, LD, KP, S2, S3);   // A9 = B4 + B1 B5 -> S5;  B3 + A9 -> S3 (epilogue)
+            cta_zgemm<TM, TN, DPT, KST, NT, 1>(S2, S0, S1, DP, LD, KP, S2, S3);   // A9 = B4 + B1 B5 -> S2 (in place);  B3 + A9 -> S3 (epilogue)
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT, 2>(S0, S3, S5, DP, LD, KP, S4);       // T18 = B2 + (B3 + A9) A9 (epilogue)
+            cta_zgemm<TM, TN, DPT, KST, NT, 2>(S0, S3, S2, DP, LD, KP, S4);       // T18 = B2 + (B3 + A9) A9 (epilogue)
             __syncthreads();
             cplx* X = S0;
             for (int i = 0; i < s; ++i) {                          // undo the scaling
@@ -381,16 +409,16 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
                 }
                 for (int e = tid; e < D * D; e += NT) {
                     const int i = e / D, j = e - i * D;
-                    o[e] = cmul(phn, X[i * LD + j]);
+                    o[e] = cmul(phn, X[mat_idx<SWZ>(i, j, LD)]);
                 }
             }
             if (n == n_begin) {
                 for (int e = tid; e < RL; e += NT) P[e] = X[e];
                 __syncthreads();
             } else {
-                cta_zgemm<TM, TN, DPT, KST, NT>(Q, X, P, DP, LD, KP);
+                cta_zgemm<TM, TN, DPT, KST, NT>(S4, X, P, DP, LD, KP);                // B2 is dead: its slot takes dU_n P
                 __syncthreads();
-                cplx* t = P; P = Q; Q = t;
+                cplx* t = P; P = S4; S4 = t;
             }
         }
         cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * D * D) : (p.seg_out + ((size_t)b * p.S + sidx) * D * D);
@@ -398,7 +426,7 @@ __global__ void __launch_bounds__(NT, (DPT == 0 && NT == 256) ? 2 : 1) pwc_t18_c
             const cplx phu = shifted ? cexp_(mu_acc) : cmake(1.0, 0.0);
             for (int e = tid; e < D * D; e += NT) {
                 const int i = e / D, j = e - i * D;
-                o[e] = cmul(phu, P[i * LD + j]);
+                o[e] = cmul(phu, P[mat_idx<SWZ>(i, j, LD)]);
             }
         } else {
             for (int e = tid; e < D * D; e += NT) o[e] = cmake((e / D) == (e % D) ? 1.0 : 0.0, 0.0);
