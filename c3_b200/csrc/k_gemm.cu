@@ -36,6 +36,9 @@ int launch_gemm(const CtaParams& cp, const cplx* TR, const double* RS, int grid,
     // 11 x 11 blocks at D = 81: 3 x 2 macro tiles give 24 tiles = 3 full rounds of the 8 warps (144 block slots for 121
     // blocks) where 2 x 2 gives 36 tiles = 5 rounds (160 slots): 20.5 -> 19.9 ms on the 296 x 40 probe (2 x 3: 20.5, 3 x 3: 23.9)
     if (gp.DP == 88 && tn.gemm_big == 0) return launch_gemm_t<3, 2>(gp, grid, st);
+    // one 384-thread CTA per SM: 24 macro tiles = 2 full rounds of 12 warps, and 148 x 6 x 124 KB = 110 MB of workspace stays
+    // inside the 126 MB L2 (two 256-thread CTAs per SM: 220 MB, L2 hit rate 52 %)
+    if (gp.DP == 88 && tn.gemm_big == 2) return launch_gemm_t<3, 2, 0, 0, 384>(gp, grid, st);
     return launch_gemm_t<2, 2>(gp, grid, st);
 }
 

@@ -37,6 +37,84 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a
                  : "d"(a), "d"(b));
 }
 
+// One macro tile of TI x TJ m8n8 blocks with run-time leading dimension (the global-workspace path): accumulate over k, then the
+// (optionally fused) epilogue of cta_zgemm.  Instantiated for every block count a partial macro tile at the matrix edge can
+// have, so that those tiles issue DMMAs for the blocks they own only.
+template <int TI, int TJ, int EPI>
+__device__ __forceinline__ void zgemm_tile(cplx* C, const cplx* A, const cplx* B, const int bi0, const int bj0, const int LD, const int KP,
+                                           const cplx* E1, cplx* E2, const int fr, const int fc) {
+    double p1[TI][TJ][2], p2[TI][TJ][2], p3[TI][TJ][2];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) { p1[i][j][0] = p1[i][j][1] = p2[i][j][0] = p2[i][j][1] = p3[i][j][0] = p3[i][j][1] = 0.0; }
+    int arow[TI], bcol[TJ];
+#pragma unroll
+    for (int i = 0; i < TI; ++i) arow[i] = ((bi0 + i) * 8 + fr) * LD + fc;
+#pragma unroll
+    for (int j = 0; j < TJ; ++j) bcol[j] = fc * LD + (bj0 + j) * 8 + fr;
+#pragma unroll 2
+    for (int k0 = 0; k0 < KP; k0 += 4) {
+        cplx a[TI], b[TJ];
+#pragma unroll
+        for (int i = 0; i < TI; ++i) a[i] = A[arow[i] + k0];
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) b[j] = B[bcol[j] + k0 * LD];
+        double as[TI], bs[TJ];
+#pragma unroll
+        for (int i = 0; i < TI; ++i) as[i] = a[i].x + a[i].y;
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) bs[j] = b[j].x + b[j].y;
+#pragma unroll
+        for (int i = 0; i < TI; ++i)
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) {
+                dmma8x8x4(p1[i][j][0], p1[i][j][1], a[i].x, b[j].x);
+                dmma8x8x4(p2[i][j][0], p2[i][j][1], a[i].y, b[j].y);
+                dmma8x8x4(p3[i][j][0], p3[i][j][1], as[i], bs[j]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+            const int idx = ((bi0 + i) * 8 + fr) * LD + (bj0 + j) * 8 + 2 * fc;
+            cplx c0 = cmake(p1[i][j][0] - p2[i][j][0], p3[i][j][0] - p1[i][j][0] - p2[i][j][0]);
+            cplx c1 = cmake(p1[i][j][1] - p2[i][j][1], p3[i][j][1] - p1[i][j][1] - p2[i][j][1]);
+            if constexpr (EPI != 0) {
+                const cplx e0 = E1[idx], e1 = E1[idx + 1];
+                c0.x += e0.x; c0.y += e0.y; c1.x += e1.x; c1.y += e1.y;
+            }
+            if constexpr (EPI == 1) {
+                const cplx f0 = E2[idx], f1 = E2[idx + 1];
+                E2[idx] = cmake(f0.x + c0.x, f0.y + c0.y);
+                E2[idx + 1] = cmake(f1.x + c1.x, f1.y + c1.y);
+            }
+            C[idx] = c0;
+            C[idx + 1] = c1;
+        }
+}
+
+// dispatch on the (warp-uniform) block counts of a partial macro tile
+template <int TM, int TN, int EPI>
+__device__ __forceinline__ void zgemm_edge_tile(cplx* C, const cplx* A, const cplx* B, const int bi0, const int bj0, const int ti, const int tj,
+                                                const int LD, const int KP, const cplx* E1, cplx* E2, const int fr, const int fc) {
+    if constexpr (TM >= 3) {
+        if (ti == 2 && tj == TN) return zgemm_tile<2, TN, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, fr, fc);
+        if constexpr (TN >= 2) { if (ti == 2 && tj == 1) return zgemm_tile<2, 1, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, fr, fc); }
+    }
+    if constexpr (TM >= 2) {
+        if (ti == 1 && tj == TN) return zgemm_tile<1, TN, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, fr, fc);
+    }
+    if constexpr (TN >= 2) {
+        if (ti == TM && tj == 1) return zgemm_tile<TM, 1, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, fr, fc);
+    }
+    if (ti == 1 && tj == 1) return zgemm_tile<1, 1, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, fr, fc);
+    // block counts without an instance (TM, TN > 3): one block at a time
+    for (int i = 0; i < ti; ++i)
+        for (int j = 0; j < tj; ++j) zgemm_tile<1, 1, EPI>(C, A, B, bi0 + i, bj0 + j, LD, KP, E1, E2, fr, fc);
+}
+
 // C = A * B for zero-padded DP x DP complex matrices (row-major, leading dimension DP, DP % 8 == 0).
 // Warp w owns macro tiles of TM x TN m8n8 blocks, assigned round-robin.  No __restrict__: operands
 // may be global-workspace buffers written earlier by this CTA.
@@ -48,7 +126,7 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a
 // operand, so they stay zero.
 template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads, int EPI = 0>
 __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP_, const int LD_, const int KP,
-                                          const cplx* E1 = nullptr, cplx* E2 = nullptr) {
+                                          const cplx* E1 = nullptr, cplx* E2 = nullptr, const unsigned char* sched = nullptr) {
     // DPT > 0: tile extent and leading dimension are compile-time (DPT, DPT + 4): the k loop unrolls fully and
     // every fragment address is base + immediate
     constexpr bool SWZ = (DPT == 32);
@@ -59,8 +137,21 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
     const int nb = DP >> 3;                       // m8n8 blocks per dimension
     const int mt_r = (nb + TM - 1) / TM, mt_c = (nb + TN - 1) / TN;
     const int fr = lane >> 2, fc = lane & 3;      // fragment coordinates
-    for (int mt = warp; mt < mt_r * mt_c; mt += NW) {
+    // macro tiles of this warp: round-robin, or (sched) the balanced list built by gemm_build_schedule -- partial macro tiles
+    // at the matrix edge carry fewer blocks, and their DMMAs are skipped
+    const int rounds = (mt_r * mt_c + NW - 1) / NW;
+    for (int rd = 0; rd < rounds; ++rd) {
+        const int mt = sched ? (int)sched[warp * rounds + rd] : warp + rd * NW;
+        if (mt >= mt_r * mt_c) continue;
         const int bi0 = (mt / mt_c) * TM, bj0 = (mt % mt_c) * TN;
+        if constexpr (DPT == 0 && (TM > 1 || TN > 1)) {
+            // run-time extents: a macro tile at the matrix edge is computed by the instance with exactly its block counts
+            const int ti = min(TM, nb - bi0), tj = min(TN, nb - bj0);
+            if (ti != TM || tj != TN) {
+                zgemm_edge_tile<TM, TN, EPI>(C, A, B, bi0, bj0, ti, tj, LD, KP, E1, E2, fr, fc);
+                continue;
+            }
+        }
         // 3M complex product: P1 = Ar Br, P2 = Ai Bi, P3 = (Ar + Ai)(Br + Bi); Cr = P1 - P2, Ci = P3 - P1 - P2 -- three real
         // DMMAs per tile step instead of four (the operand sums cost one DADD per loaded fragment element)
         double p1[TM][TN][2], p2[TM][TN][2], p3[TM][TN][2];
@@ -142,8 +233,38 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
                     }
             }
         } else {
-#pragma unroll 2
-            for (int k0 = 0; k0 < KP; k0 += 4) kstep(k0);
+            // fragments of the next k step are requested before the DMMAs of this one are issued (operands come from L1 / L2:
+            // long_scoreboard was the top stall at 7.6 per issue)
+            cplx a[TM], b[TN], an[TM], bn[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = A[arow[i]];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = B[bcol[j]];
+#pragma unroll 1
+            for (int k0 = 0; k0 < KP; k0 += 4) {
+                const int kn = (k0 + 4 < KP) ? k0 + 4 : k0;
+#pragma unroll
+                for (int i = 0; i < TM; ++i) an[i] = A[arow[i] + kn];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) bn[j] = B[bcol[j] + kn * LD];
+                double as[TM], bs[TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) as[i] = a[i].x + a[i].y;
+#pragma unroll
+                for (int j = 0; j < TN; ++j) bs[j] = b[j].x + b[j].y;
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) {
+                        dmma8x8x4(p1[i][j][0], p1[i][j][1], a[i].x, b[j].x);
+                        dmma8x8x4(p2[i][j][0], p2[i][j][1], a[i].y, b[j].y);
+                        dmma8x8x4(p3[i][j][0], p3[i][j][1], as[i], bs[j]);
+                    }
+#pragma unroll
+                for (int i = 0; i < TM; ++i) a[i] = an[i];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) b[j] = bn[j];
+            }
         }
 #pragma unroll
         for (int i = 0; i < TM; ++i)
@@ -167,6 +288,33 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
                 }
             }
     }
+}
+
+// Balanced static assignment of macro tiles to warps (longest-processing-time first): a macro tile at the matrix edge holds
+// fewer m8n8 blocks than TM x TN, and round-robin leaves some warps with full tiles only (D = 81, 3 x 2 macro tiles on 11 x 11
+// blocks, 8 warps: 18 blocks on the busiest warp against 15.1 on average; balanced: 16).  sched[w * rounds + r] = macro tile
+// index or 255.  Called by one thread; at most 64 macro tiles.
+template <int TM, int TN>
+__device__ inline void gemm_build_schedule(unsigned char* sched, int* load, const int nb, const int nw) {
+    const int mt_r = (nb + TM - 1) / TM, mt_c = (nb + TN - 1) / TN, nt = mt_r * mt_c;
+    const int rounds = (nt + nw - 1) / nw;
+    for (int w = 0; w < nw; ++w) {
+        load[w] = 0;
+        load[nw + w] = 0;     // tiles taken
+        for (int r = 0; r < rounds; ++r) sched[w * rounds + r] = 255;
+    }
+    for (int size = TM * TN; size >= 1; --size)
+        for (int mt = 0; mt < nt; ++mt) {
+            const int bi0 = (mt / mt_c) * TM, bj0 = (mt % mt_c) * TN;
+            const int blocks = min(TM, nb - bi0) * min(TN, nb - bj0);
+            if (blocks != size) continue;
+            int best = -1;
+            for (int w = 0; w < nw; ++w)
+                if (load[nw + w] < rounds && (best < 0 || load[w] < load[best])) best = w;
+            sched[best * rounds + load[nw + best]] = (unsigned char)mt;
+            load[best] += blocks;
+            load[nw + best] += 1;
+        }
 }
 
 // inf-norm (largest row sum of |a_ij|) over the D x D part of an LD-strided matrix, all threads busy:
@@ -226,6 +374,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(cons
     cplx* P = mats + (size_t)5 * PP;
     const bool shifted = gp.TR != nullptr && p.hlist == nullptr;
 
+    __shared__ unsigned char s_sched[64];
+    __shared__ int s_load[2 * (NT / 32)];
+    const unsigned char* sched = nullptr;
+    if (DPT == 0 && ((DP >> 3) + TM - 1) / TM * (((DP >> 3) + TN - 1) / TN) <= 64 - NT / 32) {
+        if (tid == 0) gemm_build_schedule<TM, TN>(s_sched, s_load, DP >> 3, NT / 32);
+        sched = s_sched;
+    }
     // zero everything once: the padding rows/columns stay zero through every product
     for (int e = tid; e < kGemmSlots * PP; e += NT) mats[e] = cmake(0.0, 0.0);
     const cplx* Gs = nullptr;                       // generators staged in shared memory (shared model only)
@@ -347,11 +502,11 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(cons
                 }
             }
             // ---- T18: A2 = S1, A3 = S2, A6 = S3 -----------------------------------------------------
-            cta_zgemm<TM, TN, DPT, KST, NT>(S1, A, A, DP, LD, KP);
+            cta_zgemm<TM, TN, DPT, KST, NT>(S1, A, A, DP, LD, KP, nullptr, nullptr, sched);
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT>(S2, S1, A, DP, LD, KP);
+            cta_zgemm<TM, TN, DPT, KST, NT>(S2, S1, A, DP, LD, KP, nullptr, nullptr, sched);
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT>(S3, S2, S2, DP, LD, KP);
+            cta_zgemm<TM, TN, DPT, KST, NT>(S3, S2, S2, DP, LD, KP, nullptr, nullptr, sched);
             __syncthreads();
             // in place: B1 -> S0, B5 -> S1, B4 -> S2, B3 -> S3, B2 -> S4
             // element-wise passes in batches of EU elements per thread, loads first: the compiler may not hoist a load over
@@ -384,14 +539,14 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(cons
                 }
             }
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT, 1>(S2, S0, S1, DP, LD, KP, S2, S3);   // A9 = B4 + B1 B5 -> S2 (in place);  B3 + A9 -> S3 (epilogue)
+            cta_zgemm<TM, TN, DPT, KST, NT, 1>(S2, S0, S1, DP, LD, KP, S2, S3, sched);   // A9 = B4 + B1 B5 -> S2 (in place);  B3 + A9 -> S3 (epilogue)
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT, 2>(S0, S3, S2, DP, LD, KP, S4);       // T18 = B2 + (B3 + A9) A9 (epilogue)
+            cta_zgemm<TM, TN, DPT, KST, NT, 2>(S0, S3, S2, DP, LD, KP, S4, nullptr, sched);       // T18 = B2 + (B3 + A9) A9 (epilogue)
             __syncthreads();
             cplx* X = S0;
             for (int i = 0; i < s; ++i) {                          // undo the scaling
                 cplx* nxt = (X == S0) ? S1 : S0;
-                cta_zgemm<TM, TN, DPT, KST, NT>(nxt, X, X, DP, LD, KP);
+                cta_zgemm<TM, TN, DPT, KST, NT>(nxt, X, X, DP, LD, KP, nullptr, nullptr, sched);
                 __syncthreads();
                 X = nxt;
             }
@@ -416,7 +571,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(cons
                 for (int e = tid; e < RL; e += NT) P[e] = X[e];
                 __syncthreads();
             } else {
-                cta_zgemm<TM, TN, DPT, KST, NT>(S4, X, P, DP, LD, KP);                // B2 is dead: its slot takes dU_n P
+                cta_zgemm<TM, TN, DPT, KST, NT>(S4, X, P, DP, LD, KP, nullptr, nullptr, sched);                // B2 is dead: its slot takes dU_n P
                 __syncthreads();
                 cplx* t = P; P = S4; S4 = t;
             }
