@@ -325,6 +325,28 @@ def run_configs(engine, synth, dev, rank, world, dfma_peak, all_gather, check):
         out["cfg5"]["parity_rel_fro_max"] = max(rel(U5[r].cpu().numpy(), want[i]) for i, r in enumerate(rows))
     del U5, sig5
 
+    # ---- f-1: forward + gradient w.r.t. the control fields against the forward pass alone (rank 0's GPU, reduced batches) ----
+    if rank == 0:
+        gr = {}
+        rng = np.random.default_rng(0)
+        for name, mm, Bg, Ng, lind in (("d9", m2, 1024, N, False), ("d27", m5, 296, 200, False), ("D81_lindblad", m2, 148, 40, True)):
+            sg = torch.as_tensor(synth.controls_fast(mm, Bg, Ng, DT, seed=3)).to(dev)
+            Dg = mm.d * mm.d if lind else mm.d
+            Ub = torch.as_tensor(rng.normal(size=(Bg, Dg, Dg)) + 1j * rng.normal(size=(Bg, Dg, Dg))).to(dev)
+            if lind:
+                fwd = lambda: engine.pwc_lindblad(mm.h0, mm.hks, mm.col_ops, sg, DT)
+                bwd = lambda: engine.pwc_lindblad_grad(mm.h0, mm.hks, mm.col_ops, sg, DT, Ub, max_workspace_bytes=24 << 30)
+            else:
+                fwd = lambda: engine.pwc_closed(mm.h0, mm.hks, sg, DT)
+                bwd = lambda: engine.pwc_closed_grad(mm.h0, mm.hks, sg, DT, Ub, max_workspace_bytes=24 << 30)
+            ms_f, _ = _timed(fwd, 2, torch, dist, 1)
+            ms_g, _ = _timed(bwd, 2, torch, dist, 1)
+            gr[name] = {"B": Bg, "N": Ng, "forward_ms": ms_f, "forward_plus_gradient_ms": ms_g, "ratio": ms_g / ms_f,
+                        "slices_per_s_with_gradient": Bg * Ng / (ms_g * 1e-3)}
+        out["gradient"] = {"what": "U and dL/d signals[B,K,N] for a given cotangent of U (c3b_pwc_closed_grad / c3b_pwc_lindblad_grad): "
+                                   "d <= 16 warp-per-slice Frechet kernels, above CTA kernels on the DMMA product", **gr}
+        engine.release_workspaces()
+
     # ---- strong scaling: the headline batch of 4096 signal sets in TOTAL, split over the ranks --------------------------
     lo, hi = shard_bounds(B_PER_GPU, world, rank)
     sig_s = torch.as_tensor(synth.controls_fast(m2, B_PER_GPU, N, DT, seed=4242)[lo:hi]).to(dev)

@@ -456,10 +456,17 @@ int c3b_kron(const void* A, const void* Bm, void* out, int batch, int ra, int ca
 // ---- gradient -------------------------------------------------------------
 // variant 1 (default, d <= 16): Frechet derivative of the Taylor scheme on (X, dX) pairs, fused contraction
 // variant 0: augmented 2d x 2d exponential through the forward kernels (any d <= 32)
-static int grad_variant_for(int d) { return (tuning().grad_variant == 1 && d <= 16) ? 1 : 0; }
+// variant 1 (default): Frechet derivative of the Taylor scheme on (X, dX) pairs, fused contraction -- warp-per-slice kernels for
+//   matrix dimension <= 16, CTA kernels on the DMMA product above (variant 2 here)
+// variant 0: augmented 2d x 2d exponential through the forward kernels (closed systems, d <= 32; cross-check)
+static int grad_variant_for(int D) {
+    if (tuning().grad_variant == 0 && D <= 32) return 0;
+    return D <= 16 ? 1 : 2;
+}
+constexpr int kGradMaxDim = 128;
 
 // D: matrix dimension of the propagators (d, or d^2 for Lindblad); dh: Hilbert dimension passed to the workspace query
-static size_t grad_chunk_bytes(int Bc, int K, int N, int dh, int lindblad, size_t* off /*[9]*/) {
+static size_t grad_chunk_bytes(int Bc, int K, int N, int dh, int lindblad, size_t* off /*[10]*/) {
     const int D = lindblad ? dh * dh : dh;
     const size_t dd = (size_t)D * D * sizeof(cplx), dd2 = 4 * dd;
     const bool aug = grad_variant_for(D) == 0;
@@ -473,20 +480,21 @@ static size_t grad_chunk_bytes(int Bc, int K, int N, int dh, int lindblad, size_
     off[6] = o; if (aug) o += align_up((size_t)Bc * N * dd2);                      // Haug
     off[7] = o; if (aug) o += align_up((size_t)Bc * N * dd2);                      // exp(hscale Haug)
     off[8] = o; if (aug) o += align_up((size_t)Bc * dd2);                          // product of the augmented slices (unused)
+    off[9] = o; if (grad_variant_for(D) == 2) o += grad_cta_workspace_bytes(Bc, N, D);   // per-CTA matrix slots (D > 32)
     return o;
 }
 
 size_t c3b_pwc_grad_workspace_bytes(int B, int K, int N, int d, int chunk) {
     if (B <= 0 || N <= 0 || d <= 0 || K <= 0) return 0;
     const int Bc = (chunk > 0 && chunk < B) ? chunk : B;
-    size_t off[9];
+    size_t off[10];
     return grad_chunk_bytes(Bc, K, N, d, 0, off);
 }
 
 size_t c3b_pwc_lindblad_grad_workspace_bytes(int B, int K, int N, int d, int chunk) {
     if (B <= 0 || N <= 0 || d <= 0 || K <= 0) return 0;
     const int Bc = (chunk > 0 && chunk < B) ? chunk : B;
-    size_t off[9];
+    size_t off[10];
     return grad_chunk_bytes(Bc, K, N, d, 1, off);
 }
 
@@ -496,12 +504,12 @@ static int pwc_grad_impl(int lindblad, const void* h0, const void* hks, const vo
     if (B <= 0 || N <= 0 || dh <= 0 || K <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d N=%d d=%d)", B, K, N, dh);
     if (!h0 || !hks || !signals || !Ubar || !grad_out || !workspace) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
     const int d = lindblad ? dh * dh : dh;                      // dimension of the propagators
-    if (d > 32) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gradient path supports matrix dimension <= 32 (got %d)", d);
+    if (d > kGradMaxDim) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gradient path supports matrix dimension <= %d (got %d)", kGradMaxDim, d);
     const int variant = grad_variant_for(d);
-    if (lindblad && variant != 1)
-        return fail(C3B_EUNSUPPORTED, "C3:ERROR: the Lindblad gradient needs d^2 <= 16 and grad_variant 1 (got d=%d)", dh);
+    if (lindblad && variant == 0)
+        return fail(C3B_EUNSUPPORTED, "C3:ERROR: the augmented-exponential gradient (grad_variant 0) is built for closed systems only");
     const int Bc = (chunk > 0 && chunk < B) ? chunk : B;
-    size_t off[9];
+    size_t off[10];
     const size_t need = grad_chunk_bytes(Bc, K, N, dh, lindblad, off);
     if (workspace_bytes < need) return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small: %zu < %zu bytes", workspace_bytes, need);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -523,6 +531,15 @@ static int pwc_grad_impl(int lindblad, const void* h0, const void* hks, const vo
             : c3b_pwc_closed(h0, hks, sig, dt, nb, K, N, dh, 0, Udst, dUs, ws + off[0], off[1] - off[0], stream);
         if (rc) return rc;
         const cplx* ub = static_cast<const cplx*>(Ubar) + (size_t)b0 * dd;
+        if (variant == 2) {
+            const ModelLayout ml = model_layout(K, d, 1);
+            const char* fws = ws + off[0];
+            rc = launch_grad_cta(reinterpret_cast<const cplx*>(fws + ml.off_G), reinterpret_cast<const double*>(fws + ml.off_RS),
+                                 reinterpret_cast<const cplx*>(fws + ml.off_TR), sig, dUs, ub, Psi, alpha, grad_out + (size_t)b0 * K * N,
+                                 nb, K, N, d, reinterpret_cast<cplx*>(ws + off[9]), st);
+            if (rc) return rc;
+            continue;
+        }
         if ((rc = launch_grad_suffix(variant, dUs, ub, Psi, alpha, nb, N, d, st)) != 0) return rc;
         if (variant == 1) {
             if ((rc = launch_grad_prefix_frechet(dUs, Psi, nb, N, d, st)) != 0) return rc;

@@ -118,4 +118,11 @@ int launch_grad_frechet(const cplx* G, const double* RS, const cplx* TR, const d
 int launch_grad_contract(const cplx* Eaug, const cplx* hks, const double* alpha, double* grad, double dt, int nb, int K, int N, int d,
                          cudaStream_t st);
 
+// k_grad_cta.cu: the same adjoint scheme on the CTA-cooperative DMMA product (closed d > 16, Lindblad superoperators)
+bool grad_cta_uses_smem(int D);
+int grad_cta_frechet_grid(int D, long long units);
+size_t grad_cta_workspace_bytes(int Bc, int N, int D);
+int launch_grad_cta(const cplx* G, const double* RS, const cplx* TR, const double* sig, const cplx* dUs, const cplx* Ubar, cplx* PsiM,
+                    double* alpha, double* grad, int nb, int K, int N, int D, cplx* ws, cudaStream_t st);
+
 }  // namespace c3b

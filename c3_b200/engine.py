@@ -196,13 +196,18 @@ def _gate_marks(bounds) -> torch.Tensor:
 
 
 _gates_in_flight = []
+_flag_pool = []
 
 
 def _watch_gate(gate: torch.Tensor, stream) -> None:
-    """Remember the status word of a gated launch; it is read once the launch has finished (see check_gated_launches)."""
+    """Queue an asynchronous read-back of a gated launch's status word (gate[1]) into pinned host memory behind the
+    kernel; check_gated_launches looks at it once the copy has completed.  Nothing here blocks the host."""
+    flag = _flag_pool.pop() if _flag_pool else torch.zeros((1,), dtype=torch.int32).pin_memory()
+    with torch.cuda.stream(stream):
+        flag.copy_(gate[1:2], non_blocking=True)
     ev = torch.cuda.Event()
     ev.record(stream)
-    _gates_in_flight.append((ev, gate))
+    _gates_in_flight.append((ev, flag, gate))
     check_gated_launches(wait=False)
 
 
@@ -213,13 +218,14 @@ def check_gated_launches(wait: bool = True) -> None:
     outstanding ones first -- call it wherever the result is consumed on the host."""
     keep = []
     failed = False
-    for ev, gate in _gates_in_flight:
+    for ev, flag, gate in _gates_in_flight:
         if wait:
             ev.synchronize()
         if ev.query():
-            failed = failed or bool(gate[1].item() != 0)
+            failed = failed or bool(int(flag[0]) != 0)
+            _flag_pool.append(flag)
         else:
-            keep.append((ev, gate))
+            keep.append((ev, flag, gate))
     _gates_in_flight[:] = keep
     if failed:
         raise _lib.C3BError("C3:ERROR: gated launch timed out waiting for host control fields; the affected rows of U are NaN")
@@ -270,7 +276,8 @@ def pwc_closed_grad(h0, hks, signals, dt: float, Ubar, max_workspace_bytes: int 
 
 def pwc_lindblad_grad(h0, hks, col_ops, signals, dt: float, Ubar, max_workspace_bytes: int = 6 << 30, device=None):
     """Forward U [B,D,D] (D = d^2) and the gradient [B,K,N] of a real scalar loss w.r.t. the control fields through the
-    Lindblad superoperator propagators; ``Ubar`` as in :func:`pwc_closed_grad`.  Needs d^2 <= 16."""
+    Lindblad superoperator propagators; ``Ubar`` as in :func:`pwc_closed_grad`.  Any d with d^2 <= 128 (warp kernels up to
+    d^2 = 16, CTA kernels on the DMMA product above)."""
     lib = _lib.load()
     device = torch.device(device) if device is not None else default_device()
     with torch.cuda.device(device):

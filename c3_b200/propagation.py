@@ -182,7 +182,7 @@ class _PwcClosedFn(torch.autograd.Function):
 
 
 class _PwcLindbladFn(torch.autograd.Function):
-    """U = pwc_batch(..., lindbladian=True), differentiable w.r.t. ``signals`` (d^2 <= 16)."""
+    """U = pwc_batch(..., lindbladian=True), differentiable w.r.t. ``signals`` (d^2 <= 128)."""
 
     @staticmethod
     def forward(ctx, signals, h0, hks, col_ops, dt):
@@ -201,8 +201,8 @@ class _PwcLindbladFn(torch.autograd.Function):
 def pwc_batch_autograd(h0, hks, signals: torch.Tensor, dt, col_ops=None, lindbladian: bool = False) -> torch.Tensor:
     """Differentiable batched propagators: ``signals`` is a CUDA float64 tensor [B,K,N] with
     ``requires_grad``; gradients of any real loss of U flow back to it (what the reference gets from
-    tf.GradientTape, c3/optimizers/optimizer.py:210-215).  Shared model; closed system (d <= 32) or, with
-    ``lindbladian=True`` and ``col_ops``, the Lindblad superoperator propagators (d^2 <= 16)."""
+    tf.GradientTape, c3/optimizers/optimizer.py:210-215).  Shared model; closed system (d <= 128) or, with
+    ``lindbladian=True`` and ``col_ops``, the Lindblad superoperator propagators (d^2 <= 128, e.g. D = 81)."""
     if not (isinstance(signals, torch.Tensor) and signals.is_cuda):
         raise ValueError("C3:ERROR: pwc_batch_autograd needs a CUDA tensor for `signals`")
     dev = signals.device

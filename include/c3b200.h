@@ -116,9 +116,10 @@ int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C
  *   Ubar     [B,d,d]  cotangent of U with dL = Re tr(Ubar^dag dU)  (torch's grad_output for U)
  *   grad_out [B,K,N]  float64, dL/d signals[b,k,n]
  *   U_out    [B,d,d]  or NULL: the forward result is produced on the way
- *   chunk    batch rows processed per pass (bounds the workspace: ~2 N d^2 16 bytes per row for d <= 16,
- *            ~10 N d^2 16 above); <= 0: all
- * Shared model only (h0 [d,d], hks [K,d,d]), d <= 32. */
+ *   chunk    batch rows processed per pass (bounds the workspace: ~2 N d^2 16 bytes per row; ~10 N d^2 16 with the
+ *            augmented-exponential cross-check, tuning "grad_variant" 0, d <= 32); <= 0: all
+ * Shared model only (h0 [d,d], hks [K,d,d]).  d <= 16: one warp per slice (Frechet derivative of the Taylor scheme in shared
+ * memory); 16 < d <= 128: CTA kernels on the fp64 tensor-core product (sweeps + Frechet derivative on (X, dX) pairs). */
 size_t c3b_pwc_grad_workspace_bytes(int B, int K, int N, int d, int chunk);
 int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
                         const void* Ubar, double* grad_out, void* U_out, int chunk, void* workspace,
@@ -188,7 +189,8 @@ int c3b_generate_signals_grad(const double* env_params, const int32_t* env_shape
                               double* grad_lo, double* grad_v2hz, void* stream);
 
 /* Same for the Lindblad superoperator propagators (Ubar, U_out [B,D,D], D = d*d): the generators dA/dc_k are the
- * commutator superoperators -i dt (h_k (x) I - I (x) h_k^T).  Needs D <= 16 (d <= 4: one qutrit, two qubits). */
+ * commutator superoperators -i dt (h_k (x) I - I (x) h_k^T).  D <= 128: the BASELINE Lindblad shape D = 81 runs on the CTA
+ * kernels with a per-CTA global workspace. */
 size_t c3b_pwc_lindblad_grad_workspace_bytes(int B, int K, int N, int d, int chunk);
 int c3b_pwc_lindblad_grad(const void* h0, const void* hks, const void* col_ops, int C, const double* signals, double dt,
                           int B, int K, int N, int d, const void* Ubar, double* grad_out, void* U_out, int chunk,
