@@ -78,16 +78,26 @@ int c3b_signal_slice_num(double t_start, double t_end, double resolution) {
 int c3b_generate_signals(const double* env_params, const int32_t* env_shape, const int32_t* env_flags,
                          const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
                          int B, int K, int E, int N, double* signals_out, void* stream) {
+    return c3b_generate_signals_noisy(env_params, env_shape, env_flags, lo_freq, chain, chain_batched, t_start, t_end, B, K, E, N,
+                                      nullptr, 0, 0ull, signals_out, nullptr, stream);
+}
+
+int c3b_generate_signals_noisy(const double* env_params, const int32_t* env_shape, const int32_t* env_flags,
+                               const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
+                               int B, int K, int E, int N, const double* noise, int noise_batched, unsigned long long seed,
+                               double* signals_out, double* noise_out, void* stream) {
     if (B <= 0 || K <= 0 || E <= 0 || N <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d E=%d N=%d)", B, K, E, N);
     if (!env_params || !env_shape || !env_flags || !lo_freq || !chain || !signals_out) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (noise_out != nullptr && noise == nullptr) return fail(C3B_EINVAL, "C3:ERROR: noise traces requested without noise parameters");
     SignalParams sp{};
     sp.env = env_params; sp.shape = env_shape; sp.flags = env_flags; sp.lo_freq = lo_freq; sp.chain = chain;
     sp.chain_batched = chain_batched; sp.t_start = t_start; sp.t_end = t_end;
     sp.B = B; sp.K = K; sp.E = E; sp.N = N; sp.out = signals_out;
+    sp.noise = noise; sp.noise_batched = noise_batched; sp.seed = seed; sp.noise_out = noise_out;
     // the AWG grid and the response taps live in shared memory: bounded by the simulation grid / 4096 taps
     sp.max_awg = N + 1;
     sp.max_taps = 4096;
-    const size_t smem = ((size_t)2 * sp.max_awg + sp.max_taps) * sizeof(double);
+    const size_t smem = ((size_t)2 * sp.max_awg + sp.max_taps) * sizeof(double) + (noise ? (size_t)N * sizeof(int) : 0);   // + Pink_Noise sums
     if (smem > 200 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gate too long for the on-chip signal chain (N=%d)", N);
     CUDA_TRY(cudaFuncSetAttribute(signal_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     signal_chain_kernel<<<B * K, 128, smem, static_cast<cudaStream_t>(stream)>>>(sp);

@@ -31,7 +31,57 @@ struct SignalParams {
     double t_start, t_end;
     int B, K, E, N, max_awg, max_taps;
     double* out;             // [B, K, N]
+    // noise devices (c3/generator/devices.py:943-1035), all optional (noise == nullptr: noise-free chain)
+    const double* noise;     // [K, NOISE_NPAR] or [B, K, NOISE_NPAR]: see the NOISE_* enum
+    int noise_batched;
+    unsigned long long seed; // one noise realisation per (seed, batch row, line): counter-based, reproducible
+    double* noise_out;       // [B, K, NOISE_NTRACE, N] realised noise traces (what Device.signal["noise"] holds) or null
 };
+
+// one drive line's noise row and the layout of the realised traces
+enum { NOISE_AWG_AMP = 0,    // Additive_Noise after the AWG: amp * N(0,1) on every in-phase and quadrature AWG sample
+       NOISE_LO_PERC,        // LONoise: perc * N(0,1) on the LO's cos and sin at every simulation sample
+       NOISE_ADD_AMP,        // Additive_Noise after the mixer: amp * N(0,1) per simulation sample
+       NOISE_DC_AMP,         // DC_Noise: ONE amp * N(0,1) offset per realisation
+       NOISE_PINK_AMP,       // Pink_Noise: amp * (sum of bfl_num bistable fluctuators)
+       NOISE_PINK_BFL,       //             number of fluctuators (<= 32)
+       NOISE_DC_OFFSET,      // DC_Offset: deterministic offset added after the mixer
+       NOISE_NPAR };
+enum { TRACE_AWG_I = 0, TRACE_AWG_Q, TRACE_LO_COS, TRACE_LO_SIN, TRACE_ADD, TRACE_DC, TRACE_PINK, NOISE_NTRACE };
+enum { STREAM_AWG = 1, STREAM_LO, STREAM_ADD, STREAM_DC, STREAM_PINK_INIT, STREAM_PINK_FLIP };
+
+// ---- Philox4x32-10 (Salmon et al., SC'11): counter-based, so every (realisation, line, stream, sample) has its own
+// random numbers without any state or ordering between threads; restated in oracle/c3_noise_oracle.py
+__device__ __forceinline__ void philox4x32_10(unsigned int k0, unsigned int k1, unsigned int c0, unsigned int c1, unsigned int c2,
+                                              unsigned int c3, unsigned int (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// random words of (seed, line bk, stream, index)
+__device__ __forceinline__ void noise_words(unsigned long long seed, int bk, int stream, unsigned int idx, unsigned int (&w)[4]) {
+    philox4x32_10((unsigned int)seed, (unsigned int)(seed >> 32), idx, (unsigned int)bk, (unsigned int)stream, 0u, w);
+}
+__device__ __forceinline__ double u01(unsigned int hi, unsigned int lo) {      // 53-bit uniform in (0, 1)
+    const unsigned long long m = ((unsigned long long)(hi >> 5) << 26) | (lo >> 6);
+    return ((double)m + 0.5) * (1.0 / 9007199254740992.0);
+}
+// two independent standard normals (Box-Muller)
+__device__ __forceinline__ void noise_normals(unsigned long long seed, int bk, int stream, unsigned int idx, double& z0, double& z1) {
+    unsigned int w[4];
+    noise_words(seed, bk, stream, idx, w);
+    const double r = sqrt(-2.0 * log(u01(w[0], w[1])));
+    double sn, cs;
+    sincos(2.0 * M_PI * u01(w[2], w[3]), &sn, &cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
 
 // ---- forward-mode dual numbers: the SAME envelope formulas give values (T = double) and parameter derivatives
 // (T = Dual, seeded on one of the 9 envelope parameters) -- the reference differentiates them with tf.GradientTape
@@ -247,7 +297,55 @@ __global__ void __launch_bounds__(128) signal_chain_kernel(const SignalParams p)
     const int b = bk / p.K, k = bk - b * p.K;
     const ChainCtx c = chain_ctx(p, bk, k);
     fill_awg(p, c, b, k, sI, sQ);
-    fill_taps(c, sR, &s_norm);
+
+    // ---- noise devices (c3/generator/devices.py:943-1035) ------------------------------------------------------------
+    const double* nz = p.noise ? p.noise + (p.noise_batched ? (size_t)bk : (size_t)k) * NOISE_NPAR : nullptr;
+    double* tr = p.noise_out ? p.noise_out + (size_t)bk * NOISE_NTRACE * c.N : nullptr;
+    int* sPink = reinterpret_cast<int*>(sR + p.max_taps);          // [N] sum of the bistable fluctuators (Pink_Noise)
+    double dc = 0.0;
+    int bfl = 0;
+    if (nz != nullptr) {
+        if (tr != nullptr)
+            for (int e = threadIdx.x; e < NOISE_NTRACE * c.N; e += blockDim.x) tr[e] = 0.0;
+        // Additive_Noise behind the AWG: independent Gaussian noise on every in-phase and quadrature sample
+        if (nz[NOISE_AWG_AMP] >= 1e-17) {
+            __syncthreads();
+            for (int j = threadIdx.x; j < c.n_awg; j += blockDim.x) {
+                double z0, z1;
+                noise_normals(p.seed, bk, STREAM_AWG, (unsigned int)j, z0, z1);
+                sI[j] += nz[NOISE_AWG_AMP] * z0;
+                sQ[j] += nz[NOISE_AWG_AMP] * z1;
+                if (tr != nullptr && j < c.N) { tr[TRACE_AWG_I * c.N + j] = nz[NOISE_AWG_AMP] * z0; tr[TRACE_AWG_Q * c.N + j] = nz[NOISE_AWG_AMP] * z1; }
+            }
+        }
+        // DC_Noise: one Gaussian offset per realisation
+        if (nz[NOISE_DC_AMP] >= 1e-17) {
+            double z0, z1;
+            noise_normals(p.seed, bk, STREAM_DC, 0u, z0, z1);
+            dc = nz[NOISE_DC_AMP] * z0;
+        }
+        // Pink_Noise: bfl_num two-level fluctuators, fluctuator i flips at a step with probability 1 / rate_i,
+        // rate = logspace(0, ln N, bfl_num + 1, base 10)[1:]  (the reference's np.logspace(0, np.log(num_steps), ...)):
+        // one thread per fluctuator walks the time axis, the others wait (N * bfl_num draws: microseconds)
+        bfl = (nz[NOISE_PINK_AMP] >= 1e-17) ? min(32, max(0, (int)nz[NOISE_PINK_BFL])) : 0;
+        if (bfl > 0) {
+            for (int n = threadIdx.x; n < c.N; n += blockDim.x) sPink[n] = 0;
+            __syncthreads();
+            if ((int)threadIdx.x < bfl) {
+                unsigned int w[4];
+                noise_words(p.seed, bk, STREAM_PINK_INIT, threadIdx.x, w);
+                int state = (w[0] & 1u) ? 1 : -1;
+                const double rate = pow(10.0, log((double)c.N) * (double)(threadIdx.x + 1) / (double)bfl);
+                for (int n = 0; n < c.N; ++n) {
+                    if ((n & 1) == 0) noise_words(p.seed, bk, STREAM_PINK_FLIP, (unsigned int)(threadIdx.x * ((c.N + 1) / 2) + (n >> 1)), w);
+                    const double u = (n & 1) ? u01(w[2], w[3]) : u01(w[0], w[1]);
+                    if (floor(u * rate) == 0.0) state = -state;
+                    atomicAdd(&sPink[n], state);
+                }
+            }
+        }
+    }
+    fill_taps(c, sR, &s_norm);                                   // (contains the barriers that publish sI / sQ / sPink)
 
     // ---- simulation grid: resample, convolve, mix with the LO, convert ------------------------------------------
     const double f_ref = (c.out_kind == 1) ? flux_freq(c, c.ch[CH_PHI]) : 0.0;
@@ -258,7 +356,26 @@ __global__ void __launch_bounds__(128) signal_chain_kernel(const SignalParams p)
         const double t = linspace_at(c.s0, c.s1, c.N, n);
         double sn, cs;
         sincos(c.w_lo * t, &sn, &cs);
-        const double mixed = cs * vi + sn * vq;
+        double extra = 0.0;
+        if (nz != nullptr) {
+            if (nz[NOISE_LO_PERC] >= 1e-17) {                    // LONoise
+                double z0, z1;
+                noise_normals(p.seed, bk, STREAM_LO, (unsigned int)n, z0, z1);
+                cs += nz[NOISE_LO_PERC] * z0;
+                sn += nz[NOISE_LO_PERC] * z1;
+                if (tr != nullptr) { tr[TRACE_LO_COS * c.N + n] = nz[NOISE_LO_PERC] * z0; tr[TRACE_LO_SIN * c.N + n] = nz[NOISE_LO_PERC] * z1; }
+            }
+            if (nz[NOISE_ADD_AMP] >= 1e-17) {                    // Additive_Noise behind the mixer
+                double z0, z1;
+                noise_normals(p.seed, bk, STREAM_ADD, (unsigned int)n, z0, z1);
+                extra += nz[NOISE_ADD_AMP] * z0;
+                if (tr != nullptr) tr[TRACE_ADD * c.N + n] = nz[NOISE_ADD_AMP] * z0;
+            }
+            const double pink = bfl > 0 ? nz[NOISE_PINK_AMP] * (double)sPink[n] : 0.0;
+            extra += dc + pink + nz[NOISE_DC_OFFSET];
+            if (tr != nullptr) { tr[TRACE_DC * c.N + n] = dc; tr[TRACE_PINK * c.N + n] = pink; }
+        }
+        const double mixed = cs * vi + sn * vq + extra;
         out[n] = (c.out_kind == 1) ? flux_freq(c, c.ch[CH_PHI] + mixed) - f_ref : mixed * c.ch[CH_V2HZ];
     }
 }

@@ -610,9 +610,17 @@ def signal_slice_num(t_start: float, t_end: float, resolution: float) -> int:
     return int(_lib.load().c3b_signal_slice_num(float(t_start), float(t_end), float(resolution)))
 
 
+NOISE_KEYS = ("awg_amp", "lo_perc", "add_amp", "dc_amp", "pink_amp", "bfl_num", "dc_offset")
+NOISE_TRACES = ("awg_i", "awg_q", "lo_cos", "lo_sin", "add", "dc", "pink")
+
+
 def generate_signals(env_params, env_shape, env_flags, lo_freq, chain, t_start: float, t_end: float, device=None,
-                     out=None) -> torch.Tensor:
-    """signals [B,K,N] from pulse parameters (c3b_generate_signals; see include/c3b200.h for the layouts)."""
+                     out=None, noise=None, seed: int = 0, return_noise: bool = False):
+    """signals [B,K,N] from pulse parameters (c3b_generate_signals; see include/c3b200.h for the layouts).
+
+    ``noise [K,7]`` or ``[B,K,7]`` (columns NOISE_KEYS) switches the noise devices on: one independent realisation per batch
+    row, drawn from the counter-based generator keyed by ``seed`` (same seed -> same realisation).  ``return_noise`` also
+    returns the realised traces ``[B,K,7,N]`` (NOISE_TRACES)."""
     lib = _lib.load()
     device = torch.device(device) if device is not None else default_device()
     with torch.cuda.device(device):
@@ -634,9 +642,21 @@ def generate_signals(env_params, env_shape, env_flags, lo_freq, chain, t_start: 
             raise ValueError("C3:ERROR: empty time grid")
         if out is None:
             out = torch.empty((B, K, N), dtype=torch.float64, device=device)
-        _lib.check(lib.c3b_generate_signals(_ptr(env_params), _ptr(env_shape), _ptr(env_flags), _ptr(lo_freq), _ptr(chain),
-                                            int(batched), float(t_start), float(t_end), B, K, E, N, _ptr(out), _stream()))
-    return out
+        traces = None
+        nbatched = 0
+        if noise is not None:
+            noise = _as(noise, torch.float64, device)
+            nbatched = int(noise.dim() == 3)
+            if tuple(noise.shape) != ((B, K, len(NOISE_KEYS)) if nbatched else (K, len(NOISE_KEYS))):
+                raise ValueError(f"C3:ERROR: noise has shape {tuple(noise.shape)}, expected [K,{len(NOISE_KEYS)}] or [B,K,{len(NOISE_KEYS)}]")
+            if return_noise:
+                traces = torch.empty((B, K, len(NOISE_TRACES), N), dtype=torch.float64, device=device)
+        elif return_noise:
+            raise ValueError("C3:ERROR: return_noise needs noise parameters")
+        _lib.check(lib.c3b_generate_signals_noisy(_ptr(env_params), _ptr(env_shape), _ptr(env_flags), _ptr(lo_freq), _ptr(chain),
+                                                  int(batched), float(t_start), float(t_end), B, K, E, N, _ptr(noise), nbatched,
+                                                  int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out), _ptr(traces), _stream()))
+    return (out, traces) if return_noise else out
 
 
 def generate_signals_grad(env_params, env_shape, env_flags, lo_freq, chain, t_start: float, t_end: float, gsignals,

@@ -8,12 +8,15 @@ samples, output already in the ``[B,K,N]`` layout the propagator kernels read (n
         the batch axis the reference's optimisers loop over serially
 
 Model / device / instruction objects are duck-typed exactly as the reference uses them:
-  devices[name]: class name in {LO, AWG, DigitalToAnalog, Response, ResponseFFT, Mixer, VoltsToHertz, FluxTuning},
+  devices[name]: class name in {LO, AWG, DigitalToAnalog, Response, ResponseFFT, Mixer, VoltsToHertz, FluxTuning,
+                 LONoise, Additive_Noise, DC_Noise, Pink_Noise, DC_Offset},
                  ``.resolution``, ``.params[key].get_value()``
   chains[chan]:  {dev: [sources]}  -- must be the standard topology (LO, AWG -> DAC -> [Response] -> Mixer -> out)
   instr.t_start, instr.t_end, instr.comps[chan][name]: Envelope (``.shape.__name__``, ``.params``) or Carrier
-Anything else (noise devices, crosstalk, arbitrary filters, other envelope shapes) raises ``C3:ERROR`` -- those
-chains stay on the reference's CPU path; there is no silent fallback.
+The noise devices LONoise, Additive_Noise (behind the AWG or the mixer), DC_Noise, Pink_Noise and DC_Offset are part of the
+kernel (one independent realisation per batch row: the Monte-Carlo trajectory axis).  Anything else (crosstalk, arbitrary
+filters, other envelope shapes) raises ``C3:ERROR`` -- those chains stay on the reference's CPU path; there is no silent
+fallback.
 """
 from __future__ import annotations
 
@@ -52,55 +55,115 @@ class Generator:
         self.chains = chains or {}
         self.resolution = resolution
         self.callback = callback
+        self.seed = 0                 # noise realisations are a function of (seed, number of calls so far, batch row, line)
+        self.noise_draws = 0
         self._specs = {chan: self._chain_spec(chan) for chan in self.chains}
 
-    # -- chain topology -> the 11 numbers the kernel needs ----------------------------------------------------------
+    # -- chain topology -> the 11 numbers the kernel needs (+ 7 for the noise devices) -------------------------------------
+    SIGNAL_NOISE = ("Additive_Noise", "DC_Noise", "Pink_Noise", "DC_Offset")
+
     def _chain_spec(self, chan: str) -> Dict[str, float]:
+        """Walk the chain of one drive line and check that it is the topology the kernel implements:
+
+            LO -> [LONoise] ----------------------------------------------.
+            AWG -> [Additive_Noise] -> DigitalToAnalog -> [Response | ResponseFFT] -> Mixer
+                -> {Additive_Noise, DC_Noise, Pink_Noise, DC_Offset}* -> VoltsToHertz | FluxTuning
+
+        (noise devices where test/noise_exp_2.hjson of the reference puts them; at most one of a kind per position)."""
         chain = self.chains[chan]
-        by_cls: Dict[str, List[str]] = {}
-        for dev_id in chain:
-            by_cls.setdefault(_cls(self.devices[dev_id]), []).append(dev_id)
-        allowed = {"LO", "AWG", "DigitalToAnalog", "Response", "ResponseFFT", "Mixer", "VoltsToHertz", "FluxTuning"}
-        extra = set(by_cls) - allowed
+        cls = {dev_id: _cls(self.devices[dev_id]) for dev_id in chain}
+
+        def fail(msg):
+            raise Exception(f"C3:ERROR: chain '{chan}' is not a topology of the on-device signal chain: {msg}.")
+
+        def only(kind):
+            ids = [d for d, c in cls.items() if c == kind]
+            if len(ids) != 1:
+                raise Exception(f"C3:ERROR: chain '{chan}' needs exactly one {kind} device.")
+            return ids[0]
+
+        def consumer(dev_id):
+            users = [d for d, src in chain.items() if dev_id in src]
+            if len(users) != 1:
+                fail(f"'{dev_id}' must feed exactly one device")
+            return users[0]
+
+        lo, awg, mixer = only("LO"), only("AWG"), only("Mixer")
+        if list(chain[lo]) or list(chain[awg]):
+            fail("LO and AWG are sources")
+        spec = dict(rise_time=0.0, resp_kind=0.0, out_kind=0.0, v2hz=1.0, phi=0.0, phi_0=1.0, omega_0=0.0, anhar=0.0, d=float("nan"))
+        noise = {k: 0.0 for k in engine.NOISE_KEYS}
+        noise["bfl_num"] = 5.0
+        spec["noise_devices"] = {}
+        # LO branch
+        cur = consumer(lo)
+        if cls[cur] == "LONoise":
+            noise["lo_perc"] = _val(self.devices[cur].params["noise_perc"])
+            spec["noise_devices"]["lo"] = cur
+            cur = consumer(cur)
+        if cur != mixer:
+            fail(f"'{cur}' between the LO and the mixer")
+        lo_end = [d for d in chain[mixer] if d == lo or cls.get(d) == "LONoise"]
+        # signal branch
+        cur = consumer(awg)
+        if cls[cur] == "Additive_Noise":
+            noise["awg_amp"] = _val(self.devices[cur].params["noise_amp"])
+            spec["noise_devices"]["awg"] = cur
+            cur = consumer(cur)
+        if cls[cur] != "DigitalToAnalog":
+            fail(f"'{cur}' ({cls[cur]}) where the DigitalToAnalog converter belongs")
+        dac = cur
+        cur = consumer(cur)
+        if cls[cur] in ("Response", "ResponseFFT"):
+            spec["rise_time"] = _val(self.devices[cur].params["rise_time"])
+            spec["resp_kind"] = 1.0 if cls[cur] == "Response" else 2.0
+            cur = consumer(cur)
+        if cur != mixer or len(chain[mixer]) != 2 or len(lo_end) != 1 or list(chain[mixer])[0] != lo_end[0]:
+            fail(f"the mixer must take [LO branch, signal branch], got {list(chain[mixer])}")
+        cur = consumer(mixer)
+        seen = set()
+        while cls[cur] in self.SIGNAL_NOISE:
+            kind = cls[cur]
+            if kind in seen:
+                fail(f"more than one {kind} behind the mixer")
+            seen.add(kind)
+            par = self.devices[cur].params
+            if kind == "Additive_Noise":
+                noise["add_amp"] = _val(par["noise_amp"])
+                spec["noise_devices"]["add"] = cur
+            elif kind == "DC_Noise":
+                noise["dc_amp"] = _val(par["noise_amp"])
+                spec["noise_devices"]["dc"] = cur
+            elif kind == "Pink_Noise":
+                noise["pink_amp"] = _val(par["noise_amp"])
+                if "bfl_num" in par:
+                    noise["bfl_num"] = float(int(_val(par["bfl_num"])))
+                spec["noise_devices"]["pink"] = cur
+            else:
+                noise["dc_offset"] = _val(par["offset_amp"])
+            cur = consumer(cur)
+        if cls[cur] not in ("VoltsToHertz", "FluxTuning") or any(cur in src for src in chain.values()):
+            fail(f"'{cur}' ({cls[cur]}) where the VoltsToHertz / FluxTuning output belongs")
+        known = {lo, awg, dac, mixer, cur} | set(spec["noise_devices"].values())
+        extra = [d for d in chain if d not in known and cls[d] not in ("Response", "ResponseFFT", "DC_Offset")]
         if extra:
             raise Exception(f"C3:ERROR: devices {sorted(extra)} in chain '{chan}' are not part of the on-device signal chain.")
-        for need in ("LO", "AWG", "DigitalToAnalog", "Mixer"):
-            if len(by_cls.get(need, [])) != 1:
-                raise Exception(f"C3:ERROR: chain '{chan}' needs exactly one {need} device.")
-        if ("VoltsToHertz" in by_cls) == ("FluxTuning" in by_cls):
-            raise Exception(f"C3:ERROR: chain '{chan}' needs either a VoltsToHertz or a FluxTuning output device.")
-        lo, awg, dac, mixer = (by_cls[c][0] for c in ("LO", "AWG", "DigitalToAnalog", "Mixer"))
-        resp_cls = "Response" if "Response" in by_cls else ("ResponseFFT" if "ResponseFFT" in by_cls else None)
-        out_cls = "VoltsToHertz" if "VoltsToHertz" in by_cls else "FluxTuning"
-        out = by_cls[out_cls][0]
-        want = {lo: [], awg: [], dac: [awg], mixer: None, out: [mixer]}
-        if resp_cls:
-            resp = by_cls[resp_cls][0]
-            want[resp] = [dac]
-            want[mixer] = [lo, resp]
-        else:
-            want[mixer] = [lo, dac]
-        for dev_id, src in want.items():
-            if list(chain[dev_id]) != src:
-                raise Exception(f"C3:ERROR: chain '{chan}' is not the standard topology at '{dev_id}': {chain[dev_id]} != {src}.")
         sim_res = float(self.devices[dac].resolution)
         if float(self.devices[lo].resolution) != sim_res:
             raise Exception("C3:ERROR: LO and DigitalToAnalog must share the simulation resolution.")
-        spec = dict(sim_res=sim_res, awg_res=float(self.devices[awg].resolution), rise_time=0.0, resp_kind=0.0,
-                    out_kind=0.0, v2hz=1.0, phi=0.0, phi_0=1.0, omega_0=0.0, anhar=0.0, d=float("nan"))
+        spec.update(sim_res=sim_res, awg_res=float(self.devices[awg].resolution))
         if spec["awg_res"] > sim_res:
             raise Exception("C3:ERROR: the AWG grid must not be finer than the simulation grid.")
-        if resp_cls:
-            spec["rise_time"] = _val(self.devices[resp].params["rise_time"])
-            spec["resp_kind"] = 1.0 if resp_cls == "Response" else 2.0
-        if out_cls == "VoltsToHertz":
-            spec["v2hz"] = _val(self.devices[out].params["V_to_Hz"])
+        if cls[cur] == "VoltsToHertz":
+            spec["v2hz"] = _val(self.devices[cur].params["V_to_Hz"])
         else:
-            par = self.devices[out].params
+            par = self.devices[cur].params
             spec.update(out_kind=1.0, phi=_val(par["phi"]), phi_0=_val(par["phi_0"]), omega_0=_val(par["omega_0"]),
                         anhar=_val(par["anhar"]))
             if "d" in par:
                 spec["d"] = _val(par["d"])
+        spec["noise"] = noise
+        spec["noisy"] = any(noise[k] != 0.0 for k in engine.NOISE_KEYS if k != "bfl_num") or bool(spec["noise_devices"])
         return spec
 
     # -- instruction -> envelope table ----------------------------------------------------------------------------
@@ -157,6 +220,31 @@ class Generator:
             raise Exception("C3:ERROR: all channels of an instruction must share the simulation resolution.")
         return chans, env, shape, flags, lo, chain
 
+    def _noise_table(self, chans):
+        """[K,7] noise parameters of the instruction's drive lines, or None for a noise-free chain.  Re-read from the device
+        objects on every call: an optimiser may have changed a noise amplitude (test/test_noise.py:93-104)."""
+        self._specs = {chan: self._chain_spec(chan) for chan in self.chains}
+        if not any(self._specs[c]["noisy"] for c in chans):
+            return None
+        return np.array([[self._specs[c]["noise"][k] for k in engine.NOISE_KEYS] for c in chans])
+
+    def _publish_noise(self, chans, traces, chain) -> None:
+        """Leave the realised noise on the device objects as the reference does (Device.signal["noise"],
+        "noise-inphase" / "noise-quadrature" for the AWG noise; c3/generator/devices.py:975-996): first batch row."""
+        t = {name: i for i, name in enumerate(engine.NOISE_TRACES)}
+        for k, chan in enumerate(chans):
+            where = self._specs[chan]["noise_devices"]
+            span = traces.shape[-1] / float(chain[k, 0])
+            n_awg = int(span * float(chain[k, 1]) + 1e-9)
+            for slot, dev_id in where.items():
+                dev = self.devices[dev_id]
+                if slot == "awg":
+                    dev.signal = {"noise-inphase": traces[0, k, t["awg_i"], :n_awg], "noise-quadrature": traces[0, k, t["awg_q"], :n_awg]}
+                elif slot == "lo":
+                    dev.signal = {"noise": (traces[0, k, t["lo_cos"]], traces[0, k, t["lo_sin"]])}
+                else:
+                    dev.signal = {"noise": traces[0, k, t[slot]]}
+
     # -- public API ---------------------------------------------------------------------------------------------------
     def generate_signals(self, instr) -> dict:
         """Perform the signal chain for a specified instruction, including local oscillator, AWG generation
@@ -178,7 +266,17 @@ class Generator:
 
     def _run(self, instr, samples):
         chans, env, shape, flags, lo, chain = self._tables(instr, samples)
-        sig = engine.generate_signals(env, shape, flags, lo, chain, float(instr.t_start), float(instr.t_end))
+        noise = self._noise_table(chans)
+        if noise is None:
+            sig = engine.generate_signals(env, shape, flags, lo, chain, float(instr.t_start), float(instr.t_end))
+        else:
+            # a fresh realisation per call (the reference draws from numpy's global generator on every call); every batch
+            # row is an independent realisation of the same call
+            self.noise_draws += 1
+            seed = (int(self.seed) + 0x9E3779B97F4A7C15 * self.noise_draws) & 0xFFFFFFFFFFFFFFFF
+            sig, traces = engine.generate_signals(env, shape, flags, lo, chain, float(instr.t_start), float(instr.t_end),
+                                                  noise=noise, seed=seed, return_noise=True)
+            self._publish_noise(chans, traces, chain)
         N = sig.shape[-1]
         dt = 1.0 / chain[0, 0]
         ts = torch.as_tensor(np.linspace(float(instr.t_start) + dt / 2, float(instr.t_end) - dt / 2, N)).to(sig.device)

@@ -176,6 +176,26 @@ int c3b_generate_signals(const double* env_params, const int32_t* env_shape, con
                          const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
                          int B, int K, int E, int N, double* signals_out, void* stream);
 
+/* Same chain with the reference's NOISE devices in it (c3/generator/devices.py:943-1035; exercised by test/test_noise.py:93-138),
+ * one independent realisation per batch row -- the Monte-Carlo trajectory axis of the batch:
+ *   noise [K,7] (or [B,K,7] if noise_batched), per drive line:
+ *     0 awg_amp   Additive_Noise behind the AWG: amp * N(0,1) on every in-phase and quadrature AWG sample
+ *     1 lo_perc   LONoise: perc * N(0,1) on the local oscillator's cos and sin at every simulation sample
+ *     2 add_amp   Additive_Noise behind the mixer: amp * N(0,1) per simulation sample
+ *     3 dc_amp    DC_Noise: one amp * N(0,1) offset per realisation
+ *     4 pink_amp  Pink_Noise: amp * (sum of bfl_num two-level fluctuators), fluctuator i flipping at a step with probability
+ *     5 bfl_num       1 / rate_i, rate = logspace(0, ln N, bfl_num + 1, base 10)[1:]  (<= 32 fluctuators)
+ *     6 dc_offset DC_Offset: deterministic offset behind the mixer
+ *   amplitudes below 1e-17 switch a device off exactly (as the reference does).
+ *   seed: the random numbers are Philox4x32-10 words of (seed, batch row * K + line, device stream, sample index): no state,
+ *   reproducible, independent across rows, lines, devices and samples; advance the seed for a new realisation.
+ *   noise_out [B,K,7,N] or NULL: the realised traces (AWG in-phase / quadrature on the AWG grid in the first n_awg entries,
+ *   LO cos / sin, additive, dc, pink) -- what Device.signal["noise"] holds in the reference. */
+int c3b_generate_signals_noisy(const double* env_params, const int32_t* env_shape, const int32_t* env_flags,
+                               const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
+                               int B, int K, int E, int N, const double* noise, int noise_batched, unsigned long long seed,
+                               double* signals_out, double* noise_out, void* stream);
+
 /* Reverse mode of c3b_generate_signals: from dL/d signals [B,K,N] (e.g. the output of c3b_pwc_closed_grad) to the
  * gradient with respect to the pulse parameters -- what tf.GradientTape propagates through
  * Generator.generate_signals in the reference's gradient-based optimal control (c3/optimizers/optimalcontrol.py:200-228).

@@ -219,3 +219,37 @@ def drive_instruction(name, t_end, lines, freq=5e9, framechange=0.0, amp=0.5, fr
             "xy_angle": Quantity(0.0, "rad"), "freq_offset": Quantity(freq_offset, "Hz 2pi"), "delta": Quantity(0.0, "")}), line)
         instr.add_component(Carrier("carrier", {"freq": Quantity(f, "Hz 2pi"), "framechange": Quantity(fc, "rad")}), line)
     return instr
+
+
+class LONoise(_Dev):
+    pass
+
+
+class DC_Noise(_Dev):
+    pass
+
+
+class Pink_Noise(_Dev):
+    pass
+
+
+class DC_Offset(_Dev):
+    pass
+
+
+def noisy_generator_setup(awg_amp=0.0, dc_amp=0.0, pink_amp=0.0, add_amp=0.0, lo_perc=0.0, bfl_num=15, offset=0.0):
+    """The drive line of test/noise_exp_2.hjson of the reference (without its high-pass filter): AWG -> AWGNoise ->
+    DigitalToAnalog -> Response -> Mixer -> DCNoise -> PinkNoise -> DCOffset -> VoltsToHertz, plus an LO noise device."""
+    devices, _, instr = reference_generator_setup()
+    devices.update({
+        "LONoise": LONoise("lo_noise", 100e9, noise_perc=Quantity(lo_perc, "")),
+        "AWGNoise": Additive_Noise("awg_noise", 100e9, noise_amp=Quantity(awg_amp, "V")),
+        "AddNoise": Additive_Noise("add_noise", 100e9, noise_amp=Quantity(add_amp, "V")),
+        "DCNoise": DC_Noise("dc_noise", 100e9, noise_amp=Quantity(dc_amp, "V")),
+        "PinkNoise": Pink_Noise("pink_noise", 100e9, noise_amp=Quantity(pink_amp, "V"), bfl_num=Quantity(bfl_num, "")),
+        "DCOffset": DC_Offset("dc_offset", 100e9, offset_amp=Quantity(offset, "V")),
+    })
+    chain = {"LO": [], "LONoise": ["LO"], "AWG": [], "AWGNoise": ["AWG"], "DigitalToAnalog": ["AWGNoise"],
+             "Response": ["DigitalToAnalog"], "Mixer": ["LONoise", "Response"], "AddNoise": ["Mixer"], "DCNoise": ["AddNoise"],
+             "PinkNoise": ["DCNoise"], "DCOffset": ["PinkNoise"], "VoltsToHertz": ["DCOffset"]}
+    return devices, {"d1": chain}, instr
