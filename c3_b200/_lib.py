@@ -17,7 +17,7 @@ SYMBOLS = [
     "c3b_gate_infid", "c3b_gate_infid_grad", "c3b_seq_populations", "c3b_signal_slice_num", "c3b_generate_signals",
     "c3b_generate_signals_grad", "c3b_pwc_lindblad_grad_workspace_bytes", "c3b_pwc_lindblad_grad",
     "c3b_dress_models", "c3b_pwc_closed_gated", "c3b_pwc_gated_supported",
-    "c3b_generate_signals_noisy", "c3b_model_bytes", "c3b_model_prepare", "c3b_pwc_prepared_workspace_bytes", "c3b_pwc_prepared",
+    "c3b_generate_signals_noisy", "c3b_frame_dephase", "c3b_model_bytes", "c3b_model_prepare", "c3b_pwc_prepared_workspace_bytes", "c3b_pwc_prepared",
 ]
 
 _lib = None
@@ -61,6 +61,8 @@ def load() -> C.CDLL:
     lib.c3b_pwc_lindblad_grad_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.c3b_pwc_lindblad_grad.restype = i
     lib.c3b_pwc_lindblad_grad.argtypes = [vp, vp, vp, i, vp, d, i, i, i, i, vp, vp, vp, i, vp, sz, vp]
+    lib.c3b_frame_dephase.restype = i
+    lib.c3b_frame_dephase.argtypes = [vp, i, i, i, vp, i, vp, vp, i, vp]
     lib.c3b_dress_models.restype = i
     lib.c3b_dress_models.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp]
     lib.c3b_gate_infid.restype = i

@@ -4,6 +4,7 @@
 #include "fidelity.cuh"
 #include "signal_chain.cuh"
 #include "dressing.cuh"
+#include "frame.cuh"
 #include "peak.cuh"
 
 using namespace c3b;
@@ -125,6 +126,24 @@ int c3b_generate_signals_grad(const double* env_params, const int32_t* env_shape
     if (smem > 200 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: gate too long for the on-chip signal-chain gradient (N=%d)", N);
     CUDA_TRY(cudaFuncSetAttribute(signal_chain_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     signal_chain_grad_kernel<<<B * K, 128, smem, static_cast<cudaStream_t>(stream)>>>(gp);
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return C3B_OK;
+}
+
+// ---- frame rotation / dephasing channel on the device ----------------------------------------
+int c3b_frame_dephase(void* U, int B, int D, int d, const int32_t* occ, int L, const double* phases, const double* probs,
+                      int lindblad, void* stream) {
+    if (B <= 0 || D <= 0 || d <= 0 || L < 0) return fail(C3B_EINVAL, "C3:ERROR: bad size (B=%d D=%d d=%d L=%d)", B, D, d, L);
+    if (!U || (L > 0 && !occ)) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (lindblad ? (D != d * d) : (D != d)) return fail(C3B_EINVAL, "C3:ERROR: D=%d does not match d=%d (lindblad=%d)", D, d, lindblad);
+    if (probs != nullptr && !lindblad) return fail(C3B_EINVAL, "C3:ERROR: Dephasing can only be added when lindblad is on.");
+    if (L == 0 || (phases == nullptr && probs == nullptr)) return C3B_OK;
+    const long long warps = (long long)B * D;
+    long long blocks = (warps * 32 + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    frame_dephase_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<cplx*>(U), occ, phases, probs, B, D, d, L,
+                                                                                  lindblad);
     CUDA_TRY(cudaGetLastError());
     count_launch();
     return C3B_OK;

@@ -714,6 +714,42 @@ def generate_signals_autograd(env_params: torch.Tensor, lo_freq: torch.Tensor, e
     return _SignalChainFn.apply(env_params, lo_freq, env_shape, env_flags, chain, float(t_start), float(t_end))
 
 
+def frame_dephase(U: torch.Tensor, occ, phases=None, probs=None, lindblad: bool = False) -> torch.Tensor:
+    """IN PLACE: U[b] <- dephasing_b . FR_b . U[b] for a batch of propagators ``U [B,D,D]`` (or [D,D]), with the frame
+    rotation and dephasing channel of c3/model.py:536-578, 597-639 given by their exponents: ``occ [L,d]`` occupation numbers
+    of the driven qubits, ``phases [B,L]`` (freq t_final + framechange) and, for Lindblad superoperators, ``probs [B,L]``.
+    Returns U."""
+    lib = _lib.load()
+    if not (isinstance(U, torch.Tensor) and U.is_cuda and U.dtype == torch.complex128 and U.is_contiguous()):
+        raise ValueError("C3:ERROR: frame_dephase needs a contiguous complex128 CUDA tensor")
+    device = U.device
+    with torch.cuda.device(device):
+        Uv = U if U.dim() == 3 else U.unsqueeze(0)
+        B, D, _ = Uv.shape
+        occ = _as(occ, torch.int32, device)
+        if occ.dim() != 2:
+            raise ValueError("C3:ERROR: occ must be [L,d]")
+        L, d = occ.shape
+        if D != (d * d if lindblad else d):
+            raise ValueError(f"C3:ERROR: propagators of dimension {D} do not match d = {d} (lindblad = {lindblad})")
+
+        def rows(x, name):
+            if x is None:
+                return None
+            x = _as(x, torch.float64, device)
+            if x.dim() == 1:
+                x = x.unsqueeze(0).expand(B, L).contiguous()
+            if tuple(x.shape) != (B, L):
+                raise ValueError(f"C3:ERROR: {name} has shape {tuple(x.shape)}, expected {(B, L)}")
+            return x
+
+        phases, probs = rows(phases, "phases"), rows(probs, "probs")
+        if probs is not None and bool(((probs < 0) | (probs > 1)).any()):
+            raise ValueError("Dephasing channel strength is outside [0,1] range")
+        _lib.check(lib.c3b_frame_dephase(_ptr(Uv), B, D, d, _ptr(occ), L, _ptr(phases), _ptr(probs), int(bool(lindblad)), _stream()))
+    return U
+
+
 def dress_models(drift, ops=None, ordered: bool = True, device=None):
     """Dressed frame of every drift Hamiltonian ``drift [B,d,d]`` (or [d,d]) and T^dag X T of ``ops [M,d,d]`` /
     ``[B,M,d,d]`` (c3/model.py:453-534).  Returns dict(eigenframe [B,d], transform [B,d,d], drift [B,d,d],

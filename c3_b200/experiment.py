@@ -254,13 +254,70 @@ class Experiment:
             framechanges[line] = complex(_number(carrier["framechange"]))
         return freqs, framechanges
 
+    @staticmethod
+    def _line_occupations(model, lines) -> Optional[np.ndarray]:
+        """occ[l, s] = occupation number of the qubit driven by line l in product state s: the diagonal of the bare number
+        operator Model.get_Frame_Rotation / get_dephasing_channel exponentiate (c3/model.py:553-570, 620-628).  ``None`` when
+        the model does not expose the pieces (then the host matrices from the model's own methods are used)."""
+        try:
+            occ = []
+            for line in lines:
+                if hasattr(model, "line_to_index"):
+                    idx = model.line_to_index[line]
+                elif line in getattr(model, "couplings", {}):
+                    idx = model.names.index(model.couplings[line].connected[0])
+                elif line in getattr(model, "subsystems", {}):
+                    idx = model.names.index(line)
+                else:
+                    return None
+                a = prop._host(model.ann_opers[idx])
+                num = a.T.conj() @ a
+                diag = np.real(np.diag(num))
+                if np.abs(num - np.diag(np.diag(num))).max() > 1e-12 or np.abs(diag - np.rint(diag)).max() > 1e-12:
+                    return None
+                occ.append(np.rint(diag).astype(np.int32))
+            return np.stack(occ) if occ else None
+        except (AttributeError, KeyError, ValueError, IndexError):
+            return None
+
     def _apply_frame_and_dephasing(self, model, jobs: Sequence[_Job]) -> None:
+        """U <- dephasing . FR . U for every gate (c3/experiment.py:482-522).  Both factors are diagonal in the product basis,
+        so when the model exposes its number operators the whole gate set is ONE row-scaling launch on the device
+        (engine.frame_dephase); otherwise the model's own matrices are multiplied on by one batched product launch."""
         use_fr = bool(getattr(model, "use_FR", False))
         deph = getattr(model, "dephasing_strength", 0.0) != 0.0
         if deph and not model.lindbladian:
             raise ValueError("Dephasing can only be added when lindblad is on.")
         if not jobs or not (use_fr or deph):
             return
+        lines = list(jobs[0].instr.comps.keys())
+        same_lines = all(list(j.instr.comps.keys()) == lines for j in jobs)
+        same_shape = all(j.U.shape == jobs[0].U.shape for j in jobs)
+        occ = self._line_occupations(model, lines) if (same_lines and same_shape) else None
+        if occ is None:
+            return self._apply_host_factors(model, jobs, use_fr, deph)
+        phases = np.zeros((len(jobs), len(lines)))
+        probs = np.zeros((len(jobs), len(lines))) if deph else None
+        for g, job in enumerate(jobs):
+            t_final = float(job.instr.t_end - job.instr.t_start)
+            if use_fr:
+                freqs, framechanges = self._frame_arguments(job.instr)
+                phases[g] = [np.real(freqs[l] * t_final + framechanges[l]) for l in lines]
+            if deph:
+                amp, _ = self.pmap.generator.devices["awg"].get_average_amp()
+                probs[g] = t_final * float(np.real(_number(amp))) * float(model.dephasing_strength)
+        if deph and (probs.min() < 0 or probs.max() > 1):
+            raise ValueError(f"Dephasing channel strength {probs.max()} is outside [0,1] range")
+        U = torch.stack([j.U for j in jobs]).contiguous()
+        engine.frame_dephase(U, occ, phases if use_fr else None, probs, lindblad=bool(model.lindbladian))
+        for g, job in enumerate(jobs):
+            job.U = U[g]
+        if use_fr:       # the attribute the reference leaves behind: the last gate's (super-)frame rotation, as a matrix
+            f = np.exp(1j * (occ.T @ phases[-1]))
+            fr = np.diag(f)
+            self.FR = torch.as_tensor(np.kron(fr, fr.conj()) if model.lindbladian else fr, device=U.device)
+
+    def _apply_host_factors(self, model, jobs: Sequence[_Job], use_fr: bool, deph: bool) -> None:
         dev = jobs[0].U.device
         chains = []                                  # per gate: [U, FR?, dephasing?] -- later factors act from the left
         for job in jobs:
@@ -332,16 +389,44 @@ class Experiment:
             job = _Job(name, instr)
             job.U = U
             if getattr(model, "use_FR", False) or getattr(model, "dephasing_strength", 0.0) != 0.0:
-                U = self._apply_constant_factors(model, job)
+                U = self._apply_constant_factors(model, job, samples)
             out[name] = goal(name, U) if goal is not None else U
         return out
 
-    def _apply_constant_factors(self, model, job: _Job) -> torch.Tensor:
-        """FR / dephasing of one gate onto all samples U [B,D,D]: the same factor chain per sample, one launch."""
+    def _apply_constant_factors(self, model, job: _Job, samples: Optional[Dict] = None) -> torch.Tensor:
+        """FR / dephasing of one gate onto all samples U [B,D,D].  With the model's number operators at hand the frame phases
+        are PER SAMPLE (sampled carrier frequency / frame change) and the whole batch is one row-scaling launch; otherwise the
+        gate's constant factor from the model's own methods is multiplied onto every sample by one product launch."""
         U = job.U
+        B = U.shape[0]
+        lines = list(job.instr.comps.keys())
+        occ = self._line_occupations(model, lines)
+        use_fr = bool(getattr(model, "use_FR", False))
+        deph = getattr(model, "dephasing_strength", 0.0) != 0.0
+        if deph and not model.lindbladian:
+            raise ValueError("Dephasing can only be added when lindblad is on.")
+        if occ is not None:
+            t_final = float(job.instr.t_end - job.instr.t_start)
+            phases = None
+            if use_fr:
+                freqs, framechanges = self._frame_arguments(job.instr)
+                phases = np.zeros((B, len(lines)))
+                for l, line in enumerate(lines):
+                    f = np.full(B, np.real(freqs[line]))
+                    fc = np.full(B, np.real(framechanges[line]))
+                    if samples and (line, "carrier", "freq") in samples:       # the envelope's frequency offset stays on top
+                        base = _number(job.instr.comps[line]["carrier"].params["freq"])
+                        f = f - base + np.asarray(samples[(line, "carrier", "freq")], dtype=np.float64)
+                    if samples and (line, "carrier", "framechange") in samples:
+                        fc = np.asarray(samples[(line, "carrier", "framechange")], dtype=np.float64)
+                    phases[:, l] = f * t_final + fc
+            probs = None
+            if deph:
+                amp, _ = self.pmap.generator.devices["awg"].get_average_amp()
+                probs = np.full((B, len(lines)), t_final * float(np.real(_number(amp))) * float(model.dephasing_strength))
+            return engine.frame_dephase(U.contiguous(), occ, phases, probs, lindblad=bool(model.lindbladian))
         probe = _Job(job.name, job.instr)
         probe.U = torch.eye(U.shape[-1], dtype=torch.complex128, device=U.device)
-        self._apply_frame_and_dephasing(model, [probe])                              # F = (dephasing) (FR)
-        B = U.shape[0]
+        self._apply_host_factors(model, [probe], use_fr, deph)                       # F = (dephasing) (FR)
         chain = torch.stack([U, probe.U.unsqueeze(0).expand(B, -1, -1)], dim=1)      # [B,2,D,D]: F U
         return engine.ordered_product(chain)

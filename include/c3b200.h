@@ -228,6 +228,18 @@ int c3b_dress_models(const void* drift, const void* ops, int ops_batched, int B,
                      double* eigenframe, void* transform, void* dressed_drift, void* dressed_ops, int32_t* info,
                      void* stream);
 
+/* Frame rotation and dephasing channel of Experiment.compute_propagators (c3/experiment.py:482-522; Model.get_Frame_Rotation
+ * c3/model.py:536-578, Model.get_dephasing_channel :597-639) applied IN PLACE to a batch of propagators.  Both operators are
+ * functions of bare number operators, i.e. diagonal in the product basis, so the left-multiplication is a row scaling:
+ *   closed (lindblad = 0, D = d):   U[b][r, :]     *= exp(1j sum_l occ[l,r] phases[b,l])
+ *   Lindblad (D = d^2, r = i d + j): S[b][r, :]     *= exp(1j sum_l (occ[l,i] - occ[l,j]) phases[b,l])
+ *                                                     * prod_l ((1 - probs[b,l]) + probs[b,l] (-1)^(occ[l,i] - occ[l,j]))
+ *   occ    [L,d] int32   occupation number of the qubit driven by line l in product state s (diag of a_q^dag a_q)
+ *   phases [B,L]         freq_l * t_final + framechange_l per batch row (gate or parameter sample), or NULL (no frame rotation)
+ *   probs  [B,L]         t_final * amp_l * dephasing_strength in [0,1], or NULL (no dephasing); Lindblad only. */
+int c3b_frame_dephase(void* U, int B, int D, int d, const int32_t* occ, int L, const double* phases, const double* probs,
+                      int lindblad, void* stream);
+
 /* Ordered product of M matrices per batch row: out[b] = mats[b,M-1] ... mats[b,0].
  *   replaces tf_matmul_left (c3/utils/tf_utils.py:120-129) and tf_matmul_n (:144-193).
  *   mats [B,M,D,D], out [B,D,D]. */

@@ -169,7 +169,7 @@ class ArrayModel:
     optional explicit Hamiltonian list, frame rotation and dephasing channel from the oracle's restatement."""
 
     def __init__(self, h0, hks, col_ops=(), dims=None, lindbladian=False, max_excitations=0, hlist=None, use_FR=False,
-                 dephasing_strength=0.0, line_to_index=None):
+                 dephasing_strength=0.0, line_to_index=None, exact_frames=False):
         from oracle import c3_oracle as orc
         from oracle import c3_model_oracle as mo
         self._orc = orc
@@ -183,6 +183,9 @@ class ArrayModel:
         self.ex_cutter = orc.make_ex_cutter(self.dims, max_excitations) if max_excitations else None
         self.ann_opers = mo.annihilators(self.dims)
         self.line_to_index = line_to_index or {}
+        # frame rotation / dephasing exponentials: the oracle's restatement of tf.linalg.expm (default: what the reference
+        # computes, truncation error of TensorFlow's floor-scaled Pade included) or scipy's expm (accurate to rounding)
+        self.exact_frames = exact_frames
 
     def _cut(self, x):
         return self._orc.cut_excitations(self.ex_cutter, x) if self.max_excitations else x
@@ -196,11 +199,17 @@ class ArrayModel:
     def get_Lindbladians(self):
         return list(self.col_ops)
 
+    def _expm(self):
+        if not self.exact_frames:
+            return None
+        import scipy.linalg
+        return scipy.linalg.expm
+
     def get_Frame_Rotation(self, t_final, freqs, framechanges):
-        return self._orc.frame_rotation(self.ann_opers, self.line_to_index, t_final, freqs, framechanges)
+        return self._orc.frame_rotation(self.ann_opers, self.line_to_index, t_final, freqs, framechanges, expm=self._expm())
 
     def get_dephasing_channel(self, t_final, amps):
-        return self._orc.dephasing_channel(self.ann_opers, self.line_to_index, t_final, amps, self.dephasing_strength)
+        return self._orc.dephasing_channel(self.ann_opers, self.line_to_index, t_final, amps, self.dephasing_strength, expm=self._expm())
 
 
 class PMap:

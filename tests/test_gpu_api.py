@@ -139,9 +139,17 @@ def test_frame_rotation_and_dephasing(api, lindbladian, dephasing):
     model.dephasing_strength = dephasing
     exp = experiment.Experiment(fk.PMap(model, gen, instrs), sim_res=100e9)
     props = exp.compute_propagators()
+    # The engine applies the EXACT diagonal exponentials.  The reference builds FR with tf.linalg.expm, whose floor-scaled
+    # Pade loses accuracy at the norms a frame rotation has (|freq t_final| n ~ 25 here, ~ 400 for a 7 ns gate): its own
+    # truncation error, 1e-8 here, is the only difference -- so the expectation uses accurate exponentials, and the
+    # TensorFlow-restated ones are checked to agree to that error.
+    model.exact_frames = True
     want, want_partial = orc.compute_propagators(model, gen, instrs, 100e9)
+    model.exact_frames = False
+    want_tf, _ = orc.compute_propagators(model, gen, instrs, 100e9)
     for name in instrs:
         assert rel_fro(props[name].cpu().numpy(), want[name]) < TOL, name
+        assert rel_fro(props[name].cpu().numpy(), want_tf[name]) < 1e-6, name
         assert rel_fro(exp.partial_propagators[name].cpu().numpy(), want_partial[name]) < TOL, name
     # FR really does something here (otherwise the left-multiplication order would go untested)
     bare, _ = orc.compute_propagators(fk.ArrayModel(model.h0, model.hks, col_ops=model.col_ops, dims=[3, 3], lindbladian=lindbladian),
@@ -308,3 +316,110 @@ def test_unknown_gate_message(api):
     exp.set_opt_gates(["nope"])
     with pytest.raises(Exception, match="C3:Error: Gate 'nope' is not defined"):
         exp.compute_propagators()
+
+
+@pytest.mark.parametrize("lindbladian", [False, True])
+def test_frame_rotation_host_fallback_matches_device_path(api, lindbladian):
+    """A model that only offers get_Frame_Rotation / get_dephasing_channel (no number operators to read): the factors come
+    from the model's own methods and are multiplied on by one product launch -- same result as the row-scaling kernel."""
+    _, _, experiment = api
+
+    class OpaqueModel(fk.ArrayModel):
+        """hides the pieces the device path reads"""
+        def __getattribute__(self, name):
+            if name in ("line_to_index", "couplings", "subsystems", "names") and object.__getattribute__(self, "_hide"):
+                raise AttributeError(name)
+            return object.__getattribute__(self, name)
+
+    model, gen, instrs = _transmon_pair(lindbladian, 0, N=30)
+    opaque = OpaqueModel(model.h0, model.hks, col_ops=model.col_ops, dims=[3, 3], lindbladian=lindbladian,
+                         line_to_index={"d1": 0, "d2": 1})
+    for m in (model, opaque):
+        m.use_FR = True
+        m.dephasing_strength = 0.03 if lindbladian else 0.0
+    object.__setattr__(opaque, "_hide", False)
+    object.__setattr__(model, "_hide", False)
+    exp_dev = experiment.Experiment(fk.PMap(model, gen, instrs), sim_res=100e9)
+    got_dev = exp_dev.compute_propagators()
+    object.__setattr__(opaque, "_hide", True)
+    exp_host = experiment.Experiment(fk.PMap(opaque, gen, instrs), sim_res=100e9)
+    orig = fk.ArrayModel.get_Frame_Rotation
+
+    def fr_with_map(self, t_final, freqs, framechanges):
+        object.__setattr__(self, "_hide", False)
+        try:
+            return orig(self, t_final, freqs, framechanges)
+        finally:
+            object.__setattr__(self, "_hide", True)
+    OpaqueModel.get_Frame_Rotation = fr_with_map
+    origd = fk.ArrayModel.get_dephasing_channel
+
+    def deph_with_map(self, t_final, amps):
+        object.__setattr__(self, "_hide", False)
+        try:
+            return origd(self, t_final, amps)
+        finally:
+            object.__setattr__(self, "_hide", True)
+    OpaqueModel.get_dephasing_channel = deph_with_map
+    got_host = exp_host.compute_propagators()
+    # the host path reproduces whatever matrices the model hands out (here: the TensorFlow-restated exponentials) ...
+    want_tf, _ = orc.compute_propagators(model, gen, instrs, 100e9)
+    # ... the device path the exact ones
+    model.exact_frames = True
+    want, _ = orc.compute_propagators(model, gen, instrs, 100e9)
+    for name in instrs:
+        assert rel_fro(got_host[name].cpu().numpy(), want_tf[name]) < TOL
+        assert rel_fro(got_dev[name].cpu().numpy(), want[name]) < TOL
+        assert rel_fro(got_dev[name].cpu().numpy(), got_host[name].cpu().numpy()) < 1e-6
+    assert rel_fro(exp_dev.FR.cpu().numpy(), exp_host.FR.cpu().numpy()) < 1e-6
+
+
+def test_frame_dephase_kernel_directly(api):
+    """engine.frame_dephase against explicit matrices: FR U (closed), dephasing . SFR . S (Lindblad), per-row phases."""
+    engine, _, _ = api
+    from oracle import c3_model_oracle as mo
+    rng = np.random.default_rng(0)
+    dims = [3, 2]
+    d = 6
+    ann = mo.annihilators(dims)
+    occ = np.stack([np.rint(np.real(np.diag(a.T.conj() @ a))).astype(np.int32) for a in ann])
+    B = 5
+    phases = rng.uniform(-3, 3, size=(B, 2))
+    probs = rng.uniform(0, 0.3, size=(B, 2))
+    U = rng.normal(size=(B, d, d)) + 1j * rng.normal(size=(B, d, d))
+    got = engine.frame_dephase(torch.as_tensor(U).cuda(), occ, phases).cpu().numpy()
+    S = rng.normal(size=(B, d * d, d * d)) + 1j * rng.normal(size=(B, d * d, d * d))
+    gotS = engine.frame_dephase(torch.as_tensor(S).cuda(), occ, phases, probs, lindblad=True).cpu().numpy()
+    for b in range(B):
+        # exact diagonal exponential (the oracle's expm_tf restates TensorFlow's Pade evaluation, which is only good to ~1e-11
+        # at these norms -- the kernel's sincos of the exponent is the more accurate of the two)
+        FR = np.diag(np.exp(1j * (occ.T @ phases[b])))
+        assert rel_fro(got[b], FR @ U[b]) < 1e-13
+        assert rel_fro(FR, orc.frame_rotation(ann, {"a": 0, "b": 1}, 1.0, {"a": phases[b, 0], "b": phases[b, 1]}, {"a": 0.0, "b": 0.0})) < 1e-9
+        deph = orc.dephasing_channel(ann, {"a": 0, "b": 1}, 1.0, {"a": probs[b, 0], "b": probs[b, 1]}, 1.0)
+        assert rel_fro(gotS[b], deph @ orc.tf_super(FR) @ S[b]) < 1e-12
+    with pytest.raises(Exception, match="Dephasing can only be added when lindblad is on"):
+        engine.frame_dephase(torch.as_tensor(U).cuda(), occ, phases, probs)
+
+
+def test_batch_with_per_sample_frame_rotation(api):
+    """compute_propagators_batch with use_FR and a sampled carrier frequency: every sample gets ITS frame rotation on the
+    device (the phases differ per row), equal to the single-gate path evaluated at that sample's parameters."""
+    engine, prop, experiment = api
+    from c3_b200 import synth
+    from c3_b200.generator import Generator
+    devices, chains, instr = fk.reference_generator_setup()
+    gen = Generator(devices, chains)
+    m = synth.one_qubit()
+    model = fk.ArrayModel(m.h0, {"d1": m.hks[0]}, dims=[3], line_to_index={"d1": 0})
+    model.use_FR = True
+    exp = experiment.Experiment(fk.PMap(model, gen, {"rx90p": instr}), sim_res=100e9)
+    B = 9
+    base = float(instr.comps["d1"]["carrier"].params["freq"].get_value())
+    freqs = base + 2 * np.pi * np.linspace(-5e6, 5e6, B)
+    U = exp.compute_propagators_batch({("d1", "carrier", "freq"): freqs})["rx90p"]
+    for b in (0, 4, 8):
+        instr.comps["d1"]["carrier"].params["freq"] = fk.Quantity(freqs[b] / (2 * np.pi), "Hz 2pi")
+        single = exp.compute_propagators()["rx90p"]
+        assert rel_fro(U[b].cpu().numpy(), single.cpu().numpy()) < 1e-11
+    assert rel_fro(U[0].cpu().numpy(), U[8].cpu().numpy()) > 1e-3
