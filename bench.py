@@ -477,6 +477,7 @@ def run_engine(args):
     torch.cuda.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
+    engine.check_gated_launches()          # a gated launch that gave up on a row would have left NaNs: fail loudly
 
     # ---- end to end from pulse PARAMETERS: the control fields are generated on the device (f-2) --------
     # same gate length / slice count, one DRAG Gaussian per line, per-sample amplitude, angle and detuning

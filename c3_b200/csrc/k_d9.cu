@@ -35,14 +35,21 @@ int launch_d9(const RowsParams& rp, unsigned int* counter, int variant, cudaStre
         return fail(C3B_EUNSUPPORTED, "C3:ERROR: gated launch is not built for d9_variant %d", variant);
     if (variant == 0)
         return launch_persistent(pwc_blk_t18_kernel<9, 3, 4, 2>, BlkLayout<9, 3>::smem_bytes(rp.K, 4), 4, 2, rp, counter, st);
+    // gated launches: rows on their own 128-byte lines may be read through L1 (see load_signal)
+    const bool lines = rp.gate != nullptr && ((size_t)rp.K * rp.N * sizeof(double)) % 128 == 0 &&
+                       (reinterpret_cast<uintptr_t>(rp.signals) % 128) == 0;
     if (variant == 2) {
         const size_t smem8 = Shfl9::smem_bytes(rp.K, 8);
-        if (rp.gate != nullptr) return launch_persistent(pwc_shfl9_kernel<8, 1, true>, smem8, 8, 1, rp, counter, st);
-        return launch_persistent(pwc_shfl9_kernel<8, 1, false>, smem8, 8, 1, rp, counter, st);
+        if (rp.gate != nullptr)
+            return lines ? launch_persistent(pwc_shfl9_kernel<8, 1, 2>, smem8, 8, 1, rp, counter, st)
+                         : launch_persistent(pwc_shfl9_kernel<8, 1, 1>, smem8, 8, 1, rp, counter, st);
+        return launch_persistent(pwc_shfl9_kernel<8, 1, 0>, smem8, 8, 1, rp, counter, st);
     }
     const size_t smem = Blk9T<true>::smem_bytes(rp.K, 4);
-    if (rp.gate != nullptr) return launch_persistent(pwc_blk9_t18_kernel<4, 2, true, true>, smem, 4, 2, rp, counter, st);
-    return launch_persistent(pwc_blk9_t18_kernel<4, 2, true, false>, smem, 4, 2, rp, counter, st);
+    if (rp.gate != nullptr)
+        return lines ? launch_persistent(pwc_blk9_t18_kernel<4, 2, true, 2>, smem, 4, 2, rp, counter, st)
+                     : launch_persistent(pwc_blk9_t18_kernel<4, 2, true, 1>, smem, 4, 2, rp, counter, st);
+    return launch_persistent(pwc_blk9_t18_kernel<4, 2, true, 0>, smem, 4, 2, rp, counter, st);
 }
 
 }  // namespace c3b

@@ -154,7 +154,7 @@ __device__ __forceinline__ void store_own9(cplx* __restrict__ M, const int sown,
     }
 }
 
-template <int WARPS, int MINB, bool NOSEL, bool GATED>
+template <int WARPS, int MINB, bool NOSEL, int GATED>
 __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const RowsParams p, unsigned int* __restrict__ counter) {
     using LY = Blk9T<NOSEL>;
     using TB = Blk9Tab<NOSEL>;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
         const long long unit = unit_u;
         if (unit >= total_units) break;
         const int b = (int)(unit / p.S);
-        if constexpr (GATED) {
+        if constexpr (GATED != 0) {
             // gated launch: wait (all lanes, uniform code) until this unit's batch row has landed; rows arrive in order.
             // A row that never arrives ends this warp's work like an exhausted counter: the caller pre-fills U with NaN,
             // so the failure is loud and the GPU does not hang.

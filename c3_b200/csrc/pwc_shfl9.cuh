@@ -108,7 +108,7 @@ __device__ __forceinline__ void mm_shfl9_groups(const cplx (&Xsrc)[3][3], const 
     }
 }
 
-template <int WARPS, int MINB, bool GATED>
+template <int WARPS, int MINB, int GATED>
 __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_shfl9_kernel(const RowsParams p, unsigned int* __restrict__ counter) {
     constexpr int D = 9, NT = WARPS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_shfl9_kernel(const RowsP
         const long long unit = base_unit + warp;
         bool live = unit < total_units;                      // warps past the end of the work list idle through the barriers
         const int b = live ? (int)(unit / p.S) : 0;
-        if constexpr (GATED) {
+        if constexpr (GATED != 0) {
             // gated launch: wait (all lanes, uniform code) until this unit's batch row has landed; rows arrive in order.
             // A row that never arrives raises gate[1]; the warp then idles through the barriers and writes nothing.
             if (live && !wait_rows_ready(p.gate, b)) live = false;

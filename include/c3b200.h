@@ -67,7 +67,9 @@ int c3b_pwc_closed(const void* h0, const void* hks, const double* signals, doubl
  * followed by a 4-byte copy that raises gate[0] to the number of batch rows that have landed, and launches this ONE call
  * on another stream as soon as the first chunk is in.  Warps take batch rows in order and wait on gate[0] only if they
  * overtake the copy engine, so PCIe time hides behind the whole-batch kernel instead of cutting it into per-chunk
- * launches.  In-flight rows are read past L1 (ld.global.cg), never through the read-only path.
+ * launches.  In-flight rows are never read through the read-only path: past L1 (ld.global.cg) in general, through L1
+ * (ld.global.ca) when every row starts on its own 128-byte line (K*N*8 a multiple of 128 and `signals` 128-byte aligned), where
+ * a line can only be fetched after the acquire has seen its row.
  *   gate [2] uint32, device memory, both words zero before the first chunk:
  *        gate[0]  rows landed (written by the caller's copy stream, read with acquire loads by the kernel)
  *        gate[1]  set to 1 by the kernel if some row did not arrive within ~4 s WITHOUT copy progress: the warp that
