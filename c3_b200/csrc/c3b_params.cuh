@@ -77,11 +77,14 @@ struct ProductParams {
 // copy engine.  The patience counter restarts whenever the copy engine makes progress; after ~4 s WITHOUT progress the
 // warp gives up, raises gate[1] (the host reads it at its next synchronisation point and reports the failure) and
 // returns false.
-__device__ __forceinline__ bool wait_rows_ready(unsigned int* gate, const int b) {
+// `known` caches the last counter value this warp has seen: rows below it need no further look at the counter (the acquire
+// that saw them orders every later load), so once the copy engine is done the kernel runs without touching the gate.
+__device__ __forceinline__ bool wait_rows_ready(unsigned int* gate, const int b, unsigned int& known) {
+    if ((unsigned int)b < known) return true;
     unsigned int spins = 0, v, last = 0;
     for (;;) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gate) : "memory");
-        if (v > (unsigned int)b) return true;
+        if (v > (unsigned int)b) { known = v; return true; }
         if (v != last) { last = v; spins = 0; }
         __nanosleep(256);
         if (++spins > (1u << 24)) {

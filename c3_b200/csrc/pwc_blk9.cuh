@@ -233,17 +233,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
 
     for (;;) {
         unsigned int unit_u = 0;
-        if (lane == 0) unit_u = atomicAdd(counter, 1u);
+        if (lane == 0) {
+            unit_u = atomicAdd(counter, 1u);
+            if constexpr (GATED != 0) {
+                // gated launch: lane 0 waits until this unit's batch row has landed (rows arrive in order) -- all the polling
+                // state lives and dies here, nothing stays in registers across the slice loop (a per-warp cached counter or
+                // an all-lanes wait cost 5 registers = spills in this 252-register kernel: 10.18 instead of 9.7 ms).  A row
+                // that never arrives ends this warp's work like an exhausted counter and raises gate[1]; the caller pre-fills
+                // U with NaN, so the failure is loud and the GPU does not hang.
+                if ((long long)unit_u < total_units) {
+                    unsigned int known = 0;
+                    if (!wait_rows_ready(p.gate, (int)(unit_u / (unsigned int)p.S), known)) unit_u = 0xffffffffu;
+                }
+            }
+        }
         unit_u = __shfl_sync(0xffffffffu, unit_u, 0);
+        if constexpr (GATED != 0) __syncwarp();   // lane 0's acquire, then the warp barrier: every lane's loads of the row come after
         const long long unit = unit_u;
         if (unit >= total_units) break;
         const int b = (int)(unit / p.S);
-        if constexpr (GATED != 0) {
-            // gated launch: wait (all lanes, uniform code) until this unit's batch row has landed; rows arrive in order.
-            // A row that never arrives ends this warp's work like an exhausted counter: the caller pre-fills U with NaN,
-            // so the failure is loud and the GPU does not hang.
-            if (!wait_rows_ready(p.gate, b)) break;
-        }
         const int sidx = (int)(unit - (long long)b * p.S);
         const int n_begin = sidx * p.seg_len;
         const int n_end = min(p.N, n_begin + p.seg_len);

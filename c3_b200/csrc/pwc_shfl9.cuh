@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_shfl9_kernel(const RowsP
     const int warp = tid >> 5;
     const int cl_all = (p.seg_len + 2) / 3;
     const bool late = warp >= WARPS / 2;
+    unsigned int rows_known = 0;            // gated launch: batch rows this warp knows to have landed
     for (;;) {
         __syncthreads();
         if (tid == 0) s_base = atomicAdd(counter, (unsigned int)WARPS);
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_shfl9_kernel(const RowsP
         if constexpr (GATED != 0) {
             // gated launch: wait (all lanes, uniform code) until this unit's batch row has landed; rows arrive in order.
             // A row that never arrives raises gate[1]; the warp then idles through the barriers and writes nothing.
-            if (live && !wait_rows_ready(p.gate, b)) live = false;
+            if (live && !wait_rows_ready(p.gate, b, rows_known)) live = false;
         }
         const int sidx = live ? (int)(unit - (long long)b * p.S) : 0;
         const int n_begin = sidx * p.seg_len;
