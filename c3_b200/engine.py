@@ -103,7 +103,8 @@ def pwc_closed(h0, hks, signals, dt: float, return_dUs: bool = False, device=Non
     return (U, dUs) if return_dUs else U
 
 
-def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, first_chunk: int = 256, device=None):
+def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, first_chunk: int = 256, device=None,
+                         gated: bool = True):
     """Closed-system propagators for HOST-resident signals [B,K,N] (numpy or CPU tensor, ideally pinned).
 
     d = 9 (the headline kernel): ONE persistent launch over the whole batch, gated by a device counter.  The host
@@ -134,7 +135,7 @@ def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, fi
         streams = _side_streams(device)
         start = torch.cuda.Event()
         start.record(main)
-        if lib.c3b_pwc_gated_supported(int(d)):
+        if gated and lib.c3b_pwc_gated_supported(int(d)):
             if tuple(hks.shape) != (K, d, d):
                 raise ValueError(f"C3:ERROR: hks has shape {tuple(hks.shape)}, expected {(K, d, d)}")
             bounds = [0, min(B, max(1, int(first_chunk)))]
@@ -164,8 +165,9 @@ def pwc_closed_from_host(h0, hks, signals_host, dt: float, chunk: int = 1024, fi
             _watch_gate(gate, main)
             return U
         done = []
-        for i, b0 in enumerate(range(0, B, chunk)):
-            b1 = min(B, b0 + chunk)
+        starts = [0] + list(range(min(B, max(1, int(first_chunk))), B, chunk)) if not gated else list(range(0, B, chunk))
+        for i, b0 in enumerate(starts):
+            b1 = starts[i + 1] if i + 1 < len(starts) else B
             st = streams[i % 2]
             st.wait_event(start)
             with torch.cuda.stream(st):

@@ -30,6 +30,14 @@ for chunk in (512, 1024, 2048):
     U = engine.pwc_closed_from_host(m.h0, m.hks, host, 1e-11, chunk=chunk); torch.cuda.synchronize()
     print(f"chunk {chunk}: e2e {dt*1e3:.3f} ms/step  ({B*N/dt:.3e}/s); gated kernel {engine.last_kernel_ms():.3f} ms")
     engine.set_tuning("profile", 0)
+for first, chunk in ((256, 4096), (512, 4096), (1024, 4096), (512, 1792), (1024, 1536)):
+    for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(5):
+            U = engine.pwc_closed_from_host(m.h0, m.hks, host, 1e-11, chunk=chunk, first_chunk=first, gated=False)
+            Uh.copy_(U, non_blocking=True); torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 5
+    print(f"ungated chunks first {first} then {chunk}: e2e {dt*1e3:.3f} ms/step  ({B*N/dt:.3e}/s)")
 # raw copies
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(5): d = host.to("cuda", non_blocking=True); torch.cuda.synchronize()
