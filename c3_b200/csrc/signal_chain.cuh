@@ -19,7 +19,8 @@ namespace c3b {
 // layout of one envelope's parameter row and of one drive line's chain row (doubles)
 enum { ENV_AMP = 0, ENV_TFINAL, ENV_SIGMA, ENV_XY, ENV_FREQ_OFFSET, ENV_DELTA, ENV_TUP, ENV_TDOWN, ENV_RISEFALL, ENV_NPAR };
 enum { CH_SIM_RES = 0, CH_AWG_RES, CH_RISE_TIME, CH_RESP_KIND, CH_OUT_KIND, CH_V2HZ, CH_PHI, CH_PHI0, CH_OMEGA0, CH_ANHAR, CH_D, CH_NPAR };
-enum { SHAPE_NO_DRIVE = 0, SHAPE_RECT, SHAPE_GAUSSIAN_NONORM, SHAPE_GAUSSIAN_SIGMA, SHAPE_COSINE, SHAPE_FLATTOP };
+enum { SHAPE_NO_DRIVE = 0, SHAPE_RECT, SHAPE_GAUSSIAN_NONORM, SHAPE_GAUSSIAN_SIGMA, SHAPE_COSINE, SHAPE_FLATTOP,
+       SHAPE_TRAPEZOID, SHAPE_FLATTOP_RISEFALL, SHAPE_GAUSSIAN_DER_NONORM, SHAPE_GAUSSIAN_DER, SHAPE_DRAG_SIGMA, SHAPE_DRAG_DER };
 
 struct SignalParams {
     const double* env;       // [B, K, E, ENV_NPAR]
@@ -130,6 +131,33 @@ __device__ __forceinline__ T shape_value(int id, T t, const T* e) {
         case SHAPE_FLATTOP:
             return (T(1.0) + t_erf((t - e[ENV_TUP]) / e[ENV_RISEFALL])) / T(2.0) *
                    (T(1.0) + t_erf((-t + e[ENV_TDOWN]) / e[ENV_RISEFALL])) / T(2.0);
+        case SHAPE_TRAPEZOID: {             // envelopes.py:200-224: linear slopes of width 2.5 risefall (the fall wins where both apply)
+            const T w = e[ENV_RISEFALL] * T(2.5), tf = e[ENV_TFINAL];
+            if (t_val(t) >= t_val(tf - w)) return (tf - t) / w;
+            if (t_val(t) <= t_val(w)) return t / w;
+            return T(1.0);
+        }
+        case SHAPE_FLATTOP_RISEFALL: {      // envelopes.py:227-250: flattop with t_up = risefall, t_down = t_final - risefall
+            const T rf = e[ENV_RISEFALL];
+            return (T(1.0) + t_erf((t - rf) / rf)) / T(2.0) * (T(1.0) + t_erf((-t + e[ENV_TFINAL] - rf) / rf)) / T(2.0);
+        }
+        case SHAPE_GAUSSIAN_DER_NONORM:     // envelopes.py:490-500
+        case SHAPE_GAUSSIAN_DER: {          // :503-516 (same, over the norm of gaussian_sigma)
+            const T tf = e[ENV_TFINAL], s = e[ENV_SIGMA], u = t - tf / T(2.0);
+            T g = t_exp(-(u * u) / (T(2.0) * s * s)) * u / (s * s);
+            if (id == SHAPE_GAUSSIAN_DER)       // sqrt(8) in float32 as the reference has it here (envelopes.py:514)
+                g = g / (t_sqrt(T(2 * M_PI) * s * s) * t_erf(tf / (T(2.8284270763397217) * s)) - tf * t_exp(-(tf * tf) / (T(8.0) * s * s)));
+            return g;
+        }
+        case SHAPE_DRAG_SIGMA:              // envelopes.py:519-530: (gauss - offset)^2 / norm
+        case SHAPE_DRAG_DER: {              // :545-562: -2 (gauss - offset) gauss (t - t_final/2) / sigma^2 / norm
+            const T tf = e[ENV_TFINAL], s = e[ENV_SIGMA], u = t - tf / T(2.0);
+            const T gauss = t_exp(-(u * u) / (T(2.0) * s * s));
+            const T offset = t_exp(-(tf * tf) / (T(8.0) * s * s));
+            const T norm = t_sqrt(T(2 * M_PI) * s * s) * t_erf(tf / (T(sqrt(8.0)) * s)) - tf * offset;
+            if (id == SHAPE_DRAG_SIGMA) return (gauss - offset) * (gauss - offset) / norm;
+            return T(-2.0) * (gauss - offset) * gauss * u / (s * s) / norm;
+        }
         default: return T(0.0);
     }
 }
@@ -148,10 +176,37 @@ __device__ __forceinline__ T shape_deriv(int id, T t, const T* e) {
             return g;
         }
         case SHAPE_COSINE: return T(0.5) * t_sin(T(2 * M_PI) * t / e[ENV_TFINAL]) * T(2 * M_PI) / e[ENV_TFINAL];
-        case SHAPE_FLATTOP: {
-            const T rf = e[ENV_RISEFALL], up = (t - e[ENV_TUP]) / rf, dn = (-t + e[ENV_TDOWN]) / rf;
+        case SHAPE_FLATTOP:
+        case SHAPE_FLATTOP_RISEFALL: {
+            const T rf = e[ENV_RISEFALL];
+            const T tu = (id == SHAPE_FLATTOP) ? e[ENV_TUP] : rf, td = (id == SHAPE_FLATTOP) ? e[ENV_TDOWN] : e[ENV_TFINAL] - rf;
+            const T up = (t - tu) / rf, dn = (-t + td) / rf;
             const T c = T(2 / sqrt(M_PI)) / rf;
             return (c * t_exp(-(up * up)) * (T(1.0) + t_erf(dn)) - (T(1.0) + t_erf(up)) * c * t_exp(-(dn * dn))) / T(4.0);
+        }
+        case SHAPE_TRAPEZOID: {
+            const T w = e[ENV_RISEFALL] * T(2.5), tf = e[ENV_TFINAL];
+            if (t_val(t) >= t_val(tf - w)) return T(-1.0) / w;
+            if (t_val(t) <= t_val(w)) return T(1.0) / w;
+            return T(0.0);
+        }
+        case SHAPE_GAUSSIAN_DER_NONORM:
+        case SHAPE_GAUSSIAN_DER: {          // d/dt [ gauss u / s^2 ] = gauss (1 / s^2 - u^2 / s^4)
+            const T tf = e[ENV_TFINAL], s = e[ENV_SIGMA], u = t - tf / T(2.0), s2 = s * s;
+            T g = t_exp(-(u * u) / (T(2.0) * s2)) * (T(1.0) / s2 - u * u / (s2 * s2));
+            if (id == SHAPE_GAUSSIAN_DER)
+                g = g / (t_sqrt(T(2 * M_PI) * s2) * t_erf(tf / (T(2.8284270763397217) * s)) - tf * t_exp(-(tf * tf) / (T(8.0) * s2)));
+            return g;
+        }
+        case SHAPE_DRAG_SIGMA:
+        case SHAPE_DRAG_DER: {
+            const T tf = e[ENV_TFINAL], s = e[ENV_SIGMA], u = t - tf / T(2.0), s2 = s * s;
+            const T gauss = t_exp(-(u * u) / (T(2.0) * s2)), dg = -(u / s2) * gauss;
+            const T offset = t_exp(-(tf * tf) / (T(8.0) * s2));
+            const T norm = t_sqrt(T(2 * M_PI) * s2) * t_erf(tf / (T(sqrt(8.0)) * s)) - tf * offset;
+            if (id == SHAPE_DRAG_SIGMA) return T(2.0) * (gauss - offset) * dg / norm;
+            // d/dt [ (gauss - offset) gauss u ] = dg gauss u + (gauss - offset) dg u + (gauss - offset) gauss
+            return T(-2.0) / (s2 * norm) * (dg * gauss * u + (gauss - offset) * dg * u + (gauss - offset) * gauss);
         }
         default: return T(0.0);
     }

@@ -27,7 +27,14 @@ import torch
 
 from . import engine
 
-SHAPE_IDS = {"no_drive": 0, "rect": 1, "gaussian_nonorm": 2, "gaussian_sigma": 3, "cosine": 4, "flattop": 5}
+SHAPE_IDS = {"no_drive": 0, "rect": 1, "gaussian_nonorm": 2, "gaussian_sigma": 3, "cosine": 4, "flattop": 5, "trapezoid": 6,
+             "flattop_risefall": 7, "gaussian_der_nonorm": 8, "gaussian_der": 9, "drag_sigma": 10, "drag_der": 11}
+#: shapes of c3/libraries/envelopes.py that are another shape with one parameter fixed: name -> (kernel shape, parameter, rule)
+SHAPE_ALIASES = {
+    "gaussian": ("gaussian_sigma", "sigma", lambda p: p["t_final"] / 6),                 # envelopes.py:399-417
+    "drag": ("drag_sigma", "sigma", lambda p: p["t_final"] / 4),                         # :533-542
+    "flattop_risefall_1ns": ("flattop_risefall", "risefall", lambda p: 1e-9 + 0 * p["t_final"]),   # :366-370
+}
 ENV_KEYS = ("amp", "t_final", "sigma", "xy_angle", "freq_offset", "delta", "t_up", "t_down", "risefall")
 ENV_DEFAULTS = {"amp": 0.0, "t_final": 0.0, "sigma": 1.0, "xy_angle": 0.0, "freq_offset": 0.0, "delta": 0.0,
                 "t_up": 0.0, "t_down": 0.0, "risefall": 1.0}
@@ -176,12 +183,12 @@ class Generator:
                 carrier = comp
             elif cls in ("Envelope", "EnvelopeDrag"):
                 shape = getattr(comp.shape, "__name__", str(comp.shape))
-                if shape not in SHAPE_IDS:
+                if shape not in SHAPE_IDS and shape not in SHAPE_ALIASES:
                     raise Exception(f"C3:ERROR: envelope shape '{shape}' is not available in the on-device signal chain.")
                 opts = getattr(instr, "_options", {}).get(chan, {}).get(name, {})
                 if opts:
                     raise Exception("C3:ERROR: component options (delay, trigger_comp, t_final_cut) are not supported on device.")
-                envs.append((name, comp, SHAPE_IDS[shape], (1 if cls == "EnvelopeDrag" else 0)
+                envs.append((name, comp, shape, (1 if cls == "EnvelopeDrag" else 0)
                              | (2 if getattr(comp, "use_t_before", False) else 0)))
             else:
                 raise Exception(f"C3:ERROR: component type '{cls}' is not available in the on-device signal chain.")
@@ -210,12 +217,16 @@ class Generator:
             lo[:, k] = _val(carrier.params["freq"])
             if samples and (c, "carrier", "freq") in samples:
                 lo[:, k] = np.asarray(samples[(c, "carrier", "freq")], dtype=np.float64)
-            for e, (name, comp, sid, fl) in enumerate(envs):
-                shape[k, e], flags[k, e] = sid, fl
+            for e, (name, comp, sname, fl) in enumerate(envs):
+                alias = SHAPE_ALIASES.get(sname)
+                shape[k, e], flags[k, e] = SHAPE_IDS[alias[0] if alias else sname], fl
                 for i, key in enumerate(ENV_KEYS):
                     env[:, k, e, i] = _val(comp.params[key]) if key in comp.params else ENV_DEFAULTS[key]
                     if samples and (c, name, key) in samples:
                         env[:, k, e, i] = np.asarray(samples[(c, name, key)], dtype=np.float64)
+                if alias:       # e.g. "gaussian" = gaussian_sigma with sigma = t_final / 6 (per sample, after the overrides)
+                    cols = {key: env[:, k, e, i] for i, key in enumerate(ENV_KEYS)}
+                    env[:, k, e, ENV_KEYS.index(alias[1])] = alias[2](cols)
         if len({chain[k, 0] for k in range(K)}) != 1:
             raise Exception("C3:ERROR: all channels of an instruction must share the simulation resolution.")
         return chans, env, shape, flags, lo, chain

@@ -24,7 +24,7 @@ test/tunable_coupler_data.pickle) in tests/test_signal_oracle.py.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass, replace, field
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -83,7 +83,41 @@ def shape_values(shape: str, t: np.ndarray, e: EnvelopeSpec) -> np.ndarray:
         return 0.5 * (1 - np.cos(2 * np.pi * t / e.t_final))
     if shape == "flattop":
         return (1 + erf((t - e.t_up) / e.risefall)) / 2 * (1 + erf((-t + e.t_down) / e.risefall)) / 2
+    if shape == "trapezoid":                       # c3/libraries/envelopes.py:200-224
+        env = np.ones_like(t)
+        env = np.where(t <= e.risefall * 2.5, t / (e.risefall * 2.5), env)
+        env = np.where(t >= e.t_final - e.risefall * 2.5, (e.t_final - t) / (e.risefall * 2.5), env)
+        return env
+    if shape in ("flattop_risefall", "flattop_risefall_1ns"):      # :227-250, :366-370
+        rf = 1e-9 if shape.endswith("1ns") else e.risefall
+        t_up, t_down = rf, e.t_final - rf
+        return (1 + erf((t - t_up) / rf)) / 2 * (1 + erf((-t + t_down) / rf)) / 2
+    if shape == "gaussian":                        # :399-417: gaussian_sigma with sigma = t_final / 6
+        return shape_values("gaussian_sigma", t, replace(e, sigma=e.t_final / 6))
+    if shape in ("gaussian_der_nonorm", "gaussian_der"):           # :490-516
+        g = np.exp(-((t - e.t_final / 2) ** 2) / (2 * e.sigma ** 2)) * (t - e.t_final / 2) / e.sigma ** 2
+        if shape == "gaussian_der":
+            # the reference evaluates sqrt(8) in float32 here and only here (tf.cast(tf.sqrt(8.0), tf.float64), envelopes.py:514):
+            # 2.8284270763397217 instead of 2.8284271247461903, visible at 5e-10 relative -- restated as is
+            s8 = float(np.float64(np.sqrt(np.float32(8.0))))
+            g = g / (np.sqrt(2 * np.pi * e.sigma ** 2) * erf(e.t_final / (s8 * e.sigma)) - e.t_final * np.exp(-(e.t_final ** 2) / (8 * e.sigma ** 2)))
+        return g
+    if shape in ("drag_sigma", "drag"):            # :519-542 (drag: sigma = t_final / 4)
+        if shape == "drag":
+            e = replace(e, sigma=e.t_final / 4)
+        gauss = np.exp(-((t - e.t_final / 2) ** 2) / (2 * e.sigma ** 2))
+        offset = np.exp(-(e.t_final ** 2) / (8 * e.sigma ** 2))
+        return (gauss - offset) ** 2 / _gauss_norm(e)
+    if shape == "drag_der":                        # :545-562
+        gauss = np.exp(-((t - e.t_final / 2) ** 2) / (2 * e.sigma ** 2))
+        offset = np.exp(-(e.t_final ** 2) / (8 * e.sigma ** 2))
+        return -2 * (gauss - offset) * gauss * (t - e.t_final / 2) / e.sigma ** 2 / _gauss_norm(e)
     raise ValueError(f"C3:ERROR: envelope shape '{shape}' is not restated")
+
+
+def _gauss_norm(e) -> float:
+    """sqrt(2 pi sigma^2) erf(t_final / (sqrt(8) sigma)) - t_final exp(-t_final^2 / (8 sigma^2))  (envelopes.py:391-394)."""
+    return np.sqrt(2 * np.pi * e.sigma ** 2) * erf(e.t_final / (np.sqrt(8) * e.sigma)) - e.t_final * np.exp(-(e.t_final ** 2) / (8 * e.sigma ** 2))
 
 
 def shape_derivative(shape: str, t: np.ndarray, e: EnvelopeSpec) -> np.ndarray:
@@ -104,7 +138,13 @@ def shape_derivative(shape: str, t: np.ndarray, e: EnvelopeSpec) -> np.ndarray:
         up, dn = (t - e.t_up) / e.risefall, (-t + e.t_down) / e.risefall
         c = 2 / np.sqrt(np.pi) / e.risefall
         return (c * np.exp(-up ** 2) * (1 + erf(dn)) - (1 + erf(up)) * c * np.exp(-dn ** 2)) / 4
-    raise ValueError(f"C3:ERROR: envelope shape '{shape}' is not restated")
+    # the remaining shapes: central difference of the restated shape function (what tf.GradientTape returns, to 1e-9 relative;
+    # the CUDA chain evaluates the analytic derivative)
+    h = 1e-6 * max(e.t_final, 1e-12)
+    if shape == "trapezoid":                       # piecewise linear: exact one-sided slopes (TF differentiates the taken branch)
+        w = e.risefall * 2.5
+        return np.where(t >= e.t_final - w, -1.0 / w, np.where(t <= w, 1.0 / w, 0.0))
+    return (shape_values(shape, t + h, e) - shape_values(shape, t - h, e)) / (2 * h)
 
 
 def compute_mask(ts: np.ndarray, t_final: float, t_end: float) -> np.ndarray:

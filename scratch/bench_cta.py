@@ -7,6 +7,7 @@ from c3_b200 import engine, synth, flops
 which = sys.argv[1:] or ["81", "27"]
 if "t512" in which: engine.set_tuning("cta_threads", 512)
 if "big2" in which: engine.set_tuning("gemm_big", 2)
+if "big1" in which: engine.set_tuning("gemm_big", 1)
 peak = engine.measure_fp64_peak("dfma", 0.3)
 engine.set_tuning("profile", 1)
 if "81" in which:

@@ -17,6 +17,7 @@ Sources (relative to the reference checkout):
                                       are rebuilt with oracle/c3_model_oracle.py, checked on the pickled
                                       coupler_01 / coupler_12 eigenfrequencies)
   test/generator_data.pickle      <- test/test_generator.py:21-190 (signal chain, stage by stage)
+  test/envelopes.pickle           <- test/test_envelopes.py (envelope shapes on ts = linspace(0, 10e-9, 100))
 """
 import os
 import pickle
@@ -135,6 +136,18 @@ def generator_chain():
     )
 
 
+def envelopes():
+    """The shape functions the on-device signal chain implements (real part; the reference complexifies with a zero imaginary
+    part), with the parameters of test/test_envelopes.py: t_final 10 ns, sigma 5 ns, risefall 2 ns, t_up 1 ns, t_down 10 ns."""
+    d = load("envelopes.pickle")
+    keep = ["trapezoid", "flattop_risefall", "flattop_risefall_1ns", "flattop", "gaussian_sigma", "gaussian", "gaussian_nonorm",
+            "gaussian_der_nonorm", "gaussian_der", "drag_sigma", "drag_der", "drag", "cosine", "no_drive", "rect"]
+    out = {k: np.real(np.asarray(d[k])).reshape(-1).astype(np.float64) for k in keep}
+    assert all(v.shape == (100,) for v in out.values()), {k: v.shape for k, v in out.items()}
+    assert all(np.abs(np.imag(np.asarray(d[k]))).max() == 0 for k in keep)
+    np.savez_compressed(os.path.join(HERE, "envelopes.npz"), ts=np.linspace(0, 10e-9, 100), **out)
+
+
 if __name__ == "__main__":
     two_qubit()
     tunable_coupler()
@@ -142,6 +155,7 @@ if __name__ == "__main__":
     generator_chain()
     transmon_expanded()
     tf_utils()
+    envelopes()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

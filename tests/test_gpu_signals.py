@@ -286,3 +286,60 @@ def test_pulse_parameter_gradient_through_the_whole_pipeline(gen_mod):
         want = (lp - lm) / (2 * h)
         assert abs(g[b, k, 0, q] - want) < 2e-4 * abs(want) + 1e-9 * np.abs(g[..., q]).max(), (b, k, q, g[b, k, 0, q], want)
     assert lo_t.grad is not None and torch.isfinite(lo_t.grad).all()
+
+
+@pytest.mark.parametrize("resp_kind", [0, 1])
+def test_round2_envelope_shapes(gen_mod, resp_kind):
+    """trapezoid, flattop_risefall, gaussian_der(_nonorm), drag_sigma, drag_der: values, DRAG quadrature (analytic time derivative),
+    use_t_before, against the oracle (whose shape functions are pinned to the reference's test/envelopes.pickle)."""
+    from c3_b200 import engine
+    rng = np.random.default_rng(40 + resp_kind)
+    shapes = ["trapezoid", "flattop_risefall", "gaussian_der_nonorm", "gaussian_der", "drag_sigma", "drag_der"]
+    B, K, E = 3, len(shapes), 1
+    t_start, t_end = 0.0, 11.1e-9
+    env = np.zeros((B, K, E, 9))
+    sid = np.array([[gen_mod.SHAPE_IDS[s_]] for s_ in shapes], dtype=np.int32)
+    flags = np.array([[1], [1 | 2], [0], [1], [1], [2]], dtype=np.int32)
+    for k in range(K):
+        tf_ = 9.13e-9 + 0.21e-9 * np.arange(B) + 0.07e-9 * k
+        env[:, k, 0] = np.stack([rng.uniform(0.1, 0.6, B), tf_, tf_ / rng.uniform(3, 5, B), rng.uniform(-3, 3, B),
+                                 rng.uniform(-80e6, 80e6, B) * TP, rng.uniform(-2, 2, B), rng.uniform(1e-9, 2e-9, B),
+                                 tf_ - rng.uniform(1e-9, 2e-9, B), rng.uniform(0.5e-9, 1.2e-9, B)], axis=1)
+    env[:, 2, 0, 0] *= 1e-9          # gaussian_der_nonorm ~ 1 / sigma: keep the line O(1) V
+    env[:, 3:, 0, 0] *= 2e-9         # unit-area normalisations (values ~ 1 / sigma)
+    env[:, 5, 0, 0] *= 2e-9          # drag_der ~ 1 / sigma^2
+    lo = rng.uniform(4e9, 6e9, (B, K)) * TP
+    chain = np.tile([100e9, 1.9e9, 0.37e-9, resp_kind, 0, 1e9, 0, 1, 0, 0, np.nan], (K, 1))
+    got = engine.generate_signals(env, sid, flags, lo, chain, t_start, t_end).cpu().numpy()
+    for b in range(B):
+        for k in range(K):
+            v = env[b, k, 0]
+            spec = so.EnvelopeSpec(shape=shapes[k], amp=v[0], t_final=v[1], sigma=v[2], xy_angle=v[3], freq_offset=v[4], delta=v[5],
+                                   t_up=v[6], t_down=v[7], risefall=v[8], drag=bool(flags[k, 0] & 1), use_t_before=bool(flags[k, 0] & 2))
+            cs = so.ChainSpec(sim_res=100e9, awg_res=1.9e9, rise_time=0.37e-9)
+            if resp_kind == 0:
+                st = {}
+                so.generate_signal([spec], lo[b, k], t_start, t_end, cs, st)
+                want = so.mixer(st["lo_i"], st["lo_q"], st["dac_i"], st["dac_q"]) * cs.v2hz
+            else:
+                want, _ = so.generate_signal([spec], lo[b, k], t_start, t_end, cs)
+            # the oracle differentiates the shape numerically for the DRAG quadrature (1e-9 relative), the kernel analytically
+            assert _rel(got[b, k], want) < (1e-7 if flags[k, 0] & 1 else RTOL), (b, shapes[k])
+
+
+def test_alias_shapes_through_the_generator(gen_mod):
+    """gaussian (sigma = t_final / 6), drag (sigma = t_final / 4), flattop_risefall_1ns (risefall = 1 ns): envelopes.py:366-370,
+    399-417, 533-542, resolved per sample on the host and run on the kernel of the shape they alias."""
+    devices, chains, instr = fk.reference_generator_setup()
+    gen = gen_mod.Generator(devices, chains)
+    for shape in ("gaussian", "drag", "flattop_risefall_1ns"):
+        env = instr.comps["d1"]["gauss"]
+        env.shape = fk._Shape(shape)
+        env.params["risefall"] = fk.Quantity(0.7e-9, "s")
+        amp = 0.5 if shape == "flattop_risefall_1ns" else 0.5 * 2e-9
+        env.params["amp"] = fk.Quantity(amp, "V")
+        got = gen.generate_signals(instr)["d1"]["values"].cpu().numpy()
+        spec = so.EnvelopeSpec(shape=shape, amp=amp, t_final=7e-9, sigma=7e-9 / 4, xy_angle=0.0,
+                               freq_offset=(-50e6 - 3e6) * TP, delta=-1, risefall=0.7e-9)
+        want, _ = so.generate_signal([spec], (5e9 + 50e6) * TP, 0.0, 7e-9, so.ChainSpec())
+        assert _rel(got, want) < RTOL, shape
