@@ -110,8 +110,8 @@ def run_reference(args):
         "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic",
         "config": {"workload": WORKLOAD, "d": D, "K": K, "N": N, "B_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * max(args.gpus, 1),
-                   "dt": DT, "sampled": f"{cores * per_proc} of the {B_PER_GPU} signal sets per step (rate-normalised)",
-                   "parallelism": f"{cores} host processes"},
+                   "dt": DT, "parallelism": f"{cores} host processes", "l2": "n/a (host arm)"},
+        "sampled": f"each step times {cores * per_proc} of the {B_PER_GPU} signal sets of the workload (rate-normalised)",
         "cpu_baseline": {"value": value, "unit": "slices/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reference_note": "TensorFlow (the reference's arithmetic backend) is not installable in this image; "
@@ -352,8 +352,10 @@ def run_configs(engine, synth, dev, rank, world, dfma_peak, all_gather, check):
     sig_s = torch.as_tensor(synth.controls_fast(m2, B_PER_GPU, N, DT, seed=4242)[lo:hi]).to(dev)
     ms, _ = _timed(lambda: gather(engine.pwc_prepared(pm2, sig_s), B_PER_GPU), 10, torch, dist, world)
     strong = {"B_total": B_PER_GPU, "B_per_gpu": hi - lo, "n_gpus": world, "ms_per_step": ms, "slices_per_s": B_PER_GPU * N / (ms * 1e-3),
-              "note": "same d = 9, N = 1000 workload with the batch FIXED at 4096; 4 waves of 1184 warp units at 1 GPU shrink to "
-                      "half a wave at 8, so the tail of the persistent kernel and the launch + all-gather latency show"}
+              "note": "same d = 9, N = 1000 workload with the batch FIXED at 4096 in total.  Limiter when the efficiency drops: the per-GPU "
+                      "batch (512 rows at 8 GPUs) gives the persistent kernel 12 waves of warp units instead of 100, so its tail, the "
+                      "segment-fold launch, the all-gather and ~10 us of launch latency weigh on a 1.3 ms kernel (a B = 512 launch alone "
+                      "runs at 3.8e8 slices/s against 4.2e8 at B = 4096)"}
     return out, strong
 
 
@@ -558,8 +560,8 @@ def run_engine(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64 FMA)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "d": D, "K": K, "N": N, "B_per_gpu": B, "global_batch": B * n_gpus,
                        "dt": DT, "parallelism": f"batch-sharded x{n_gpus}" + (", one all-gather of U per step" if n_gpus > 1 else ""),
-                       "l2": f"{N_ROTATE} rotating input buffers ({N_ROTATE * B * K * N * 8 / 1e6:.0f} MB > 126 MB L2)",
-                       "kernel": "pwc_blk9_t18_kernel<4,2,true> (fused assemble + degree-18 Taylor expm in 5 products + ordered product; 3x3 lane blocks, own-block operands from registers, element-major conflict-free shared layout)"},
+                       "l2": f"{N_ROTATE} rotating input buffers ({N_ROTATE * B * K * N * 8 / 1e6:.0f} MB > 126 MB L2)"},
+            "kernel": "pwc_blk9_t18_kernel<4,2,true,0> (fused assemble + degree-18 Taylor expm in 5 products + ordered product; 3x3 lane blocks, own-block operands from registers, element-major conflict-free shared layout)",
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": B * K * N * 8,
                     "d2h_bytes_per_step": B * D * D * 16, "api": "c3_b200.propagation.pwc_batch(host signals) -> U.cpu()"},
             "e2e_from_params": {"value": n_gpus * B * N * args.steps / par_s, "unit": "slices/s",
