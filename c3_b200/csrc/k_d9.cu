@@ -3,6 +3,7 @@
 #include "pwc_blk.cuh"
 #include "pwc_blk9.cuh"
 #include "pwc_shfl9.cuh"
+#include "pwc_dmma9.cuh"
 
 namespace c3b {
 
@@ -28,7 +29,7 @@ int launch_persistent(Kern kern, size_t smem, int warps, int minb, const RowsPar
 
 }  // namespace
 
-bool d9_gated_supported(int variant) { return variant == 1 || variant == 2; }
+bool d9_gated_supported(int variant) { return variant >= 1 && variant <= 3; }
 
 int launch_d9(const RowsParams& rp, unsigned int* counter, int variant, cudaStream_t st) {
     if (rp.gate != nullptr && !d9_gated_supported(variant))
@@ -38,6 +39,13 @@ int launch_d9(const RowsParams& rp, unsigned int* counter, int variant, cudaStre
     // gated launches: rows on their own 128-byte lines may be read through L1 (see load_signal)
     const bool lines = rp.gate != nullptr && ((size_t)rp.K * rp.N * sizeof(double)) % 128 == 0 &&
                        (reinterpret_cast<uintptr_t>(rp.signals) % 128) == 0;
+    if (variant == 3) {
+        const size_t smem = Dmma9::smem_bytes(rp.K, 8);
+        if (rp.gate != nullptr)
+            return lines ? launch_persistent(pwc_dmma9_kernel<8, 2, 2>, smem, 8, 2, rp, counter, st)
+                         : launch_persistent(pwc_dmma9_kernel<8, 2, 1>, smem, 8, 2, rp, counter, st);
+        return launch_persistent(pwc_dmma9_kernel<8, 2, 0>, smem, 8, 2, rp, counter, st);
+    }
     if (variant == 2) {
         const size_t smem8 = Shfl9::smem_bytes(rp.K, 8);
         if (rp.gate != nullptr)

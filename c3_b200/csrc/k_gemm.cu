@@ -39,6 +39,7 @@ int launch_gemm(const CtaParams& cp, const cplx* TR, const double* RS, int grid,
     // one 384-thread CTA per SM: 24 macro tiles = 2 full rounds of 12 warps, and 148 x 6 x 124 KB = 110 MB of workspace stays
     // inside the 126 MB L2 (two 256-thread CTAs per SM: 220 MB, L2 hit rate 52 %)
     if (gp.DP == 88 && tn.gemm_big == 2) return launch_gemm_t<3, 2, 0, 0, 384>(gp, grid, st);
+    if (gp.DP == 88 && tn.gemm_big == 3) return launch_gemm_t<2, 2, 0, 0, 512>(gp, grid, st);   // 16 warps, one CTA per SM
     return launch_gemm_t<2, 2>(gp, grid, st);
 }
 

@@ -8,6 +8,7 @@ which = sys.argv[1:] or ["81", "27"]
 if "t512" in which: engine.set_tuning("cta_threads", 512)
 if "big2" in which: engine.set_tuning("gemm_big", 2)
 if "big1" in which: engine.set_tuning("gemm_big", 1)
+if "big3" in which: engine.set_tuning("gemm_big", 3)
 peak = engine.measure_fp64_peak("dfma", 0.3)
 engine.set_tuning("profile", 1)
 if "81" in which:

@@ -228,7 +228,7 @@ def test_cta_kernels_pade_and_taylor(eng, d, cta_variant):
     assert rel_fro(U.cpu().numpy(), wantU) < TOL
 
 
-D9_VARIANTS = [0, 1, 2]
+D9_VARIANTS = [0, 1, 2, 3]
 
 
 def _default_d9_variant():
