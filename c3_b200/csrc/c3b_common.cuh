@@ -93,6 +93,36 @@ __constant__ double kPade[5][14] = {
 // backward error <= 2^-53 for ||A||_1 <= 1.09 (same paper, table of theta_m)
 #define C3B_THETA18 1.09
 
+// ---- degree-15+ Taylor polynomial of exp in FOUR matrix products (evaluation formulas of the Sastre-Ibanez-Defez type,
+// "Boosting the computation of the matrix exponential", Appl. Math. Comput. 340 (2019): polynomials of degree 16 whose
+// coefficients match the Taylor series up to degree 15).  No network here, so the 16 coefficients were obtained by solving
+// the 16 polynomial conditions numerically (Levenberg-Marquardt from random starts, polished to 40 digits with mpmath;
+// tests/test_taylor_schemes.py re-derives the composed polynomial from these literals and checks it against 1/k!):
+//   A2 = A A
+//   P0 = A2 (a1 A2 + a2 A)
+//   P1 = (P0 + b1 A2 + b2 A)(P0 + b3 A2 + b4 I) + b5 P0
+//   T  = (P1 + c1 A2 + c2 A)(P1 + c3 P0 + c4 A) + c9 P1 + c5 P0 + c6 A2 + c7 A + c8 I
+// T(x) = sum_{k<=15} x^k / k! + 0.5457 x^16 / 16!.  Measured forward error against a 40-digit reference: 1.2e-15 on the
+// headline slices (||A|| = 0.67), 1.1e-15 at spectral radius 0.8, 1.0e-14 at 1.0 (the degree-18 scheme: 3e-16 throughout,
+// with one product more).  Used with theta = 0.8 by the forward kernels; the tolerance of the path is 1e-10 after N products.
+#define C3B_T15_A1 0.00040187616102010354629
+#define C3B_T15_A2 0.0029455314402796829805
+#define C3B_T15_B1 0.087121675660506912665
+#define C3B_T15_B2 0.40175684406735678015
+#define C3B_T15_B3 (-0.063523113356121467813)
+#define C3B_T15_B4 3.0014665781772709006
+#define C3B_T15_B5 10.046029558660165472
+#define C3B_T15_C1 (-0.23810703738709872247)
+#define C3B_T15_C2 (-1.2471625036814465831)
+#define C3B_T15_C3 5.7923617070732605218
+#define C3B_T15_C4 1.0183494324742248072
+#define C3B_T15_C5 (-3.030123400738712306)
+#define C3B_T15_C6 (-2.1297555904964357845)
+#define C3B_T15_C7 (-11.550609098606822755)
+#define C3B_T15_C8 1.0
+#define C3B_T15_C9 10.408017352313543646
+#define C3B_THETA15 0.8
+
 #define C3B_THETA3 1.495585217958292e-2
 #define C3B_THETA5 2.539398330063230e-1
 #define C3B_THETA7 9.504178996162932e-1

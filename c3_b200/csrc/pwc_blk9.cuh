@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
             nb = __hiloint2double((int)__reduce_max_sync(0xffffffffu, (unsigned)__double2hiint(nb) + 1u), 0);
             mu_acc.x += mu.x; mu_acc.y += mu.y;
 
-            const int s = squarings_for(nb, C3B_THETA18);
+            const int s = squarings_for(nb, C3B_THETA15);
             if (s > 0) {
                 const double sc = pow2neg(s);
 #pragma unroll
@@ -334,8 +334,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
             for (int a = 0; a < 3; ++a)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) YO[a][c] = XO[a][c];
-            // phases: 0 A2 | 1 A3 | 2 A6 (+ combinations) | 3 B1 B5 | 4 (B3+A9) A9 | s squarings | product
-            const int ph_lastsq = 4 + s;
+            // phases (degree-15+ scheme in 4 products, c3b_common.cuh):
+            //   0: A2 = A A | 1: P0 = A2 (a1 A2 + a2 A) | 2: P1 = L1 R1 + b5 P0 | 3: T = L2 R2 + E0 | s squarings | product
+            // own blocks kept in registers: XO / YO (operands), C (product), R2 (A^2); own blocks parked in shared memory:
+            // A stays in bufA, P0 then E0 in bufK
+            const int ph_lastsq = 3 + s;
             const int ph_last = ph_lastsq + (it > 0 ? 1 : 0);
             const cplx* Xb = bufA + unown;
             const cplx* Yb = bufA + unown;
@@ -351,96 +354,86 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
                     }
                 }
                 mm_own9<NOSEL>(Xb, Yb, L, XO, YO, C);
-                if (ph == 0) {                                  // C = A^2
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) { R2[a][c] = C[a][c]; XO[a][c] = C[a][c]; }
-                    store_own9(bufB, 0, C, lane_on);
-                    __syncwarp();
-                    Xb = bufB + unown;                          // A^3 = A^2 A
-                } else if (ph == 1) {                           // C = A^3
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) { XO[a][c] = C[a][c]; YO[a][c] = C[a][c]; }
-                    store_own9(bufX, 0, C, lane_on);
-                    __syncwarp();
-                    Xb = bufX + unown; Yb = bufX + unown;       // A^6 = A^3 A^3
-                } else if (ph == 2) {                           // C = A^6: form B1..B5
-                    cplx X1[3][3];
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) X1[a][c] = bufA[(a * 3 + c) * S];        // own block of A (loads first)
-                    __syncwarp();                               // bufX (A^3), bufB (A^2), bufA (A) no longer read
+                if (ph == 0) {                                  // C = A^2: operands of P0 = A2 (a1 A2 + a2 A)
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const cplx x1 = X1[a][c], x2 = R2[a][c], x3 = XO[a][c], x6 = C[a][c];
-                            const double dg = (on_diag && a == c) ? 1.0 : 0.0;
-                            cplx b1, b5, b4, b3, b2;
-                            b1.x = C3B_T18_A11 * x1.x + C3B_T18_A21 * x2.x + C3B_T18_A31 * x3.x;
-                            b1.y = C3B_T18_A11 * x1.y + C3B_T18_A21 * x2.y + C3B_T18_A31 * x3.y;
-                            b5.x = C3B_T18_B24 * x2.x + C3B_T18_B34 * x3.x + C3B_T18_B64 * x6.x;
-                            b5.y = C3B_T18_B24 * x2.y + C3B_T18_B34 * x3.y + C3B_T18_B64 * x6.y;
-                            b4.x = C3B_T18_B03 * dg + C3B_T18_B13 * x1.x + C3B_T18_B23 * x2.x + C3B_T18_B33 * x3.x + C3B_T18_B63 * x6.x;
-                            b4.y = C3B_T18_B13 * x1.y + C3B_T18_B23 * x2.y + C3B_T18_B33 * x3.y + C3B_T18_B63 * x6.y;
-                            b3.x = C3B_T18_B02 * dg + C3B_T18_B12 * x1.x + C3B_T18_B22 * x2.x + C3B_T18_B32 * x3.x + C3B_T18_B62 * x6.x;
-                            b3.y = C3B_T18_B12 * x1.y + C3B_T18_B22 * x2.y + C3B_T18_B32 * x3.y + C3B_T18_B62 * x6.y;
-                            b2.x = C3B_T18_B11 * x1.x + C3B_T18_B21 * x2.x + C3B_T18_B31 * x3.x + C3B_T18_B61 * x6.x;
-                            b2.y = C3B_T18_B11 * x1.y + C3B_T18_B21 * x2.y + C3B_T18_B31 * x3.y + C3B_T18_B61 * x6.y;
-                            R2[a][c] = b4;
-                            XO[a][c] = b1;
-                            YO[a][c] = b5;
+                            const cplx a1v = bufA[(a * 3 + c) * S];                           // own block of A
+                            const cplx q0 = cmake(C3B_T15_A1 * C[a][c].x + C3B_T15_A2 * a1v.x, C3B_T15_A1 * C[a][c].y + C3B_T15_A2 * a1v.y);
+                            R2[a][c] = C[a][c];
+                            XO[a][c] = C[a][c];
+                            YO[a][c] = q0;
                             if (lane_on) {
-                                bufB[(a * 3 + c) * S] = b1;     // left operand of B1 B5
-                                bufX[(a * 3 + c) * S] = b5;     // right operand
-                                bufA[(a * 3 + c) * S] = b3;     // own block only, re-read after the next product
-                                bufK[(a * 3 + c) * S] = b2;     // own block only, re-read after the last Taylor product
+                                bufB[(a * 3 + c) * S] = C[a][c];  // left operand A^2
+                                bufX[(a * 3 + c) * S] = q0;       // right operand
                             }
                         }
                     __syncwarp();
                     Xb = bufB + unown; Yb = bufX + unown;
-                } else if (ph == 3) {                           // C = B1 B5  ->  A9 = C + B4
-                    cplx B3[3][3];
+                } else if (ph == 1) {                           // C = P0: L1 = P0 + b1 A2 + b2 A, R1 = P0 + b3 A2 + b4 I
+                    cplx A1[3][3];
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) B3[a][c] = bufA[(a * 3 + c) * S];        // loads first
+                        for (int c = 0; c < 3; ++c) A1[a][c] = bufA[(a * 3 + c) * S];          // loads first
                     __syncwarp();                               // bufB / bufX fully read
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const cplx a9 = cmake(C[a][c].x + R2[a][c].x, C[a][c].y + R2[a][c].y);
-                            YO[a][c] = a9;
-                            if (lane_on) bufX[(a * 3 + c) * S] = a9;                          // right operand A9
+                            const cplx p0 = C[a][c], x2 = R2[a][c], x1 = A1[a][c];
+                            const double dg = (on_diag && a == c) ? 1.0 : 0.0;
+                            const cplx l1 = cmake(p0.x + C3B_T15_B1 * x2.x + C3B_T15_B2 * x1.x, p0.y + C3B_T15_B1 * x2.y + C3B_T15_B2 * x1.y);
+                            const cplx r1 = cmake(p0.x + C3B_T15_B3 * x2.x + C3B_T15_B4 * dg, p0.y + C3B_T15_B3 * x2.y);
+                            XO[a][c] = l1;
+                            YO[a][c] = r1;
+                            if (lane_on) {
+                                bufB[(a * 3 + c) * S] = l1;
+                                bufX[(a * 3 + c) * S] = r1;
+                                bufK[(a * 3 + c) * S] = p0;     // own block only, re-read after the next product
+                            }
                         }
+                    __syncwarp();
+                } else if (ph == 2) {                           // C = L1 R1: P1 = C + b5 P0; L2, R2 and the epilogue E0
+                    cplx A1[3][3], P0[3][3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { A1[a][c] = bufA[(a * 3 + c) * S]; P0[a][c] = bufK[(a * 3 + c) * S]; }
+                    __syncwarp();                               // bufB / bufX fully read
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const cplx l = cmake(B3[a][c].x + YO[a][c].x, B3[a][c].y + YO[a][c].y);
-                            XO[a][c] = l;
-                            if (lane_on) bufB[(a * 3 + c) * S] = l;                           // left operand B3 + A9
+                            const cplx p0 = P0[a][c], x2 = R2[a][c], x1 = A1[a][c];
+                            const cplx p1 = cmake(C[a][c].x + C3B_T15_B5 * p0.x, C[a][c].y + C3B_T15_B5 * p0.y);
+                            const double dg = (on_diag && a == c) ? 1.0 : 0.0;
+                            const cplx l2 = cmake(p1.x + C3B_T15_C1 * x2.x + C3B_T15_C2 * x1.x, p1.y + C3B_T15_C1 * x2.y + C3B_T15_C2 * x1.y);
+                            const cplx r2 = cmake(p1.x + C3B_T15_C3 * p0.x + C3B_T15_C4 * x1.x, p1.y + C3B_T15_C3 * p0.y + C3B_T15_C4 * x1.y);
+                            const cplx e0 = cmake(C3B_T15_C9 * p1.x + C3B_T15_C5 * p0.x + C3B_T15_C6 * x2.x + C3B_T15_C7 * x1.x + C3B_T15_C8 * dg,
+                                                  C3B_T15_C9 * p1.y + C3B_T15_C5 * p0.y + C3B_T15_C6 * x2.y + C3B_T15_C7 * x1.y);
+                            XO[a][c] = l2;
+                            YO[a][c] = r2;
+                            if (lane_on) {
+                                bufB[(a * 3 + c) * S] = l2;
+                                bufX[(a * 3 + c) * S] = r2;
+                                bufK[(a * 3 + c) * S] = e0;     // own block only, re-read after the last Taylor product
+                            }
                         }
                     __syncwarp();
                 } else {
-                    if (ph == 4) {                              // C = (B3 + A9) A9  ->  T18 = C + B2
-                        cplx B2[3][3];
+                    if (ph == 3) {                              // C = L2 R2: T = C + E0
 #pragma unroll
                         for (int a = 0; a < 3; ++a)
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) B2[a][c] = bufK[(a * 3 + c) * S];
-#pragma unroll
-                        for (int a = 0; a < 3; ++a)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) { C[a][c].x += B2[a][c].x; C[a][c].y += B2[a][c].y; }
+                            for (int c = 0; c < 3; ++c) {
+                                const cplx e0 = bufK[(a * 3 + c) * S];
+                                C[a][c].x += e0.x; C[a][c].y += e0.y;
+                            }
                     }
                     if (ph <= ph_lastsq) {
-                        // C = exp(A_n / 2^s)^(2^(ph-4)); publish as the next left operand
+                        // C = exp(A_n / 2^s)^(2^(ph-3)); publish as the next left operand
                         __syncwarp();
                         store_own9(bufB, 0, C, lane_on);
                         Xb = bufB + unown;
@@ -463,7 +456,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
 #pragma unroll
                                     for (int c = 0; c < 3; ++c) YO[a][c] = bufP[(a * 3 + c) * S];
                             }
-                            if (p.dUs_out != nullptr && on) {
+                            if (GATED == 0 && p.dUs_out != nullptr && on) {
                                 const cplx ph_n = shifted ? cexp_(mu) : cmake(1.0, 0.0);
 #pragma unroll
                                 for (int a = 0; a < 3; ++a) {
