@@ -37,12 +37,70 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a
                  : "d"(a), "d"(b));
 }
 
+// Fused epilogues of cta_zgemm: what happens to the two adjacent results c0 = (A B)[row, col], c1 = (A B)[row, col + 1] a lane
+// holds (idx = their storage index; every element is read and written by the lane that owns it, so an output may alias
+// any epilogue INPUT -- never an operand of the running product).
+//   0: C = A B                          1: C = A B + E1, E2 += C                    2: C = A B + E1
+// degree-15+ scheme (c3b_common.cuh), so that no separate element-wise pass forms the combinations:
+//   3: C = A B (= A^2),  E2 = a1 C + a2 E1                                        (E1 = A; E2 receives a1 A^2 + a2 A)
+//   4: c = A B (= P0);  C = c + b3 E1 (= R1 - b4 I),  E2 = c + b1 E1 + b2 E3 (= L1)          (E1 = A^2, E3 = A)
+//   5: p = A B (= L1 (R1 - b4 I));  with P0 = E1 - b3 E3 recovered (E1 = R1 - b4 I is an operand: read only) and
+//      P1 = p + b4 L1 + b5 P0 = p + (b4 + b5) P0 + b4 b1 A^2 + b4 b2 A:
+//      E2 <- P1 + c1 E3 + c2 E2 (= L2),  E3 <- P1 + c3 P0 + c4 E2 (= R2),  C <- c9 P1 + c5 P0 + c6 E3 + c7 E2 + c8 I (= E0)
+//      (on entry E2 = A, E3 = A^2).  The identity part of R1 is applied as b4 L1 so that P0 can be recovered from the
+//      stored operand without cancellation against a diagonal of 3 (|b3 A^2| <= 0.05: the recovery is exact to 1e-17).
+//      c8 I also lands on the padding diagonal: the padding block of T is then the identity, which products keep
+//      block-diagonal and no output reads.
+template <int EPI>
+__device__ __forceinline__ void zgemm_epilogue(cplx c0, cplx c1, const int idx, const int row, const int col, cplx* C, const cplx* E1,
+                                               cplx* E2, cplx* E3) {
+    if constexpr (EPI == 1 || EPI == 2) {
+        const cplx e0 = E1[idx], e1 = E1[idx + 1];
+        c0.x += e0.x; c0.y += e0.y; c1.x += e1.x; c1.y += e1.y;
+    }
+    if constexpr (EPI == 1) {
+        const cplx f0 = E2[idx], f1 = E2[idx + 1];
+        E2[idx] = cmake(f0.x + c0.x, f0.y + c0.y);
+        E2[idx + 1] = cmake(f1.x + c1.x, f1.y + c1.y);
+    }
+    if constexpr (EPI == 3) {
+        const cplx a0 = E1[idx], a1 = E1[idx + 1];
+        E2[idx] = cmake(C3B_T15_A1 * c0.x + C3B_T15_A2 * a0.x, C3B_T15_A1 * c0.y + C3B_T15_A2 * a0.y);
+        E2[idx + 1] = cmake(C3B_T15_A1 * c1.x + C3B_T15_A2 * a1.x, C3B_T15_A1 * c1.y + C3B_T15_A2 * a1.y);
+    }
+    if constexpr (EPI == 4) {
+        const cplx s0 = E1[idx], s1 = E1[idx + 1], a0 = E3[idx], a1 = E3[idx + 1];
+        E2[idx] = cmake(c0.x + C3B_T15_B1 * s0.x + C3B_T15_B2 * a0.x, c0.y + C3B_T15_B1 * s0.y + C3B_T15_B2 * a0.y);
+        E2[idx + 1] = cmake(c1.x + C3B_T15_B1 * s1.x + C3B_T15_B2 * a1.x, c1.y + C3B_T15_B1 * s1.y + C3B_T15_B2 * a1.y);
+        c0 = cmake(c0.x + C3B_T15_B3 * s0.x, c0.y + C3B_T15_B3 * s0.y);
+        c1 = cmake(c1.x + C3B_T15_B3 * s1.x, c1.y + C3B_T15_B3 * s1.y);
+    }
+    if constexpr (EPI == 5) {
+        constexpr double kP0 = C3B_T15_B4 + C3B_T15_B5, kS = C3B_T15_B4 * C3B_T15_B1, kA = C3B_T15_B4 * C3B_T15_B2;
+        const cplx r0 = E1[idx], r1 = E1[idx + 1], a0 = E2[idx], a1 = E2[idx + 1], s0 = E3[idx], s1 = E3[idx + 1];
+        const cplx q0 = cmake(r0.x - C3B_T15_B3 * s0.x, r0.y - C3B_T15_B3 * s0.y);
+        const cplx q1 = cmake(r1.x - C3B_T15_B3 * s1.x, r1.y - C3B_T15_B3 * s1.y);
+        const cplx p0 = cmake(c0.x + kP0 * q0.x + kS * s0.x + kA * a0.x, c0.y + kP0 * q0.y + kS * s0.y + kA * a0.y);
+        const cplx p1 = cmake(c1.x + kP0 * q1.x + kS * s1.x + kA * a1.x, c1.y + kP0 * q1.y + kS * s1.y + kA * a1.y);
+        E2[idx] = cmake(p0.x + C3B_T15_C1 * s0.x + C3B_T15_C2 * a0.x, p0.y + C3B_T15_C1 * s0.y + C3B_T15_C2 * a0.y);
+        E2[idx + 1] = cmake(p1.x + C3B_T15_C1 * s1.x + C3B_T15_C2 * a1.x, p1.y + C3B_T15_C1 * s1.y + C3B_T15_C2 * a1.y);
+        E3[idx] = cmake(p0.x + C3B_T15_C3 * q0.x + C3B_T15_C4 * a0.x, p0.y + C3B_T15_C3 * q0.y + C3B_T15_C4 * a0.y);
+        E3[idx + 1] = cmake(p1.x + C3B_T15_C3 * q1.x + C3B_T15_C4 * a1.x, p1.y + C3B_T15_C3 * q1.y + C3B_T15_C4 * a1.y);
+        c0 = cmake(C3B_T15_C9 * p0.x + C3B_T15_C5 * q0.x + C3B_T15_C6 * s0.x + C3B_T15_C7 * a0.x + (row == col ? C3B_T15_C8 : 0.0),
+                   C3B_T15_C9 * p0.y + C3B_T15_C5 * q0.y + C3B_T15_C6 * s0.y + C3B_T15_C7 * a0.y);
+        c1 = cmake(C3B_T15_C9 * p1.x + C3B_T15_C5 * q1.x + C3B_T15_C6 * s1.x + C3B_T15_C7 * a1.x + (row == col + 1 ? C3B_T15_C8 : 0.0),
+                   C3B_T15_C9 * p1.y + C3B_T15_C5 * q1.y + C3B_T15_C6 * s1.y + C3B_T15_C7 * a1.y);
+    }
+    C[idx] = c0;
+    C[idx + 1] = c1;
+}
+
 // One macro tile of TI x TJ m8n8 blocks with run-time leading dimension (the global-workspace path): accumulate over k, then the
 // (optionally fused) epilogue of cta_zgemm.  Instantiated for every block count a partial macro tile at the matrix edge can
 // have, so that those tiles issue DMMAs for the blocks they own only.
 template <int TI, int TJ, int EPI>
 __device__ __forceinline__ void zgemm_tile(cplx* C, const cplx* A, const cplx* B, const int bi0, const int bj0, const int LD, const int KP,
-                                           const cplx* E1, cplx* E2, const int fr, const int fc) {
+                                           const cplx* E1, cplx* E2, cplx* E3, const int fr, const int fc) {
     double p1[TI][TJ][2], p2[TI][TJ][2], p3[TI][TJ][2];
 #pragma unroll
     for (int i = 0; i < TI; ++i)
@@ -78,41 +136,31 @@ __device__ __forceinline__ void zgemm_tile(cplx* C, const cplx* A, const cplx* B
     for (int i = 0; i < TI; ++i)
 #pragma unroll
         for (int j = 0; j < TJ; ++j) {
-            const int idx = ((bi0 + i) * 8 + fr) * LD + (bj0 + j) * 8 + 2 * fc;
-            cplx c0 = cmake(p1[i][j][0] - p2[i][j][0], p3[i][j][0] - p1[i][j][0] - p2[i][j][0]);
-            cplx c1 = cmake(p1[i][j][1] - p2[i][j][1], p3[i][j][1] - p1[i][j][1] - p2[i][j][1]);
-            if constexpr (EPI != 0) {
-                const cplx e0 = E1[idx], e1 = E1[idx + 1];
-                c0.x += e0.x; c0.y += e0.y; c1.x += e1.x; c1.y += e1.y;
-            }
-            if constexpr (EPI == 1) {
-                const cplx f0 = E2[idx], f1 = E2[idx + 1];
-                E2[idx] = cmake(f0.x + c0.x, f0.y + c0.y);
-                E2[idx + 1] = cmake(f1.x + c1.x, f1.y + c1.y);
-            }
-            C[idx] = c0;
-            C[idx + 1] = c1;
+            const int row = (bi0 + i) * 8 + fr, col = (bj0 + j) * 8 + 2 * fc;
+            const cplx c0 = cmake(p1[i][j][0] - p2[i][j][0], p3[i][j][0] - p1[i][j][0] - p2[i][j][0]);
+            const cplx c1 = cmake(p1[i][j][1] - p2[i][j][1], p3[i][j][1] - p1[i][j][1] - p2[i][j][1]);
+            zgemm_epilogue<EPI>(c0, c1, row * LD + col, row, col, C, E1, E2, E3);
         }
 }
 
 // dispatch on the (warp-uniform) block counts of a partial macro tile
 template <int TM, int TN, int EPI>
 __device__ __forceinline__ void zgemm_edge_tile(cplx* C, const cplx* A, const cplx* B, const int bi0, const int bj0, const int ti, const int tj,
-                                                const int LD, const int KP, const cplx* E1, cplx* E2, const int fr, const int fc) {
+                                                const int LD, const int KP, const cplx* E1, cplx* E2, cplx* E3, const int fr, const int fc) {
     if constexpr (TM >= 3) {
-        if (ti == 2 && tj == TN) return zgemm_tile<2, TN, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, fr, fc);
-        if constexpr (TN >= 2) { if (ti == 2 && tj == 1) return zgemm_tile<2, 1, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, fr, fc); }
+        if (ti == 2 && tj == TN) return zgemm_tile<2, TN, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, E3, fr, fc);
+        if constexpr (TN >= 2) { if (ti == 2 && tj == 1) return zgemm_tile<2, 1, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, E3, fr, fc); }
     }
     if constexpr (TM >= 2) {
-        if (ti == 1 && tj == TN) return zgemm_tile<1, TN, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, fr, fc);
+        if (ti == 1 && tj == TN) return zgemm_tile<1, TN, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, E3, fr, fc);
     }
     if constexpr (TN >= 2) {
-        if (ti == TM && tj == 1) return zgemm_tile<TM, 1, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, fr, fc);
+        if (ti == TM && tj == 1) return zgemm_tile<TM, 1, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, E3, fr, fc);
     }
-    if (ti == 1 && tj == 1) return zgemm_tile<1, 1, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, fr, fc);
+    if (ti == 1 && tj == 1) return zgemm_tile<1, 1, EPI>(C, A, B, bi0, bj0, LD, KP, E1, E2, E3, fr, fc);
     // block counts without an instance (TM, TN > 3): one block at a time
     for (int i = 0; i < ti; ++i)
-        for (int j = 0; j < tj; ++j) zgemm_tile<1, 1, EPI>(C, A, B, bi0 + i, bj0 + j, LD, KP, E1, E2, fr, fc);
+        for (int j = 0; j < tj; ++j) zgemm_tile<1, 1, EPI>(C, A, B, bi0 + i, bj0 + j, LD, KP, E1, E2, E3, fr, fc);
 }
 
 // C = A * B for zero-padded DP x DP complex matrices (row-major, leading dimension DP, DP % 8 == 0).
@@ -126,7 +174,8 @@ __device__ __forceinline__ void zgemm_edge_tile(cplx* C, const cplx* A, const cp
 // operand, so they stay zero.
 template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads, int EPI = 0>
 __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP_, const int LD_, const int KP,
-                                          const cplx* E1 = nullptr, cplx* E2 = nullptr, const unsigned char* sched = nullptr) {
+                                          const cplx* E1 = nullptr, cplx* E2 = nullptr, const unsigned char* sched = nullptr,
+                                          cplx* E3 = nullptr) {
     // DPT > 0: tile extent and leading dimension are compile-time (DPT, DPT + 4): the k loop unrolls fully and
     // every fragment address is base + immediate
     constexpr bool SWZ = (DPT == 32);
@@ -148,7 +197,7 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
             // run-time extents: a macro tile at the matrix edge is computed by the instance with exactly its block counts
             const int ti = min(TM, nb - bi0), tj = min(TN, nb - bj0);
             if (ti != TM || tj != TN) {
-                zgemm_edge_tile<TM, TN, EPI>(C, A, B, bi0, bj0, ti, tj, LD, KP, E1, E2, fr, fc);
+                zgemm_edge_tile<TM, TN, EPI>(C, A, B, bi0, bj0, ti, tj, LD, KP, E1, E2, E3, fr, fc);
                 continue;
             }
         }
@@ -271,20 +320,10 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 if (bi0 + i < nb && bj0 + j < nb) {
-                    const int idx = mat_idx<SWZ>((bi0 + i) * 8 + fr, (bj0 + j) * 8 + 2 * fc, LD);   // idx + 1: the next column (f is even)
-                    cplx c0 = cmake(p1[i][j][0] - p2[i][j][0], p3[i][j][0] - p1[i][j][0] - p2[i][j][0]);
-                    cplx c1 = cmake(p1[i][j][1] - p2[i][j][1], p3[i][j][1] - p1[i][j][1] - p2[i][j][1]);
-                    if constexpr (EPI != 0) {
-                        const cplx e0 = E1[idx], e1 = E1[idx + 1];
-                        c0.x += e0.x; c0.y += e0.y; c1.x += e1.x; c1.y += e1.y;
-                    }
-                    if constexpr (EPI == 1) {
-                        const cplx f0 = E2[idx], f1 = E2[idx + 1];
-                        E2[idx] = cmake(f0.x + c0.x, f0.y + c0.y);
-                        E2[idx + 1] = cmake(f1.x + c1.x, f1.y + c1.y);
-                    }
-                    C[idx] = c0;
-                    C[idx + 1] = c1;
+                    const int row = (bi0 + i) * 8 + fr, col = (bj0 + j) * 8 + 2 * fc;
+                    const cplx c0 = cmake(p1[i][j][0] - p2[i][j][0], p3[i][j][0] - p1[i][j][0] - p2[i][j][0]);
+                    const cplx c1 = cmake(p1[i][j][1] - p2[i][j][1], p3[i][j][1] - p1[i][j][1] - p2[i][j][1]);
+                    zgemm_epilogue<EPI>(c0, c1, mat_idx<SWZ>(row, col, LD), row, col, C, E1, E2, E3);   // idx + 1: the next column (f is even)
                 }
             }
     }
@@ -343,11 +382,15 @@ __device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, co
 }
 
 
-// Slot plan (6 matrices of DP x LD): the Taylor combinations overwrite the powers they are formed from and the fused
-// epilogues write in place (an epilogue reads E1[idx] and writes C[idx] from the same thread, so C may alias E1)
-//   S0: A -> B1 -> T18 (squaring ping)    S1: A2 -> B5 (squaring pong)    S2: A3 -> B4 -> A9 = B1 B5 + B4 (in place)
-//   S3: A6 -> B3 -> B3 + A9               S4: B2 -> receives the updated running product dU_n P
-//   P:  running product; after each slice P and S4 swap roles (pointers, no copy)
+// Slot plan (6 matrices of DP x LD), degree-15+ Taylor scheme in FOUR products (c3b_common.cuh); every combination is
+// formed in the epilogue of the product before it (zgemm_epilogue), so a slice is 4 + s + 1 products and as many barriers,
+// with no element-wise pass:
+//   product 1 (EPI 3)  S1 = A A = A2,                 S2 = a1 A2 + a2 A = Q0              (A = S0)
+//   product 2 (EPI 4)  S3 = A2 Q0 + b3 A2 = R1',      S4 = A2 Q0 + b1 A2 + b2 A = L1
+//   product 3 (EPI 5)  p  = L1 R1';   S0 <- L2,  S1 <- R2,  S2 <- E0                     (A, A2 consumed in place)
+//   product 4 (EPI 2)  S3 = L2 R2 + E0 = T                                                (R1' is dead)
+//   squarings ping-pong S3 <-> S4;  the fold X P goes to S2 (E0 is dead) and S2 / P swap roles (pointers, no copy);
+//   the first slice of a segment swaps X and P instead of copying.
 template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(const GemmParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -368,8 +411,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(cons
                            : (p.use_smem ? reinterpret_cast<cplx*>(smem_raw) : p.ws + (size_t)blockIdx.x * kGemmSlots * PP);
     cplx* const S0 = mats;
     cplx* const S1 = mats + (size_t)1 * PP;
-    cplx* const S2 = mats + (size_t)2 * PP;
-    cplx* const S3 = mats + (size_t)3 * PP;
+    cplx* S2 = mats + (size_t)2 * PP;
+    cplx* S3 = mats + (size_t)3 * PP;
     cplx* S4 = mats + (size_t)4 * PP;
     cplx* P = mats + (size_t)5 * PP;
     const bool shifted = gp.TR != nullptr && p.hlist == nullptr;
@@ -419,7 +462,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(cons
                     for (int k = 0; k < K; ++k) t = fma(fabs(__ldg(sig_b + (size_t)k * p.N + n)), RSb[(size_t)(k + 1) * D + r], t);
                     v = fmax(v, t);
                 }
-                s_pre = squarings_for(warp_max(v), C3B_THETA18);
+                s_pre = squarings_for(warp_max(v), C3B_THETA15);
                 asc = pow2neg(s_pre);
             }
             // ---- assemble (D x D part; padding stays zero) ---------------------------------------
@@ -494,61 +537,28 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(cons
             int s = s_pre;
             if (s_pre < 0) {                                   // explicit slices (H list): exact inf-norm of the slice
                 const double nrm = cta_norm_inf_ld<NT>(A, D, LD, red, SWZ ? LD : D);
-                s = squarings_for(nrm, C3B_THETA18);
+                s = squarings_for(nrm, C3B_THETA15);
                 if (s > 0) {
                     const double sc = pow2neg(s);
                     for (int e = tid; e < RL; e += NT) { A[e].x *= sc; A[e].y *= sc; }
                     __syncthreads();
                 }
             }
-            // ---- T18: A2 = S1, A3 = S2, A6 = S3 -----------------------------------------------------
-            cta_zgemm<TM, TN, DPT, KST, NT>(S1, A, A, DP, LD, KP, nullptr, nullptr, sched);
+            // ---- degree-15+ Taylor polynomial in four products (slot plan above) ---------------------------------------
+            cta_zgemm<TM, TN, DPT, KST, NT, 3>(S1, A, A, DP, LD, KP, A, S2, sched);
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT>(S2, S1, A, DP, LD, KP, nullptr, nullptr, sched);
+            cta_zgemm<TM, TN, DPT, KST, NT, 4>(S3, S1, S2, DP, LD, KP, S1, S4, sched, S0);
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT>(S3, S2, S2, DP, LD, KP, nullptr, nullptr, sched);
+            cta_zgemm<TM, TN, DPT, KST, NT, 5>(S2, S4, S3, DP, LD, KP, S3, S0, sched, S1);
             __syncthreads();
-            // in place: B1 -> S0, B5 -> S1, B4 -> S2, B3 -> S3, B2 -> S4
-            // element-wise passes in batches of EU elements per thread, loads first: the compiler may not hoist a load over
-            // the previous element's stores (same buffers), and at D = 81 the operands come from L2
-            constexpr int EU = (DPT > 0) ? 2 : 4;      // shared-memory matrices (d = 27): 2 is enough and 4 costs registers
-            for (int e0 = tid; e0 < RL; e0 += EU * NT) {
-                cplx x1[EU], x2[EU], x3[EU], x6[EU];
-#pragma unroll
-                for (int u = 0; u < EU; ++u) {
-                    const int e = min(e0 + u * NT, RL - 1);
-                    x1[u] = S0[e]; x2[u] = S1[e]; x3[u] = S2[e]; x6[u] = S3[e];
-                }
-#pragma unroll
-                for (int u = 0; u < EU; ++u) {
-                    const int e = e0 + u * NT;
-                    if (e < RL) {
-                        const int i = e / LD, j = SWZ ? ((e - i * LD) ^ swz_of_row(i)) : (e - i * LD);
-                        const double dg = (i == j) ? 1.0 : 0.0;
-                        S0[e] = cmake(C3B_T18_A11 * x1[u].x + C3B_T18_A21 * x2[u].x + C3B_T18_A31 * x3[u].x,
-                                      C3B_T18_A11 * x1[u].y + C3B_T18_A21 * x2[u].y + C3B_T18_A31 * x3[u].y);
-                        S1[e] = cmake(C3B_T18_B24 * x2[u].x + C3B_T18_B34 * x3[u].x + C3B_T18_B64 * x6[u].x,
-                                      C3B_T18_B24 * x2[u].y + C3B_T18_B34 * x3[u].y + C3B_T18_B64 * x6[u].y);
-                        S2[e] = cmake(C3B_T18_B03 * dg + C3B_T18_B13 * x1[u].x + C3B_T18_B23 * x2[u].x + C3B_T18_B33 * x3[u].x + C3B_T18_B63 * x6[u].x,
-                                      C3B_T18_B13 * x1[u].y + C3B_T18_B23 * x2[u].y + C3B_T18_B33 * x3[u].y + C3B_T18_B63 * x6[u].y);
-                        S3[e] = cmake(C3B_T18_B02 * dg + C3B_T18_B12 * x1[u].x + C3B_T18_B22 * x2[u].x + C3B_T18_B32 * x3[u].x + C3B_T18_B62 * x6[u].x,
-                                      C3B_T18_B12 * x1[u].y + C3B_T18_B22 * x2[u].y + C3B_T18_B32 * x3[u].y + C3B_T18_B62 * x6[u].y);
-                        S4[e] = cmake(C3B_T18_B11 * x1[u].x + C3B_T18_B21 * x2[u].x + C3B_T18_B31 * x3[u].x + C3B_T18_B61 * x6[u].x,
-                                      C3B_T18_B11 * x1[u].y + C3B_T18_B21 * x2[u].y + C3B_T18_B31 * x3[u].y + C3B_T18_B61 * x6[u].y);
-                    }
-                }
-            }
+            cta_zgemm<TM, TN, DPT, KST, NT, 2>(S3, S0, S1, DP, LD, KP, S2, nullptr, sched);
             __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT, 1>(S2, S0, S1, DP, LD, KP, S2, S3, sched);   // A9 = B4 + B1 B5 -> S2 (in place);  B3 + A9 -> S3 (epilogue)
-            __syncthreads();
-            cta_zgemm<TM, TN, DPT, KST, NT, 2>(S0, S3, S2, DP, LD, KP, S4, nullptr, sched);       // T18 = B2 + (B3 + A9) A9 (epilogue)
-            __syncthreads();
-            cplx* X = S0;
+            cplx* X = S3;
+            cplx* Y = S4;
             for (int i = 0; i < s; ++i) {                          // undo the scaling
-                cplx* nxt = (X == S0) ? S1 : S0;
-                cta_zgemm<TM, TN, DPT, KST, NT>(nxt, X, X, DP, LD, KP, nullptr, nullptr, sched);
+                cta_zgemm<TM, TN, DPT, KST, NT>(Y, X, X, DP, LD, KP, nullptr, nullptr, sched);
                 __syncthreads();
-                X = nxt;
+                cplx* t = X; X = Y; Y = t;
             }
             if (p.dUs_out != nullptr) {
                 cplx* o = p.dUs_out + ((size_t)b * p.N + n) * D * D;
@@ -567,13 +577,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(cons
                     o[e] = cmul(phn, X[mat_idx<SWZ>(i, j, LD)]);
                 }
             }
-            if (n == n_begin) {
-                for (int e = tid; e < RL; e += NT) P[e] = X[e];
-                __syncthreads();
+            if (n == n_begin) {                                    // P <- dU_n: swap the roles of the two slots
+                S3 = P; P = X; S4 = Y;
             } else {
-                cta_zgemm<TM, TN, DPT, KST, NT>(S4, X, P, DP, LD, KP, nullptr, nullptr, sched);                // B2 is dead: its slot takes dU_n P
+                cta_zgemm<TM, TN, DPT, KST, NT>(S2, X, P, DP, LD, KP, nullptr, nullptr, sched);                // E0 is dead: its slot takes dU_n P
                 __syncthreads();
-                cplx* t = P; P = S4; S4 = t;
+                cplx* t = P; P = S2; S2 = t;
+                S3 = X; S4 = Y;
             }
         }
         cplx* o = (p.S == 1) ? (p.U_out + (size_t)b * D * D) : (p.seg_out + ((size_t)b * p.S + sidx) * D * D);
