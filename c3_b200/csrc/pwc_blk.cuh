@@ -1,19 +1,12 @@
 // Block-layout PWC propagator kernel for small Hilbert dimensions (D = NB * BS).
 //
-// Same fused contract as pwc_rows.cuh (assemble -> Pade expm -> ordered product, replacing
-// c3/libraries/propagation.py:426-440,460-515 and c3/utils/tf_utils.py:120-193), different mapping:
-// a group of NB x NB lanes owns one matrix, lane (bi, bj) holds the BS x BS block (bi, bj) of every
-// register-resident matrix (accumulator, W, V, Q, R: 4*BS*BS registers each).  A product streams
-// BOTH operands from shared memory: per k, BS elements of X's block-row and BS of Y's block-column
-// feed BS*BS complex MACs, i.e. BS/2 cfma per 16-byte operand instead of 1 in the one-row-per-lane
-// layout -- the shared-memory wavefront pipe (128 lane-bytes/clk/SM, every LDS.128 = 4 wavefronts)
-// is what bounds these kernels (profiles/README_r01.md).  Register use is ~1/2 of the row layout,
-// so 12 warps per SM stay resident and cover the serial phases (Gauss-Jordan, syncs).
-//
-// Gauss-Jordan runs in the block layout too: at step k every lane needs 1 + BS + 2*BS complex
-// numbers from three other lanes (pivot, its rows' multipliers, its columns' pivot-row entries),
-// fetched with warp shuffles from registers; no pivoting (norm scaled below 2 ln 2, see
-// c3b_common.cuh).  Orders m in {3,5,7,9}; powers A^2, A^4, A^6 = A^4 A^2, A^8 = A^4 A^4.
+// Fused contract (assemble -> expm -> ordered product, replacing c3/libraries/propagation.py:426-440,460-515 and
+// c3/utils/tf_utils.py:120-193): a group of NB x NB lanes owns one matrix, lane (bi, bj) holds the BS x BS block
+// (bi, bj) of every register-resident matrix (4*BS*BS registers each).  A product streams BOTH operands from shared
+// memory: per k, BS elements of X's block-row and BS of Y's block-column feed BS*BS complex MACs, i.e. BS/2 cfma per
+// 16-byte operand instead of 1 in a one-row-per-lane layout -- the shared-memory wavefront pipe (128 lane-bytes/clk/SM,
+// every LDS.128 = 4 wavefronts) is what bounds these kernels (profiles/README_r01.md).  The exponential is a Taylor
+// polynomial evaluated in four products (c3b_common.cuh): no division, no shuffles, no pivot chain.
 #pragma once
 #include "c3b_common.cuh"
 #include "c3b_params.cuh"
@@ -86,7 +79,7 @@ __device__ __forceinline__ cplx shfl_c(const cplx v, const int src) {
 }
 
 // =============================================================================================
-// Same mapping, exponential by the degree-18 Taylor scheme in 5 products (c3b_common.cuh) instead
+// Same mapping, exponential by the degree-15+ Taylor scheme in 4 products (c3b_common.cuh) instead
 // of Pade + Gauss-Jordan: no division, no shuffles, no serial pivot chain -- every phase is a dense
 // block product or an element-wise combination, which is what a kernel with 2 warps per
 // scheduler needs (ncu: the Gauss-Jordan sweep took 33 % of the Pade kernel's time at 1/6 of its
@@ -219,7 +212,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_t18_kernel(const Row
             nb = warp_max(nb);
             mu_acc.x += mu.x; mu_acc.y += mu.y;
 
-            const int s = squarings_for(nb, C3B_THETA18);
+            const int s = squarings_for(nb, C3B_THETA15);
             if (s > 0) {
                 const double sc = pow2neg(s);
 #pragma unroll
@@ -231,8 +224,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_t18_kernel(const Row
             __syncwarp();
 
             cplx R2[BS][BS], R3[BS][BS], R4[BS][BS], C[BS][BS];
-            // phases: 0 A2 | 1 A3 | 2 A6 (+ combinations) | 3 B1 B5 | 4 (B3+A9) A9 | s squarings | product
-            const int ph_lastsq = 4 + s;
+            // phases (degree-15+ scheme in four products, c3b_common.cuh):
+            //   0 A2 (-> Q0) | 1 P0 = A2 Q0 (-> L1, R1) | 2 L1 R1 (-> P1, L2, R2, E0) | 3 T = L2 R2 + E0 | s squarings | product
+            const int ph_lastsq = 3 + s;
             const int ph_last = ph_lastsq + (it > 0 ? 1 : 0);
             const cplx* Xr = bufA + r0 * LD;
             const cplx* Yc = bufA + c0;
@@ -240,75 +234,63 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_t18_kernel(const Row
 #pragma unroll 1
             for (int ph = 0; ph <= ph_last; ++ph) {
                 mm_blk<D, BS, LD>(Xr, Yc, C);
-                if (ph == 0) {                                  // C = A^2
-#pragma unroll
-                    for (int a = 0; a < BS; ++a)
-#pragma unroll
-                        for (int c = 0; c < BS; ++c) R2[a][c] = C[a][c];
-                    store_blk<D, BS, LD>(bufB + rc_off, C, lane_on);
-                    __syncwarp();
-                    Xr = bufB + r0 * LD; Yc = bufA + c0;         // A^3 = A^2 A
-                } else if (ph == 1) {                           // C = A^3
-#pragma unroll
-                    for (int a = 0; a < BS; ++a)
-#pragma unroll
-                        for (int c = 0; c < BS; ++c) R3[a][c] = C[a][c];
-                    store_blk<D, BS, LD>(bufX + rc_off, C, lane_on);
-                    __syncwarp();
-                    Xr = bufX + r0 * LD; Yc = bufX + c0;         // A^6 = A^3 A^3
-                } else if (ph == 2) {                           // C = A^6: form B1..B5
-                    __syncwarp();                               // bufX (A^3) and bufB (A^2) no longer read
+                if (ph == 0) {                                  // C = A^2;  Q0 = a1 A2 + a2 A
 #pragma unroll
                     for (int a = 0; a < BS; ++a)
 #pragma unroll
                         for (int c = 0; c < BS; ++c) {
-                            const cplx x1 = R1[a][c], x2 = R2[a][c], x3 = R3[a][c], x6 = C[a][c];
-                            const double dg = (on_diag && a == c) ? 1.0 : 0.0;
-                            cplx b1, b5, b4, b3, b2;
-                            b1.x = C3B_T18_A11 * x1.x + C3B_T18_A21 * x2.x + C3B_T18_A31 * x3.x;
-                            b1.y = C3B_T18_A11 * x1.y + C3B_T18_A21 * x2.y + C3B_T18_A31 * x3.y;
-                            b5.x = C3B_T18_B24 * x2.x + C3B_T18_B34 * x3.x + C3B_T18_B64 * x6.x;
-                            b5.y = C3B_T18_B24 * x2.y + C3B_T18_B34 * x3.y + C3B_T18_B64 * x6.y;
-                            b4.x = C3B_T18_B03 * dg + C3B_T18_B13 * x1.x + C3B_T18_B23 * x2.x + C3B_T18_B33 * x3.x + C3B_T18_B63 * x6.x;
-                            b4.y = C3B_T18_B13 * x1.y + C3B_T18_B23 * x2.y + C3B_T18_B33 * x3.y + C3B_T18_B63 * x6.y;
-                            b3.x = C3B_T18_B02 * dg + C3B_T18_B12 * x1.x + C3B_T18_B22 * x2.x + C3B_T18_B32 * x3.x + C3B_T18_B62 * x6.x;
-                            b3.y = C3B_T18_B12 * x1.y + C3B_T18_B22 * x2.y + C3B_T18_B32 * x3.y + C3B_T18_B62 * x6.y;
-                            b2.x = C3B_T18_B11 * x1.x + C3B_T18_B21 * x2.x + C3B_T18_B31 * x3.x + C3B_T18_B61 * x6.x;
-                            b2.y = C3B_T18_B11 * x1.y + C3B_T18_B21 * x2.y + C3B_T18_B31 * x3.y + C3B_T18_B61 * x6.y;
-                            R4[a][c] = b4;
-                            R1[a][c] = b2;
+                            R2[a][c] = C[a][c];
+                            const cplx q = cmake(C3B_T15_A1 * C[a][c].x + C3B_T15_A2 * R1[a][c].x, C3B_T15_A1 * C[a][c].y + C3B_T15_A2 * R1[a][c].y);
                             if (lane_on) {
-                                bufB[rc_off + a * LD + c] = b1;     // left operand of B1 B5
-                                bufX[rc_off + a * LD + c] = b5;     // right operand
-                                bufA[rc_off + a * LD + c] = b3;     // own block only, re-read after the product
+                                bufB[rc_off + a * LD + c] = C[a][c];    // left operand A2
+                                bufX[rc_off + a * LD + c] = q;          // right operand Q0
                             }
                         }
                     __syncwarp();
                     Xr = bufB + r0 * LD; Yc = bufX + c0;
-                } else if (ph == 3) {                           // C = B1 B5  ->  A9 = C + B4
-                    __syncwarp();                               // bufB / bufX fully read
+                } else if (ph == 1) {                           // C = P0 = A2 Q0;  L1 = P0 + b1 A2 + b2 A,  R1 = P0 + b3 A2 + b4 I
+                    __syncwarp();                               // bufB (A2) and bufX (Q0) fully read
 #pragma unroll
                     for (int a = 0; a < BS; ++a)
 #pragma unroll
                         for (int c = 0; c < BS; ++c) {
-                            const cplx a9 = cmake(C[a][c].x + R4[a][c].x, C[a][c].y + R4[a][c].y);
-                            const cplx b3 = bufA[rc_off + a * LD + c];
+                            const cplx x1 = R1[a][c], x2 = R2[a][c], q = C[a][c];
+                            const double dg = (on_diag && a == c) ? 1.0 : 0.0;
+                            R3[a][c] = q;
                             if (lane_on) {
-                                bufX[rc_off + a * LD + c] = a9;                                   // right operand A9
-                                bufB[rc_off + a * LD + c] = cmake(b3.x + a9.x, b3.y + a9.y);      // left operand B3 + A9
+                                bufB[rc_off + a * LD + c] = cmake(q.x + C3B_T15_B1 * x2.x + C3B_T15_B2 * x1.x, q.y + C3B_T15_B1 * x2.y + C3B_T15_B2 * x1.y);
+                                bufX[rc_off + a * LD + c] = cmake(q.x + C3B_T15_B3 * x2.x + C3B_T15_B4 * dg, q.y + C3B_T15_B3 * x2.y);
+                            }
+                        }
+                    __syncwarp();
+                    Xr = bufB + r0 * LD; Yc = bufX + c0;
+                } else if (ph == 2) {                           // C = L1 R1;  P1 = C + b5 P0 -> L2, R2 (published), E0 (kept)
+                    __syncwarp();
+#pragma unroll
+                    for (int a = 0; a < BS; ++a)
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) {
+                            const cplx x1 = R1[a][c], x2 = R2[a][c], q = R3[a][c];
+                            const double dg = (on_diag && a == c) ? 1.0 : 0.0;
+                            const cplx p1 = cmake(C[a][c].x + C3B_T15_B5 * q.x, C[a][c].y + C3B_T15_B5 * q.y);
+                            R4[a][c] = cmake(C3B_T15_C9 * p1.x + C3B_T15_C5 * q.x + C3B_T15_C6 * x2.x + C3B_T15_C7 * x1.x + C3B_T15_C8 * dg,
+                                             C3B_T15_C9 * p1.y + C3B_T15_C5 * q.y + C3B_T15_C6 * x2.y + C3B_T15_C7 * x1.y);
+                            if (lane_on) {
+                                bufB[rc_off + a * LD + c] = cmake(p1.x + C3B_T15_C1 * x2.x + C3B_T15_C2 * x1.x, p1.y + C3B_T15_C1 * x2.y + C3B_T15_C2 * x1.y);
+                                bufX[rc_off + a * LD + c] = cmake(p1.x + C3B_T15_C3 * q.x + C3B_T15_C4 * x1.x, p1.y + C3B_T15_C3 * q.y + C3B_T15_C4 * x1.y);
                             }
                         }
                     __syncwarp();
                     Xr = bufB + r0 * LD; Yc = bufX + c0;
                 } else {
-                    if (ph == 4) {                              // C = (B3 + A9) A9  ->  T18 = C + B2
+                    if (ph == 3) {                              // C = L2 R2  ->  T = C + E0
 #pragma unroll
                         for (int a = 0; a < BS; ++a)
 #pragma unroll
-                            for (int c = 0; c < BS; ++c) { C[a][c].x += R1[a][c].x; C[a][c].y += R1[a][c].y; }
+                            for (int c = 0; c < BS; ++c) { C[a][c].x += R4[a][c].x; C[a][c].y += R4[a][c].y; }
                     }
                     if (ph <= ph_lastsq) {
-                        // C = exp(A_n / 2^s)^(2^(ph-4)); publish as the next left operand
+                        // C = exp(A_n / 2^s)^(2^(ph-3)); publish as the next left operand
                         __syncwarp();
                         store_blk<D, BS, LD>(bufB + rc_off, C, lane_on);
                         __syncwarp();
