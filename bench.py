@@ -561,7 +561,7 @@ def run_engine(args):
             "config": {"workload": WORKLOAD, "d": D, "K": K, "N": N, "B_per_gpu": B, "global_batch": B * n_gpus,
                        "dt": DT, "parallelism": f"batch-sharded x{n_gpus}" + (", one all-gather of U per step" if n_gpus > 1 else ""),
                        "l2": f"{N_ROTATE} rotating input buffers ({N_ROTATE * B * K * N * 8 / 1e6:.0f} MB > 126 MB L2)"},
-            "kernel": "pwc_blk9_t18_kernel<4,2,true,0> (fused assemble + degree-18 Taylor expm in 5 products + ordered product; 3x3 lane blocks, own-block operands from registers, element-major conflict-free shared layout)",
+            "kernel": "pwc_blk9_taylor_kernel<4,2,true,0> (fused assemble + degree-15+ Taylor expm in 4 products + ordered product; 3x3 lane blocks, own-block operands from registers, element-major conflict-free shared layout)",
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": B * K * N * 8,
                     "d2h_bytes_per_step": B * D * D * 16, "api": "c3_b200.propagation.pwc_batch(host signals) -> U.cpu()"},
             "e2e_from_params": {"value": n_gpus * B * N * args.steps / par_s, "unit": "slices/s",

@@ -38,7 +38,7 @@ struct Tuning {
     long long d9_variant = 1;        // d = 9: 0 generic 3x3-block kernel, 1 own-block shared-memory kernel, 2 shuffle-exchange kernel
     long long d9_skew = 120;         // shuffle kernel: clocks between the early and the late half of a CTA's warps
     long long force_cta = 0;         // route everything to the CTA kernels (testing)
-    long long cta_variant = 1;       // 0: literal Higham (Pade + pivoted Gauss-Jordan) cross-check, 1: Taylor-18 on DMMA tiles
+    long long cta_variant = 1;       // 0: literal Higham (Pade + pivoted Gauss-Jordan) cross-check, 1: four-product Taylor scheme on DMMA tiles
     long long cta_threads = 256;     // DMMA CTA kernel, DP = 32: 256 threads (two CTAs per SM) or 512 (one)
     long long gemm_big = 0;          // DMMA CTA kernel, DP = 88 (D = 81): macro-tile shape (0: 3 x 2, 1: 2 x 2)
     long long norm_bound = 1;        // DMMA CTA kernel: scaling from the row-sum bound (1) or the exact inf-norm of every slice (0)
@@ -96,7 +96,7 @@ int launch_seq_small(const cplx* gates, int Gn, const int* idx, const int* lens,
 // k_d9.cu
 int launch_d9(const RowsParams& rp, unsigned int* counter, int variant, cudaStream_t st);
 bool d9_gated_supported(int variant);
-// k_gemm.cu: Taylor-18 on DMMA tiles (any d)
+// k_gemm.cu: four-product Taylor scheme on DMMA tiles (any d)
 int launch_gemm(const CtaParams& cp, const cplx* TR, const double* RS, int grid, cudaStream_t st);
 // k_cta.cu: literal Higham kernel, ordered products, model setup, Kronecker product
 int launch_cta(const CtaParams& cp, const cplx* TR, int grid, cudaStream_t st);

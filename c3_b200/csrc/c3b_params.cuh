@@ -49,7 +49,7 @@ struct CtaParams {
 constexpr int kCtaThreads = 256;
 constexpr int kCtaSlots = 9;  // M0..M7 scratch + P
 
-constexpr int kGemmSlots = 6;    // S0..S4 scratch + P (see the slot plan in pwc_t18_cta_kernel)
+constexpr int kGemmSlots = 6;    // S0..S4 scratch + P (see the slot plan in pwc_taylor_cta_kernel)
 
 struct GemmParams {
     CtaParams c;       // same fields as the Pade CTA kernel (G, signals, hlist, sizes, outputs, ws, use_smem)

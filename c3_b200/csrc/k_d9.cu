@@ -35,7 +35,7 @@ int launch_d9(const RowsParams& rp, unsigned int* counter, int variant, cudaStre
     if (rp.gate != nullptr && !d9_gated_supported(variant))
         return fail(C3B_EUNSUPPORTED, "C3:ERROR: gated launch is not built for d9_variant %d", variant);
     if (variant == 0)
-        return launch_persistent(pwc_blk_t18_kernel<9, 3, 4, 2>, BlkLayout<9, 3>::smem_bytes(rp.K, 4), 4, 2, rp, counter, st);
+        return launch_persistent(pwc_blk_taylor_kernel<9, 3, 4, 2>, BlkLayout<9, 3>::smem_bytes(rp.K, 4), 4, 2, rp, counter, st);
     // gated launches: rows on their own 128-byte lines may be read through L1 (see load_signal)
     const bool lines = rp.gate != nullptr && ((size_t)rp.K * rp.N * sizeof(double)) % 128 == 0 &&
                        (reinterpret_cast<uintptr_t>(rp.signals) % 128) == 0;
@@ -55,9 +55,9 @@ int launch_d9(const RowsParams& rp, unsigned int* counter, int variant, cudaStre
     }
     const size_t smem = Blk9T<true>::smem_bytes(rp.K, 4);
     if (rp.gate != nullptr)
-        return lines ? launch_persistent(pwc_blk9_t18_kernel<4, 2, true, 2>, smem, 4, 2, rp, counter, st)
-                     : launch_persistent(pwc_blk9_t18_kernel<4, 2, true, 1>, smem, 4, 2, rp, counter, st);
-    return launch_persistent(pwc_blk9_t18_kernel<4, 2, true, 0>, smem, 4, 2, rp, counter, st);
+        return lines ? launch_persistent(pwc_blk9_taylor_kernel<4, 2, true, 2>, smem, 4, 2, rp, counter, st)
+                     : launch_persistent(pwc_blk9_taylor_kernel<4, 2, true, 1>, smem, 4, 2, rp, counter, st);
+    return launch_persistent(pwc_blk9_taylor_kernel<4, 2, true, 0>, smem, 4, 2, rp, counter, st);
 }
 
 }  // namespace c3b

@@ -1,4 +1,4 @@
-// Taylor-18 PWC propagators on fp64 tensor-core (DMMA) tiles, one CTA per (batch row, segment): d > 12, Lindblad
+// Taylor (degree 15+, four products) PWC propagators on fp64 tensor-core (DMMA) tiles, one CTA per (batch row, segment): d > 12, Lindblad
 // superoperators (D = d^2), per-sample models.
 #include "c3b_host.cuh"
 #include "pwc_gemm.cuh"
@@ -9,7 +9,7 @@ namespace {
 
 template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
 int launch_gemm_t(const GemmParams& gp, int grid, cudaStream_t st) {
-    auto kern = pwc_t18_cta_kernel<TM, TN, DPT, KST, NT>;
+    auto kern = pwc_taylor_cta_kernel<TM, TN, DPT, KST, NT>;
     const size_t smem = gp.c.use_smem ? gemm_smem_bytes(gp.c.D, gp.g_in_smem ? gp.c.K : -1, gp.g_in_smem ? 0 : 1) : 0;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NT, smem, st>>>(gp);

@@ -11,7 +11,7 @@ int launch_blk_t18_t(const RowsParams& rp, unsigned int* counter, cudaStream_t s
     using L = BlkLayout<D, BS>;
     const size_t smem = L::smem_bytes(rp.K, WARPS);
     if (smem > 227 * 1024) return fail(C3B_EUNSUPPORTED, "C3:ERROR: too many control lines (K=%d) for the d=%d lane-group kernel", rp.K, rp.d);
-    auto kern = pwc_blk_t18_kernel<D, BS, WARPS, MINB>;
+    auto kern = pwc_blk_taylor_kernel<D, BS, WARPS, MINB>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     const long long units = (long long)rp.B * rp.S;

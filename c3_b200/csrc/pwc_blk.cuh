@@ -89,7 +89,7 @@ __device__ __forceinline__ cplx shfl_c(const cplx v, const int src) {
 // and applied once per segment (per slice only when the partial propagators are stored).
 // =============================================================================================
 template <int D, int BS, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_t18_kernel(const RowsParams p, unsigned int* __restrict__ counter) {
+__global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk_taylor_kernel(const RowsParams p, unsigned int* __restrict__ counter) {
     using L = BlkLayout<D, BS>;
     constexpr int NB = L::NB, LPM = L::LPM, MPW = L::MPW, LD = L::LD;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -1,10 +1,10 @@
 // d = 9 (and zero-padded d = 7) fused PWC propagator kernel, second generation of the 3x3-lane block layout
 // (pwc_blk.cuh): "own-block" products in a block-interleaved shared layout.
 //
-// Same contract as pwc_blk_t18_kernel (assemble -> trace-shifted degree-18 Taylor exponential in 5 products ->
+// Same contract as pwc_blk_taylor_kernel (assemble -> trace-shifted degree-15+ Taylor exponential in 4 products ->
 // ordered product; replaces c3/libraries/propagation.py:426-440,460-515 and c3/utils/tf_utils.py:120-193).
 //
-// What changed.  pwc_blk_t18_kernel streams BOTH operands of every 9x9 product from shared memory: per lane
+// What changed.  pwc_blk_taylor_kernel streams BOTH operands of every 9x9 product from shared memory: per lane
 // 54 LDS.128 for 81 complex MACs, and the shared-memory return path (128 lane-bytes per clock per SM) is what
 // bounds it (82 % busy at 53 % fp64 pipe).  Lane (bi,bj) of a 3x3 lane group owns block (bi,bj) of every matrix it
 // produces, so two of the six operand blocks of  C(bi,bj) = sum_k X(bi,k) Y(k,bj)  are already in its registers:
@@ -30,7 +30,7 @@ template <bool NOSEL>
 struct Blk9T {
     static constexpr int S = 9;                    // element stride: slots 0..8
     static constexpr int BUF = 9 * S;              // one 9x9 matrix
-    static constexpr int NBUF = 5;                 // A/B3, A2/B1/.., A3/B5/A9, P, B2 per lane group
+    static constexpr int NBUF = 5;                 // A, B, X, P, K (parked P0 / E0) per lane group
     // group bases (mod 8) as searched with the tables below; warp stride = 0 (mod 8)
     static constexpr int G1 = NOSEL ? 409 : 410;
     static constexpr int G2 = NOSEL ? 821 : 822;
@@ -155,7 +155,7 @@ __device__ __forceinline__ void store_own9(cplx* __restrict__ M, const int sown,
 }
 
 template <int WARPS, int MINB, bool NOSEL, int GATED>
-__global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const RowsParams p, unsigned int* __restrict__ counter) {
+__global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_taylor_kernel(const RowsParams p, unsigned int* __restrict__ counter) {
     using LY = Blk9T<NOSEL>;
     using TB = Blk9Tab<NOSEL>;
     constexpr int D = 9, S = Blk9::S, BUF = Blk9::BUF;
@@ -225,7 +225,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
     cplx* bufB = gbase + BUF + L.sown;        // A^2, then B1, then the left operands of the later products
     cplx* bufX = gbase + 2 * BUF + L.sown;    // A^3, then B5, then A9
     cplx* bufP = gbase + 3 * BUF + L.sown;    // running product of this group's slices
-    cplx* bufK = gbase + 4 * BUF + L.sown;    // own block only: B2
     const int unown = -L.sown;                // back to the buffer base for the operand loads
     const cplx hs = cmake(p.hscale_re, p.hscale_im);
     const long long total_units = (long long)p.B * p.S;
@@ -267,7 +266,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
             const int n = my_begin + it;
             const bool on = lane_on && (n < my_end);
 
-            cplx XO[3][3], YO[3][3], C[3][3], R2[3][3];     // own blocks: X, Y operands, product, A^2 then B4
+            cplx XO[3][3], YO[3][3], C[3][3], R2[3][3];     // own blocks: X, Y operands, product, A^2 then E0
             cplx mu = cmake(0.0, 0.0);
             double nb = 0.0;
             if (!hmode) {
@@ -286,7 +285,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
                     for (int a = 0; a < 3; ++a) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const cplx gv = gk[(a * 3 + c) * S];
+                            const cplx gv = lane_on ? gk[(a * 3 + c) * S] : cmake(0.0, 0.0);   // shadow lanes off: 3 wavefronts, not 4
                             XO[a][c].x = fma(cs, gv.x, XO[a][c].x);
                             XO[a][c].y = fma(cs, gv.y, XO[a][c].y);
                         }
@@ -336,8 +335,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
                 for (int c = 0; c < 3; ++c) YO[a][c] = XO[a][c];
             // phases (degree-15+ scheme in 4 products, c3b_common.cuh):
             //   0: A2 = A A | 1: P0 = A2 (a1 A2 + a2 A) | 2: P1 = L1 R1 + b5 P0 | 3: T = L2 R2 + E0 | s squarings | product
-            // own blocks kept in registers: XO / YO (operands), C (product), R2 (A^2); own blocks parked in shared memory:
-            // A stays in bufA, P0 then E0 in bufK
+            // own blocks kept in registers: XO / YO (operands), C (product), R2 (A^2, then E0); A stays in bufA
             const int ph_lastsq = 3 + s;
             const int ph_last = ph_lastsq + (it > 0 ? 1 : 0);
             const cplx* Xb = bufA + unown;
@@ -359,7 +357,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const cplx a1v = bufA[(a * 3 + c) * S];                           // own block of A
+                            const cplx a1v = XO[a][c];                                        // own block of A: still the X operand
                             const cplx q0 = cmake(C3B_T15_A1 * C[a][c].x + C3B_T15_A2 * a1v.x, C3B_T15_A1 * C[a][c].y + C3B_T15_A2 * a1v.y);
                             R2[a][c] = C[a][c];
                             XO[a][c] = C[a][c];
@@ -371,7 +369,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
                         }
                     __syncwarp();
                     Xb = bufB + unown; Yb = bufX + unown;
-                } else if (ph == 1) {                           // C = P0: L1 = P0 + b1 A2 + b2 A, R1 = P0 + b3 A2 + b4 I
+                } else if (ph == 1) {                           // C = P0: L1 = P0 + b1 A2 + b2 A, R1' = P0 + b3 A2  (R1 = R1' + b4 I)
                     cplx A1[3][3];
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
@@ -383,42 +381,46 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             const cplx p0 = C[a][c], x2 = R2[a][c], x1 = A1[a][c];
-                            const double dg = (on_diag && a == c) ? 1.0 : 0.0;
                             const cplx l1 = cmake(p0.x + C3B_T15_B1 * x2.x + C3B_T15_B2 * x1.x, p0.y + C3B_T15_B1 * x2.y + C3B_T15_B2 * x1.y);
-                            const cplx r1 = cmake(p0.x + C3B_T15_B3 * x2.x + C3B_T15_B4 * dg, p0.y + C3B_T15_B3 * x2.y);
+                            const cplx r1 = cmake(p0.x + C3B_T15_B3 * x2.x, p0.y + C3B_T15_B3 * x2.y);
                             XO[a][c] = l1;
                             YO[a][c] = r1;
                             if (lane_on) {
                                 bufB[(a * 3 + c) * S] = l1;
                                 bufX[(a * 3 + c) * S] = r1;
-                                bufK[(a * 3 + c) * S] = p0;     // own block only, re-read after the next product
                             }
                         }
                     __syncwarp();
-                } else if (ph == 2) {                           // C = L1 R1: P1 = C + b5 P0; L2, R2 and the epilogue E0
-                    cplx A1[3][3], P0[3][3];
+                } else if (ph == 2) {
+                    // C = L1 R1'.  Nothing was parked: L1 is still the X operand, R1' is re-read (a diagonal lane's YO holds
+                    // another block), and P0 = R1' - b3 A2, A = (L1 - P0 - b1 A2) / b2 are recovered from them (no cancellation:
+                    // |b3 A2| ~ |P0| / 25 ... and L1 is dominated by b2 A).  P1 = C + b4 L1 + b5 P0; then L2, R2 and the epilogue
+                    // E0, which takes over the registers of A2.
+                    cplx R1[3][3];
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) { A1[a][c] = bufA[(a * 3 + c) * S]; P0[a][c] = bufK[(a * 3 + c) * S]; }
+                        for (int c = 0; c < 3; ++c) R1[a][c] = bufX[(a * 3 + c) * S];
                     __syncwarp();                               // bufB / bufX fully read
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const cplx p0 = P0[a][c], x2 = R2[a][c], x1 = A1[a][c];
-                            const cplx p1 = cmake(C[a][c].x + C3B_T15_B5 * p0.x, C[a][c].y + C3B_T15_B5 * p0.y);
+                            constexpr double kIB2 = 1.0 / C3B_T15_B2;
+                            const cplx x2 = R2[a][c], l1 = XO[a][c];
+                            const cplx p0 = cmake(R1[a][c].x - C3B_T15_B3 * x2.x, R1[a][c].y - C3B_T15_B3 * x2.y);
+                            const cplx x1 = cmake((l1.x - p0.x - C3B_T15_B1 * x2.x) * kIB2, (l1.y - p0.y - C3B_T15_B1 * x2.y) * kIB2);
+                            const cplx p1 = cmake(C[a][c].x + C3B_T15_B4 * l1.x + C3B_T15_B5 * p0.x, C[a][c].y + C3B_T15_B4 * l1.y + C3B_T15_B5 * p0.y);
                             const double dg = (on_diag && a == c) ? 1.0 : 0.0;
                             const cplx l2 = cmake(p1.x + C3B_T15_C1 * x2.x + C3B_T15_C2 * x1.x, p1.y + C3B_T15_C1 * x2.y + C3B_T15_C2 * x1.y);
                             const cplx r2 = cmake(p1.x + C3B_T15_C3 * p0.x + C3B_T15_C4 * x1.x, p1.y + C3B_T15_C3 * p0.y + C3B_T15_C4 * x1.y);
-                            const cplx e0 = cmake(C3B_T15_C9 * p1.x + C3B_T15_C5 * p0.x + C3B_T15_C6 * x2.x + C3B_T15_C7 * x1.x + C3B_T15_C8 * dg,
-                                                  C3B_T15_C9 * p1.y + C3B_T15_C5 * p0.y + C3B_T15_C6 * x2.y + C3B_T15_C7 * x1.y);
+                            R2[a][c] = cmake(C3B_T15_C9 * p1.x + C3B_T15_C5 * p0.x + C3B_T15_C6 * x2.x + C3B_T15_C7 * x1.x + C3B_T15_C8 * dg,
+                                             C3B_T15_C9 * p1.y + C3B_T15_C5 * p0.y + C3B_T15_C6 * x2.y + C3B_T15_C7 * x1.y);
                             XO[a][c] = l2;
                             YO[a][c] = r2;
                             if (lane_on) {
                                 bufB[(a * 3 + c) * S] = l2;
                                 bufX[(a * 3 + c) * S] = r2;
-                                bufK[(a * 3 + c) * S] = e0;     // own block only, re-read after the last Taylor product
                             }
                         }
                     __syncwarp();
@@ -427,10 +429,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pwc_blk9_t18_kernel(const Ro
 #pragma unroll
                         for (int a = 0; a < 3; ++a)
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const cplx e0 = bufK[(a * 3 + c) * S];
-                                C[a][c].x += e0.x; C[a][c].y += e0.y;
-                            }
+                            for (int c = 0; c < 3; ++c) { C[a][c].x += R2[a][c].x; C[a][c].y += R2[a][c].y; }
                     }
                     if (ph <= ph_lastsq) {
                         // C = exp(A_n / 2^s)^(2^(ph-3)); publish as the next left operand

@@ -1,7 +1,7 @@
 // d <= 9 fused PWC propagator kernel on the fp64 tensor-core instruction: ONE WARP PER SLICE CHAIN, every 9 x 9 complex
 // product as an 8 x 8 DMMA core plus a 1-wide edge.
 //
-// Same contract as pwc_blk9_t18_kernel (assemble -> trace-shifted degree-18 Taylor exponential in 5 products -> ordered
+// Same contract as pwc_blk9_taylor_kernel (assemble -> trace-shifted degree-18 Taylor exponential in 5 products -> ordered
 // product; replaces c3/libraries/propagation.py:426-440,460-515 and c3/utils/tf_utils.py:120-193).
 //
 // Why.  The lane-group kernels (pwc_blk9.cuh, pwc_shfl9.cuh) spend 540 issued instructions per 3 matrix products (324

@@ -392,7 +392,7 @@ __device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, co
 //   squarings ping-pong S3 <-> S4;  the fold X P goes to S2 (E0 is dead) and S2 / P swap roles (pointers, no copy);
 //   the first slice of a segment swaps X and P instead of copying.
 template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_t18_cta_kernel(const GemmParams gp) {
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_taylor_cta_kernel(const GemmParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[NT / 32];
     const CtaParams& p = gp.c;

@@ -1,10 +1,10 @@
 // d = 9 (and zero-padded d = 7, 8... any d <= 9) fused PWC propagator kernel, third generation of the 3x3-lane block
 // layout: operand blocks are EXCHANGED BY WARP SHUFFLES, never published through shared memory.
 //
-// Same contract as pwc_blk9_t18_kernel (assemble -> trace-shifted degree-18 Taylor exponential in 5 products -> ordered
+// Same contract as pwc_blk9_taylor_kernel (assemble -> trace-shifted degree-18 Taylor exponential in 5 products -> ordered
 // product; replaces c3/libraries/propagation.py:426-440,460-515 and c3/utils/tf_utils.py:120-193).
 //
-// Why.  ncu on pwc_blk9_t18_kernel (profiles/r01_prof_blk9_own_final.txt): the shared-memory / shuffle pipe (MIO, 128
+// Why.  ncu on pwc_blk9_taylor_kernel (profiles/r01_prof_blk9_own_final.txt): the shared-memory / shuffle pipe (MIO, 128
 // lane-bytes per clock per SM) is 83 % busy while the fp64 pipe is at 59.5 %.  Of the 1 720 wavefronts a warp spends per
 // slice-triple, 868 are the operand loads of the six 9x9 products and 470 are STORES whose only purpose is to publish a
 // freshly computed block to the other lanes of its group.  A SHFL.32 costs one wavefront, an LDS.128 four

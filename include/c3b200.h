@@ -265,7 +265,7 @@ int c3b_kron(const void* A, const void* Bm, void* out, int batch, int ra, int ca
 /* Tuning knobs of the CALLING THREAD (thread-local: one thread per GPU is the intended use, and a thread that flips a
  * knob for an experiment cannot disturb another thread's launches).  Keys: "target_units", "min_chunk" (segmentation of
  * the time axis), "d9_variant" (0 generic 3x3-block kernel, 1 own-block shared-memory kernel, 2 shuffle-exchange kernel),
- * "force_cta", "cta_variant" (0 literal Higham cross-check, 1 Taylor-18 on DMMA tiles), "cta_threads", "gemm_big",
+ * "force_cta", "cta_variant" (0 literal Higham cross-check, 1 four-product Taylor scheme on DMMA tiles), "cta_threads", "gemm_big",
  * "norm_bound", "seq_variant", "grad_variant", "profile".  Returns C3B_EINVAL for an unknown key. */
 int c3b_set_tuning(const char* key, long long value);
 
