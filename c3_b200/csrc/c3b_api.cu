@@ -133,12 +133,16 @@ struct Plan {
     size_t off_seg, off_cta, off_prod, off_counter, total;
 };
 
-Plan make_plan(int B, int N, int D, int batched_model) {
+// seg_len_override > 0: segments of exactly that many slices (the fused gradient path wants the chunk products)
+Plan make_plan(int B, int N, int D, int batched_model, int seg_len_override = 0) {
     const Tuning& tn = tuning();
     Plan pl{};
     pl.path = pwc_path(D, batched_model);
     long long S, smax;
-    if (pl.path == 1) {
+    if (seg_len_override > 0) {
+        S = (N + seg_len_override - 1) / seg_len_override;
+        smax = S;
+    } else if (pl.path == 1) {
         S = (tn.target_units + B - 1) / B;
         smax = N / (tn.min_chunk * blk_groups_per_warp(D));
     } else {
@@ -294,6 +298,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (!strcmp(key, "norm_bound")) { t.norm_bound = value; return C3B_OK; }
     if (!strcmp(key, "seq_variant")) { t.seq_variant = value; return C3B_OK; }
     if (!strcmp(key, "grad_variant")) { t.grad_variant = value; return C3B_OK; }
+    if (!strcmp(key, "grad_unitary")) { t.grad_unitary = value; return C3B_OK; }
     if (!strcmp(key, "profile")) { t.profile = value; return C3B_OK; }
     return fail(C3B_EINVAL, "C3:ERROR: unknown tuning key '%s'", key);
 }
@@ -459,11 +464,43 @@ int c3b_kron(const void* A, const void* Bm, void* out, int batch, int ra, int ca
 // variant 1 (default): Frechet derivative of the Taylor scheme on (X, dX) pairs, fused contraction -- warp-per-slice kernels for
 //   matrix dimension <= 16, CTA kernels on the DMMA product above (variant 2 here)
 // variant 0: augmented 2d x 2d exponential through the forward kernels (closed systems, d <= 32; cross-check)
+// variant 3 (default for closed d = 7..9 with Hermitian Hamiltonians): the fused lockstep kernel of grad_blk9.cuh -- no stored
+//   propagators at all.  "grad_variant" 2 forces the stored-propagator kernels there (cross-check); "grad_unitary" says whether
+//   the Hamiltonians are Hermitian (1), are not (0), or must be checked on the device (-1: one 4-byte read-back per call).
 static int grad_variant_for(int D) {
     if (tuning().grad_variant == 0 && D <= 32) return 0;
     return D <= 16 ? 1 : 2;
 }
 constexpr int kGradMaxDim = 128;
+
+static bool grad9_wanted(int lindblad, int K, int d) {
+    return !lindblad && tuning().grad_variant == 1 && tuning().grad_unitary != 0 && tuning().force_cta == 0 && grad9_supported(K, d);
+}
+// chunk length of the fused gradient kernel: enough chunks to fill the machine, at least 8 slices, at most 48
+static int grad9_chunk_len(int B, int N) {
+    const long long want = 3LL * 8 * num_sms() * 4;                 // lane groups x 4 waves
+    long long cl = ((long long)B * N + want - 1) / want;
+    if (cl < 8) cl = 8;
+    if (cl > 48) cl = 48;
+    if (cl > N) cl = N;
+    return (int)cl;
+}
+struct Grad9Layout { size_t off_model, off_plan, off_U, off_Y, off_counter, total; int CL, Q; Plan pl; };
+static Grad9Layout grad9_layout(int Bc, int K, int N, int d) {
+    Grad9Layout g{};
+    g.CL = grad9_chunk_len(Bc, N);
+    g.Q = (N + g.CL - 1) / g.CL;
+    g.pl = make_plan(Bc, N, d, 0, g.CL);
+    const ModelLayout ml = model_layout(K, d, 1);
+    size_t o = 0;
+    g.off_model = o; o += ml.total;
+    g.off_plan = o; o += align_up(g.pl.total);
+    g.off_U = o; o += align_up((size_t)Bc * d * d * sizeof(cplx));
+    g.off_Y = o; o += align_up((size_t)Bc * g.Q * d * d * sizeof(cplx));
+    g.off_counter = o; o += 256;
+    g.total = o;
+    return g;
+}
 
 // D: matrix dimension of the propagators (d, or d^2 for Lindblad); dh: Hilbert dimension passed to the workspace query
 static size_t grad_chunk_bytes(int Bc, int K, int N, int dh, int lindblad, size_t* off /*[10]*/) {
@@ -488,6 +525,12 @@ size_t c3b_pwc_grad_workspace_bytes(int B, int K, int N, int d, int chunk) {
     if (B <= 0 || N <= 0 || d <= 0 || K <= 0) return 0;
     const int Bc = (chunk > 0 && chunk < B) ? chunk : B;
     size_t off[10];
+    if (grad9_wanted(0, K, d)) {
+        const size_t fused = grad9_layout(Bc, K, N, d).total;
+        if (tuning().grad_unitary == 1) return fused;
+        const size_t stored = grad_chunk_bytes(Bc, K, N, d, 0, off);     // the device check may send the call there
+        return fused > stored ? fused : stored;
+    }
     return grad_chunk_bytes(Bc, K, N, d, 0, off);
 }
 
@@ -509,6 +552,48 @@ static int pwc_grad_impl(int lindblad, const void* h0, const void* hks, const vo
     if (lindblad && variant == 0)
         return fail(C3B_EUNSUPPORTED, "C3:ERROR: the augmented-exponential gradient (grad_variant 0) is built for closed systems only");
     const int Bc = (chunk > 0 && chunk < B) ? chunk : B;
+    if (grad9_wanted(lindblad, K, dh)) {
+        cudaStream_t st9 = static_cast<cudaStream_t>(stream);
+        const Grad9Layout gl = grad9_layout(Bc, K, N, dh);
+        if (workspace_bytes < gl.total) return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small: %zu < %zu bytes", workspace_bytes, gl.total);
+        char* w9 = static_cast<char*>(workspace);
+        unsigned int* flag = reinterpret_cast<unsigned int*>(w9 + gl.off_counter) + 16;
+        bool unitary = tuning().grad_unitary == 1;
+        if (!unitary) {                                // -1: look at the Hamiltonians (one small kernel + a 4-byte read-back)
+            int rc = launch_hermitian_check(static_cast<const cplx*>(h0), static_cast<const cplx*>(hks), K, dh, flag, st9);
+            if (rc) return rc;
+            unsigned int host_flag = 1;
+            CUDA_TRY(cudaMemcpyAsync(&host_flag, flag, sizeof(host_flag), cudaMemcpyDeviceToHost, st9));
+            CUDA_TRY(cudaStreamSynchronize(st9));
+            unitary = host_flag == 0;
+        }
+        if (unitary) {
+            int rc = build_model(h0, hks, nullptr, 0, dt, K, dh, 0, 1, w9 + gl.off_model, st9);
+            if (rc) return rc;
+            const ModelLayout ml = model_layout(K, dh, 1);
+            for (int b0 = 0; b0 < B; b0 += Bc) {
+                const int nb = (B - b0 < Bc) ? (B - b0) : Bc;
+                const double* sig = signals + (size_t)b0 * K * N;
+                cplx* Udst = U_out ? static_cast<cplx*>(U_out) + (size_t)b0 * dh * dh : reinterpret_cast<cplx*>(w9 + gl.off_U);
+                Plan pl = make_plan(nb, N, dh, 0, gl.CL);
+                rc = run_pwc(pl, w9 + gl.off_model, sig, nullptr, dt, nb, K, N, dh, 0, Udst, nullptr, nullptr, w9 + gl.off_plan, st9);
+                if (rc) return rc;
+                const cplx* seg = pl.S > 1 ? reinterpret_cast<const cplx*>(w9 + gl.off_plan + pl.off_seg) : nullptr;
+                cplx* Yb = reinterpret_cast<cplx*>(w9 + gl.off_Y);
+                rc = launch_grad9_boundary(Udst, static_cast<const cplx*>(Ubar) + (size_t)b0 * dh * dh, seg, Yb, nb, pl.S, dh, st9);
+                if (rc) return rc;
+                Grad9Params gp{};
+                gp.G = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_G);
+                gp.RS = reinterpret_cast<const double*>(w9 + gl.off_model + ml.off_RS);
+                gp.TR = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_TR);
+                gp.signals = sig; gp.Ybound = Yb; gp.grad = grad_out + (size_t)b0 * K * N;
+                gp.B = nb; gp.K = K; gp.N = N; gp.d = dh; gp.Q = pl.S; gp.CL = pl.seg_len;
+                rc = launch_grad9(gp, reinterpret_cast<unsigned int*>(w9 + gl.off_counter), st9);
+                if (rc) return rc;
+            }
+            return C3B_OK;
+        }
+    }
     size_t off[10];
     const size_t need = grad_chunk_bytes(Bc, K, N, dh, lindblad, off);
     if (workspace_bytes < need) return fail(C3B_EWORKSPACE, "C3:ERROR: workspace too small: %zu < %zu bytes", workspace_bytes, need);

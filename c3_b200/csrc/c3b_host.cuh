@@ -43,7 +43,9 @@ struct Tuning {
     long long gemm_big = 0;          // DMMA CTA kernel, DP = 88 (D = 81): macro-tile shape (0: 3 x 2, 1: 2 x 2)
     long long norm_bound = 1;        // DMMA CTA kernel: scaling from the row-sum bound (1) or the exact inf-norm of every slice (0)
     long long seq_variant = 1;       // evaluate_sequences: 1 lane-group kernel for small d, 0 CTA-per-sequence product kernel
-    long long grad_variant = 1;      // 1: Frechet derivative of the Taylor scheme, 0: augmented exponential
+    long long grad_variant = 1;      // 1: best available (fused lockstep kernel at closed d = 7..9, Frechet kernels elsewhere), 0: augmented
+                                     // exponential, 2: the stored-propagator Frechet kernels everywhere (cross-check)
+    long long grad_unitary = -1;     // closed-system Hamiltonians Hermitian? 1 yes, 0 no, -1 check on the device (4-byte read-back)
     long long profile = 0;           // bracket the main PWC kernel of each call by events (c3b_last_kernel_ms)
 };
 Tuning& tuning();
@@ -117,6 +119,12 @@ int launch_grad_frechet(const cplx* G, const double* RS, const cplx* TR, const d
                         double* grad, int nb, int K, int N, int d, cudaStream_t st);
 int launch_grad_contract(const cplx* Eaug, const cplx* hks, const double* alpha, double* grad, double dt, int nb, int K, int N, int d,
                          cudaStream_t st);
+
+// k_grad9.cu: fused lockstep gradient kernel for closed d = 7..9 (grad_blk9.cuh)
+bool grad9_supported(int K, int d);
+int launch_hermitian_check(const cplx* h0, const cplx* hks, int K, int d, unsigned int* flag, cudaStream_t st);
+int launch_grad9_boundary(const cplx* U, const cplx* Ubar, const cplx* seg, cplx* Ybound, int B, int Q, int d, cudaStream_t st);
+int launch_grad9(const Grad9Params& gp, unsigned int* counter, cudaStream_t st);
 
 // k_grad_cta.cu: the same adjoint scheme on the CTA-cooperative DMMA product (closed d > 16, Lindblad superoperators)
 bool grad_cta_uses_smem(int D);

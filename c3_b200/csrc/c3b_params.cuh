@@ -108,4 +108,16 @@ __device__ __forceinline__ double load_signal(const double* ptr) {
     else return __ldg(ptr);
 }
 
+// fused d = 9 gradient kernel (grad_blk9.cuh)
+struct Grad9Params {
+    const cplx* G;          // [(K+1), d, d] trace-shifted generators (forward model blob)
+    const double* RS;       // [(K+1), d] row sums
+    const cplx* TR;         // [K+1] trace shifts
+    const double* signals;  // [B, K, N]
+    const cplx* Ybound;     // [B, Q, d, d]: Y at the first slice of every chunk
+    double* grad;           // [B, K, N]
+    int B, K, N, d, Q, CL;
+};
+
+
 }  // namespace c3b

@@ -72,7 +72,7 @@ struct Blk9Lane {
 };
 
 // C = X * Y for this lane's block.  XO / YO: own blocks of X and Y (registers); Xb / Yb: the matrices in shared memory.
-template <bool NOSEL>
+template <bool NOSEL, bool ACC = false>
 __device__ __forceinline__ void mm_own9(const cplx* __restrict__ Xb, const cplx* __restrict__ Yb, const Blk9Lane& L,
                                         const cplx (&XO)[3][3], const cplx (&YO)[3][3], cplx (&c)[3][3]) {
     constexpr int S = Blk9::S;
@@ -80,10 +80,12 @@ __device__ __forceinline__ void mm_own9(const cplx* __restrict__ Xb, const cplx*
     const cplx* y1 = Yb + L.sy1;
     const cplx* x2 = Xb + L.sx2;
     const cplx* y2 = Yb + L.sy2;
+    if constexpr (!ACC) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+        for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int b = 0; b < 3; ++b) c[a][b] = cmake(0.0, 0.0);
+            for (int b = 0; b < 3; ++b) c[a][b] = cmake(0.0, 0.0);
+    }
 #pragma unroll
     for (int kk = 0; kk < 3; ++kk) {
         cplx lx[3], ly[3], ya[3], yb[3];

@@ -534,12 +534,13 @@ def test_gradient_matches_autograd_oracle(eng, levels, N, B):
     assert rel_fro(g, g_ref) < 1e-8
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("scale,d", [(1.0, 9), (6.0, 9), (40.0, 9), (3.0, 5), (1.0, 12), (1.0, 16)])
 def test_gradient_variants_and_squarings(eng, variant, scale, d):
-    """Both gradient implementations (0: augmented exponential, 1: Frechet derivative of the Taylor scheme with the
-    fused contraction) against torch-CPU autograd, including slices that need 1 .. 6 squarings and every
-    chunk width of the shared-memory product (d divisible by 3, by 2, by neither)."""
+    """The gradient implementations (0: augmented exponential, 1: default -- the fused lockstep kernel at d = 9, the
+    Frechet kernels elsewhere, 2: the stored-propagator Frechet kernels everywhere) against torch-CPU autograd, including
+    slices that need 1 .. 6 squarings and every chunk width of the shared-memory product (d divisible by 3, by 2, by
+    neither)."""
     from oracle import c3_grad_oracle as gorc
     rng = np.random.default_rng(int(scale) + d)
     K, B, N = 2, 3, 17
@@ -646,6 +647,62 @@ def test_lindblad_gradient_cta_path(eng, model, N):
     assert rel_fro(s.grad.cpu().numpy(), s_ref.grad.numpy()) < 1e-8
 
 
+@pytest.mark.parametrize("d,K,B,N,scale", [(9, 2, 4, 131, 1.0), (9, 1, 1, 5, 1.0), (9, 3, 2, 50, 6.0), (8, 2, 3, 33, 1.0),
+                                           (7, 2, 5, 64, 3.0), (9, 2, 1, 700, 0.5), (9, 5, 2, 40, 1.0)])
+def test_gradient_fused_d9_kernel(eng, d, K, B, N, scale):
+    """The fused d = 9 gradient kernel (grad_blk9.cuh: Y_n recurrence by unitarity, lockstep Frechet derivative, no stored
+    propagators) against torch-CPU autograd and against the stored-propagator kernels: zero-padded d = 7, 8, ragged last
+    chunks, a single slice chunk, several chunks per row, K = 1 .. 5, slices that need squarings."""
+    from oracle import c3_grad_oracle as gorc
+    rng = np.random.default_rng(d * 100 + K * 10 + N)
+    h0, hks = _rand_model(rng, d, K, 0.9 * scale)
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    Ubar = rng.normal(size=(B, d, d)) + 1j * rng.normal(size=(B, d, d))
+    U1, g1 = eng.pwc_closed_grad(h0, hks, sig, 1.0, Ubar)
+    eng.set_tuning("grad_variant", 2)
+    try:
+        U2, g2 = eng.pwc_closed_grad(h0, hks, sig, 1.0, Ubar)
+    finally:
+        eng.set_tuning("grad_variant", 1)
+    assert rel_fro(U1.cpu().numpy(), U2.cpu().numpy()) < 1e-12
+    assert rel_fro(g1.cpu().numpy(), g2.cpu().numpy()) < 1e-9
+    if N <= 131:
+        q = np.stack([np.linalg.qr(rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d)))[0] for _ in range(B)])
+        L_ref, g_ref, U_ref = gorc.loss_and_grad(h0, hks, sig, 1.0, q)
+        Uc = torch.tensor(U_ref, requires_grad=True)
+        ((1.0 - (torch.einsum("bij,bij->b", torch.as_tensor(q).conj(), Uc).abs() ** 2) / d ** 2).sum()).backward()
+        U, g = eng.pwc_closed_grad(h0, hks, sig, 1.0, Uc.grad.numpy())
+        assert rel_fro(U.cpu().numpy(), U_ref) < TOL
+        assert rel_fro(g.cpu().numpy(), g_ref) < 1e-8
+
+
+def test_gradient_non_hermitian_falls_back(eng):
+    """The fused kernel assumes unitary slice propagators; a non-Hermitian 'Hamiltonian' must be detected on the device and
+    served by the stored-propagator kernels (same result as forcing them), and the caller's assertion 'grad_unitary' = 0
+    / 1 skips the check."""
+    rng = np.random.default_rng(77)
+    d, K, B, N = 9, 2, 3, 21
+    h0, hks = _rand_model(rng, d, K, 0.9, hermitian=False)
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    Ubar = rng.normal(size=(B, d, d)) + 1j * rng.normal(size=(B, d, d))
+    U1, g1 = eng.pwc_closed_grad(h0, hks, sig, 1.0, Ubar)
+    eng.set_tuning("grad_variant", 2)
+    try:
+        U2, g2 = eng.pwc_closed_grad(h0, hks, sig, 1.0, Ubar)
+    finally:
+        eng.set_tuning("grad_variant", 1)
+    assert torch.equal(g1, g2) and torch.equal(U1, U2)
+    h0h, hksh = _rand_model(rng, d, K, 0.9)
+    ref = eng.pwc_closed_grad(h0h, hksh, sig, 1.0, Ubar)[1]
+    for flag in (1, 0):
+        eng.set_tuning("grad_unitary", flag)
+        try:
+            g = eng.pwc_closed_grad(h0h, hksh, sig, 1.0, Ubar)[1]
+        finally:
+            eng.set_tuning("grad_unitary", -1)
+        assert rel_fro(g.cpu().numpy(), ref.cpu().numpy()) < 1e-9
+
+
 def test_gradient_chunking_and_finite_difference(eng):
     """Chunked passes give the same gradient; a central finite difference agrees to 1e-6."""
     from c3_b200 import synth
@@ -656,8 +713,8 @@ def test_gradient_chunking_and_finite_difference(eng):
     Ubar = rng.normal(size=(B, 9, 9)) + 1j * rng.normal(size=(B, 9, 9))
     U1, g1 = eng.pwc_closed_grad(m.h0, m.hks, sig, 1e-11, Ubar)
     U2, g2 = eng.pwc_closed_grad(m.h0, m.hks, sig, 1e-11, Ubar, max_workspace_bytes=1 << 20)   # forces small chunks
-    assert torch.equal(U1, U2)
-    assert rel_fro(g2.cpu().numpy(), g1.cpu().numpy()) < 1e-12
+    assert rel_fro(U2.cpu().numpy(), U1.cpu().numpy()) < 1e-13     # the chunk length follows the batch chunk: other rounding
+    assert rel_fro(g2.cpu().numpy(), g1.cpu().numpy()) < 1e-11
     b, k, n = 2, 1, 17
     eps = 1e3          # signals are ~1e9 rad/s
     sp, sm = sig.copy(), sig.copy()
