@@ -34,7 +34,9 @@ namespace c3b {
 struct Grad9T {
     static constexpr int BUF = Blk9::BUF;
     static constexpr int NBUF = 7;
-    // group bases: the residues (mod 8) of the annealed forward layout (Blk9T<true>: 0, 409, 821)
+    // group bases: the residues (mod 8) of the annealed forward layout (Blk9T<true>: 0, 409, 821).  Measured and dropped:
+    // the select-based tables (every lane fetches its own block of Y: 4 wavefronts instead of 6) + 6 %, skipping the
+    // operand fetches whose block is still in registers behind run-time flags + 3 %.
     static constexpr int G1 = 569, G2 = 1141, WARP_ELEMS = 1712;
     static_assert(G1 % 8 == 409 % 8 && G2 % 8 == 821 % 8 && WARP_ELEMS % 8 == 0, "bank residues of the searched layout");
     static_assert(G1 >= NBUF * BUF && G2 >= G1 + NBUF * BUF && WARP_ELEMS >= G2 + NBUF * BUF, "layout");
