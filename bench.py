@@ -354,8 +354,8 @@ def run_configs(engine, synth, dev, rank, world, dfma_peak, all_gather, check):
     strong = {"B_total": B_PER_GPU, "B_per_gpu": hi - lo, "n_gpus": world, "ms_per_step": ms, "slices_per_s": B_PER_GPU * N / (ms * 1e-3),
               "note": "same d = 9, N = 1000 workload with the batch FIXED at 4096 in total.  Limiter when the efficiency drops: the per-GPU "
                       "batch (512 rows at 8 GPUs) gives the persistent kernel 12 waves of warp units instead of 100, so its tail, the "
-                      "segment-fold launch, the all-gather and ~10 us of launch latency weigh on a 1.3 ms kernel (a B = 512 launch alone "
-                      "runs at 3.8e8 slices/s against 4.2e8 at B = 4096)"}
+                      "segment-fold launch, the all-gather and ~10 us of launch latency weigh on a 1.1 ms kernel (a B = 512 launch alone "
+                      "runs about 10 % below the B = 4096 rate)"}
     return out, strong
 
 
