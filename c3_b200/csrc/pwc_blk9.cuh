@@ -30,11 +30,11 @@ template <bool NOSEL>
 struct Blk9T {
     static constexpr int S = 9;                    // element stride: slots 0..8
     static constexpr int BUF = 9 * S;              // one 9x9 matrix
-    static constexpr int NBUF = 5;                 // A, B, X, P, K (parked P0 / E0) per lane group
+    static constexpr int NBUF = 4;                 // A, B, X, P per lane group
     // group bases (mod 8) as searched with the tables below; warp stride = 0 (mod 8)
-    static constexpr int G1 = NOSEL ? 409 : 410;
-    static constexpr int G2 = NOSEL ? 821 : 822;
-    static constexpr int WARP_ELEMS = NOSEL ? 1232 : 1232;
+    static constexpr int G1 = NOSEL ? 329 : 330;   // = 409 / 410 (mod 8)
+    static constexpr int G2 = NOSEL ? 653 : 654;   // = 821 / 822 (mod 8)
+    static constexpr int WARP_ELEMS = 984;
     static_assert(G1 >= NBUF * BUF && G2 >= G1 + NBUF * BUF && WARP_ELEMS >= G2 + NBUF * BUF && WARP_ELEMS % 8 == 0, "layout");
     __host__ __device__ static constexpr int group_off(int g) { return g == 0 ? 0 : (g == 1 ? G1 : G2); }
     __host__ __device__ static size_t smem_bytes(int K, int warps) {

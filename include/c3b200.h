@@ -120,8 +120,13 @@ int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C
  *   U_out    [B,d,d]  or NULL: the forward result is produced on the way
  *   chunk    batch rows processed per pass (bounds the workspace: ~2 N d^2 16 bytes per row; ~10 N d^2 16 with the
  *            augmented-exponential cross-check, tuning "grad_variant" 0, d <= 32); <= 0: all
- * Shared model only (h0 [d,d], hks [K,d,d]).  d <= 16: one warp per slice (Frechet derivative of the Taylor scheme in shared
- * memory); 16 < d <= 128: CTA kernels on the fp64 tensor-core product (sweeps + Frechet derivative on (X, dX) pairs). */
+ * Shared model only (h0 [d,d], hks [K,d,d]).  d = 7..9 with Hermitian h0 / hks (the headline shape): ONE fused kernel,
+ * no stored slice propagators -- Y_n = F_n Ubar^dag U F_n^-1 is carried forward by unitarity and the Frechet derivative of
+ * the Taylor scheme runs in lockstep with the scheme (workspace ~ N/8 d^2 16 bytes per row).  Whether the Hamiltonians are
+ * Hermitian is checked on the device (one 4-byte read-back per call, i.e. a stream synchronisation; tuning "grad_unitary"
+ * 1 / 0 asserts the answer and skips it); if they are not, or tuning "grad_variant" is 2, the stored-propagator kernels
+ * below serve the call.  Other d <= 16: one warp per slice (Frechet derivative of the Taylor scheme in shared memory);
+ * 16 < d <= 128: CTA kernels on the fp64 tensor-core product (sweeps + Frechet derivative on (X, dX) pairs). */
 size_t c3b_pwc_grad_workspace_bytes(int B, int K, int N, int d, int chunk);
 int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d,
                         const void* Ubar, double* grad_out, void* U_out, int chunk, void* workspace,
@@ -266,7 +271,8 @@ int c3b_kron(const void* A, const void* Bm, void* out, int batch, int ra, int ca
  * knob for an experiment cannot disturb another thread's launches).  Keys: "target_units", "min_chunk" (segmentation of
  * the time axis), "d9_variant" (0 generic 3x3-block kernel, 1 own-block shared-memory kernel, 2 shuffle-exchange kernel),
  * "force_cta", "cta_variant" (0 literal Higham cross-check, 1 four-product Taylor scheme on DMMA tiles), "cta_threads", "gemm_big",
- * "norm_bound", "seq_variant", "grad_variant", "profile".  Returns C3B_EINVAL for an unknown key. */
+ * "norm_bound", "seq_variant", "grad_variant" (1 best available, 0 augmented exponential, 2 stored-propagator kernels),
+ * "grad_unitary" (-1 check the Hamiltonians on the device, 1 Hermitian, 0 not), "profile".  Returns C3B_EINVAL for an unknown key. */
 int c3b_set_tuning(const char* key, long long value);
 
 /* Which kernel c3b_pwc_* would pick for this shape: 1 = lane-group kernel (d <= 12, shared model),

@@ -35,9 +35,10 @@ def test_blk9_tables_are_conflict_free(nosel):
     pick = 1 if nosel else 2
     g1 = int(re.search(r"G1 = NOSEL \? (\d+) : (\d+)", src).group(pick))
     g2 = int(re.search(r"G2 = NOSEL \? (\d+) : (\d+)", src).group(pick))
-    we = int(re.search(r"WARP_ELEMS = NOSEL \? (\d+) : (\d+)", src).group(pick))
+    we = int(re.search(r"WARP_ELEMS = (\d+);", src).group(1))
+    nbuf = int(re.search(r"NBUF = (\d+);", src).group(1))
     assert sorted(slot) == list(range(9)) and sorted(perm) == list(range(27)) and all(0 <= x < 27 for x in shadow)
-    assert g1 >= 5 * BUF and g2 >= g1 + 5 * BUF and we >= g2 + 5 * BUF and we % 8 == 0      # 5 buffers per group, no overlap
+    assert g1 >= nbuf * BUF and g2 >= g1 + nbuf * BUF and we >= g2 + nbuf * BUF and we % 8 == 0   # buffers of the groups do not overlap
     goff = [0, g1, g2]
     lanes = []
     for lane in range(32):
