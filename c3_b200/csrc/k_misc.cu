@@ -87,6 +87,15 @@ int c3b_generate_signals_noisy(const double* env_params, const int32_t* env_shap
                                const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
                                int B, int K, int E, int N, const double* noise, int noise_batched, unsigned long long seed,
                                double* signals_out, double* noise_out, void* stream) {
+    return c3b_generate_signals_table(env_params, env_shape, env_flags, nullptr, 0, lo_freq, chain, chain_batched, t_start, t_end, B, K, E, N,
+                                      noise, noise_batched, seed, signals_out, noise_out, stream);
+}
+
+int c3b_generate_signals_table(const double* env_params, const int32_t* env_shape, const int32_t* env_flags, const double* env_table,
+                               int T, const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
+                               int B, int K, int E, int N, const double* noise, int noise_batched, unsigned long long seed,
+                               double* signals_out, double* noise_out, void* stream) {
+    if (T < 0 || (T > 0 && env_table == nullptr)) return fail(C3B_EINVAL, "C3:ERROR: T=%d but env_table is NULL", T);
     if (B <= 0 || K <= 0 || E <= 0 || N <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d E=%d N=%d)", B, K, E, N);
     if (!env_params || !env_shape || !env_flags || !lo_freq || !chain || !signals_out) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
     if (noise_out != nullptr && noise == nullptr) return fail(C3B_EINVAL, "C3:ERROR: noise traces requested without noise parameters");
@@ -95,6 +104,7 @@ int c3b_generate_signals_noisy(const double* env_params, const int32_t* env_shap
     sp.chain_batched = chain_batched; sp.t_start = t_start; sp.t_end = t_end;
     sp.B = B; sp.K = K; sp.E = E; sp.N = N; sp.out = signals_out;
     sp.noise = noise; sp.noise_batched = noise_batched; sp.seed = seed; sp.noise_out = noise_out;
+    sp.table = T > 0 ? env_table : nullptr; sp.T = T;
     // the AWG grid and the response taps live in shared memory: bounded by the simulation grid / 4096 taps
     sp.max_awg = N + 1;
     sp.max_taps = 4096;

@@ -20,7 +20,23 @@ namespace c3b {
 enum { ENV_AMP = 0, ENV_TFINAL, ENV_SIGMA, ENV_XY, ENV_FREQ_OFFSET, ENV_DELTA, ENV_TUP, ENV_TDOWN, ENV_RISEFALL, ENV_NPAR };
 enum { CH_SIM_RES = 0, CH_AWG_RES, CH_RISE_TIME, CH_RESP_KIND, CH_OUT_KIND, CH_V2HZ, CH_PHI, CH_PHI0, CH_OMEGA0, CH_ANHAR, CH_D, CH_NPAR };
 enum { SHAPE_NO_DRIVE = 0, SHAPE_RECT, SHAPE_GAUSSIAN_NONORM, SHAPE_GAUSSIAN_SIGMA, SHAPE_COSINE, SHAPE_FLATTOP,
-       SHAPE_TRAPEZOID, SHAPE_FLATTOP_RISEFALL, SHAPE_GAUSSIAN_DER_NONORM, SHAPE_GAUSSIAN_DER, SHAPE_DRAG_SIGMA, SHAPE_DRAG_DER };
+       SHAPE_TRAPEZOID, SHAPE_FLATTOP_RISEFALL, SHAPE_GAUSSIAN_DER_NONORM, SHAPE_GAUSSIAN_DER, SHAPE_DRAG_SIGMA, SHAPE_DRAG_DER,
+       // "extended" shapes: grid-dependent (normalised by their maximum over the AWG grid, defined by sample index) or
+       // parametrised by arrays (table row of the envelope, SignalParams::table); forward only
+       SHAPE_FIRST_EXT,
+       SHAPE_FLATTOP_CUT = SHAPE_FIRST_EXT,   // envelopes.py:281-302   erf product clipped to [0,1], over its grid maximum
+       SHAPE_FLATTOP_CUT_CENTER,              // :305-327   width in the sigma slot; clipped to [0,2], not normalised
+       SHAPE_FLATTOP_VARIANT,                 // :565-587   ramp in the sigma slot
+       SHAPE_COSINE_FLATTOP,                  // :440-466   t_rise in the sigma slot; defined on sample indices
+       SHAPE_DELTA_PULSE,                     // :128-139   table: M, t_sig[M]
+       SHAPE_PWC,                             // :31-34     table: M, inphase[M], quadrature[M]  (complex, by sample index)
+       SHAPE_PWC_SHAPE,                       // :37-68     table: M, t_bin_start, t_bin_end, inphase[M]  (linear interpolation)
+       SHAPE_PWC_SYMMETRIC,                   // :104-125   same, mirrored at t_final / 2
+       SHAPE_PWC_SHAPE_PLATEAU,               // :71-101    same + width (< 0: none)
+       SHAPE_FOURIER_SIN,                     // :142-168   table: M, amps[M], freqs[M], phases[M]
+       SHAPE_FOURIER_COS,                     // :171-191   table: M, amps[M], freqs[M]
+       SHAPE_SLEPIAN_FOURIER,                 // :330-363   table: width, offset, risefall (< 0: none), M, coeffs[M], S, sin_coeffs[S]
+       SHAPE_END };
 
 struct SignalParams {
     const double* env;       // [B, K, E, ENV_NPAR]
@@ -37,6 +53,8 @@ struct SignalParams {
     int noise_batched;
     unsigned long long seed; // one noise realisation per (seed, batch row, line): counter-based, reproducible
     double* noise_out;       // [B, K, NOISE_NTRACE, N] realised noise traces (what Device.signal["noise"] holds) or null
+    const double* table;     // [K, E, T] array parameters of the extended shapes (shared by the batch) or null
+    int T;
 };
 
 // one drive line's noise row and the layout of the realised traces
@@ -272,22 +290,183 @@ __device__ __forceinline__ ChainCtx chain_ctx(const SignalParams& p, const int b
     return c;
 }
 
-// AWG samples: sum of the line's envelopes on the AWG time grid -> sI, sQ [n_awg]
-__device__ __forceinline__ void fill_awg(const SignalParams& p, const ChainCtx& c, const int b, const int k, double* sI, double* sQ) {
-    for (int j = threadIdx.x; j < c.n_awg; j += blockDim.x) {
-        const double t = linspace_at(c.a0, c.a1, c.n_awg, j) - p.t_start;
-        double re = 0.0, im = 0.0;
-        for (int e = 0; e < p.E; ++e) {
-            const int id = p.shape[k * p.E + e];
-            if (id < 0) continue;
-            const double* ev = p.env + (((size_t)b * p.K + k) * p.E + e) * ENV_NPAR;
-            double tr, ti;
-            awg_term<double>(id, p.flags[k * p.E + e], t, ev, c.off0, c.off1, tr, ti);
-            re += tr;
-            im += ti;
+
+// ---- extended shapes (forward only) ------------------------------------------------------------------------------------
+// tfp.math.interp_regular_1d_grid(x, x_min, x_max, y[M], fill_value_below = fill_value_above = 0)
+__device__ __forceinline__ double interp_regular(double x, double x_min, double x_max, const double* y, int M) {
+    if (x < x_min || x > x_max) return 0.0;
+    if (M == 1) return y[0];
+    double u = (x - x_min) / (x_max - x_min) * (double)(M - 1);
+    u = fmin(fmax(u, 0.0), (double)(M - 1));
+    int lo = (int)floor(u);
+    int hi = min(lo + 1, M - 1);
+    lo = max(hi - 1, 0);
+    const double w = u - (double)lo;
+    return w * y[hi] + (1.0 - w) * y[lo];
+}
+
+__device__ __forceinline__ double slepian_x(double t, double t_final, double width, double risefall, double& length) {
+    if (risefall >= 0.0) {
+        const double plateau = width - risefall * 2;
+        double x = t;
+        if (t > (t_final + plateau) / 2) x = t - plateau / 2;
+        if (t < (t_final - plateau) / 2) x = t + plateau / 2;
+        if (fabs(t - t_final / 2) < plateau / 2) x = t_final / 2;
+        length = risefall * 2;
+        return x;
+    }
+    length = width;
+    return t;
+}
+
+// value of an extended shape at AWG sample j (time offset t); im: the quadrature of the complex "pwc" shape.
+// NOT normalised for FLATTOP_CUT / SLEPIAN_FOURIER (fill_awg divides by the grid maximum).
+__device__ __forceinline__ double shape_value_ext(int id, double t, int j, const double* e, const double* tab, const ChainCtx& c,
+                                                  double t_start, double& im) {
+    im = 0.0;
+    switch (id) {
+        case SHAPE_FLATTOP_CUT: {
+            const double v = erf((t - e[ENV_TUP]) / e[ENV_RISEFALL]) * erf((-t + e[ENV_TDOWN]) / e[ENV_RISEFALL]);
+            return fmin(fmax(v, 0.0), 1.0);
         }
-        sI[j] = re;
-        sQ[j] = im;
+        case SHAPE_FLATTOP_CUT_CENTER: {
+            const double t_up = e[ENV_TFINAL] / 2 - e[ENV_SIGMA] / 2, t_down = e[ENV_TFINAL] / 2 + e[ENV_SIGMA] / 2;
+            const double v = erf((t - t_up) / e[ENV_RISEFALL]) * erf((-t + t_down) / e[ENV_RISEFALL]);
+            return fmin(fmax(v, 0.0), 2.0);
+        }
+        case SHAPE_FLATTOP_VARIANT: {
+            const double t_up = e[ENV_TUP], t_down = e[ENV_TDOWN];
+            double ramp = e[ENV_SIGMA];
+            if (ramp > (t_down - t_up) / 2) ramp = (t_down - t_up) / 2;
+            const double sigma = sqrt(2.0) * ramp * 0.2;
+            if (t_up <= t && t <= t_up + ramp) return exp(-((t - t_up - ramp) * (t - t_up - ramp)) / (2 * sigma * sigma));
+            if (t_up + ramp < t && t < t_down - ramp) return 1.0;
+            if (t_down >= t && t >= t_down - ramp) return exp(-((t - t_down + ramp) * (t - t_down + ramp)) / (2 * sigma * sigma));
+            return 0.0;
+        }
+        case SHAPE_COSINE_FLATTOP: {           // rise over the first n_rise samples, the same n_rise time values again for the fall
+            const double t_rise = e[ENV_SIGMA];
+            const int n_rise = (int)(t_rise / (c.off1 - c.off0));
+            const int n_flat = c.n_awg - 2 * n_rise;
+            if (j < n_rise) return 0.5 * (1.0 - cos(M_PI * t / t_rise));
+            if (j < n_rise + n_flat) return 1.0;
+            const double tf = linspace_at(c.a0, c.a1, c.n_awg, j - n_rise - n_flat) - t_start;
+            return 0.5 * (1.0 + cos(M_PI * tf / t_rise));
+        }
+        case SHAPE_DELTA_PULSE: {              // 1 on the grid point(s) closest to t_sig + 1 ns
+            const int M = (int)tab[0];
+            const double dts = c.off1 - c.off0;
+            double v = 0.0;
+            for (int m = 0; m < M; ++m) {
+                const double ts = tab[1 + m];
+                const double mine = (t - ts - 1e-9) * (t - ts - 1e-9);
+                int j0 = (int)floor((ts + 1e-9 - c.off0) / dts);
+                double best = 1e300;
+                for (int q = j0 - 1; q <= j0 + 2; ++q) {
+                    const int qq = min(max(q, 0), c.n_awg - 1);
+                    const double tq = linspace_at(c.a0, c.a1, c.n_awg, qq) - t_start;
+                    best = fmin(best, (tq - ts - 1e-9) * (tq - ts - 1e-9));
+                }
+                if (mine == best) v = 1.0;
+            }
+            return v;
+        }
+        case SHAPE_PWC: {
+            const int M = (int)tab[0];
+            if (j >= M) return 0.0;
+            im = tab[1 + M + j];
+            return tab[1 + j];
+        }
+        case SHAPE_PWC_SHAPE: return interp_regular(t, tab[1], tab[2], tab + 4, (int)tab[0]);
+        case SHAPE_PWC_SYMMETRIC: return interp_regular(t > e[ENV_TFINAL] / 2 ? -t + e[ENV_TFINAL] : t, tab[1], tab[2], tab + 4, (int)tab[0]);
+        case SHAPE_PWC_SHAPE_PLATEAU: {
+            const double width = tab[3];
+            if (width < 0.0) return interp_regular(t, tab[1], tab[2], tab + 4, (int)tab[0]);
+            const double plateau = width - (tab[2] - tab[1]), t_mid = (tab[2] - tab[1]) / 2;
+            double x = t;
+            if (t > t_mid + plateau) x = t - plateau;
+            if (t < t_mid) x = t;
+            if (t < t_mid + plateau && t > t_mid) x = t_mid;
+            if (x == t_mid) return 1.0;
+            return interp_regular(x, tab[1], tab[2], tab + 4, (int)tab[0]);
+        }
+        case SHAPE_FOURIER_SIN: {
+            const int M = (int)tab[0];
+            double v = 0.0;
+            for (int m = 0; m < M; ++m) v += tab[1 + m] * sin(tab[1 + M + m] * t + tab[1 + 2 * M + m]);
+            return v;
+        }
+        case SHAPE_FOURIER_COS: {
+            const int M = (int)tab[0];
+            double v = 0.0;
+            for (int m = 0; m < M; ++m) v += tab[1 + m] * cos(tab[1 + M + m] * t);
+            return v;
+        }
+        case SHAPE_SLEPIAN_FOURIER: {
+            const double t_final = e[ENV_TFINAL], width = tab[0];
+            double length;
+            const double x = slepian_x(t, t_final, width, tab[2], length);
+            const int M = (int)tab[3];
+            const int S = (int)tab[4 + M];
+            double v = 0.0;
+            for (int m = 0; m < M; ++m) v += tab[4 + m] * (1.0 - cos(2 * M_PI * (m + 1) * (x - (t_final - length) / 2) / length));
+            for (int m = 0; m < S; ++m) v += tab[5 + M + m] * sin((M_PI * (2 * m + 1)) * (x - (t_final - length) / 2) / length);
+            if (fabs(t_final / 2 - t) > width / 2) v = 0.0;
+            return v;
+        }
+        default: return 0.0;
+    }
+}
+
+__device__ __forceinline__ double block_max_128(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+}
+
+// AWG samples: sum of the line's envelopes on the AWG time grid -> sI, sQ [n_awg].  Called by the whole CTA (barriers).
+__device__ __forceinline__ void fill_awg(const SignalParams& p, const ChainCtx& c, const int b, const int k, double* sI, double* sQ) {
+    __shared__ double s_red[4];
+    for (int j = threadIdx.x; j < c.n_awg; j += blockDim.x) { sI[j] = 0.0; sQ[j] = 0.0; }
+    for (int e = 0; e < p.E; ++e) {
+        const int id = p.shape[k * p.E + e];                 // CTA-uniform
+        if (id < 0) continue;
+        const double* ev = p.env + (((size_t)b * p.K + k) * p.E + e) * ENV_NPAR;
+        const int fl = p.flags[k * p.E + e];
+        if (id < SHAPE_FIRST_EXT) {
+            for (int j = threadIdx.x; j < c.n_awg; j += blockDim.x) {
+                const double t = linspace_at(c.a0, c.a1, c.n_awg, j) - p.t_start;
+                double tr, ti;
+                awg_term<double>(id, fl, t, ev, c.off0, c.off1, tr, ti);
+                sI[j] += tr;
+                sQ[j] += ti;
+            }
+            continue;
+        }
+        const double* tab = p.table ? p.table + ((size_t)k * p.E + e) * p.T : nullptr;
+        double norm = 1.0;
+        if (id == SHAPE_FLATTOP_CUT || id == SHAPE_SLEPIAN_FOURIER) {       // shape /= reduce_max(shape) over the AWG grid
+            double mx = -1e300, dummy;
+            for (int j = threadIdx.x; j < c.n_awg; j += blockDim.x)
+                mx = fmax(mx, shape_value_ext(id, linspace_at(c.a0, c.a1, c.n_awg, j) - p.t_start, j, ev, tab, c, p.t_start, dummy));
+            norm = block_max_128(mx, s_red);
+        }
+        const double dts = c.off1 - c.off0;
+        for (int j = threadIdx.x; j < c.n_awg; j += blockDim.x) {
+            const double t = linspace_at(c.a0, c.a1, c.n_awg, j) - p.t_start;
+            double qv;
+            double sv = shape_value_ext(id, t, j, ev, tab, c, p.t_start, qv) / norm;
+            if (id == SHAPE_SLEPIAN_FOURIER) sv = sv * (1.0 - tab[1] / ev[ENV_AMP]) + tab[1] / ev[ENV_AMP];
+            const double mask = t_sigmoid((t / dts + 0.001) * 1e6) * t_sigmoid((0.999 * ev[ENV_TFINAL] - t) / dts * 1e6);
+            const double env_re = mask * sv, env_im = mask * qv;
+            const double ph = ev[ENV_XY] - ev[ENV_FREQ_OFFSET] * t;
+            const double cs = cos(ph), sn = sin(ph);
+            sI[j] += ev[ENV_AMP] * (env_re * cs - env_im * sn);
+            sQ[j] += ev[ENV_AMP] * (env_re * sn + env_im * cs);
+        }
     }
 }
 
@@ -551,6 +730,10 @@ __global__ void __launch_bounds__(128) signal_chain_grad_kernel(const SignalGrad
         double* out = g.genv + (((size_t)b * p.K + k) * p.E + e) * ENV_NPAR;
         if (id < 0) {
             if (threadIdx.x < ENV_NPAR) out[threadIdx.x] = 0.0;
+            continue;
+        }
+        if (id >= SHAPE_FIRST_EXT) {           // extended shapes are forward only: a loud NaN, never a silent zero
+            if (threadIdx.x < ENV_NPAR) out[threadIdx.x] = __longlong_as_double(0x7ff8000000000000LL);
             continue;
         }
         const int fl = p.flags[k * p.E + e];

@@ -617,8 +617,10 @@ NOISE_TRACES = ("awg_i", "awg_q", "lo_cos", "lo_sin", "add", "dc", "pink")
 
 
 def generate_signals(env_params, env_shape, env_flags, lo_freq, chain, t_start: float, t_end: float, device=None,
-                     out=None, noise=None, seed: int = 0, return_noise: bool = False):
+                     out=None, noise=None, seed: int = 0, return_noise: bool = False, env_table=None):
     """signals [B,K,N] from pulse parameters (c3b_generate_signals; see include/c3b200.h for the layouts).
+
+    ``env_table [K,E,T]``: the array parameters of the extended envelope shapes (pwc, fourier_*, slepian_fourier, ...).
 
     ``noise [K,7]`` or ``[B,K,7]`` (columns NOISE_KEYS) switches the noise devices on: one independent realisation per batch
     row, drawn from the counter-based generator keyed by ``seed`` (same seed -> same realisation).  ``return_noise`` also
@@ -655,9 +657,16 @@ def generate_signals(env_params, env_shape, env_flags, lo_freq, chain, t_start: 
                 traces = torch.empty((B, K, len(NOISE_TRACES), N), dtype=torch.float64, device=device)
         elif return_noise:
             raise ValueError("C3:ERROR: return_noise needs noise parameters")
-        _lib.check(lib.c3b_generate_signals_noisy(_ptr(env_params), _ptr(env_shape), _ptr(env_flags), _ptr(lo_freq), _ptr(chain),
-                                                  int(batched), float(t_start), float(t_end), B, K, E, N, _ptr(noise), nbatched,
-                                                  int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out), _ptr(traces), _stream()))
+        T = 0
+        if env_table is not None:
+            env_table = _as(env_table, torch.float64, device)
+            if env_table.dim() != 3 or tuple(env_table.shape[:2]) != (K, E):
+                raise ValueError(f"C3:ERROR: env_table has shape {tuple(env_table.shape)}, expected [K={K},E={E},T]")
+            T = int(env_table.shape[2])
+        _lib.check(lib.c3b_generate_signals_table(_ptr(env_params), _ptr(env_shape), _ptr(env_flags), _ptr(env_table) if T else None, T,
+                                                  _ptr(lo_freq), _ptr(chain), int(batched), float(t_start), float(t_end), B, K, E, N,
+                                                  _ptr(noise), nbatched, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out), _ptr(traces),
+                                                  _stream()))
     return (out, traces) if return_noise else out
 
 

@@ -28,7 +28,57 @@ import torch
 from . import engine
 
 SHAPE_IDS = {"no_drive": 0, "rect": 1, "gaussian_nonorm": 2, "gaussian_sigma": 3, "cosine": 4, "flattop": 5, "trapezoid": 6,
-             "flattop_risefall": 7, "gaussian_der_nonorm": 8, "gaussian_der": 9, "drag_sigma": 10, "drag_der": 11}
+             "flattop_risefall": 7, "gaussian_der_nonorm": 8, "gaussian_der": 9, "drag_sigma": 10, "drag_der": 11,
+             # extended shapes (csrc/signal_chain.cuh SHAPE_FIRST_EXT...): grid-defined or parametrised by arrays, forward only
+             "flattop_cut": 12, "flattop_cut_center": 13, "flattop_variant": 14, "cosine_flattop": 15, "delta_pulse": 16, "pwc": 17,
+             "pwc_shape": 18, "pwc_symmetric": 19, "pwc_shape_plateau": 20, "fourier_sin": 21, "fourier_cos": 22,
+             "slepian_fourier": 23}
+FIRST_EXTENDED_SHAPE = 12
+#: extended shapes whose extra SCALAR parameter rides in the sigma column of the envelope row
+SIGMA_SLOT = {"flattop_cut_center": "width", "flattop_variant": "ramp", "cosine_flattop": "t_rise"}
+
+
+def _arr(q) -> np.ndarray:
+    """Quantity-like -> 1-d float64 array."""
+    if hasattr(q, "get_value"):
+        q = q.get_value()
+    if hasattr(q, "numpy"):
+        q = q.numpy()
+    return np.real(np.asarray(q)).astype(np.float64).reshape(-1)
+
+
+def shape_table_row(shape: str, params) -> np.ndarray:
+    """The array parameters of an extended shape in the order the kernel reads them (csrc/signal_chain.cuh, next to the shape
+    ids); empty for the shapes that have none."""
+    P = params
+    if shape == "delta_pulse":
+        t = _arr(P["t_sig"])
+        return np.concatenate([[len(t)], t])
+    if shape == "pwc":
+        i, q = _arr(P["inphase"]), _arr(P["quadrature"])
+        if len(i) != len(q):
+            raise Exception("C3:ERROR: pwc envelope: inphase and quadrature differ in length.")
+        return np.concatenate([[len(i)], i, q])
+    if shape in ("pwc_shape", "pwc_symmetric", "pwc_shape_plateau"):
+        y = _arr(P["inphase"])
+        width = _val(P["width"]) if (shape == "pwc_shape_plateau" and "width" in P) else -1.0
+        return np.concatenate([[len(y), _val(P["t_bin_start"]), _val(P["t_bin_end"]), width], y])
+    if shape == "fourier_sin":
+        a, f, ph = _arr(P["amps"]), _arr(P["freqs"]), _arr(P["phases"])
+        if not (len(a) == len(f) == len(ph)):
+            raise Exception("C3:ERROR: fourier_sin envelope: amps, freqs and phases differ in length.")
+        return np.concatenate([[len(a)], a, f, ph])
+    if shape == "fourier_cos":
+        a, f = _arr(P["amps"]), _arr(P["freqs"])
+        if len(a) != len(f):
+            raise Exception("C3:ERROR: fourier_cos envelope: amps and freqs differ in length.")
+        return np.concatenate([[len(a)], a, f])
+    if shape == "slepian_fourier":
+        c = _arr(P["fourier_coeffs"])
+        sc = _arr(P["sin_coeffs"]) if "sin_coeffs" in P else np.zeros(0)
+        rf = _val(P["risefall"]) if "risefall" in P else -1.0
+        return np.concatenate([[_val(P["width"]), _val(P["offset"]), rf, len(c)], c, [len(sc)], sc])
+    return np.zeros(0)
 #: shapes of c3/libraries/envelopes.py that are another shape with one parameter fixed: name -> (kernel shape, parameter, rule)
 SHAPE_ALIASES = {
     "gaussian": ("gaussian_sigma", "sigma", lambda p: p["t_final"] / 6),                 # envelopes.py:399-417
@@ -188,8 +238,10 @@ class Generator:
                 opts = getattr(instr, "_options", {}).get(chan, {}).get(name, {})
                 if opts:
                     raise Exception("C3:ERROR: component options (delay, trigger_comp, t_final_cut) are not supported on device.")
-                envs.append((name, comp, shape, (1 if cls == "EnvelopeDrag" else 0)
-                             | (2 if getattr(comp, "use_t_before", False) else 0)))
+                fl = (1 if cls == "EnvelopeDrag" else 0) | (2 if getattr(comp, "use_t_before", False) else 0)
+                if fl and SHAPE_IDS.get(shape, 0) >= FIRST_EXTENDED_SHAPE:
+                    raise Exception(f"C3:ERROR: envelope shape '{shape}' is available on the device without DRAG / use_t_before only.")
+                envs.append((name, comp, shape, fl))
             else:
                 raise Exception(f"C3:ERROR: component type '{cls}' is not available in the on-device signal chain.")
         if carrier is None:
@@ -209,6 +261,7 @@ class Generator:
         flags = np.zeros((K, E), dtype=np.int32)
         lo = np.zeros((B, K))
         chain = np.zeros((K, len(CHAIN_KEYS)))
+        rows = {}                                   # (k, e) -> array parameters of an extended shape
         for k, c in enumerate(chans):
             if c not in self._specs:
                 raise Exception(f"C3:ERROR: no signal chain for channel '{c}'.")
@@ -227,6 +280,24 @@ class Generator:
                 if alias:       # e.g. "gaussian" = gaussian_sigma with sigma = t_final / 6 (per sample, after the overrides)
                     cols = {key: env[:, k, e, i] for i, key in enumerate(ENV_KEYS)}
                     env[:, k, e, ENV_KEYS.index(alias[1])] = alias[2](cols)
+                try:
+                    if sname in SIGMA_SLOT:             # width / ramp / t_rise travel in the sigma column
+                        key = SIGMA_SLOT[sname]
+                        env[:, k, e, ENV_KEYS.index("sigma")] = _val(comp.params[key])
+                        if samples and (c, name, key) in samples:
+                            env[:, k, e, ENV_KEYS.index("sigma")] = np.asarray(samples[(c, name, key)], dtype=np.float64)
+                    if shape[k, e] >= FIRST_EXTENDED_SHAPE:
+                        row = shape_table_row(sname, comp.params)
+                        if len(row):
+                            rows[(k, e)] = row
+                except KeyError as err:
+                    raise Exception(f"C3:ERROR: envelope '{name}' of shape '{sname}' lacks the parameter {err}.") from None
+        # array parameters: one zero-padded row per envelope, shared by the batch (read by engine.generate_signals via self._table)
+        self._table = None
+        if rows:
+            self._table = np.zeros((K, E, max(len(r) for r in rows.values())))
+            for (k, e), r in rows.items():
+                self._table[k, e, :len(r)] = r
         if len({chain[k, 0] for k in range(K)}) != 1:
             raise Exception("C3:ERROR: all channels of an instruction must share the simulation resolution.")
         return chans, env, shape, flags, lo, chain
@@ -279,14 +350,15 @@ class Generator:
         chans, env, shape, flags, lo, chain = self._tables(instr, samples)
         noise = self._noise_table(chans)
         if noise is None:
-            sig = engine.generate_signals(env, shape, flags, lo, chain, float(instr.t_start), float(instr.t_end))
+            sig = engine.generate_signals(env, shape, flags, lo, chain, float(instr.t_start), float(instr.t_end),
+                                          env_table=self._table)
         else:
             # a fresh realisation per call (the reference draws from numpy's global generator on every call); every batch
             # row is an independent realisation of the same call
             self.noise_draws += 1
             seed = (int(self.seed) + 0x9E3779B97F4A7C15 * self.noise_draws) & 0xFFFFFFFFFFFFFFFF
             sig, traces = engine.generate_signals(env, shape, flags, lo, chain, float(instr.t_start), float(instr.t_end),
-                                                  noise=noise, seed=seed, return_noise=True)
+                                                  noise=noise, seed=seed, return_noise=True, env_table=self._table)
             self._publish_noise(chans, traces, chain)
         N = sig.shape[-1]
         dt = 1.0 / chain[0, 0]

@@ -203,6 +203,18 @@ int c3b_generate_signals_noisy(const double* env_params, const int32_t* env_shap
                                int B, int K, int E, int N, const double* noise, int noise_batched, unsigned long long seed,
                                double* signals_out, double* noise_out, void* stream);
 
+/* Same with the array-parametrised and grid-defined envelope shapes of c3/libraries/envelopes.py (shape ids 12..23: flattop_cut,
+ * flattop_cut_center, flattop_variant, cosine_flattop, delta_pulse, pwc, pwc_shape, pwc_symmetric, pwc_shape_plateau, fourier_sin,
+ * fourier_cos, slepian_fourier):
+ *   env_table [K,E,T] float64 or NULL (T = 0): per envelope, the array parameters in the order signal_chain.cuh documents next
+ *             to each shape id (e.g. pwc: M, inphase[M], quadrature[M]); shared by the batch rows.
+ * Scalar parameters without a column of their own ride in the sigma column (width, ramp, t_rise).  These shapes are forward
+ * only: c3b_generate_signals_grad writes NaN into their grad_env rows. */
+int c3b_generate_signals_table(const double* env_params, const int32_t* env_shape, const int32_t* env_flags, const double* env_table,
+                               int T, const double* lo_freq, const double* chain, int chain_batched, double t_start, double t_end,
+                               int B, int K, int E, int N, const double* noise, int noise_batched, unsigned long long seed,
+                               double* signals_out, double* noise_out, void* stream);
+
 /* Reverse mode of c3b_generate_signals: from dL/d signals [B,K,N] (e.g. the output of c3b_pwc_closed_grad) to the
  * gradient with respect to the pulse parameters -- what tf.GradientTape propagates through
  * Generator.generate_signals in the reference's gradient-based optimal control (c3/optimizers/optimalcontrol.py:200-228).

@@ -49,6 +49,9 @@ class EnvelopeSpec:
     risefall: float = 1.0
     drag: bool = False          # EnvelopeDrag: quadrature = -delta * d env/dt * dt
     use_t_before: bool = False
+    extra: Dict = field(default_factory=dict)   # parameters outside the nine scalars: width, ramp, t_rise, t_sig, inphase,
+                                                # quadrature, t_bin_start, t_bin_end, amps, freqs, phases, fourier_coeffs,
+                                                # sin_coeffs, offset (and risefall as "present" for slepian_fourier)
 
 
 def create_ts(t_start: float, t_end: float, resolution: float, centered: bool = True) -> np.ndarray:
@@ -112,7 +115,99 @@ def shape_values(shape: str, t: np.ndarray, e: EnvelopeSpec) -> np.ndarray:
         gauss = np.exp(-((t - e.t_final / 2) ** 2) / (2 * e.sigma ** 2))
         offset = np.exp(-(e.t_final ** 2) / (8 * e.sigma ** 2))
         return -2 * (gauss - offset) * gauss * (t - e.t_final / 2) / e.sigma ** 2 / _gauss_norm(e)
+    x = e.extra
+    if shape == "flattop_cut":                     # :281-302
+        v = erf((t - e.t_up) / e.risefall) * erf((-t + e.t_down) / e.risefall)
+        v = np.clip(v, 0, 1)
+        return v / np.max(v)
+    if shape == "flattop_cut_center":              # :305-327
+        t_up, t_down = e.t_final / 2 - x["width"] / 2, e.t_final / 2 + x["width"] / 2
+        return np.clip(erf((t - t_up) / e.risefall) * erf((-t + t_down) / e.risefall), 0, 2)
+    if shape == "flattop_variant":                 # :565-587
+        ramp = min(x["ramp"], (e.t_down - e.t_up) / 2)
+        sigma = np.sqrt(2) * ramp * 0.2
+        v = np.zeros_like(t)
+        for i, tt in enumerate(t):
+            if e.t_up <= tt <= e.t_up + ramp:
+                v[i] = np.exp(-((tt - e.t_up - ramp) ** 2) / (2 * sigma ** 2))
+            elif e.t_up + ramp < tt < e.t_down - ramp:
+                v[i] = 1
+            elif e.t_down >= tt >= e.t_down - ramp:
+                v[i] = np.exp(-((tt - e.t_down + ramp) ** 2) / (2 * sigma ** 2))
+        return v
+    if shape == "cosine_flattop":                  # :440-466: indices, and the SAME first n_rise time values for the fall
+        t_rise = x["t_rise"]
+        n_rise = int(t_rise / (t[1] - t[0]))
+        n_flat = len(t) - 2 * n_rise
+        return np.concatenate([0.5 * (1 - np.cos(np.pi * t[:n_rise] / t_rise)), np.ones(n_flat),
+                               0.5 * (1 + np.cos(np.pi * t[:n_rise] / t_rise))])
+    if shape == "delta_pulse":                     # :128-139
+        v = np.zeros_like(t)
+        for t_s in np.atleast_1d(x["t_sig"]):
+            dist = (t - t_s - 1e-9) ** 2
+            v = np.where(np.min(dist) == dist, 1.0, v)
+        return v
+    if shape == "pwc":                             # :31-34 (complex: in-phase + i quadrature, one value per AWG sample)
+        return np.asarray(x["inphase"], dtype=np.float64) + 1j * np.asarray(x["quadrature"], dtype=np.float64)
+    if shape == "pwc_shape":                       # :37-68
+        return interp_regular_1d_grid(t, x["t_bin_start"], x["t_bin_end"], x["inphase"])
+    if shape == "pwc_symmetric":                   # :104-125
+        return interp_regular_1d_grid(np.where(t > e.t_final / 2, -t + e.t_final, t), x["t_bin_start"], x["t_bin_end"], x["inphase"])
+    if shape == "pwc_shape_plateau":               # :71-101
+        if "width" not in x:
+            return interp_regular_1d_grid(t, x["t_bin_start"], x["t_bin_end"], x["inphase"])
+        plateau = x["width"] - (x["t_bin_end"] - x["t_bin_start"])
+        t_mid = (x["t_bin_end"] - x["t_bin_start"]) / 2
+        xx = t.copy()
+        xx = np.where(t > t_mid + plateau, t - plateau, xx)
+        xx = np.where(t < t_mid, t, xx)
+        xx = np.where((t < t_mid + plateau) & (t > t_mid), t_mid, xx)
+        v = interp_regular_1d_grid(xx, x["t_bin_start"], x["t_bin_end"], x["inphase"])
+        return np.where(xx == t_mid, 1.0, v)
+    if shape == "fourier_sin":                     # :142-168
+        a, f, ph = (np.asarray(x[k], dtype=np.float64).reshape(-1, 1) for k in ("amps", "freqs", "phases"))
+        return np.sum(a * np.sin(f * t.reshape(1, -1) + ph), axis=0)
+    if shape == "fourier_cos":                     # :171-191
+        a, f = (np.asarray(x[k], dtype=np.float64).reshape(-1, 1) for k in ("amps", "freqs"))
+        return np.sum(a * np.cos(f * t.reshape(1, -1)), axis=0)
+    if shape == "slepian_fourier":                 # :330-363
+        width = x["width"]
+        if "risefall" in x:
+            plateau = width - x["risefall"] * 2
+            xx = t.copy()
+            xx = np.where(t > (e.t_final + plateau) / 2, t - plateau / 2, xx)
+            xx = np.where(t < (e.t_final - plateau) / 2, t + plateau / 2, xx)
+            xx = np.where(np.abs(t - e.t_final / 2) < plateau / 2, e.t_final / 2, xx)
+            length = x["risefall"] * 2
+        else:
+            xx, length = t, width
+        v = np.zeros_like(t)
+        for n, coeff in enumerate(np.atleast_1d(x["fourier_coeffs"])):
+            v = v + coeff * (1 - np.cos(2 * np.pi * (n + 1) * (xx - (e.t_final - length) / 2) / length))
+        for n, coeff in enumerate(np.atleast_1d(x.get("sin_coeffs", []))):
+            v = v + coeff * np.sin((np.pi * (2 * n + 1)) * (xx - (e.t_final - length) / 2) / length)
+        v = np.where(np.abs(e.t_final / 2 - t) > width / 2, 0.0, v)
+        v = v / np.max(v)
+        return v * (1 - x["offset"] / e.amp) + x["offset"] / e.amp
     raise ValueError(f"C3:ERROR: envelope shape '{shape}' is not restated")
+
+
+def interp_regular_1d_grid(x, x_min: float, x_max: float, y_ref, fill: float = 0.0) -> np.ndarray:
+    """tfp.math.interp_regular_1d_grid(x, x_ref_min, x_ref_max, y_ref, fill_value_below = fill_value_above = 0): y_ref sits on
+    linspace(x_min, x_max, len(y_ref)); linear interpolation inside, the fill value outside (tensorflow_probability
+    math/interpolation.py; the dependency is absent from /root/reference -- pinned through the envelope golden vectors that
+    use it: pwc_shape, pwc_symmetric, pwc_shape_plateau1/2)."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y_ref, dtype=np.float64).reshape(-1)
+    ny = len(y)
+    u = (x - x_min) / (x_max - x_min) * (ny - 1)
+    uc = np.clip(u, 0, ny - 1)
+    lo = np.floor(uc).astype(int)
+    hi = np.minimum(lo + 1, ny - 1)
+    lo = np.maximum(hi - 1, 0)
+    w = uc - lo
+    v = w * y[hi] + (1 - w) * y[lo]
+    return np.where((x < x_min) | (x > x_max), fill, v)
 
 
 def _gauss_norm(e) -> float:
@@ -157,7 +252,7 @@ def envelope_values(e: EnvelopeSpec, ts_off: np.ndarray, t_len: float) -> np.nda
     """Complex envelope samples: Envelope.get_shape_values (mask * shape, optionally minus the value one
     sample before the start) and the DRAG quadrature of EnvelopeDrag."""
     mask = compute_mask(ts_off, e.t_final, t_len)
-    env = mask * shape_values(e.shape, ts_off, e)
+    env = mask * shape_values(e.shape, ts_off, e)        # complex for "pwc"
     if e.use_t_before:
         t_before = 2 * ts_off[0] - ts_off[1]
         env = mask * (shape_values(e.shape, ts_off, e) - shape_values(e.shape, np.array([t_before]), e)[0])

@@ -142,7 +142,15 @@ def envelopes():
     d = load("envelopes.pickle")
     keep = ["trapezoid", "flattop_risefall", "flattop_risefall_1ns", "flattop", "gaussian_sigma", "gaussian", "gaussian_nonorm",
             "gaussian_der_nonorm", "gaussian_der", "drag_sigma", "drag_der", "drag", "cosine", "no_drive", "rect"]
+    # the array-parametrised / grid-defined shapes (test_pwc_shape, test_delta_pulse, test_fourier, test_flattop,
+    # test_flattop_cut, test_cosine of test/test_envelopes.py; the parameters are restated in tests/test_signal_oracle.py)
+    keep += ["pwc_shape", "pwc_symmetric", "pwc_shape_plateau1", "pwc_shape_plateau2", "delta_pulse", "fourier_sin", "fourier_cos",
+             "slepian_fourier", "slepian_fourier_risefall", "slepian_fourier_sin", "flattop_variant", "flattop_cut",
+             "flattop_cut_center", "cosine_flattop"]
     out = {k: np.real(np.asarray(d[k])).reshape(-1).astype(np.float64) for k in keep}
+    # pwc_shape_plateau with "width": the reference's tf.where broadcasts its [100, 1] shape against the [100] time vector into
+    # [100, 100] (entry [i, j] = 1 where x[j] == t_mid else shape[i]); the element-wise result is the diagonal
+    out["pwc_shape_plateau2"] = np.real(np.asarray(d["pwc_shape_plateau2"])).reshape(100, 100).diagonal().astype(np.float64).copy()
     assert all(v.shape == (100,) for v in out.values()), {k: v.shape for k, v in out.items()}
     assert all(np.abs(np.imag(np.asarray(d[k]))).max() == 0 for k in keep)
     np.savez_compressed(os.path.join(HERE, "envelopes.npz"), ts=np.linspace(0, 10e-9, 100), **out)

@@ -343,3 +343,70 @@ def test_alias_shapes_through_the_generator(gen_mod):
                                freq_offset=(-50e6 - 3e6) * TP, delta=-1, risefall=0.7e-9)
         want, _ = so.generate_signal([spec], (5e9 + 50e6) * TP, 0.0, 7e-9, so.ChainSpec())
         assert _rel(got, want) < RTOL, shape
+
+
+# shape name -> (scalar envelope parameters as EnvelopeSpec fields, extra parameters); t_final = 7 ns, 14 AWG samples at 2 GS/s
+_PWC_X = dict(t_bin_start=0.2e-9, t_bin_end=6.7e-9, inphase=[0.0, 0.1, 0.3, 0.5, 0.1, 1.1, 0.4, 0.1])
+EXTENDED_SHAPES = {
+    "flattop_cut": (dict(t_up=1.1e-9, t_down=5.9e-9, risefall=0.8e-9), {}),
+    "flattop_cut_center": (dict(risefall=0.9e-9), dict(width=4.4e-9)),
+    "flattop_variant": (dict(t_up=0.6e-9, t_down=6.6e-9), dict(ramp=1.7e-9)),
+    "flattop_variant/wide-ramp": (dict(t_up=0.6e-9, t_down=6.6e-9), dict(ramp=4e-9)),
+    "cosine_flattop": ({}, dict(t_rise=2.1e-9)),
+    "delta_pulse": ({}, dict(t_sig=[0.5e-9, 4.2e-9])),
+    "pwc": ({}, dict(inphase=np.linspace(-0.4, 0.9, 14) ** 2, quadrature=np.cos(np.arange(14.0)))),
+    "pwc_shape": ({}, _PWC_X),
+    "pwc_symmetric": ({}, _PWC_X),
+    "pwc_shape_plateau": ({}, _PWC_X),
+    "pwc_shape_plateau/width": ({}, dict(_PWC_X, t_bin_start=0.0, t_bin_end=3e-9, width=5.5e-9)),
+    "fourier_sin": ({}, dict(amps=[0.5, 0.2, -0.1], freqs=[1e6, 1e9, 3.3e9], phases=[0.0, 1.0, -0.4])),
+    "fourier_cos": ({}, dict(amps=[0.5, 0.2], freqs=[1e6, 2.5e9])),
+    "slepian_fourier": ({}, dict(width=6e-9, fourier_coeffs=[1, 0.5, 0.2], offset=0.1)),
+    "slepian_fourier/risefall": ({}, dict(width=6e-9, fourier_coeffs=[1, 0.5, 0.2], offset=0.1, risefall=1.5e-9)),
+    "slepian_fourier/sin": ({}, dict(width=6e-9, fourier_coeffs=[1, 0.5, 0.2], offset=0.1, risefall=1.5e-9, sin_coeffs=[0.3, -0.1])),
+}
+
+
+@pytest.mark.parametrize("case", sorted(EXTENDED_SHAPES))
+def test_extended_envelope_shapes_through_the_generator(gen_mod, case):
+    """The array-parametrised and grid-defined shapes of c3/libraries/envelopes.py (pwc*, delta_pulse, fourier_*, slepian_fourier,
+    flattop_cut*, flattop_variant, cosine_flattop) through Generator.generate_signals on the device, against the oracle whose
+    shape functions are pinned to the reference's test/envelopes.pickle; a second envelope of a closed-form shape shares the
+    line so that the per-envelope accumulation and the table rows of a mixed instruction are exercised."""
+    shape = case.split("/")[0]
+    fields, extra = EXTENDED_SHAPES[case]
+    devices, chains, instr = fk.reference_generator_setup()
+    gen = gen_mod.Generator(devices, chains)
+    params = {"amp": fk.Quantity(0.45, "V"), "t_final": fk.Quantity(7e-9, "s"), "xy_angle": fk.Quantity(0.3, "rad"),
+              "freq_offset": fk.Quantity(-53e6, "Hz 2pi"), "delta": fk.Quantity(0.0, "")}
+    for key, val in {**fields, **extra}.items():
+        params[key] = fk.Quantity(val, "")
+    instr.add_component(fk.Envelope("ext", shape, params), "d1")
+    got = gen.generate_signals(instr)["d1"]["values"].cpu().numpy()
+    first = so.EnvelopeSpec(shape="gaussian_nonorm", amp=0.5, t_final=7e-9, sigma=7e-9 / 4, xy_angle=0.0,
+                            freq_offset=(-50e6 - 3e6) * TP, delta=-1)
+    spec = so.EnvelopeSpec(shape=shape, amp=0.45, t_final=7e-9, xy_angle=0.3, freq_offset=-53e6 * TP, **fields, extra=dict(extra))
+    want, _ = so.generate_signal([first, spec], (5e9 + 50e6) * TP, 0.0, 7e-9, so.ChainSpec())
+    assert np.abs(want).max() > 1e6          # the line carries a signal (Hz)
+    assert _rel(got, want) < RTOL, case
+    # the closed-form envelope alone gives a different line: the extended envelope really contributed
+    alone, _ = so.generate_signal([first], (5e9 + 50e6) * TP, 0.0, 7e-9, so.ChainSpec())
+    assert _rel(alone, want) > 1e-3
+
+
+def test_extended_shapes_are_forward_only(gen_mod):
+    """DRAG / use_t_before on an extended shape is refused by the host, and the reverse mode marks their rows with NaN."""
+    from c3_b200 import engine
+    devices, chains, instr = fk.reference_generator_setup()
+    gen = gen_mod.Generator(devices, chains)
+    instr.add_component(fk.EnvelopeDrag("ext", "fourier_cos", {"amp": fk.Quantity(0.1, "V"), "t_final": fk.Quantity(7e-9, "s"),
+                                                               "amps": fk.Quantity([1.0], ""), "freqs": fk.Quantity([1e9], "")}), "d1")
+    with pytest.raises(Exception, match="without DRAG"):
+        gen.generate_signals(instr)
+    env = np.zeros((1, 1, 1, 9)); env[0, 0, 0, :2] = [0.3, 7e-9]; env[0, 0, 0, 2] = 1e-9; env[0, 0, 0, 8] = 1e-9
+    sid = np.array([[gen_mod.SHAPE_IDS["flattop_cut"]]], dtype=np.int32)
+    chain = np.tile([100e9, 2e9, 0.3e-9, 1, 0, 1e9, 0, 1, 0, 0, np.nan], (1, 1))
+    N = engine.signal_slice_num(0.0, 7e-9, 100e9)
+    genv, glo, _ = engine.generate_signals_grad(env, sid, np.zeros((1, 1), np.int32), np.full((1, 1), 5e9 * TP), chain, 0.0, 7e-9,
+                                                torch.ones((1, 1, N), dtype=torch.float64, device="cuda"))
+    assert torch.isnan(genv).all()

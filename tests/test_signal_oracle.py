@@ -86,7 +86,10 @@ def test_generator_mirror_host_logic():
         Generator(bad, {"d1": dict(chains["d1"], Noise=["Mixer"])})
     with pytest.raises(Exception, match="C3:ERROR"):
         Generator(devices, {"d1": dict(chains["d1"], Mixer=["Response", "LO"])})
-    instr.add_component(fk.Envelope("odd", "slepian_fourier", {}), "d1")
+    instr.add_component(fk.Envelope("odd", "slepian_fourier", {}), "d1")          # known shape, its parameters missing
+    with pytest.raises(Exception, match="C3:ERROR.*lacks the parameter"):
+        gen._tables(instr)
+    instr.comps["d1"]["odd"].shape = fk._Shape("hann_window")                     # a shape the reference does not have either
     with pytest.raises(Exception, match="C3:ERROR"):
         gen._tables(instr)
 
@@ -109,6 +112,41 @@ def test_envelope_shapes_against_the_reference_pickle(shape):
     e = so.EnvelopeSpec(shape=shape, t_final=10e-9, sigma=sigma, risefall=2e-9, t_up=1e-9, t_down=10e-9)
     got = so.shape_values(shape, g["ts"], e)
     assert np.abs(got - g[shape]).max() <= 1e-11 * max(np.abs(g[shape]).max(), 1e-300)
+
+
+#: golden key -> (shape, EnvelopeSpec fields, extra parameters): the parameters of test/test_envelopes.py:33-130,158-207,279-289
+_PWC = dict(t_bin_start=1e-10, t_bin_end=9.9e-9, inphase=[0, 0.1, 0.3, 0.5, 0.1, 1.1, 0.4, 0.1])
+_SLEP = dict(width=9e-9, fourier_coeffs=[1, 0.5, 0.2], offset=0.1)
+EXTENDED_CASES = {
+    "pwc_shape": ("pwc_shape", {}, _PWC),
+    "pwc_symmetric": ("pwc_symmetric", {}, _PWC),
+    "pwc_shape_plateau1": ("pwc_shape_plateau", {}, _PWC),
+    "pwc_shape_plateau2": ("pwc_shape_plateau", {}, dict(_PWC, width=5e-9)),
+    "delta_pulse": ("delta_pulse", {}, dict(t_sig=[0.5e-9])),
+    "fourier_sin": ("fourier_sin", {}, dict(amps=[0.5, 0.2], freqs=[1e6, 1e10], phases=[0, 1])),
+    "fourier_cos": ("fourier_cos", {}, dict(amps=[0.5, 0.2], freqs=[1e6, 1e10], phases=[0, 1])),
+    "slepian_fourier": ("slepian_fourier", dict(amp=0.5), _SLEP),
+    "slepian_fourier_risefall": ("slepian_fourier", dict(amp=0.5), dict(_SLEP, risefall=4e-9)),
+    "slepian_fourier_sin": ("slepian_fourier", dict(amp=0.5), dict(_SLEP, risefall=4e-9, sin_coeffs=[0.3])),
+    "flattop_variant": ("flattop_variant", dict(t_up=1e-9, t_down=10e-9), dict(ramp=2e-9)),
+    "flattop_cut": ("flattop_cut", dict(risefall=2e-9, t_up=1e-9, t_down=10e-9), {}),
+    "flattop_cut_center": ("flattop_cut_center", dict(risefall=2e-9), dict(width=9e-9)),
+    "cosine_flattop": ("cosine_flattop", {}, dict(t_rise=2e-9)),
+}
+
+
+@pytest.mark.parametrize("key", sorted(EXTENDED_CASES))
+def test_extended_envelope_shapes_against_the_reference_pickle(key):
+    """The array-parametrised and grid-defined shapes (pwc_*, delta_pulse, fourier_*, slepian_fourier, flattop_cut*,
+    flattop_variant, cosine_flattop) against test/envelopes.pickle with the parameters of the reference's tests.  This also
+    pins the restated tfp.math.interp_regular_1d_grid (tensorflow_probability is not vendored in the reference)."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "envelopes.npz")))
+    shape, fields, extra = EXTENDED_CASES[key]
+    e = so.EnvelopeSpec(shape=shape, t_final=10e-9, **fields, extra=dict(extra))
+    got = so.shape_values(shape, g["ts"], e)
+    assert np.abs(got - g[key]).max() <= 1e-11 * max(np.abs(g[key]).max(), 1e-300)
 
 
 @pytest.mark.parametrize("shape", [s_ for s_ in ENVELOPE_SHAPES if s_ not in ("no_drive", "rect")])
