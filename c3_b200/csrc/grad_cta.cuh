@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(NT) grad_prefix_cta_kernel(const GradCtaParams
     }
 }
 
-// One CTA per (b, n): W_n = L(A_n, M_n), the Frechet derivative of the degree-18 Taylor scheme on (X, dX) pairs (see grad.cuh
-// for the recurrences), then grad[b,k,n] = (1 / alpha_b) Re tr(e^{mu_n} W_n G_k).  Ten matrix slots: X0..X4 values, Y0..Y4
+// One CTA per (b, n): W_n = L(A_n, M_n), the Frechet derivative of the four-product Taylor scheme on (X, dX) pairs (the
+// recurrences of grad_blk9.cuh), then grad[b,k,n] = (1 / alpha_b) Re tr(e^{mu_n} W_n G_k).  Ten matrix slots: X0..X4 values, Y0..Y4
 // derivatives; the fused epilogues of cta_zgemm accumulate in place (C = A B + C).
 template <int TM, int TN, int NT>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) grad_frechet_cta_kernel(const GradCtaParams p) {
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) grad_frechet_cta_kernel
             for (int k = 0; k < K; ++k) v = fma(fabs(__ldg(sig_b + (size_t)k * p.N + n)), p.RS[(size_t)(k + 1) * D + r], v);
             nb = fmax(nb, v);
         }
-        const int s = squarings_for(warp_max(nb), C3B_THETA18);
+        const int s = squarings_for(warp_max(nb), C3B_THETA15);
         const double sc = pow2neg(s);
         cplx mu = p.TR[0];
         for (int k = 0; k < K; ++k) {
@@ -171,57 +171,69 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) grad_frechet_cta_kernel
             Y[0][i * LD + j] = cmake(m.x * sc, m.y * sc);
         }
         __syncthreads();
-        // ---- powers and their derivatives -------------------------------------------------------------------------------------
-        cta_zgemm<TM, TN, 0, 0, NT>(X[1], X[0], X[0], DP, LD, KP);                         // A2
-        cta_zgemm<TM, TN, 0, 0, NT>(Y[1], X[0], Y[0], DP, LD, KP);                         // dA2 = A M
+        // ---- the four-product scheme (c3b_common.cuh) and its derivative, two independent products per barrier where possible ----
+        //   X0 = A, Y0 = M;   X1 = A2, Y1 = dA2 = A M + M A
+        cta_zgemm<TM, TN, 0, 0, NT>(X[1], X[0], X[0], DP, LD, KP);
+        cta_zgemm<TM, TN, 0, 0, NT>(Y[1], X[0], Y[0], DP, LD, KP);
         __syncthreads();
-        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[1], Y[0], X[0], DP, LD, KP, Y[1]);                //     + M A
-        cta_zgemm<TM, TN, 0, 0, NT>(X[2], X[1], X[0], DP, LD, KP);                         // A3 = A2 A
+        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[1], Y[0], X[0], DP, LD, KP, Y[1]);
         __syncthreads();
-        cta_zgemm<TM, TN, 0, 0, NT>(Y[2], Y[1], X[0], DP, LD, KP);                         // dA3 = dA2 A
+        //   X2 = Q0 = a1 A2 + a2 A,  Y2 = dQ0
+        for (int e = tid; e < RL; e += NT) {
+            const cplx x1 = X[0][e], x2 = X[1][e], y1 = Y[0][e], y2 = Y[1][e];
+            X[2][e] = cmake(C3B_T15_A1 * x2.x + C3B_T15_A2 * x1.x, C3B_T15_A1 * x2.y + C3B_T15_A2 * x1.y);
+            Y[2][e] = cmake(C3B_T15_A1 * y2.x + C3B_T15_A2 * y1.x, C3B_T15_A1 * y2.y + C3B_T15_A2 * y1.y);
+        }
         __syncthreads();
-        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[2], X[1], Y[0], DP, LD, KP, Y[2]);                //     + A2 M
-        cta_zgemm<TM, TN, 0, 0, NT>(X[3], X[2], X[2], DP, LD, KP);                         // A6 = A3 A3
+        //   X3 = P0 = A2 Q0,  Y3 = dP0 = dA2 Q0 + A2 dQ0
+        cta_zgemm<TM, TN, 0, 0, NT>(X[3], X[1], X[2], DP, LD, KP);
+        cta_zgemm<TM, TN, 0, 0, NT>(Y[3], Y[1], X[2], DP, LD, KP);
         __syncthreads();
-        cta_zgemm<TM, TN, 0, 0, NT>(Y[3], Y[2], X[2], DP, LD, KP);                         // dA6 = dA3 A3
+        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[3], X[1], Y[2], DP, LD, KP, Y[3]);
         __syncthreads();
-        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[3], X[2], Y[2], DP, LD, KP, Y[3]);                //     + A3 dA3
-        __syncthreads();
-        // ---- combinations in place: X0..X4 <- B1, B5, B4, B3, B2 and Y0..Y4 <- their derivatives -----------------------------
+        //   X2 = L1 = P0 + b1 A2 + b2 A,  X4 = R1 = P0 + b3 A2 + b4 I,  X3 = b5 P0 (the addend of the next product); Y likewise
         for (int e = tid; e < RL; e += NT) {
             const int i = e / LD, j = e - i * LD;
             const double dg = (i == j) ? 1.0 : 0.0;
-            const cplx x1 = X[0][e], x2 = X[1][e], x3 = X[2][e], x6 = X[3][e];
-            const cplx y1 = Y[0][e], y2 = Y[1][e], y3 = Y[2][e], y6 = Y[3][e];
-            X[0][e] = cmake(C3B_T18_A11 * x1.x + C3B_T18_A21 * x2.x + C3B_T18_A31 * x3.x, C3B_T18_A11 * x1.y + C3B_T18_A21 * x2.y + C3B_T18_A31 * x3.y);
-            Y[0][e] = cmake(C3B_T18_A11 * y1.x + C3B_T18_A21 * y2.x + C3B_T18_A31 * y3.x, C3B_T18_A11 * y1.y + C3B_T18_A21 * y2.y + C3B_T18_A31 * y3.y);
-            X[1][e] = cmake(C3B_T18_B24 * x2.x + C3B_T18_B34 * x3.x + C3B_T18_B64 * x6.x, C3B_T18_B24 * x2.y + C3B_T18_B34 * x3.y + C3B_T18_B64 * x6.y);
-            Y[1][e] = cmake(C3B_T18_B24 * y2.x + C3B_T18_B34 * y3.x + C3B_T18_B64 * y6.x, C3B_T18_B24 * y2.y + C3B_T18_B34 * y3.y + C3B_T18_B64 * y6.y);
-            X[2][e] = cmake(C3B_T18_B03 * dg + C3B_T18_B13 * x1.x + C3B_T18_B23 * x2.x + C3B_T18_B33 * x3.x + C3B_T18_B63 * x6.x,
-                            C3B_T18_B13 * x1.y + C3B_T18_B23 * x2.y + C3B_T18_B33 * x3.y + C3B_T18_B63 * x6.y);
-            Y[2][e] = cmake(C3B_T18_B13 * y1.x + C3B_T18_B23 * y2.x + C3B_T18_B33 * y3.x + C3B_T18_B63 * y6.x,
-                            C3B_T18_B13 * y1.y + C3B_T18_B23 * y2.y + C3B_T18_B33 * y3.y + C3B_T18_B63 * y6.y);
-            X[3][e] = cmake(C3B_T18_B02 * dg + C3B_T18_B12 * x1.x + C3B_T18_B22 * x2.x + C3B_T18_B32 * x3.x + C3B_T18_B62 * x6.x,
-                            C3B_T18_B12 * x1.y + C3B_T18_B22 * x2.y + C3B_T18_B32 * x3.y + C3B_T18_B62 * x6.y);
-            Y[3][e] = cmake(C3B_T18_B12 * y1.x + C3B_T18_B22 * y2.x + C3B_T18_B32 * y3.x + C3B_T18_B62 * y6.x,
-                            C3B_T18_B12 * y1.y + C3B_T18_B22 * y2.y + C3B_T18_B32 * y3.y + C3B_T18_B62 * y6.y);
-            X[4][e] = cmake(C3B_T18_B11 * x1.x + C3B_T18_B21 * x2.x + C3B_T18_B31 * x3.x + C3B_T18_B61 * x6.x,
-                            C3B_T18_B11 * x1.y + C3B_T18_B21 * x2.y + C3B_T18_B31 * x3.y + C3B_T18_B61 * x6.y);
-            Y[4][e] = cmake(C3B_T18_B11 * y1.x + C3B_T18_B21 * y2.x + C3B_T18_B31 * y3.x + C3B_T18_B61 * y6.x,
-                            C3B_T18_B11 * y1.y + C3B_T18_B21 * y2.y + C3B_T18_B31 * y3.y + C3B_T18_B61 * y6.y);
+            const cplx x1 = X[0][e], x2 = X[1][e], p0 = X[3][e], y1 = Y[0][e], y2 = Y[1][e], q0 = Y[3][e];
+            X[2][e] = cmake(p0.x + C3B_T15_B1 * x2.x + C3B_T15_B2 * x1.x, p0.y + C3B_T15_B1 * x2.y + C3B_T15_B2 * x1.y);
+            X[4][e] = cmake(p0.x + C3B_T15_B3 * x2.x + C3B_T15_B4 * dg, p0.y + C3B_T15_B3 * x2.y);
+            X[3][e] = cmake(C3B_T15_B5 * p0.x, C3B_T15_B5 * p0.y);
+            Y[2][e] = cmake(q0.x + C3B_T15_B1 * y2.x + C3B_T15_B2 * y1.x, q0.y + C3B_T15_B1 * y2.y + C3B_T15_B2 * y1.y);
+            Y[4][e] = cmake(q0.x + C3B_T15_B3 * y2.x, q0.y + C3B_T15_B3 * y2.y);
+            Y[3][e] = cmake(C3B_T15_B5 * q0.x, C3B_T15_B5 * q0.y);
         }
         __syncthreads();
-        // ---- A9 = B4 + B1 B5 -> X2 (S = B3 + A9 -> X3);  dA9 = dB4 + dB1 B5 + B1 dB5 -> Y2 (dS = dB3 + dA9 -> Y3) --------------
-        cta_zgemm<TM, TN, 0, 0, NT, 1>(X[2], X[0], X[1], DP, LD, KP, X[2], X[3]);
-        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[2], Y[0], X[1], DP, LD, KP, Y[2]);
+        //   X3 = P1 = L1 R1 + b5 P0,  Y3 = dP1 = dL1 R1 + L1 dR1 + b5 dP0   (in place on the addend)
+        cta_zgemm<TM, TN, 0, 0, NT, 2>(X[3], X[2], X[4], DP, LD, KP, X[3]);
+        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[3], Y[2], X[4], DP, LD, KP, Y[3]);
         __syncthreads();
-        cta_zgemm<TM, TN, 0, 0, NT, 1>(Y[2], X[0], Y[1], DP, LD, KP, Y[2], Y[3]);
+        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[3], X[2], Y[4], DP, LD, KP, Y[3]);
         __syncthreads();
-        // ---- T18 = B2 + S A9 -> X0 (needed only to undo a scaling);  dT18 = dB2 + dS A9 + S dA9 -> Y0 -----------------------------
-        if (s > 0) cta_zgemm<TM, TN, 0, 0, NT, 2>(X[0], X[3], X[2], DP, LD, KP, X[4]);
-        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[0], Y[3], X[2], DP, LD, KP, Y[4]);
+        //   P0 = L1 - b1 A2 - b2 A is recovered (|L1| ~ 0.4 |A|: the cancellation costs 1e-16 absolute);
+        //   X2 = L2, X4 = R2, X3 = E0 and their derivatives in the Y slots
+        for (int e = tid; e < RL; e += NT) {
+            const int i = e / LD, j = e - i * LD;
+            const double dg = (i == j) ? 1.0 : 0.0;
+            const cplx x1 = X[0][e], x2 = X[1][e], l1 = X[2][e], p1 = X[3][e];
+            const cplx y1 = Y[0][e], y2 = Y[1][e], dl1 = Y[2][e], q1 = Y[3][e];
+            const cplx p0 = cmake(l1.x - C3B_T15_B1 * x2.x - C3B_T15_B2 * x1.x, l1.y - C3B_T15_B1 * x2.y - C3B_T15_B2 * x1.y);
+            const cplx q0 = cmake(dl1.x - C3B_T15_B1 * y2.x - C3B_T15_B2 * y1.x, dl1.y - C3B_T15_B1 * y2.y - C3B_T15_B2 * y1.y);
+            X[2][e] = cmake(p1.x + C3B_T15_C1 * x2.x + C3B_T15_C2 * x1.x, p1.y + C3B_T15_C1 * x2.y + C3B_T15_C2 * x1.y);
+            X[4][e] = cmake(p1.x + C3B_T15_C3 * p0.x + C3B_T15_C4 * x1.x, p1.y + C3B_T15_C3 * p0.y + C3B_T15_C4 * x1.y);
+            X[3][e] = cmake(C3B_T15_C9 * p1.x + C3B_T15_C5 * p0.x + C3B_T15_C6 * x2.x + C3B_T15_C7 * x1.x + C3B_T15_C8 * dg,
+                            C3B_T15_C9 * p1.y + C3B_T15_C5 * p0.y + C3B_T15_C6 * x2.y + C3B_T15_C7 * x1.y);
+            Y[2][e] = cmake(q1.x + C3B_T15_C1 * y2.x + C3B_T15_C2 * y1.x, q1.y + C3B_T15_C1 * y2.y + C3B_T15_C2 * y1.y);
+            Y[4][e] = cmake(q1.x + C3B_T15_C3 * q0.x + C3B_T15_C4 * y1.x, q1.y + C3B_T15_C3 * q0.y + C3B_T15_C4 * y1.y);
+            Y[3][e] = cmake(C3B_T15_C9 * q1.x + C3B_T15_C5 * q0.x + C3B_T15_C6 * y2.x + C3B_T15_C7 * y1.x,
+                            C3B_T15_C9 * q1.y + C3B_T15_C5 * q0.y + C3B_T15_C6 * y2.y + C3B_T15_C7 * y1.y);
+        }
         __syncthreads();
-        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[0], X[3], Y[2], DP, LD, KP, Y[0]);
+        //   X0 = T = L2 R2 + E0 (needed only to undo a scaling);  Y0 = dT = dL2 R2 + L2 dR2 + dE0
+        if (s > 0) cta_zgemm<TM, TN, 0, 0, NT, 2>(X[0], X[2], X[4], DP, LD, KP, X[3]);
+        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[0], Y[2], X[4], DP, LD, KP, Y[3]);
+        __syncthreads();
+        cta_zgemm<TM, TN, 0, 0, NT, 2>(Y[0], X[2], Y[4], DP, LD, KP, Y[0]);
         __syncthreads();
         cplx *Xc = X[0], *dXc = Y[0], *Xn = X[1], *dXn = Y[1];
         for (int q = 0; q < s; ++q) {                           // (X, dX) <- (X X, dX X + X dX)
