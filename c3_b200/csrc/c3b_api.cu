@@ -82,7 +82,7 @@ int num_sms() {
 }
 
 int cta_grid(int D, long long units) {
-    int per_sm = (tuning().gemm_big >= 2) ? 1 : 2;              // global-workspace kernels: 2 x 256 threads, or 1 x 384 / 1 x 512
+    int per_sm = (tuning().gemm_big >= 2) ? 1 : 2;              // global-workspace kernels: 2 x 256 threads, or 1 x 384 / 512 / 704
     if (D <= 32) {
         if (tuning().cta_variant == 1) {
             per_sm = gemm_ctas_per_sm(D);

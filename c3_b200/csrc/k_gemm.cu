@@ -10,7 +10,8 @@ namespace {
 template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
 int launch_gemm_t(const GemmParams& gp, int grid, cudaStream_t st) {
     auto kern = pwc_taylor_cta_kernel<TM, TN, DPT, KST, NT>;
-    const size_t smem = gp.c.use_smem ? gemm_smem_bytes(gp.c.D, gp.g_in_smem ? gp.c.K : -1, gp.g_in_smem ? 0 : 1) : 0;
+    size_t smem = gp.c.use_smem ? gemm_smem_bytes(gp.c.D, gp.g_in_smem ? gp.c.K : -1, gp.g_in_smem ? 0 : 1) : 0;
+    if (TM == 0) smem = (size_t)3 * (12 * gp.DP + 8 * (gp.DP + 2)) * sizeof(cplx);      // panel ring of cta_zgemm_rows
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NT, smem, st>>>(gp);
     CUDA_TRY(cudaGetLastError());
@@ -40,6 +41,14 @@ int launch_gemm(const CtaParams& cp, const cplx* TR, const double* RS, int grid,
     // inside the 126 MB L2 (two 256-thread CTAs per SM: 220 MB, L2 hit rate 52 %)
     if (gp.DP == 88 && tn.gemm_big == 2) return launch_gemm_t<3, 2, 0, 0, 384>(gp, grid, st);
     if (gp.DP == 88 && tn.gemm_big == 3) return launch_gemm_t<2, 2, 0, 0, 512>(gp, grid, st);   // 16 warps, one CTA per SM
+    // Measured alternatives, not default: operand panels staged through shared memory by cp.async (cta_zgemm_rows), one CTA
+    // per SM.  5: 12 warps, a warp owns a block-row (66 accumulators, no spills): 0.73 against 0.79 for the default -- the
+    // fragment loads no longer wait on L2 (long_scoreboard 14.8 -> 4.2 per issue) but one CTA per SM exposes the per-panel
+    // barrier (15 % of the samples) and leaves 3 warps per scheduler.  4: 22 warps, half a block-row each: 80 registers per
+    // thread spill the accumulators inside the panel loop: 0.55.  (Two 6-warp CTAs per SM with two block-rows per warp need
+    // 132 accumulators: 1.8 KB of spills, not kept.)
+    if (gp.DP == 88 && !cp.use_smem && tn.gemm_big == 4) return launch_gemm_t<0, 11, 0, 0, 704>(gp, grid, st);
+    if (gp.DP == 88 && !cp.use_smem && tn.gemm_big == 5) return launch_gemm_t<0, 11, 0, 0, 384>(gp, grid, st);
     return launch_gemm_t<2, 2>(gp, grid, st);
 }
 

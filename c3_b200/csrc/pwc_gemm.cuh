@@ -163,6 +163,120 @@ __device__ __forceinline__ void zgemm_edge_tile(cplx* C, const cplx* A, const cp
         for (int j = 0; j < tj; ++j) zgemm_tile<1, 1, EPI>(C, A, B, bi0 + i, bj0 + j, LD, KP, E1, E2, E3, fr, fc);
 }
 
+// ---- cp.async (Ampere-style asynchronous global -> shared copies, 16 bytes per thread) ----------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gptr) {
+    const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(__cvta_generic_to_global(gptr)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// C = A B with the k-panels of BOTH operands staged through shared memory (global-workspace matrices, 64 < DP <= 8 NBMAX):
+// the per-warp macro tiles of cta_zgemm read every operand fragment straight from the L2-resident workspace, and at D = 81
+// the product waited on those loads (long_scoreboard 14.8 stalls per issue, tensor pipe 51 %).  Here the CTA streams panels
+// of 8 k-values -- A[:, k0:k0+8] and B[k0:k0+8, :] -- into a 3-stage ring with cp.async, one barrier per panel, and a warp
+// owns HALF a block-row of C: one A fragment and 6 B fragments per k-step feed 18 DMMAs (3M product), its accumulators stay
+// in registers across the panel loop, every operand byte leaves L2 once per product.
+// Panel layouts: A rows padded to 12 elements, B rows to DP + 2: both fragment patterns of mma.m8n8k4 are then conflict-free
+// per quarter-warp.  Needs DP == 8 NBMAX, 2 NBMAX <= NT / 32 warps and 3 (12 DP + 8 (DP + 2)) 16 bytes of dynamic shared memory at offset 0.
+// __noinline__: a real call gives the panel loop its own register allocation (inlined into the kernel, whose ~40 live
+// values surround every product, the accumulators spilled inside the loop: 0.6 local-memory accesses per DMMA).
+template <int NBMAX, int NT, int EPI>
+__device__ __noinline__ void cta_zgemm_rows(cplx* C, const cplx* A, const cplx* B, const int LD, const int KP,
+                                            const cplx* E1, cplx* E2, cplx* E3) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int KB = 8, LDA = 12, NSTG = 3, DP = 8 * NBMAX, LDB = DP + 2;
+    constexpr int PER = (DP * KB + NT - 1) / NT;           // panel elements per thread and operand (1 at NT = 704, 2 at 384)
+    constexpr bool HALF = (NT / 32 >= 2 * NBMAX);          // enough warps to split every block-row in two
+    const int npan = (KP + KB - 1) / KB;
+    constexpr int stage_elems = DP * LDA + KB * LDB;
+    cplx* stage = reinterpret_cast<cplx*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
+    // this thread's elements of every A panel (row e / 8, k e % 8) and of every B panel (k e / DP, column e % DP)
+    const cplx* a_src[PER];
+    const cplx* b_src[PER];
+    int a_dst[PER], b_dst[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int e = min(tid + q * NT, DP * KB - 1);      // (a clamped duplicate copies the same element twice: harmless)
+        a_src[q] = A + (size_t)(e >> 3) * LD + (e & 7);
+        b_src[q] = B + (size_t)(e / DP) * LD + (e % DP);
+        a_dst[q] = (e >> 3) * LDA + (e & 7);
+        b_dst[q] = DP * LDA + (e / DP) * LDB + (e % DP);
+    }
+    auto issue = [&](const int pan) {
+        cplx* st = stage + (pan % NSTG) * stage_elems;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            cp_async16(st + a_dst[q], a_src[q] + pan * KB);
+            cp_async16(st + b_dst[q], b_src[q] + (size_t)pan * KB * LD);
+        }
+        cp_async_commit();
+    };
+    // Work split.  HALF (>= 2 NBMAX warps): warp w owns block-row w / 2, column half w % 2 (blocks 0..NJ-1 or NBMAX-NJ..NBMAX-1;
+    // with NBMAX odd the middle block is computed twice and stored by the first half -- branch-free).  Otherwise warp w owns
+    // R = ceil(NBMAX / warps) whole block-rows w R .. w R + R - 1 (a row past the end is a clamped duplicate that is not stored).
+    constexpr int NW = NT / 32;
+    constexpr int R = HALF ? 1 : (NBMAX + NW - 1) / NW;
+    constexpr int NJ = HALF ? (NBMAX + 1) / 2 : NBMAX;
+    const int brow0 = HALF ? (warp >> 1) : warp * R, half = HALF ? (warp & 1) : 0, jbase = half ? NBMAX - NJ : 0;
+    double p1[R][NJ][2], p2[R][NJ][2], p3[R][NJ][2];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { p1[r][j][0] = p1[r][j][1] = p2[r][j][0] = p2[r][j][1] = p3[r][j][0] = p3[r][j][1] = 0.0; }
+    int a_off[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) a_off[r] = (min(brow0 + r, NBMAX - 1) * 8 + fr) * LDA + fc;
+    issue(0);
+    if (npan > 1) issue(1);
+    for (int pan = 0; pan < npan; ++pan) {
+        if (pan + 1 < npan) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();                                   // panel pan has landed for everyone; stage (pan + 2) % 3 is free
+        if (pan + 2 < npan) issue(pan + 2);
+        if (brow0 < NBMAX) {
+            const cplx* As = stage + (pan % NSTG) * stage_elems;
+            const cplx* Bs = stage + (pan % NSTG) * stage_elems + DP * LDA + fc * LDB + jbase * 8 + fr;
+            auto kstep = [&](const int ks) {
+                cplx a[R];
+                double as[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) { a[r] = As[a_off[r] + ks * 4]; as[r] = a[r].x + a[r].y; }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    // at most two B fragments in flight: hoisting all of them spilled the accumulators inside the loop
+                    if ((j & 1) == 0) asm volatile("" ::: "memory");
+                    const cplx b = Bs[ks * 4 * LDB + j * 8];
+                    const double bs = b.x + b.y;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        dmma8x8x4(p1[r][j][0], p1[r][j][1], a[r].x, b.x);
+                        dmma8x8x4(p2[r][j][0], p2[r][j][1], a[r].y, b.y);
+                        dmma8x8x4(p3[r][j][0], p3[r][j][1], as[r], bs);
+                    }
+                }
+            };
+            kstep(0);
+            if (KP - pan * KB > 4) kstep(1);               // the last panel may hold one k-step only
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (brow0 + r < NBMAX) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (half == 0 || 2 * NJ == NBMAX || j > 0) {   // the duplicated middle block belongs to the first half
+                    const int row = (brow0 + r) * 8 + fr, col = (jbase + j) * 8 + 2 * fc;
+                    const cplx c0 = cmake(p1[r][j][0] - p2[r][j][0], p3[r][j][0] - p1[r][j][0] - p2[r][j][0]);
+                    const cplx c1 = cmake(p1[r][j][1] - p2[r][j][1], p3[r][j][1] - p1[r][j][1] - p2[r][j][1]);
+                    zgemm_epilogue<EPI>(c0, c1, row * LD + col, row, col, C, E1, E2, E3);
+                }
+            }
+        }
+    }
+}
+
 // C = A * B for zero-padded DP x DP complex matrices (row-major, leading dimension DP, DP % 8 == 0).
 // Warp w owns macro tiles of TM x TN m8n8 blocks, assigned round-robin.  No __restrict__: operands
 // may be global-workspace buffers written earlier by this CTA.
@@ -172,10 +286,9 @@ __device__ __forceinline__ void zgemm_edge_tile(cplx* C, const cplx* A, const cp
 // EPI fuses the element-wise step that follows two of the scheme's products into the epilogue (the accumulators are still in
 // registers): 1: C = A B + E1 (= A9), E2 += C (= B3 + A9);  2: C = A B + E1 (= T18).  Padding rows / columns are zero in every
 // operand, so they stay zero.
-template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads, int EPI = 0>
-__device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP_, const int LD_, const int KP,
-                                          const cplx* E1 = nullptr, cplx* E2 = nullptr, const unsigned char* sched = nullptr,
-                                          cplx* E3 = nullptr) {
+template <int TM, int TN, int DPT, int KST, int NT, int EPI>
+__device__ __forceinline__ void cta_zgemm_tiles(cplx* C, const cplx* A, const cplx* B, const int DP_, const int LD_, const int KP,
+                                                const cplx* E1, cplx* E2, const unsigned char* sched, cplx* E3) {
     // DPT > 0: tile extent and leading dimension are compile-time (DPT, DPT + 4): the k loop unrolls fully and
     // every fragment address is base + immediate
     constexpr bool SWZ = (DPT == 32);
@@ -329,6 +442,15 @@ __device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B,
     }
 }
 
+// TM > 0: per-warp macro tiles (cta_zgemm_tiles); TM == 0: staged block-row product with at most TN blocks per row
+template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads, int EPI = 0>
+__device__ __forceinline__ void cta_zgemm(cplx* C, const cplx* A, const cplx* B, const int DP_, const int LD_, const int KP,
+                                          const cplx* E1 = nullptr, cplx* E2 = nullptr, const unsigned char* sched = nullptr,
+                                          cplx* E3 = nullptr) {
+    if constexpr (TM == 0) cta_zgemm_rows<TN, NT, EPI>(C, A, B, LD_, KP, E1, E2, E3);
+    else cta_zgemm_tiles<TM, TN, DPT, KST, NT, EPI>(C, A, B, DP_, LD_, KP, E1, E2, sched, E3);
+}
+
 // Balanced static assignment of macro tiles to warps (longest-processing-time first): a macro tile at the matrix edge holds
 // fewer m8n8 blocks than TM x TN, and round-robin leaves some warps with full tiles only (D = 81, 3 x 2 macro tiles on 11 x 11
 // blocks, 8 warps: 18 blocks on the busiest warp against 15.1 on average; balanced: 16).  sched[w * rounds + r] = macro tile
@@ -392,7 +514,7 @@ __device__ __forceinline__ double cta_norm_inf_ld(const cplx* A, const int D, co
 //   squarings ping-pong S3 <-> S4;  the fold X P goes to S2 (E0 is dead) and S2 / P swap roles (pointers, no copy);
 //   the first slice of a segment swaps X and P instead of copying.
 template <int TM, int TN, int DPT = 0, int KST = 0, int NT = kCtaThreads>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_taylor_cta_kernel(const GemmParams gp) {
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) pwc_taylor_cta_kernel(const GemmParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[NT / 32];
     const CtaParams& p = gp.c;
@@ -420,9 +542,11 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) pwc_taylor_cta_kernel(c
     __shared__ unsigned char s_sched[64];
     __shared__ int s_load[2 * (NT / 32)];
     const unsigned char* sched = nullptr;
-    if (DPT == 0 && ((DP >> 3) + TM - 1) / TM * (((DP >> 3) + TN - 1) / TN) <= 64 - NT / 32) {
-        if (tid == 0) gemm_build_schedule<TM, TN>(s_sched, s_load, DP >> 3, NT / 32);
-        sched = s_sched;
+    if constexpr (TM > 0) {
+        if (DPT == 0 && ((DP >> 3) + TM - 1) / TM * (((DP >> 3) + TN - 1) / TN) <= 64 - NT / 32) {
+            if (tid == 0) gemm_build_schedule<TM, TN>(s_sched, s_load, DP >> 3, NT / 32);
+            sched = s_sched;
+        }
     }
     // zero everything once: the padding rows/columns stay zero through every product
     for (int e = tid; e < kGemmSlots * PP; e += NT) mats[e] = cmake(0.0, 0.0);

@@ -9,6 +9,8 @@ if "t512" in which: engine.set_tuning("cta_threads", 512)
 if "big2" in which: engine.set_tuning("gemm_big", 2)
 if "big1" in which: engine.set_tuning("gemm_big", 1)
 if "big3" in which: engine.set_tuning("gemm_big", 3)
+if "big4" in which: engine.set_tuning("gemm_big", 4)
+if "big5" in which: engine.set_tuning("gemm_big", 5)
 peak = engine.measure_fp64_peak("dfma", 0.3)
 engine.set_tuning("profile", 1)
 if "81" in which:

@@ -298,13 +298,20 @@ def test_cta_kernel_scaling_from_row_sum_bound(eng, d, scale, norm_bound):
         assert rel_fro(Ub[b].cpu().numpy(), want) < TOL
 
 
-def test_lindblad_config3_shape(eng):
-    """BASELINE config 3 shape (two 3-level transmons, D=81) on a small batch / few slices."""
+@pytest.mark.parametrize("gemm_big", [0, 1, 2, 3, 4, 5])
+def test_lindblad_config3_shape(eng, gemm_big):
+    """BASELINE config 3 shape (two 3-level transmons, D=81) on a small batch / few slices, with every instantiation of the
+    global-workspace DMMA kernel: macro-tile shapes / CTA sizes (0 default, 1..3) and the cp.async-staged block-row product
+    (4: 22 warps, 5: 12 warps)."""
     from c3_b200 import synth
     m = synth.two_transmon()
     B, N = 2, 12
     sig = synth.controls(m, B, 1000)[:, :, 494:494 + N].copy()
-    U, dUs = eng.pwc_lindblad(m.h0, m.hks, m.col_ops, sig, 1e-11, return_dUs=True)
+    eng.set_tuning("gemm_big", gemm_big)
+    try:
+        U, dUs = eng.pwc_lindblad(m.h0, m.hks, m.col_ops, sig, 1e-11, return_dUs=True)
+    finally:
+        eng.set_tuning("gemm_big", 0)
     for b in range(B):
         want = orc.tf_batch_propagate(m.h0, m.hks, sig[b], 1e-11, N, col_ops=m.col_ops, lindbladian=True)
         assert rel_fro(dUs[b].cpu().numpy(), want) < TOL
