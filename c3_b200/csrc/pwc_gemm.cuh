@@ -1,17 +1,16 @@
 // CTA-cooperative PWC propagator kernel for larger dimensions (closed d > 12, Lindblad D = d^2 up to
 // 81 and beyond), built on fp64 tensor-core tiles.
 //
-// Per slice: A_n (trace-shifted generators, exact 1-norm -> s) -> degree-18 Taylor scheme in 5 complex
-// products (c3b_common.cuh) -> s squarings -> running ordered product.  Every O(D^3) step is ONE
-// routine, cta_zgemm: C = A B on zero-padded DP x DP complex matrices (DP = D rounded up to 8), each
-// warp owning 2x2 (or 1x2) m8n8 tiles and issuing mma.sync.m8n8k4.f64 (DMMA): a complex tile step is
-// 3 real DMMAs (the 3M product: Ar Br, Ai Bi, (Ar + Ai)(Br + Bi)) on fragments loaded straight from the
-// interleaved complex storage (one 16-byte load = re and im of a fragment element).  One operand
-// load feeds 8 complex MACs per lane (vs 1-1.5 in the register kernels), so the D^2 x D^2 Lindblad
-// superoperator is a genuinely dense contraction on the fp64 pipe, as BASELINE.json's north_star
-// asks.  Matrices live in shared memory (DP <= 32) or in a per-CTA global workspace that stays in
-// L1/L2 (D = 81: 10 x 124 KB).  Replaces c3/libraries/propagation.py:426-440,551-585 and
-// c3/utils/tf_utils.py:120-193 for these shapes; no linear solve, no pivoting.
+// Per slice: A_n (trace-shifted generators, scaled by 2^-s from the row-sum bound) -> degree-15+ Taylor polynomial in FOUR
+// complex products (c3b_common.cuh), every linear combination formed in the epilogue of the product before it -> s squarings
+// -> running ordered product.  Every O(D^3) step is ONE routine, cta_zgemm: C = A B on zero-padded DP x DP complex
+// matrices (DP = D rounded up to 8), each warp owning macro tiles of m8n8 blocks and issuing mma.sync.m8n8k4.f64 (DMMA):
+// a complex tile step is 3 real DMMAs (the 3M product: Ar Br, Ai Bi, (Ar + Ai)(Br + Bi)) on fragments loaded straight from
+// the interleaved complex storage (one 16-byte load = re and im of a fragment element).  One operand load feeds 8 complex
+// MACs per lane (vs 1-1.5 in the register kernels), so the D^2 x D^2 Lindblad superoperator is a genuinely dense
+// contraction on the fp64 pipe, as BASELINE.json's north_star asks.  Matrices live in shared memory (DP <= 32, XOR
+// swizzled) or in a per-CTA global workspace that stays in L1/L2 (D = 81: 6 x 124 KB).  Replaces
+// c3/libraries/propagation.py:426-440,551-585 and c3/utils/tf_utils.py:120-193 for these shapes; no linear solve, no pivoting.
 #pragma once
 #include "c3b_common.cuh"
 #include "pwc_cta.cuh"   // CtaParams, kCtaThreads
@@ -284,8 +283,8 @@ __device__ __noinline__ void cta_zgemm_rows(cplx* C, const cplx* A, const cplx* 
 // are zero).  In shared memory LD = DP + 4 (= 4 mod 8 in 16-byte units) makes the A-fragment loads
 // bank-conflict free and the B-fragment loads 2-way (with LD = DP = 32 they were 8-way / 4-way).
 // EPI fuses the element-wise step that follows two of the scheme's products into the epilogue (the accumulators are still in
-// registers): 1: C = A B + E1 (= A9), E2 += C (= B3 + A9);  2: C = A B + E1 (= T18).  Padding rows / columns are zero in every
-// operand, so they stay zero.
+// registers), see zgemm_epilogue.  Padding rows / columns are zero in every operand, so they stay zero (mode 5 puts the
+// identity on the padding diagonal: block-diagonal, never read).
 template <int TM, int TN, int DPT, int KST, int NT, int EPI>
 __device__ __forceinline__ void cta_zgemm_tiles(cplx* C, const cplx* A, const cplx* B, const int DP_, const int LD_, const int KP,
                                                 const cplx* E1, cplx* E2, const unsigned char* sched, cplx* E3) {
