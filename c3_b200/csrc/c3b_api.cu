@@ -473,22 +473,28 @@ static int grad_variant_for(int D) {
 }
 constexpr int kGradMaxDim = 128;
 
-static bool grad9_wanted(int lindblad, int K, int d) {
-    return !lindblad && tuning().grad_variant == 1 && tuning().grad_unitary != 0 && tuning().force_cta == 0 && grad9_supported(K, d);
+// which fused (unitary-recurrence) kernel serves a closed-system call: 0 none, 1 the d = 9 lane-group kernel (grad_blk9.cuh),
+// 2 the CTA kernel on the DMMA product for 16 < d <= 32 (grad_ucta.cuh)
+static int grad9_wanted(int lindblad, int K, int d) {
+    if (lindblad || tuning().grad_variant != 1 || tuning().grad_unitary == 0) return 0;
+    if (tuning().force_cta == 0 && grad9_supported(K, d)) return 1;
+    if (grad_ucta_supported(d) && pwc_path(d, 0) == 2 && tuning().cta_variant == 1) return 2;
+    return 0;
 }
-// chunk length of the fused gradient kernel: enough chunks to fill the machine, at least 8 slices, at most 48
-static int grad9_chunk_len(int B, int N) {
-    const long long want = 3LL * 8 * num_sms() * 4;                 // lane groups x 4 waves
+// chunk length of the fused gradient kernels: enough chunks to fill the machine (lane groups / CTAs x 4 waves), bounded
+static int grad9_chunk_len(int B, int N, int kind) {
+    const long long want = kind == 1 ? 3LL * 8 * num_sms() * 4 : 2LL * num_sms() * 4;
     long long cl = ((long long)B * N + want - 1) / want;
-    if (cl < 8) cl = 8;
-    if (cl > 48) cl = 48;
+    const long long lo = kind == 1 ? 8 : 4, hi = kind == 1 ? 48 : 64;
+    if (cl < lo) cl = lo;
+    if (cl > hi) cl = hi;
     if (cl > N) cl = N;
     return (int)cl;
 }
 struct Grad9Layout { size_t off_model, off_plan, off_U, off_Y, off_counter, total; int CL, Q; Plan pl; };
 static Grad9Layout grad9_layout(int Bc, int K, int N, int d) {
     Grad9Layout g{};
-    g.CL = grad9_chunk_len(Bc, N);
+    g.CL = grad9_chunk_len(Bc, N, grad9_wanted(0, K, d));
     g.Q = (N + g.CL - 1) / g.CL;
     g.pl = make_plan(Bc, N, d, 0, g.CL);
     const ModelLayout ml = model_layout(K, d, 1);
@@ -582,6 +588,16 @@ static int pwc_grad_impl(int lindblad, const void* h0, const void* hks, const vo
                 cplx* Yb = reinterpret_cast<cplx*>(w9 + gl.off_Y);
                 rc = launch_grad9_boundary(Udst, static_cast<const cplx*>(Ubar) + (size_t)b0 * dh * dh, seg, Yb, nb, pl.S, dh, st9);
                 if (rc) return rc;
+                if (grad9_wanted(lindblad, K, dh) == 2) {
+                    GradUParams gu{};
+                    gu.G = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_G);
+                    gu.RS = reinterpret_cast<const double*>(w9 + gl.off_model + ml.off_RS);
+                    gu.TR = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_TR);
+                    gu.signals = sig; gu.Ybound = Yb; gu.grad = grad_out + (size_t)b0 * K * N;
+                    gu.B = nb; gu.K = K; gu.N = N; gu.D = dh; gu.Q = pl.S; gu.CL = pl.seg_len;
+                    if ((rc = launch_grad_ucta(gu, st9)) != 0) return rc;
+                    continue;
+                }
                 Grad9Params gp{};
                 gp.G = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_G);
                 gp.RS = reinterpret_cast<const double*>(w9 + gl.off_model + ml.off_RS);

@@ -126,6 +126,10 @@ int launch_hermitian_check(const cplx* h0, const cplx* hks, int K, int d, unsign
 int launch_grad9_boundary(const cplx* U, const cplx* Ubar, const cplx* seg, cplx* Ybound, int B, int Q, int d, cudaStream_t st);
 int launch_grad9(const Grad9Params& gp, unsigned int* counter, cudaStream_t st);
 
+// k_grad_cta.cu: fused unitary-recurrence gradient on the DMMA product (closed 16 < d <= 32, grad_ucta.cuh)
+bool grad_ucta_supported(int D);
+int launch_grad_ucta(GradUParams gp, cudaStream_t st);
+
 // k_grad_cta.cu: the same adjoint scheme on the CTA-cooperative DMMA product (closed d > 16, Lindblad superoperators)
 bool grad_cta_uses_smem(int D);
 int grad_cta_frechet_grid(int D, long long units);

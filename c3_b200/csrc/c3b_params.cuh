@@ -120,4 +120,16 @@ struct Grad9Params {
 };
 
 
+// fused unitary-recurrence gradient kernel on the DMMA product (grad_ucta.cuh)
+struct GradUParams {
+    const cplx* G;          // [(K+1), D, D] trace-shifted generators
+    const double* RS;       // [(K+1), D]
+    const cplx* TR;         // [K+1]
+    const double* signals;  // [B, K, N]
+    const cplx* Ybound;     // [B, Q, D, D]
+    double* grad;           // [B, K, N]
+    int B, K, N, D, DP, LD, Q, CL;
+};
+
+
 }  // namespace c3b

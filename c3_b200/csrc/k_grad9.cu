@@ -44,8 +44,9 @@ int launch_hermitian_check(const cplx* h0, const cplx* hks, int K, int d, unsign
 }
 
 int launch_grad9_boundary(const cplx* U, const cplx* Ubar, const cplx* seg, cplx* Ybound, int B, int Q, int d, cudaStream_t st) {
-    const int wpb = 4;
+    const int wpb = d <= 16 ? 4 : 1;                                 // three d x d matrices per warp: <= 48 KB per block up to d = 32
     const size_t smem = (size_t)wpb * 3 * d * d * sizeof(cplx);
+    CUDA_TRY(cudaFuncSetAttribute(grad9_boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     grad9_boundary_kernel<<<(B + wpb - 1) / wpb, wpb * 32, smem, st>>>(U, Ubar, seg, Ybound, B, Q, d);
     CUDA_TRY(cudaGetLastError());
     count_launch();

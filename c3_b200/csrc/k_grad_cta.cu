@@ -1,6 +1,7 @@
 // CTA-level gradient kernels on the DMMA product (closed d > 16, Lindblad superoperators): launchers.
 #include "c3b_host.cuh"
 #include "grad_cta.cuh"
+#include "grad_ucta.cuh"
 
 namespace c3b {
 
@@ -38,6 +39,37 @@ int launch_frechet_t(GradCtaParams gp, size_t smem, int grid, cudaStream_t st) {
 }  // namespace
 
 bool grad_cta_uses_smem(int D) { return round8(D) <= 32; }
+
+// fused unitary-recurrence kernel (grad_ucta.cuh): closed systems whose matrices fit seven shared-memory slots twice per SM
+bool grad_ucta_supported(int D) { return D > 16 && round8(D) <= 32; }
+
+namespace {
+template <int TM, int TN, int DPT, int KST>
+int launch_ucta_t(const GradUParams& gp, size_t smem, cudaStream_t st) {
+    constexpr int NT = 256;
+    auto kern = grad_unitary_cta_kernel<TM, TN, DPT, KST, NT>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = 2LL * num_sms();
+    const long long units = (long long)gp.B * gp.Q;
+    if (grid > units) grid = units;
+    kern<<<(int)grid, NT, smem, st>>>(gp);
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return C3B_OK;
+}
+}  // namespace
+
+int launch_grad_ucta(GradUParams gp, cudaStream_t st) {
+    gp.DP = round8(gp.D);
+    if (gp.DP == 32) {
+        gp.LD = 32;
+        const size_t smem = (size_t)kGradUSlots * 32 * 32 * sizeof(cplx);
+        return gp.D <= 28 ? launch_ucta_t<1, 2, 32, 7>(gp, smem, st) : launch_ucta_t<1, 2, 32, 8>(gp, smem, st);
+    }
+    gp.LD = gp.DP + 4;
+    const size_t smem = (size_t)kGradUSlots * gp.DP * gp.LD * sizeof(cplx);
+    return launch_ucta_t<1, 2, 0, 0>(gp, smem, st);
+}
 
 size_t grad_cta_workspace_bytes(int Bc, int N, int D) {
     if (grad_cta_uses_smem(D)) return 0;

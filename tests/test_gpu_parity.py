@@ -683,6 +683,35 @@ def test_gradient_fused_d9_kernel(eng, d, K, B, N, scale):
         assert rel_fro(g.cpu().numpy(), g_ref) < 1e-8
 
 
+@pytest.mark.parametrize("d,K,B,N,scale", [(27, 3, 3, 37, 1.0), (27, 3, 2, 9, 5.0), (17, 1, 2, 21, 1.0), (24, 2, 2, 30, 3.0), (32, 2, 1, 12, 1.0),
+                                           (20, 2, 5, 3, 25.0), (29, 4, 2, 70, 1.0)])
+def test_gradient_fused_cta_kernel(eng, d, K, B, N, scale):
+    """The fused unitary-recurrence kernel on the DMMA product (grad_ucta.cuh, closed 16 < d <= 32: the swizzled DP = 32
+    instances and the padded ones, several chunks per row, ragged last chunks, 1 .. 5 squarings) against the
+    stored-propagator kernels and torch-CPU autograd."""
+    from oracle import c3_grad_oracle as gorc
+    rng = np.random.default_rng(d * 100 + K * 10 + N)
+    h0, hks = _rand_model(rng, d, K, 0.9 * scale)
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    Ubar = rng.normal(size=(B, d, d)) + 1j * rng.normal(size=(B, d, d))
+    U1, g1 = eng.pwc_closed_grad(h0, hks, sig, 1.0, Ubar)
+    eng.set_tuning("grad_variant", 2)
+    try:
+        U2, g2 = eng.pwc_closed_grad(h0, hks, sig, 1.0, Ubar)
+    finally:
+        eng.set_tuning("grad_variant", 1)
+    assert rel_fro(U1.cpu().numpy(), U2.cpu().numpy()) < 1e-12
+    assert rel_fro(g1.cpu().numpy(), g2.cpu().numpy()) < 1e-9
+    if N <= 40:
+        q = np.stack([np.linalg.qr(rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d)))[0] for _ in range(B)])
+        L_ref, g_ref, U_ref = gorc.loss_and_grad(h0, hks, sig, 1.0, q)
+        Uc = torch.tensor(U_ref, requires_grad=True)
+        ((1.0 - (torch.einsum("bij,bij->b", torch.as_tensor(q).conj(), Uc).abs() ** 2) / d ** 2).sum()).backward()
+        U, g = eng.pwc_closed_grad(h0, hks, sig, 1.0, Uc.grad.numpy())
+        assert rel_fro(U.cpu().numpy(), U_ref) < TOL
+        assert rel_fro(g.cpu().numpy(), g_ref) < 1e-8
+
+
 def test_gradient_non_hermitian_falls_back(eng):
     """The fused kernel assumes unitary slice propagators; a non-Hermitian 'Hamiltonian' must be detected on the device and
     served by the stored-propagator kernels (same result as forcing them), and the caller's assertion 'grad_unitary' = 0
