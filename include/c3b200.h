@@ -120,7 +120,7 @@ int c3b_pwc_lindblad(const void* h0, const void* hks, const void* col_ops, int C
  *   U_out    [B,d,d]  or NULL: the forward result is produced on the way
  *   chunk    batch rows processed per pass (bounds the workspace: ~2 N d^2 16 bytes per row; ~10 N d^2 16 with the
  *            augmented-exponential cross-check, tuning "grad_variant" 0, d <= 32); <= 0: all
- * Shared model only (h0 [d,d], hks [K,d,d]).  d = 7..9 with Hermitian h0 / hks (the headline shape): ONE fused kernel,
+ * Shared model only (h0 [d,d], hks [K,d,d]).  d = 7..9 and 16 < d <= 32 with Hermitian h0 / hks: ONE fused kernel,
  * no stored slice propagators -- Y_n = F_n Ubar^dag U F_n^-1 is carried forward by unitarity and the Frechet derivative of
  * the Taylor scheme runs in lockstep with the scheme (workspace ~ N/8 d^2 16 bytes per row).  Whether the Hamiltonians are
  * Hermitian is checked on the device (one 4-byte read-back per call, i.e. a stream synchronisation; tuning "grad_unitary"
