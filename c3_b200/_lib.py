@@ -17,7 +17,7 @@ SYMBOLS = [
     "c3b_gate_infid", "c3b_gate_infid_grad", "c3b_seq_populations", "c3b_signal_slice_num", "c3b_generate_signals",
     "c3b_generate_signals_grad", "c3b_pwc_lindblad_grad_workspace_bytes", "c3b_pwc_lindblad_grad",
     "c3b_dress_models", "c3b_pwc_closed_gated", "c3b_pwc_gated_supported",
-    "c3b_generate_signals_noisy", "c3b_generate_signals_table", "c3b_frame_dephase", "c3b_model_bytes", "c3b_model_prepare", "c3b_pwc_prepared_workspace_bytes", "c3b_pwc_prepared",
+    "c3b_generate_signals_noisy", "c3b_generate_signals_table", "c3b_crosstalk", "c3b_frame_dephase", "c3b_model_bytes", "c3b_model_prepare", "c3b_pwc_prepared_workspace_bytes", "c3b_pwc_prepared",
 ]
 
 _lib = None
@@ -77,6 +77,8 @@ def load() -> C.CDLL:
     lib.c3b_generate_signals.argtypes = [vp, vp, vp, vp, vp, i, d, d, i, i, i, i, vp, vp]
     lib.c3b_generate_signals_noisy.restype = i
     lib.c3b_generate_signals_noisy.argtypes = [vp, vp, vp, vp, vp, i, d, d, i, i, i, i, vp, i, C.c_ulonglong, vp, vp, vp]
+    lib.c3b_crosstalk.restype = i
+    lib.c3b_crosstalk.argtypes = [vp, i, i, i, vp, i, vp, vp]
     lib.c3b_generate_signals_table.restype = i
     lib.c3b_generate_signals_table.argtypes = [vp, vp, vp, vp, i, vp, vp, i, d, d, i, i, i, i, vp, i, C.c_ulonglong, vp, vp, vp]
     lib.c3b_generate_signals_grad.restype = i

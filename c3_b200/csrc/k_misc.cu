@@ -141,6 +141,50 @@ int c3b_generate_signals_grad(const double* env_params, const int32_t* env_shape
     return C3B_OK;
 }
 
+// ---- Crosstalk device (c3/generator/devices.py:225-293): the drive lines listed in chan mixed by a C x C matrix, in place:
+//      out[b, chan[i], n] = sum_j M[i, j] in[b, chan[j], n]   (Generator.generate_signals applies it to the finished lines,
+//      c3/generator/generator.py:229-234).  One thread per (batch row, sample); C <= 16 values in registers.
+namespace c3b {
+namespace {
+constexpr int kMaxCrossed = 16;
+__global__ void crosstalk_kernel(double* __restrict__ sig, const int* __restrict__ chan, const double* __restrict__ M, const int B,
+                                 const int K, const int N, const int C) {
+    const long long total = (long long)B * N;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / N), n = (int)(t - (long long)b * N);
+        double* row = sig + (size_t)b * K * N + n;
+        double in[kMaxCrossed];
+#pragma unroll
+        for (int j = 0; j < kMaxCrossed; ++j) in[j] = j < C ? row[(size_t)chan[j] * N] : 0.0;
+#pragma unroll
+        for (int i = 0; i < kMaxCrossed; ++i) {
+            if (i < C) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < kMaxCrossed; ++j)
+                    if (j < C) acc += M[i * C + j] * in[j];          // same summation order as the reference's matmul row
+                row[(size_t)chan[i] * N] = acc;
+            }
+        }
+    }
+}
+}  // namespace
+}  // namespace c3b
+
+extern "C" int c3b_crosstalk(double* signals, int B, int K, int N, const int32_t* chan, int C, const double* matrix, void* stream) {
+    using namespace c3b;
+    if (B <= 0 || K <= 0 || N <= 0 || C <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d N=%d C=%d)", B, K, N, C);
+    if (!signals || !chan || !matrix) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (C > kMaxCrossed || C > K) return fail(C3B_EUNSUPPORTED, "C3:ERROR: crosstalk between %d lines (at most %d, and at most K = %d)", C, kMaxCrossed, K);
+    const long long total = (long long)B * N;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    crosstalk_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(signals, chan, matrix, B, K, N, C);
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return C3B_OK;
+}
+
 // ---- frame rotation / dephasing channel on the device ----------------------------------------
 int c3b_frame_dephase(void* U, int B, int D, int d, const int32_t* occ, int L, const double* phases, const double* probs,
                       int lindblad, void* stream) {

@@ -670,6 +670,26 @@ def generate_signals(env_params, env_shape, env_flags, lo_freq, chain, t_start: 
     return (out, traces) if return_noise else out
 
 
+def crosstalk(signals: torch.Tensor, chan, matrix) -> torch.Tensor:
+    """IN PLACE: mix the drive lines ``chan [C]`` of ``signals [B,K,N]`` by ``matrix [C,C]`` (the Crosstalk device,
+    c3/generator/devices.py:225-293).  Returns signals."""
+    lib = _lib.load()
+    if not (isinstance(signals, torch.Tensor) and signals.is_cuda and signals.dtype == torch.float64 and signals.is_contiguous()
+            and signals.dim() == 3):
+        raise ValueError("C3:ERROR: crosstalk needs a contiguous float64 CUDA tensor [B,K,N]")
+    with torch.cuda.device(signals.device):
+        B, K, N = signals.shape
+        chan = _as(chan, torch.int32, signals.device).reshape(-1)
+        C = int(chan.shape[0])
+        matrix = _as(matrix, torch.float64, signals.device)
+        if tuple(matrix.shape) != (C, C):
+            raise ValueError(f"C3:ERROR: crosstalk matrix has shape {tuple(matrix.shape)}, expected {(C, C)}")
+        if len(set(chan.tolist())) != C or not all(0 <= int(c) < K for c in chan.tolist()):
+            raise ValueError("C3:ERROR: crosstalk channels must be distinct line indices")
+        _lib.check(lib.c3b_crosstalk(_ptr(signals), B, K, N, _ptr(chan), C, _ptr(matrix), _stream()))
+    return signals
+
+
 def generate_signals_grad(env_params, env_shape, env_flags, lo_freq, chain, t_start: float, t_end: float, gsignals,
                           device=None):
     """(grad_env [B,K,E,9], grad_lo [B,K], grad_v2hz [B,K]) from dL/dsignals [B,K,N] (c3b_generate_signals_grad)."""

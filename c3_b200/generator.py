@@ -38,6 +38,15 @@ FIRST_EXTENDED_SHAPE = 12
 SIGMA_SLOT = {"flattop_cut_center": "width", "flattop_variant": "ramp", "cosine_flattop": "t_rise"}
 
 
+def _np_value(q) -> np.ndarray:
+    """Quantity-like -> real numpy array of its shape."""
+    if hasattr(q, "get_value"):
+        q = q.get_value()
+    if hasattr(q, "numpy"):
+        q = q.numpy()
+    return np.real(np.asarray(q))
+
+
 def _arr(q) -> np.ndarray:
     """Quantity-like -> 1-d float64 array."""
     if hasattr(q, "get_value"):
@@ -360,6 +369,15 @@ class Generator:
             sig, traces = engine.generate_signals(env, shape, flags, lo, chain, float(instr.t_start), float(instr.t_end),
                                                   noise=noise, seed=seed, return_noise=True, env_table=self._table)
             self._publish_noise(chans, traces, chain)
+        # the Crosstalk post-processing of the reference (c3/generator/generator.py:229-234): a device NAMED "crosstalk" mixes the
+        # finished lines of its channels
+        if "crosstalk" in self.devices:
+            xt = self.devices["crosstalk"]
+            crossed = list(xt.crossed_channels)
+            missing = [c for c in crossed if c not in chans]
+            if missing:
+                raise Exception(f"C3:ERROR: crosstalk channels {missing} are not driven by this instruction.")
+            engine.crosstalk(sig, [chans.index(c) for c in crossed], np.asarray(_np_value(xt.params["crosstalk_matrix"]), dtype=np.float64))
         N = sig.shape[-1]
         dt = 1.0 / chain[0, 0]
         ts = torch.as_tensor(np.linspace(float(instr.t_start) + dt / 2, float(instr.t_end) - dt / 2, N)).to(sig.device)

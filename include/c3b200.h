@@ -259,6 +259,11 @@ int c3b_dress_models(const void* drift, const void* ops, int ops_batched, int B,
 int c3b_frame_dephase(void* U, int B, int D, int d, const int32_t* occ, int L, const double* phases, const double* probs,
                       int lindblad, void* stream);
 
+/* Crosstalk device (c3/generator/devices.py:225-293, applied by Generator.generate_signals to the finished lines,
+ * c3/generator/generator.py:229-234), IN PLACE on signals [B,K,N]:
+ *   out[b, chan[i], n] = sum_j matrix[i,j] * in[b, chan[j], n],   chan [C] int32 (distinct line indices), matrix [C,C], C <= 16. */
+int c3b_crosstalk(double* signals, int B, int K, int N, const int32_t* chan, int C, const double* matrix, void* stream);
+
 /* Ordered product of M matrices per batch row: out[b] = mats[b,M-1] ... mats[b,0].
  *   replaces tf_matmul_left (c3/utils/tf_utils.py:120-129) and tf_matmul_n (:144-193).
  *   mats [B,M,D,D], out [B,D,D]. */

@@ -273,6 +273,17 @@ def awg_signal(envelopes: Sequence[EnvelopeSpec], ts: np.ndarray, t_start: float
     return np.real(signal), np.imag(signal)
 
 
+def crosstalk(signals: Dict[str, np.ndarray], channels: Sequence[str], matrix) -> Dict[str, np.ndarray]:
+    """Crosstalk.process (c3/generator/devices.py:281-293): the listed channels mixed by the crosstalk matrix, the others
+    untouched.  Pinned to the reference's known answers (test/test_crosstalk.py:7-27) in tests/test_signal_oracle.py."""
+    stacked = np.stack([np.asarray(signals[ch], dtype=np.float64) for ch in channels])
+    crossed = np.asarray(matrix, dtype=np.float64) @ stacked
+    out = dict(signals)
+    for i, ch in enumerate(channels):
+        out[ch] = crossed[i]
+    return out
+
+
 def resize_nearest(x: np.ndarray, new_dim: int) -> np.ndarray:
     """tf.image.resize(method="nearest") along one axis: TF2 samples at floor((i + 0.5) * old / new)
     (half-pixel centres) -- pinned by the 2.4 GS/s -> 100 GS/s fixture (ratio 41.67)."""

@@ -246,6 +246,14 @@ class DC_Offset(_Dev):
     pass
 
 
+class Crosstalk(_Dev):
+    """c3/generator/devices.py:225-263: channels + crosstalk_matrix."""
+
+    def __init__(self, name="crosstalk", channels=None, crosstalk_matrix=None):
+        super().__init__(name, crosstalk_matrix=crosstalk_matrix)
+        self.crossed_channels = channels
+
+
 def noisy_generator_setup(awg_amp=0.0, dc_amp=0.0, pink_amp=0.0, add_amp=0.0, lo_perc=0.0, bfl_num=15, offset=0.0):
     """The drive line of test/noise_exp_2.hjson of the reference (without its high-pass filter): AWG -> AWGNoise ->
     DigitalToAnalog -> Response -> Mixer -> DCNoise -> PinkNoise -> DCOffset -> VoltsToHertz, plus an LO noise device."""

@@ -410,3 +410,34 @@ def test_extended_shapes_are_forward_only(gen_mod):
     genv, glo, _ = engine.generate_signals_grad(env, sid, np.zeros((1, 1), np.int32), np.full((1, 1), 5e9 * TP), chain, 0.0, 7e-9,
                                                 torch.ones((1, 1, N), dtype=torch.float64, device="cuda"))
     assert torch.isnan(genv).all()
+
+
+def test_crosstalk_device(gen_mod):
+    """The Crosstalk post-processing of Generator.generate_signals (c3/generator/generator.py:229-234, devices.py:281-293) on the
+    device: the reference's known answers on raw lines, and a three-line instruction whose first and third lines are crossed."""
+    from c3_b200 import engine
+    raw = torch.tensor(np.stack([np.linspace(0, 100, 101), np.ones(101), np.linspace(100, 200, 101)])[None], device="cuda")
+    flip = engine.crosstalk(raw.clone(), [0, 2], [[0, 1], [1, 0]]).cpu().numpy()[0]
+    assert (flip[2] == np.linspace(0, 100, 101)).all() and (flip[0] == np.linspace(100, 200, 101)).all() and (flip[1] == 1).all()
+    mix = engine.crosstalk(raw.clone(), [0, 2], [[0.5, 0.5], [0.5, 0.5]]).cpu().numpy()[0]
+    assert (mix[0] == mix[2]).all()
+    with pytest.raises(ValueError):
+        engine.crosstalk(raw.clone(), [0, 0], np.eye(2))
+
+    devices, chains, _ = fk.reference_generator_setup()
+    lines = ["d1", "d2", "d3"]
+    instr = fk.drive_instruction("xt", 7e-9, lines, freq=[5e9, 5.3e9, 4.7e9], amp=0.4)
+    chains3 = {c: chains["d1"] for c in lines}
+    plain = gen_mod.Generator(dict(devices), chains3).generate_signals(instr)
+    M = np.array([[0.9, 0.25], [-0.1, 1.05]])
+    devices["crosstalk"] = fk.Crosstalk(channels=["d1", "d3"], crosstalk_matrix=fk.Quantity(M, ""))
+    crossed = gen_mod.Generator(devices, chains3).generate_signals(instr)
+    base = {c: plain[c]["values"].cpu().numpy() for c in lines}
+    want = so.crosstalk(base, ["d1", "d3"], M)
+    for c in lines:
+        assert _rel(crossed[c]["values"].cpu().numpy(), want[c]) < 1e-15, c
+    assert _rel(crossed["d1"]["values"].cpu().numpy(), base["d1"]) > 1e-2
+    bad = dict(devices)
+    bad["crosstalk"] = fk.Crosstalk(channels=["d1", "q9"], crosstalk_matrix=fk.Quantity(M, ""))
+    with pytest.raises(Exception, match="C3:ERROR"):
+        gen_mod.Generator(bad, chains3).generate_signals(instr)

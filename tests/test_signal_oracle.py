@@ -159,3 +159,14 @@ def test_envelope_time_derivatives(shape):
     fd = (so.shape_values(shape, t + 1e-13, e) - so.shape_values(shape, t - 1e-13, e)) / 2e-13
     got = so.shape_derivative(shape, t, e)
     assert np.abs(got - fd).max() <= 2e-5 * max(np.abs(fd).max(), 1e-300)
+
+
+def test_crosstalk_known_answers():
+    """test/test_crosstalk.py:7-27 of the reference: identity, flip and equal mix of two lines."""
+    sig = {"TC1": np.linspace(0, 100, 101), "TC2": np.linspace(100, 200, 101), "other": np.ones(101)}
+    same = so.crosstalk(sig, ["TC1", "TC2"], [[1, 0], [0, 1]])
+    assert all((same[k] == sig[k]).all() for k in sig)
+    flip = so.crosstalk(sig, ["TC1", "TC2"], [[0, 1], [1, 0]])
+    assert (flip["TC2"] == np.linspace(0, 100, 101)).all() and (flip["TC1"] == np.linspace(100, 200, 101)).all()
+    mix = so.crosstalk(sig, ["TC1", "TC2"], [[0.5, 0.5], [0.5, 0.5]])
+    assert (mix["TC1"] == mix["TC2"]).all() and (mix["other"] == 1).all()
