@@ -186,7 +186,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grad_blk9_kernel(const Grad9Par
             for (int c = 0; c < 3; ++c) YO[a][c] = buf[(a * 3 + c) * S + L.syd];
     };
     auto store = [&](cplx* buf, const cplx (&x)[3][3]) { store_own9(buf + L.sown, 0, x, lane_on); };
-    auto own = [&](const cplx* buf, const int a, const int c) { return buf[(a * 3 + c) * S + L.sown]; };
+    // own-slot reads are predicated off on the 5 shadow lanes: a shadow lane shares its slot address with a working lane, and
+    // where that lane rewrites the slot without a warp barrier in between (state 6) the read would be a (harmless, but
+    // racecheck-visible) hazard
+    auto own = [&](const cplx* buf, const int a, const int c) { return lane_on ? buf[(a * 3 + c) * S + L.sown] : cmake(0.0, 0.0); };
 
     for (;;) {
         unsigned int unit_u = 0;
