@@ -143,7 +143,8 @@ Plan make_plan(int B, int N, int D, int batched_model, int seg_len_override = 0)
         S = (N + seg_len_override - 1) / seg_len_override;
         smax = S;
     } else if (pl.path == 1) {
-        S = (tn.target_units + B - 1) / B;
+        const long long target = tn.target_units > 0 ? tn.target_units : (B <= 768 ? 4096 : 12288);
+        S = (target + B - 1) / B;
         smax = N / (tn.min_chunk * blk_groups_per_warp(D));
     } else {
         S = (8LL * num_sms() + B - 1) / B;
@@ -154,6 +155,10 @@ Plan make_plan(int B, int N, int D, int batched_model, int seg_len_override = 0)
     if (S < 1) S = 1;
     pl.S = (int)S;
     pl.seg_len = (N + pl.S - 1) / pl.S;
+    if (pl.path == 1 && seg_len_override <= 0 && pl.S > 1) {       // whole iterations: every lane group of a warp gets the same count
+        const int G = blk_groups_per_warp(D);
+        pl.seg_len = (pl.seg_len + G - 1) / G * G;
+    }
     pl.S = (N + pl.seg_len - 1) / pl.seg_len;  // drop empty trailing segments
     if (pl.S < 1) pl.S = 1;
     pl.grid = cta_grid(D, (long long)B * pl.S);
@@ -287,7 +292,7 @@ const char* c3b_last_error(void) { return g_err; }
 int c3b_set_tuning(const char* key, long long value) {
     if (key == nullptr) return fail(C3B_EINVAL, "C3:ERROR: null tuning key");
     Tuning& t = tuning();
-    if (!strcmp(key, "target_units")) { t.target_units = value < 1 ? 1 : value; return C3B_OK; }
+    if (!strcmp(key, "target_units")) { t.target_units = value < 0 ? 0 : value; return C3B_OK; }
     if (!strcmp(key, "min_chunk")) { t.min_chunk = value < 1 ? 1 : value; return C3B_OK; }
     if (!strcmp(key, "d9_variant")) { t.d9_variant = value; return C3B_OK; }
     if (!strcmp(key, "d9_skew")) { t.d9_skew = value < 0 ? 0 : value; return C3B_OK; }

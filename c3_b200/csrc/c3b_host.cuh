@@ -33,7 +33,8 @@ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 // PER CALLING THREAD (thread_local): one thread per GPU is the intended use, and a thread that changes a knob (tests,
 // A/B measurements) cannot disturb the launches of another.  c3b_set_tuning edits the calling thread's copy.
 struct Tuning {
-    long long target_units = 32768;  // lane-group kernels: aim for this many warp work units per launch
+    long long target_units = 0;      // lane-group kernels: aim for this many warp work units per launch; 0: 4096 up to 768 batch rows,
+                                     // 12288 above (scratch/seg_sweep.py: fewer, longer units win until the tail of the last wave shows)
     long long min_chunk = 8;         // lane-group kernels: minimum slices per lane group
     long long d9_variant = 1;        // d = 9: 0 generic 3x3-block kernel, 1 own-block shared-memory kernel, 2 shuffle-exchange kernel
     long long d9_skew = 120;         // shuffle kernel: clocks between the early and the late half of a CTA's warps

@@ -187,7 +187,7 @@ def test_ragged_lengths_and_segments(eng):
             try:
                 U = eng.pwc_closed(h0, hks, sig, 1.0)
             finally:
-                eng.set_tuning("target_units", 32768)
+                eng.set_tuning("target_units", 0)
                 eng.set_tuning("min_chunk", 8)
             assert rel_fro(U.cpu().numpy(), want) < TOL
 
