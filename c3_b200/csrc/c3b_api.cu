@@ -304,6 +304,7 @@ int c3b_set_tuning(const char* key, long long value) {
     if (!strcmp(key, "seq_variant")) { t.seq_variant = value; return C3B_OK; }
     if (!strcmp(key, "grad_variant")) { t.grad_variant = value; return C3B_OK; }
     if (!strcmp(key, "grad_unitary")) { t.grad_unitary = value; return C3B_OK; }
+    if (!strcmp(key, "grad_chunk")) { t.grad_chunk = value < 0 ? 0 : value; return C3B_OK; }
     if (!strcmp(key, "profile")) { t.profile = value; return C3B_OK; }
     return fail(C3B_EINVAL, "C3:ERROR: unknown tuning key '%s'", key);
 }
@@ -488,11 +489,20 @@ static int grad9_wanted(int lindblad, int K, int d) {
 }
 // chunk length of the fused gradient kernels: enough chunks to fill the machine (lane groups / CTAs x 4 waves), bounded
 static int grad9_chunk_len(int B, int N, int kind) {
-    const long long want = kind == 1 ? 3LL * 8 * num_sms() * 4 : 2LL * num_sms() * 4;
-    long long cl = ((long long)B * N + want - 1) / want;
-    const long long lo = kind == 1 ? 8 : 4, hi = kind == 1 ? 48 : 64;
-    if (cl < lo) cl = lo;
-    if (cl > hi) cl = hi;
+    if (tuning().grad_chunk > 0) return (int)(tuning().grad_chunk < N ? tuning().grad_chunk : N);
+    // Measured (B200): d = 9 lane-group kernel -- 24 slices per chunk when that fills the machine (12 .. 63 is flat within 2 % at
+    // B = 1024), 16 for small batches (B = 1, N = 1000: 0.74 ms; the stored-propagator kernels take 4.3 ms there); CTA kernel
+    // (d = 27) -- 4 waves of CTAs, at least 25 slices (B = 16, N = 400: 2.5 ms against 5.4 ms at 6 slices: the boundary kernel
+    // is one warp per row and sequential in the chunks), at most 64
+    long long cl;
+    if (kind == 1) {
+        cl = ((long long)B * N / 24 >= 3LL * 8 * num_sms() / 2) ? 24 : 16;
+    } else {
+        const long long want = 2LL * num_sms() * 4;
+        cl = ((long long)B * N + want - 1) / want;
+        if (cl < 25) cl = 25;
+        if (cl > 64) cl = 64;
+    }
     if (cl > N) cl = N;
     return (int)cl;
 }

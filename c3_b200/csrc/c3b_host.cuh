@@ -46,6 +46,7 @@ struct Tuning {
     long long seq_variant = 1;       // evaluate_sequences: 1 lane-group kernel for small d, 0 CTA-per-sequence product kernel
     long long grad_variant = 1;      // 1: best available (fused lockstep kernel at closed d = 7..9, Frechet kernels elsewhere), 0: augmented
                                      // exponential, 2: the stored-propagator Frechet kernels everywhere (cross-check)
+    long long grad_chunk = 0;        // fused gradient kernels: slices per chunk (0: chosen from the batch size)
     long long grad_unitary = -1;     // closed-system Hamiltonians Hermitian? 1 yes, 0 no, -1 check on the device (4-byte read-back)
     long long profile = 0;           // bracket the main PWC kernel of each call by events (c3b_last_kernel_ms)
 };

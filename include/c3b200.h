@@ -285,11 +285,12 @@ int c3b_kron(const void* A, const void* Bm, void* out, int batch, int ra, int ca
              int b_batched, void* stream);
 
 /* Tuning knobs of the CALLING THREAD (thread-local: one thread per GPU is the intended use, and a thread that flips a
- * knob for an experiment cannot disturb another thread's launches).  Keys: "target_units", "min_chunk" (segmentation of
+ * knob for an experiment cannot disturb another thread's launches).  Keys: "target_units" (0 automatic), "min_chunk" (segmentation of
  * the time axis), "d9_variant" (0 generic 3x3-block kernel, 1 own-block shared-memory kernel, 2 shuffle-exchange kernel),
  * "force_cta", "cta_variant" (0 literal Higham cross-check, 1 four-product Taylor scheme on DMMA tiles), "cta_threads", "gemm_big",
  * "norm_bound", "seq_variant", "grad_variant" (1 best available, 0 augmented exponential, 2 stored-propagator kernels),
- * "grad_unitary" (-1 check the Hamiltonians on the device, 1 Hermitian, 0 not), "profile".  Returns C3B_EINVAL for an unknown key. */
+ * "grad_unitary" (-1 check the Hamiltonians on the device, 1 Hermitian, 0 not), "grad_chunk" (slices per chunk of the fused
+ * gradient kernels, 0 automatic), "profile".  Returns C3B_EINVAL for an unknown key. */
 int c3b_set_tuning(const char* key, long long value);
 
 /* Which kernel c3b_pwc_* would pick for this shape: 1 = lane-group kernel (d <= 12, shared model),
