@@ -201,7 +201,7 @@ int build_model(const void* h0, const void* hks, const void* col_ops, int C, dou
 
 // common tail of the pwc entry points once the model blob (or the H list) is in place
 int run_pwc(const Plan& pl, const char* blob, const double* signals, const cplx* hlist, double dt, int B, int K, int N, int D,
-            int batched_model, cplx* U_out, cplx* dUs_out, unsigned int* gate, char* ws, cudaStream_t st) {
+            int batched_model, cplx* U_out, cplx* dUs_out, unsigned int* gate, char* ws, cudaStream_t st, bool fold = true) {
     const Tuning& tn = tuning();
     const cplx* G = nullptr;
     const double* RS = nullptr;
@@ -248,7 +248,7 @@ int run_pwc(const Plan& pl, const char* blob, const double* signals, const cplx*
         if (rc) return rc;
     }
     if (tn.profile) { CUDA_TRY(cudaEventRecord(g_prof.e1, st)); g_prof.valid = true; }
-    if (pl.S > 1) {
+    if (pl.S > 1 && fold) {              // (fold == false: the caller folds the segment products itself)
         ProductParams pp{};
         pp.mats = seg; pp.idx = nullptr; pp.lens = nullptr;
         pp.B = B; pp.M = pl.S; pp.D = D; pp.S = 1; pp.seg_len = pl.S;
@@ -506,7 +506,7 @@ static int grad9_chunk_len(int B, int N, int kind) {
     if (cl > N) cl = N;
     return (int)cl;
 }
-struct Grad9Layout { size_t off_model, off_plan, off_U, off_Y, off_counter, total; int CL, Q; Plan pl; };
+struct Grad9Layout { size_t off_model, off_plan, off_U, off_Y, off_F, off_counter, total; int CL, Q; Plan pl; };
 static Grad9Layout grad9_layout(int Bc, int K, int N, int d) {
     Grad9Layout g{};
     g.CL = grad9_chunk_len(Bc, N, grad9_wanted(0, K, d));
@@ -518,6 +518,7 @@ static Grad9Layout grad9_layout(int Bc, int K, int N, int d) {
     g.off_plan = o; o += align_up(g.pl.total);
     g.off_U = o; o += align_up((size_t)Bc * d * d * sizeof(cplx));
     g.off_Y = o; o += align_up((size_t)Bc * g.Q * d * d * sizeof(cplx));
+    g.off_F = o; o += align_up((size_t)Bc * g.Q * d * d * sizeof(cplx));          // prefix products of the chunk products
     g.off_counter = o; o += 256;
     g.total = o;
     return g;
@@ -597,11 +598,14 @@ static int pwc_grad_impl(int lindblad, const void* h0, const void* hks, const vo
                 const double* sig = signals + (size_t)b0 * K * N;
                 cplx* Udst = U_out ? static_cast<cplx*>(U_out) + (size_t)b0 * dh * dh : reinterpret_cast<cplx*>(w9 + gl.off_U);
                 Plan pl = make_plan(nb, N, dh, 0, gl.CL);
-                rc = run_pwc(pl, w9 + gl.off_model, sig, nullptr, dt, nb, K, N, dh, 0, Udst, nullptr, nullptr, w9 + gl.off_plan, st9);
+                rc = run_pwc(pl, w9 + gl.off_model, sig, nullptr, dt, nb, K, N, dh, 0, Udst, nullptr, nullptr, w9 + gl.off_plan, st9,
+                             /*fold=*/false);
                 if (rc) return rc;
-                const cplx* seg = pl.S > 1 ? reinterpret_cast<const cplx*>(w9 + gl.off_plan + pl.off_seg) : nullptr;
+                // chunk products -> prefix products (sequential, one product per chunk; yields U) -> Y at every chunk head
+                const cplx* seg = pl.S > 1 ? reinterpret_cast<const cplx*>(w9 + gl.off_plan + pl.off_seg) : Udst;
                 cplx* Yb = reinterpret_cast<cplx*>(w9 + gl.off_Y);
-                rc = launch_grad9_boundary(Udst, static_cast<const cplx*>(Ubar) + (size_t)b0 * dh * dh, seg, Yb, nb, pl.S, dh, st9);
+                rc = launch_grad9_boundary(seg, static_cast<const cplx*>(Ubar) + (size_t)b0 * dh * dh, reinterpret_cast<cplx*>(w9 + gl.off_F),
+                                           Udst, Yb, nb, pl.S, dh, st9);
                 if (rc) return rc;
                 if (grad9_wanted(lindblad, K, dh) == 2) {
                     GradUParams gu{};

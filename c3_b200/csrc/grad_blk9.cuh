@@ -47,60 +47,84 @@ struct Grad9T {
     }
 };
 
-// Y at the chunk boundaries of one batch row:  Y_0 = Ubar^dag U,  Y_{q+1} = E_q Y_q E_q^dag  (E_q: product of chunk q, from
-// the forward launch; unit-modulus phases cancel).  One warp per row, three d x d matrices in shared memory.
-__global__ void grad9_boundary_kernel(const cplx* __restrict__ U, const cplx* __restrict__ Ubar, const cplx* __restrict__ seg,
-                                      cplx* __restrict__ Ybound, const int B, const int Q, const int d) {
+// Y at the chunk boundaries, in two kernels.  (1) grad9_prefix_kernel, one warp per batch row: the prefix products
+// F_0 = I, F_{q+1} = E_q F_q of the chunk products E_q of the forward launch -- the only sequential part, ONE product per chunk
+// with the next E_q prefetched into registers -- and U = F_Q, which replaces the forward pass's own fold.  (2)
+// grad9_ybound_kernel, one warp per (row, chunk), fully parallel:  Y_q = F_q (Ubar^dag U) F_q^dag  (unit-modulus phases of the
+// trace shift cancel).  Three d x d matrices in shared memory per warp; element (i, j) of a product is one lane's dot product.
+__device__ __forceinline__ void warp_mm(cplx* __restrict__ C, const cplx* __restrict__ A, const cplx* __restrict__ B, const int d,
+                                        const int lane, const int mode) {
+    // mode 0: C = A B;  1: C = A B^dag;  2: C = A^dag B
+    for (int e = lane; e < d * d; e += 32) {
+        const int i = e / d, j = e - i * d;
+        cplx acc = cmake(0.0, 0.0);
+        for (int k = 0; k < d; ++k) {
+            const cplx a = (mode == 2) ? A[k * d + i] : A[i * d + k];
+            const cplx bb = (mode == 1) ? B[j * d + k] : B[k * d + j];
+            const double ay = (mode == 2) ? -a.y : a.y, by = (mode == 1) ? -bb.y : bb.y;
+            acc.x += a.x * bb.x - ay * by;
+            acc.y += a.x * by + ay * bb.x;
+        }
+        C[e] = acc;
+    }
+}
+
+__global__ void grad9_prefix_kernel(const cplx* __restrict__ seg, cplx* __restrict__ F, cplx* __restrict__ U, const int B, const int Q,
+                                    const int d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= B) return;
     const int dd = d * d;
-    cplx* Y = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * 3 * dd;
-    cplx* E = Y + dd;
+    cplx* P = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * 3 * dd;
+    cplx* E = P + dd;
     cplx* T = E + dd;
-    const cplx* Ub = U + (size_t)b * dd;
-    const cplx* Ubb = Ubar + (size_t)b * dd;
-    for (int e = lane; e < dd; e += 32) { E[e] = Ub[e]; T[e] = Ubb[e]; }
-    __syncwarp();
-    for (int e = lane; e < dd; e += 32) {
-        const int i = e / d, j = e - i * d;
-        cplx acc = cmake(0.0, 0.0);
-        for (int k = 0; k < d; ++k) {
-            const cplx u = T[k * d + i], v = E[k * d + j];               // conj(Ubar[k,i]) U[k,j]
-            acc.x += u.x * v.x + u.y * v.y;
-            acc.y += u.x * v.y - u.y * v.x;
-        }
-        Y[e] = acc;
-    }
-    __syncwarp();
-    cplx* out = Ybound + (size_t)b * Q * dd;
-    for (int e = lane; e < dd; e += 32) out[e] = Y[e];
-    for (int q = 0; q + 1 < Q; ++q) {
+    for (int e = lane; e < dd; e += 32) P[e] = cmake((e / d) == (e % d) ? 1.0 : 0.0, 0.0);
+    constexpr int kPre = 32;                               // dd <= 1024: at most 32 elements per lane
+    cplx nxt[kPre];
+    auto prefetch = [&](const int q) {
         const cplx* Eq = seg + ((size_t)b * Q + q) * dd;
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) { const int e = lane + u * 32; if (e < dd) nxt[u] = Eq[e]; }
+    };
+    prefetch(0);
+    cplx* Fb = F + (size_t)b * Q * dd;
+    for (int q = 0; q < Q; ++q) {
         __syncwarp();
-        for (int e = lane; e < dd; e += 32) E[e] = Eq[e];
+        for (int e = lane; e < dd; e += 32) Fb[(size_t)q * dd + e] = P[e];          // F_q
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) { const int e = lane + u * 32; if (e < dd) E[e] = nxt[u]; }
         __syncwarp();
-        for (int e = lane; e < dd; e += 32) {                             // T = E Y
-            const int i = e / d, j = e - i * d;
-            cplx acc = cmake(0.0, 0.0);
-            for (int k = 0; k < d; ++k) cfma(acc, E[i * d + k], Y[k * d + j]);
-            T[e] = acc;
-        }
-        __syncwarp();
-        for (int e = lane; e < dd; e += 32) {                             // Y = T E^dag
-            const int i = e / d, j = e - i * d;
-            cplx acc = cmake(0.0, 0.0);
-            for (int k = 0; k < d; ++k) {
-                const cplx t = T[i * d + k], v = E[j * d + k];
-                acc.x += t.x * v.x + t.y * v.y;
-                acc.y += t.y * v.x - t.x * v.y;
-            }
-            Y[e] = acc;
-        }
-        __syncwarp();
-        for (int e = lane; e < dd; e += 32) out[(size_t)(q + 1) * dd + e] = Y[e];
+        if (q + 1 < Q) prefetch(q + 1);
+        warp_mm(T, E, P, d, lane, 0);                      // F_{q+1} = E_q F_q
+        cplx* t = P; P = T; T = t;
     }
+    __syncwarp();
+    for (int e = lane; e < dd; e += 32) U[(size_t)b * dd + e] = P[e];
+}
+
+__global__ void grad9_ybound_kernel(const cplx* __restrict__ F, const cplx* __restrict__ U, const cplx* __restrict__ Ubar,
+                                    cplx* __restrict__ Ybound, const int B, const int Q, const int d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (w >= (long long)B * Q) return;
+    const int b = (int)(w / Q);
+    const int dd = d * d;
+    cplx* X = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * 3 * dd;
+    cplx* Y = X + dd;
+    cplx* Z = Y + dd;
+    for (int e = lane; e < dd; e += 32) { X[e] = Ubar[(size_t)b * dd + e]; Y[e] = U[(size_t)b * dd + e]; }
+    __syncwarp();
+    warp_mm(Z, X, Y, d, lane, 2);                          // C = Ubar^dag U
+    __syncwarp();
+    for (int e = lane; e < dd; e += 32) X[e] = F[(size_t)w * dd + e];
+    __syncwarp();
+    warp_mm(Y, X, Z, d, lane, 0);                          // F C
+    __syncwarp();
+    warp_mm(Z, Y, X, d, lane, 1);                          // (F C) F^dag
+    __syncwarp();
+    for (int e = lane; e < dd; e += 32) Ybound[(size_t)w * dd + e] = Z[e];
 }
 
 template <int WARPS>

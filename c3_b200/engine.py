@@ -9,6 +9,7 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -55,8 +56,18 @@ def release_workspaces() -> None:
     _workspaces.clear()
 
 
+_TUNING_SET = {}      # knobs this thread has set through set_tuning (the library keeps the values; this mirrors the non-default ones)
+
+
+def _tuning_value(key: str, default: int = -1) -> int:
+    import threading
+    return _TUNING_SET.get((threading.get_ident(), key), default)
+
+
 def set_tuning(key: str, value: int) -> None:
+    import threading
     _lib.check(_lib.load().c3b_set_tuning(key.encode(), int(value)))
+    _TUNING_SET[(threading.get_ident(), key)] = int(value)
 
 
 def pwc_path(K: int, D: int, batched_model: bool = False) -> int:
@@ -256,6 +267,15 @@ def pwc_closed_grad(h0, hks, signals, dt: float, Ubar, max_workspace_bytes: int 
         if signals.dim() == 2:
             signals = signals.unsqueeze(0)
         B, K, N = signals.shape
+        # Hamiltonians handed over as host arrays: look at them here, so that the library need not read a flag back from the
+        # device (a stream synchronisation per call) to choose the fused unitary-recurrence kernels
+        hermitian = None
+        if not isinstance(h0, torch.Tensor) and not isinstance(hks, torch.Tensor):
+            a0, ak = np.asarray(h0), np.asarray(hks)
+            if a0.ndim == 2 and ak.ndim == 3:
+                scale = max(float(np.abs(a0).max(initial=0.0)), float(np.abs(ak).max(initial=0.0)))
+                hermitian = bool(np.abs(a0 - a0.conj().T).max(initial=0.0) <= 1e-13 * scale
+                                 and np.abs(ak - ak.conj().transpose(0, 2, 1)).max(initial=0.0) <= 1e-13 * scale)
         h0 = _as(h0, torch.complex128, device)
         hks = _as(hks, torch.complex128, device)
         if h0.dim() != 2:
@@ -266,13 +286,20 @@ def pwc_closed_grad(h0, hks, signals, dt: float, Ubar, max_workspace_bytes: int 
             raise ValueError(f"C3:ERROR: Ubar has shape {tuple(Ubar.shape)}, expected {(B, d, d)}")
         U = torch.empty((B, d, d), dtype=torch.complex128, device=device)
         grad = torch.empty((B, K, N), dtype=torch.float64, device=device)
-        chunk = B
-        while chunk > 1 and lib.c3b_pwc_grad_workspace_bytes(B, K, N, d, chunk) > max_workspace_bytes:
-            chunk = (chunk + 1) // 2
-        nbytes = lib.c3b_pwc_grad_workspace_bytes(B, K, N, d, chunk)
-        ws = _workspace(nbytes, device)
-        _lib.check(lib.c3b_pwc_closed_grad(_ptr(h0), _ptr(hks), _ptr(signals), float(dt), B, K, N, d, _ptr(Ubar),
-                                           _ptr(grad), _ptr(U), chunk, _ptr(ws), ws.numel(), _stream()))
+        assert_flag = hermitian is not None and _tuning_value("grad_unitary") == -1
+        if assert_flag:
+            set_tuning("grad_unitary", 1 if hermitian else 0)
+        try:
+            chunk = B
+            while chunk > 1 and lib.c3b_pwc_grad_workspace_bytes(B, K, N, d, chunk) > max_workspace_bytes:
+                chunk = (chunk + 1) // 2
+            nbytes = lib.c3b_pwc_grad_workspace_bytes(B, K, N, d, chunk)
+            ws = _workspace(nbytes, device)
+            _lib.check(lib.c3b_pwc_closed_grad(_ptr(h0), _ptr(hks), _ptr(signals), float(dt), B, K, N, d, _ptr(Ubar),
+                                               _ptr(grad), _ptr(U), chunk, _ptr(ws), ws.numel(), _stream()))
+        finally:
+            if assert_flag:
+                set_tuning("grad_unitary", -1)
     return U, grad
 
 
