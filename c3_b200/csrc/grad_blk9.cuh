@@ -14,7 +14,7 @@
 // propagators, no backward sweep, no second pass over memory -- the same streaming structure as the forward kernel
 // (pwc_blk9.cuh), whose lane layout, tables and own-block product this kernel reuses.  A lane group walks a chunk of CL
 // consecutive slices; Y at the chunk boundaries comes from the chunk products of one forward launch
-// (grad9_boundary_kernel).  The trace shift drops out (|e^mu| = 1).
+// (grad9_prefix_kernel + grad9_ybound_kernel).  The trace shift drops out (|e^mu| = 1).
 //
 // Per slice: the Frechet derivative of the four-product Taylor scheme (c3b_common.cuh) in direction Y, in lockstep with
 // the scheme itself --

@@ -6,7 +6,7 @@
 //   dL/dc_k[n] = Re tr( L(A_n, Y_n) dU_n^dag G_k ),      Y_{n+1} = dU_n Y_n dU_n^dag,      Y_0 = Ubar^dag U
 //
 // No stored slice propagators and no sweeps: a CTA walks a chunk of CL consecutive slices of one batch row, Y at the head of
-// the chunk comes from the chunk products of one forward launch (grad9_boundary_kernel).  Per slice the Frechet derivative of
+// the chunk comes from the chunk products of one forward launch (grad9_prefix_kernel + grad9_ybound_kernel).  Per slice the Frechet derivative of
 // the four-product Taylor scheme in direction Y runs next to the scheme: 15 products (+ 3 per squaring) against 6 of a
 // forward slice, two independent products per barrier where the data flow allows.
 //
