@@ -343,8 +343,18 @@ def run_configs(engine, synth, dev, rank, world, dfma_peak, all_gather, check):
             ms_g, _ = _timed(bwd, 2, torch, dist, 1)
             gr[name] = {"B": Bg, "N": Ng, "forward_ms": ms_f, "forward_plus_gradient_ms": ms_g, "ratio": ms_g / ms_f,
                         "slices_per_s_with_gradient": Bg * Ng / (ms_g * 1e-3)}
-        out["gradient"] = {"what": "U and dL/d signals[B,K,N] for a given cotangent of U (c3b_pwc_closed_grad / c3b_pwc_lindblad_grad): "
-                                   "d <= 16 warp-per-slice Frechet kernels, above CTA kernels on the DMMA product", **gr}
+            if not lind:        # the autograd node's pair: a forward pass that keeps its chunk products + the backward pass from them
+                def step():
+                    U, saved = engine.pwc_closed_saving(mm.h0, mm.hks, sg, DT)
+                    return engine.pwc_closed_grad_saved(sg, Ub, saved)
+                ms_s, _ = _timed(step, 2, torch, dist, 1)
+                gr[name]["forward_saving_plus_backward_ms"] = ms_s
+                gr[name]["ratio_saving"] = ms_s / ms_f
+        out["gradient"] = {"what": "U and dL/d signals[B,K,N] for a given cotangent of U.  forward_plus_gradient: one call "
+                                   "(c3b_pwc_closed_grad / c3b_pwc_lindblad_grad); forward_saving_plus_backward: the two calls of an autograd "
+                                   "node (c3b_pwc_closed_fwd_saved + c3b_pwc_closed_bwd_saved), i.e. a whole optimiser step.  Closed d = 9 "
+                                   "and d = 27: fused unitary-recurrence kernels without stored propagators; Lindblad D = 81: stored "
+                                   "propagators, sweeps and Frechet derivative on the DMMA product", **gr}
         engine.release_workspaces()
 
     # ---- strong scaling: the headline batch of 4096 signal sets in TOTAL, split over the ranks --------------------------

@@ -17,7 +17,8 @@ SYMBOLS = [
     "c3b_gate_infid", "c3b_gate_infid_grad", "c3b_seq_populations", "c3b_signal_slice_num", "c3b_generate_signals",
     "c3b_generate_signals_grad", "c3b_pwc_lindblad_grad_workspace_bytes", "c3b_pwc_lindblad_grad",
     "c3b_dress_models", "c3b_pwc_closed_gated", "c3b_pwc_gated_supported",
-    "c3b_generate_signals_noisy", "c3b_generate_signals_table", "c3b_crosstalk", "c3b_frame_dephase", "c3b_model_bytes", "c3b_model_prepare", "c3b_pwc_prepared_workspace_bytes", "c3b_pwc_prepared",
+    "c3b_generate_signals_noisy", "c3b_generate_signals_table", "c3b_crosstalk", "c3b_pwc_closed_saved_bytes", "c3b_pwc_closed_saved_chunks",
+    "c3b_pwc_closed_fwd_saved", "c3b_pwc_closed_bwd_saved", "c3b_frame_dephase", "c3b_model_bytes", "c3b_model_prepare", "c3b_pwc_prepared_workspace_bytes", "c3b_pwc_prepared",
 ]
 
 _lib = None
@@ -77,6 +78,14 @@ def load() -> C.CDLL:
     lib.c3b_generate_signals.argtypes = [vp, vp, vp, vp, vp, i, d, d, i, i, i, i, vp, vp]
     lib.c3b_generate_signals_noisy.restype = i
     lib.c3b_generate_signals_noisy.argtypes = [vp, vp, vp, vp, vp, i, d, d, i, i, i, i, vp, i, C.c_ulonglong, vp, vp, vp]
+    lib.c3b_pwc_closed_saved_bytes.restype = C.c_size_t
+    lib.c3b_pwc_closed_saved_bytes.argtypes = [i, i, i, i]
+    lib.c3b_pwc_closed_saved_chunks.restype = i
+    lib.c3b_pwc_closed_saved_chunks.argtypes = [i, i, i, i, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.c3b_pwc_closed_fwd_saved.restype = i
+    lib.c3b_pwc_closed_fwd_saved.argtypes = [vp, vp, vp, d, i, i, i, i, vp, vp, C.c_size_t, vp]
+    lib.c3b_pwc_closed_bwd_saved.restype = i
+    lib.c3b_pwc_closed_bwd_saved.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, C.c_size_t, vp]
     lib.c3b_crosstalk.restype = i
     lib.c3b_crosstalk.argtypes = [vp, i, i, i, vp, i, vp, vp]
     lib.c3b_generate_signals_table.restype = i
@@ -109,6 +118,9 @@ def load() -> C.CDLL:
     lib.c3b_pwc_prepared.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp, vp, sz, vp]
     _lib = lib
     return lib
+
+
+C3B_EUNSUPPORTED = -4      # include/c3b200.h
 
 
 def check(rc: int) -> None:

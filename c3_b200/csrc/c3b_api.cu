@@ -563,6 +563,44 @@ size_t c3b_pwc_lindblad_grad_workspace_bytes(int B, int K, int N, int d, int chu
     return grad_chunk_bytes(Bc, K, N, d, 1, off);
 }
 
+// forward pass of the fused gradient path for one batch chunk: chunk products (segments of CL slices, not folded) and their
+// prefix products, which also yield U
+static int fused_forward(const Grad9Layout& gl, int nb, const double* sig, double dt, int K, int N, int dh, cplx* Udst, char* w9,
+                         cudaStream_t st, int* Q_out, int* CL_out) {
+    const Plan pl = make_plan(nb, N, dh, 0, gl.CL);
+    int rc = run_pwc(pl, w9 + gl.off_model, sig, nullptr, dt, nb, K, N, dh, 0, Udst, nullptr, nullptr, w9 + gl.off_plan, st, /*fold=*/false);
+    if (rc) return rc;
+    const cplx* seg = pl.S > 1 ? reinterpret_cast<const cplx*>(w9 + gl.off_plan + pl.off_seg) : Udst;
+    *Q_out = pl.S;
+    *CL_out = pl.seg_len;
+    return launch_grad9_prefix(seg, reinterpret_cast<cplx*>(w9 + gl.off_F), Udst, nb, pl.S, dh, st);
+}
+
+// backward pass from what fused_forward left in the workspace: Y at the chunk heads, then the lockstep gradient kernel
+static int fused_backward(const Grad9Layout& gl, int nb, const double* sig, int K, int N, int dh, int Q, int CL, const cplx* U,
+                          const cplx* Ubar, double* grad, char* w9, cudaStream_t st) {
+    const ModelLayout ml = model_layout(K, dh, 1);
+    cplx* Yb = reinterpret_cast<cplx*>(w9 + gl.off_Y);
+    int rc = launch_grad9_ybound(reinterpret_cast<const cplx*>(w9 + gl.off_F), U, Ubar, Yb, nb, Q, dh, st);
+    if (rc) return rc;
+    if (grad9_wanted(0, K, dh) == 2) {
+        GradUParams gu{};
+        gu.G = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_G);
+        gu.RS = reinterpret_cast<const double*>(w9 + gl.off_model + ml.off_RS);
+        gu.TR = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_TR);
+        gu.signals = sig; gu.Ybound = Yb; gu.grad = grad;
+        gu.B = nb; gu.K = K; gu.N = N; gu.D = dh; gu.Q = Q; gu.CL = CL;
+        return launch_grad_ucta(gu, st);
+    }
+    Grad9Params gp{};
+    gp.G = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_G);
+    gp.RS = reinterpret_cast<const double*>(w9 + gl.off_model + ml.off_RS);
+    gp.TR = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_TR);
+    gp.signals = sig; gp.Ybound = Yb; gp.grad = grad;
+    gp.B = nb; gp.K = K; gp.N = N; gp.d = dh; gp.Q = Q; gp.CL = CL;
+    return launch_grad9(gp, reinterpret_cast<unsigned int*>(w9 + gl.off_counter), st);
+}
+
 static int pwc_grad_impl(int lindblad, const void* h0, const void* hks, const void* col_ops, int C, const double* signals,
                          double dt, int B, int K, int N, int dh, const void* Ubar, double* grad_out, void* U_out,
                          int chunk, void* workspace, size_t workspace_bytes, void* stream) {
@@ -592,38 +630,14 @@ static int pwc_grad_impl(int lindblad, const void* h0, const void* hks, const vo
         if (unitary) {
             int rc = build_model(h0, hks, nullptr, 0, dt, K, dh, 0, 1, w9 + gl.off_model, st9);
             if (rc) return rc;
-            const ModelLayout ml = model_layout(K, dh, 1);
             for (int b0 = 0; b0 < B; b0 += Bc) {
                 const int nb = (B - b0 < Bc) ? (B - b0) : Bc;
                 const double* sig = signals + (size_t)b0 * K * N;
                 cplx* Udst = U_out ? static_cast<cplx*>(U_out) + (size_t)b0 * dh * dh : reinterpret_cast<cplx*>(w9 + gl.off_U);
-                Plan pl = make_plan(nb, N, dh, 0, gl.CL);
-                rc = run_pwc(pl, w9 + gl.off_model, sig, nullptr, dt, nb, K, N, dh, 0, Udst, nullptr, nullptr, w9 + gl.off_plan, st9,
-                             /*fold=*/false);
-                if (rc) return rc;
-                // chunk products -> prefix products (sequential, one product per chunk; yields U) -> Y at every chunk head
-                const cplx* seg = pl.S > 1 ? reinterpret_cast<const cplx*>(w9 + gl.off_plan + pl.off_seg) : Udst;
-                cplx* Yb = reinterpret_cast<cplx*>(w9 + gl.off_Y);
-                rc = launch_grad9_boundary(seg, static_cast<const cplx*>(Ubar) + (size_t)b0 * dh * dh, reinterpret_cast<cplx*>(w9 + gl.off_F),
-                                           Udst, Yb, nb, pl.S, dh, st9);
-                if (rc) return rc;
-                if (grad9_wanted(lindblad, K, dh) == 2) {
-                    GradUParams gu{};
-                    gu.G = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_G);
-                    gu.RS = reinterpret_cast<const double*>(w9 + gl.off_model + ml.off_RS);
-                    gu.TR = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_TR);
-                    gu.signals = sig; gu.Ybound = Yb; gu.grad = grad_out + (size_t)b0 * K * N;
-                    gu.B = nb; gu.K = K; gu.N = N; gu.D = dh; gu.Q = pl.S; gu.CL = pl.seg_len;
-                    if ((rc = launch_grad_ucta(gu, st9)) != 0) return rc;
-                    continue;
-                }
-                Grad9Params gp{};
-                gp.G = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_G);
-                gp.RS = reinterpret_cast<const double*>(w9 + gl.off_model + ml.off_RS);
-                gp.TR = reinterpret_cast<const cplx*>(w9 + gl.off_model + ml.off_TR);
-                gp.signals = sig; gp.Ybound = Yb; gp.grad = grad_out + (size_t)b0 * K * N;
-                gp.B = nb; gp.K = K; gp.N = N; gp.d = dh; gp.Q = pl.S; gp.CL = pl.seg_len;
-                rc = launch_grad9(gp, reinterpret_cast<unsigned int*>(w9 + gl.off_counter), st9);
+                int Q = 0, CLrun = 0;
+                if ((rc = fused_forward(gl, nb, sig, dt, K, N, dh, Udst, w9, st9, &Q, &CLrun)) != 0) return rc;
+                rc = fused_backward(gl, nb, sig, K, N, dh, Q, CLrun, Udst, static_cast<const cplx*>(Ubar) + (size_t)b0 * dh * dh,
+                                    grad_out + (size_t)b0 * K * N, w9, st9);
                 if (rc) return rc;
             }
             return C3B_OK;
@@ -687,6 +701,69 @@ int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, 
                         size_t workspace_bytes, void* stream) {
     return pwc_grad_impl(0, h0, hks, nullptr, 0, signals, dt, B, K, N, d, Ubar, grad_out, U_out, chunk, workspace,
                          workspace_bytes, stream);
+}
+
+// ---- forward / backward as two calls (what an autograd node needs): the forward call leaves the model blob, the chunk
+//      products and their prefix products in a caller-owned state buffer, the backward call turns a cotangent into the gradient
+//      without recomputing the forward pass
+constexpr size_t kSavedHeaderBytes = 0;
+
+size_t c3b_pwc_closed_saved_bytes(int B, int K, int N, int d) {
+    if (B <= 0 || K <= 0 || N <= 0 || d <= 0 || !grad9_wanted(0, K, d)) return 0;
+    return kSavedHeaderBytes + grad9_layout(B, K, N, d).total;
+}
+
+int c3b_pwc_closed_fwd_saved(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d, void* U_out,
+                             void* state, size_t state_bytes, void* stream) {
+    if (B <= 0 || K <= 0 || N <= 0 || d <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size (B=%d K=%d N=%d d=%d)", B, K, N, d);
+    if (!h0 || !hks || !signals || !U_out || !state) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (!grad9_wanted(0, K, d))
+        return fail(C3B_EUNSUPPORTED, "C3:ERROR: no fused gradient kernel for this shape (d=%d, K=%d): use c3b_pwc_closed_grad", d, K);
+    const Grad9Layout gl = grad9_layout(B, K, N, d);
+    if (state_bytes < kSavedHeaderBytes + gl.total)
+        return fail(C3B_EWORKSPACE, "C3:ERROR: state buffer too small: %zu < %zu bytes", state_bytes, kSavedHeaderBytes + gl.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* w9 = static_cast<char*>(state) + kSavedHeaderBytes;
+    if (tuning().grad_unitary != 1) {
+        unsigned int* flag = reinterpret_cast<unsigned int*>(w9 + gl.off_counter) + 16;
+        int rc = launch_hermitian_check(static_cast<const cplx*>(h0), static_cast<const cplx*>(hks), K, d, flag, st);
+        if (rc) return rc;
+        unsigned int host_flag = 1;
+        CUDA_TRY(cudaMemcpyAsync(&host_flag, flag, sizeof(host_flag), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (host_flag != 0) return fail(C3B_EUNSUPPORTED, "C3:ERROR: the Hamiltonians are not Hermitian: use c3b_pwc_closed_grad");
+    }
+    int rc = build_model(h0, hks, nullptr, 0, dt, K, d, 0, 1, w9 + gl.off_model, st);
+    if (rc) return rc;
+    cplx* Ust = reinterpret_cast<cplx*>(w9 + gl.off_U);
+    int Q = 0, CL = 0;
+    if ((rc = fused_forward(gl, B, signals, dt, K, N, d, Ust, w9, st, &Q, &CL)) != 0) return rc;
+    CUDA_TRY(cudaMemcpyAsync(U_out, Ust, (size_t)B * d * d * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    return C3B_OK;
+}
+
+int c3b_pwc_closed_bwd_saved(const double* signals, int B, int K, int N, int d, int Q, int CL, const void* Ubar, double* grad_out,
+                             void* state, size_t state_bytes, void* stream) {
+    if (B <= 0 || K <= 0 || N <= 0 || d <= 0 || Q <= 0 || CL <= 0) return fail(C3B_EINVAL, "C3:ERROR: non-positive size");
+    if (!signals || !Ubar || !grad_out || !state) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (!grad9_wanted(0, K, d)) return fail(C3B_EUNSUPPORTED, "C3:ERROR: no fused gradient kernel for this shape (d=%d, K=%d)", d, K);
+    const Grad9Layout gl = grad9_layout(B, K, N, d);
+    if (state_bytes < kSavedHeaderBytes + gl.total)
+        return fail(C3B_EWORKSPACE, "C3:ERROR: state buffer too small: %zu < %zu bytes", state_bytes, kSavedHeaderBytes + gl.total);
+    if (Q > gl.Q) return fail(C3B_EINVAL, "C3:ERROR: Q=%d does not belong to this state (at most %d chunks)", Q, gl.Q);
+    char* w9 = static_cast<char*>(state) + kSavedHeaderBytes;
+    return fused_backward(gl, B, signals, K, N, d, Q, CL, reinterpret_cast<const cplx*>(w9 + gl.off_U), static_cast<const cplx*>(Ubar), grad_out, w9,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int c3b_pwc_closed_saved_chunks(int B, int K, int N, int d, int* Q_out, int* CL_out) {
+    if (!Q_out || !CL_out) return fail(C3B_EINVAL, "C3:ERROR: NULL pointer");
+    if (B <= 0 || K <= 0 || N <= 0 || d <= 0 || !grad9_wanted(0, K, d)) return fail(C3B_EUNSUPPORTED, "C3:ERROR: no fused gradient kernel for this shape");
+    const Grad9Layout gl = grad9_layout(B, K, N, d);
+    const Plan pl = make_plan(B, N, d, 0, gl.CL);
+    *Q_out = pl.S;
+    *CL_out = pl.seg_len;
+    return C3B_OK;
 }
 
 int c3b_pwc_lindblad_grad(const void* h0, const void* hks, const void* col_ops, int C, const double* signals, double dt,

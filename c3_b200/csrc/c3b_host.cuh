@@ -125,7 +125,8 @@ int launch_grad_contract(const cplx* Eaug, const cplx* hks, const double* alpha,
 // k_grad9.cu: fused lockstep gradient kernel for closed d = 7..9 (grad_blk9.cuh)
 bool grad9_supported(int K, int d);
 int launch_hermitian_check(const cplx* h0, const cplx* hks, int K, int d, unsigned int* flag, cudaStream_t st);
-int launch_grad9_boundary(const cplx* seg, const cplx* Ubar, cplx* F, cplx* U, cplx* Ybound, int B, int Q, int d, cudaStream_t st);
+int launch_grad9_prefix(const cplx* seg, cplx* F, cplx* U, int B, int Q, int d, cudaStream_t st);
+int launch_grad9_ybound(const cplx* F, const cplx* U, const cplx* Ubar, cplx* Ybound, int B, int Q, int d, cudaStream_t st);
 int launch_grad9(const Grad9Params& gp, unsigned int* counter, cudaStream_t st);
 
 // k_grad_cta.cu: fused unitary-recurrence gradient on the DMMA product (closed 16 < d <= 32, grad_ucta.cuh)

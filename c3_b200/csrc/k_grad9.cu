@@ -43,16 +43,27 @@ int launch_hermitian_check(const cplx* h0, const cplx* hks, int K, int d, unsign
     return C3B_OK;
 }
 
-// seg [B,Q,d,d] chunk products of the forward launch (Q == 1: seg may be the forward result itself) -> U [B,d,d] and
-// Ybound [B,Q,d,d]; F [B,Q,d,d] is scratch
-int launch_grad9_boundary(const cplx* seg, const cplx* Ubar, cplx* F, cplx* U, cplx* Ybound, int B, int Q, int d, cudaStream_t st) {
-    const int wpb = d <= 16 ? 4 : 1;                                 // three d x d matrices per warp: <= 48 KB per block up to d = 32
+namespace {
+int boundary_wpb(int d) { return d <= 16 ? 4 : 1; }      // three d x d matrices per warp: <= 48 KB per block up to d = 32
+}  // namespace
+
+// seg [B,Q,d,d] chunk products of the forward launch (Q == 1: seg may be the forward result itself) -> prefix products
+// F [B,Q,d,d] and U [B,d,d]
+int launch_grad9_prefix(const cplx* seg, cplx* F, cplx* U, int B, int Q, int d, cudaStream_t st) {
+    const int wpb = boundary_wpb(d);
     const size_t smem = (size_t)wpb * 3 * d * d * sizeof(cplx);
     CUDA_TRY(cudaFuncSetAttribute(grad9_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(grad9_ybound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     grad9_prefix_kernel<<<(B + wpb - 1) / wpb, wpb * 32, smem, st>>>(seg, F, U, B, Q, d);
     CUDA_TRY(cudaGetLastError());
     count_launch();
+    return C3B_OK;
+}
+
+// Ybound [B,Q,d,d] = F_q (Ubar^dag U) F_q^dag
+int launch_grad9_ybound(const cplx* F, const cplx* U, const cplx* Ubar, cplx* Ybound, int B, int Q, int d, cudaStream_t st) {
+    const int wpb = boundary_wpb(d);
+    const size_t smem = (size_t)wpb * 3 * d * d * sizeof(cplx);
+    CUDA_TRY(cudaFuncSetAttribute(grad9_ybound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long warps = (long long)B * Q;
     grad9_ybound_kernel<<<(int)((warps + wpb - 1) / wpb), wpb * 32, smem, st>>>(F, U, Ubar, Ybound, B, Q, d);
     CUDA_TRY(cudaGetLastError());

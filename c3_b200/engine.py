@@ -269,13 +269,7 @@ def pwc_closed_grad(h0, hks, signals, dt: float, Ubar, max_workspace_bytes: int 
         B, K, N = signals.shape
         # Hamiltonians handed over as host arrays: look at them here, so that the library need not read a flag back from the
         # device (a stream synchronisation per call) to choose the fused unitary-recurrence kernels
-        hermitian = None
-        if not isinstance(h0, torch.Tensor) and not isinstance(hks, torch.Tensor):
-            a0, ak = np.asarray(h0), np.asarray(hks)
-            if a0.ndim == 2 and ak.ndim == 3:
-                scale = max(float(np.abs(a0).max(initial=0.0)), float(np.abs(ak).max(initial=0.0)))
-                hermitian = bool(np.abs(a0 - a0.conj().T).max(initial=0.0) <= 1e-13 * scale
-                                 and np.abs(ak - ak.conj().transpose(0, 2, 1)).max(initial=0.0) <= 1e-13 * scale)
+        hermitian = _hermitian_host(h0, hks)
         h0 = _as(h0, torch.complex128, device)
         hks = _as(hks, torch.complex128, device)
         if h0.dim() != 2:
@@ -301,6 +295,95 @@ def pwc_closed_grad(h0, hks, signals, dt: float, Ubar, max_workspace_bytes: int 
             if assert_flag:
                 set_tuning("grad_unitary", -1)
     return U, grad
+
+
+class SavedForward:
+    """What pwc_closed_saving leaves for pwc_closed_grad_saved: the state buffer (model, chunk products, prefix products,
+    U) and the chunking of the forward call."""
+    __slots__ = ("state", "B", "K", "N", "d", "Q", "CL")
+
+
+def _hermitian_host(h0, hks) -> Optional[bool]:
+    """True / False for Hamiltonians handed over as host arrays, None when they live on the device."""
+    if isinstance(h0, torch.Tensor) or isinstance(hks, torch.Tensor):
+        return None
+    a0, ak = np.asarray(h0), np.asarray(hks)
+    if a0.ndim != 2 or ak.ndim != 3:
+        return None
+    scale = max(float(np.abs(a0).max(initial=0.0)), float(np.abs(ak).max(initial=0.0)))
+    return bool(np.abs(a0 - a0.conj().T).max(initial=0.0) <= 1e-13 * scale
+                and np.abs(ak - ak.conj().transpose(0, 2, 1)).max(initial=0.0) <= 1e-13 * scale)
+
+
+def pwc_closed_saving(h0, hks, signals, dt: float, hermitian: Optional[bool] = None, device=None):
+    """Forward pass that keeps what the backward pass needs: returns (U [B,d,d], SavedForward), or (U, None) where no fused
+    gradient kernel serves the shape (the caller then differentiates with pwc_closed_grad).  ``hermitian``: the caller's
+    knowledge about h0 / hks (None: host arrays are inspected here, device tensors by the library)."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else default_device()
+    with torch.cuda.device(device):
+        if hermitian is None:
+            hermitian = _hermitian_host(h0, hks)
+        signals = _as(signals, torch.float64, device)
+        if signals.dim() == 2:
+            signals = signals.unsqueeze(0)
+        B, K, N = signals.shape
+        h0 = _as(h0, torch.complex128, device)
+        hks = _as(hks, torch.complex128, device)
+        if h0.dim() != 2 or K == 0:
+            return pwc_closed(h0, hks, signals, dt), None
+        d = h0.shape[-1]
+        assert_flag = hermitian is not None and _tuning_value("grad_unitary") == -1
+        if assert_flag:
+            set_tuning("grad_unitary", 1 if hermitian else 0)
+        try:
+            nbytes = int(lib.c3b_pwc_closed_saved_bytes(B, K, N, d))
+            if nbytes == 0:
+                return pwc_closed(h0, hks, signals, dt), None
+            state = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            U = torch.empty((B, d, d), dtype=torch.complex128, device=device)
+            rc = lib.c3b_pwc_closed_fwd_saved(_ptr(h0), _ptr(hks), _ptr(signals), float(dt), B, K, N, d, _ptr(U), _ptr(state), nbytes,
+                                              _stream())
+            if rc == _lib.C3B_EUNSUPPORTED:                  # non-Hermitian Hamiltonians found on the device
+                return pwc_closed(h0, hks, signals, dt), None
+            _lib.check(rc)
+            import ctypes
+            q, cl = ctypes.c_int(0), ctypes.c_int(0)
+            _lib.check(lib.c3b_pwc_closed_saved_chunks(B, K, N, d, ctypes.byref(q), ctypes.byref(cl)))
+        finally:
+            if assert_flag:
+                set_tuning("grad_unitary", -1)
+        sv = SavedForward()
+        sv.state, sv.B, sv.K, sv.N, sv.d, sv.Q, sv.CL = state, B, K, N, d, int(q.value), int(cl.value)
+    return U, sv
+
+
+def pwc_closed_grad_saved(signals, Ubar, saved: SavedForward) -> torch.Tensor:
+    """grad [B,K,N] of a real loss w.r.t. the control fields from the cotangent ``Ubar`` of U and the state of
+    pwc_closed_saving (same signals): no forward pass is repeated."""
+    lib = _lib.load()
+    device = saved.state.device
+    with torch.cuda.device(device):
+        signals = _as(signals, torch.float64, device)
+        if signals.dim() == 2:
+            signals = signals.unsqueeze(0)
+        if tuple(signals.shape) != (saved.B, saved.K, saved.N):
+            raise ValueError(f"C3:ERROR: signals have shape {tuple(signals.shape)}, the saved forward pass had {(saved.B, saved.K, saved.N)}")
+        Ubar = _as(Ubar, torch.complex128, device)
+        if tuple(Ubar.shape) != (saved.B, saved.d, saved.d):
+            raise ValueError(f"C3:ERROR: Ubar has shape {tuple(Ubar.shape)}, expected {(saved.B, saved.d, saved.d)}")
+        grad = torch.empty((saved.B, saved.K, saved.N), dtype=torch.float64, device=device)
+        # the shape was served by a fused kernel in the forward call; keep the library's choice the same here
+        set_flag = _tuning_value("grad_unitary") == -1
+        if set_flag:
+            set_tuning("grad_unitary", 1)
+        try:
+            _lib.check(lib.c3b_pwc_closed_bwd_saved(_ptr(signals), saved.B, saved.K, saved.N, saved.d, saved.Q, saved.CL, _ptr(Ubar),
+                                                    _ptr(grad), _ptr(saved.state), saved.state.numel(), _stream()))
+        finally:
+            if set_flag:
+                set_tuning("grad_unitary", -1)
+    return grad
 
 
 def pwc_lindblad_grad(h0, hks, col_ops, signals, dt: float, Ubar, max_workspace_bytes: int = 6 << 30, device=None):

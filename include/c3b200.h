@@ -132,6 +132,21 @@ int c3b_pwc_closed_grad(const void* h0, const void* hks, const double* signals, 
                         const void* Ubar, double* grad_out, void* U_out, int chunk, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* The same gradient as two calls, for an autograd node (forward now, backward when the cotangent arrives) -- available where
+ * the fused kernels are (closed d = 7..9 and 16 < d <= 32, Hermitian h0 / hks; c3b_pwc_closed_saved_bytes returns 0 elsewhere
+ * and c3b_pwc_closed_fwd_saved returns C3B_EUNSUPPORTED for non-Hermitian Hamiltonians: use c3b_pwc_closed_grad then):
+ *   c3b_pwc_closed_fwd_saved   U_out [B,d,d]; leaves the model, the chunk products and their prefix products in `state`
+ *                              (caller-owned device buffer of c3b_pwc_closed_saved_bytes bytes, untouched until the backward call)
+ *   c3b_pwc_closed_saved_chunks  the chunking (Q chunks of CL slices) the forward call used for this shape and tuning
+ *   c3b_pwc_closed_bwd_saved   grad_out [B,K,N] from Ubar [B,d,d], the same signals and the state: no forward pass is repeated
+ * forward + backward = 3.0 + 1.0 forward passes' worth of work instead of 1.0 + 4.0 through c3b_pwc_closed + c3b_pwc_closed_grad. */
+size_t c3b_pwc_closed_saved_bytes(int B, int K, int N, int d);
+int c3b_pwc_closed_saved_chunks(int B, int K, int N, int d, int* Q_out, int* CL_out);
+int c3b_pwc_closed_fwd_saved(const void* h0, const void* hks, const double* signals, double dt, int B, int K, int N, int d, void* U_out,
+                             void* state, size_t state_bytes, void* stream);
+int c3b_pwc_closed_bwd_saved(const double* signals, int B, int K, int N, int d, int Q, int CL, const void* Ubar, double* grad_out,
+                             void* state, size_t state_bytes, void* stream);
+
 /* Gate infidelities straight from a batch of propagators: every goal function
  * of c3/libraries/fidelities.py on a single gate is a function of the gathered overlap
  *     t[b] = sum_{I,J} U[b, sel[I], sel[J]] * conj(ideal[I,J])

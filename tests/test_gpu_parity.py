@@ -712,6 +712,36 @@ def test_gradient_fused_cta_kernel(eng, d, K, B, N, scale):
         assert rel_fro(g.cpu().numpy(), g_ref) < 1e-8
 
 
+@pytest.mark.parametrize("d,K,B,N", [(9, 2, 3, 61), (27, 3, 2, 29), (9, 2, 1, 7), (5, 2, 2, 11)])
+def test_gradient_forward_saved_backward(eng, d, K, B, N):
+    """Forward that keeps its chunk products + backward from the saved state (c3b_pwc_closed_fwd_saved / _bwd_saved, what the
+    autograd node uses) against the one-call gradient; shapes without a fused kernel and non-Hermitian models return no state."""
+    from c3_b200 import propagation as prop
+    rng = np.random.default_rng(d + N)
+    h0, hks = _rand_model(rng, d, K, 0.9)
+    sig = rng.uniform(-1, 1, size=(B, K, N))
+    Ubar = rng.normal(size=(B, d, d)) + 1j * rng.normal(size=(B, d, d))
+    U_ref, g_ref = eng.pwc_closed_grad(h0, hks, sig, 1.0, Ubar)
+    U, saved = eng.pwc_closed_saving(h0, hks, sig, 1.0)
+    assert rel_fro(U.cpu().numpy(), U_ref.cpu().numpy()) < 1e-13
+    if d == 5:
+        assert saved is None
+    else:
+        assert saved is not None and saved.Q * saved.CL >= N
+        g = eng.pwc_closed_grad_saved(sig, Ubar, saved)
+        assert rel_fro(g.cpu().numpy(), g_ref.cpu().numpy()) < 1e-12
+        g2 = eng.pwc_closed_grad_saved(sig, 2.0 * Ubar, saved)            # the state serves any number of cotangents
+        assert rel_fro(g2.cpu().numpy(), 2.0 * g_ref.cpu().numpy()) < 1e-12
+        hn, hkn = _rand_model(rng, d, K, 0.9, hermitian=False)
+        assert eng.pwc_closed_saving(hn, hkn, sig, 1.0)[1] is None
+        assert eng.pwc_closed_saving(torch.as_tensor(hn).cuda(), torch.as_tensor(hkn).cuda(), sig, 1.0)[1] is None   # found on the device
+    # the autograd node takes whichever path exists
+    s_t = torch.tensor(sig, device="cuda", requires_grad=True)
+    Ua = prop.pwc_batch_autograd(h0, hks, s_t, 1.0)
+    (torch.view_as_real(Ua) * torch.view_as_real(torch.as_tensor(Ubar, device="cuda"))).sum().backward()
+    assert rel_fro(s_t.grad.cpu().numpy(), g_ref.cpu().numpy()) < 1e-11
+
+
 def test_gradient_non_hermitian_falls_back(eng):
     """The fused kernel assumes unitary slice propagators; a non-Hermitian 'Hamiltonian' must be detected on the device and
     served by the stored-propagator kernels (same result as forcing them), and the caller's assertion 'grad_unitary' = 0
