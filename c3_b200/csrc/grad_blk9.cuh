@@ -36,7 +36,9 @@ struct Grad9T {
     static constexpr int NBUF = 7;
     // group bases: the residues (mod 8) of the annealed forward layout (Blk9T<true>: 0, 409, 821).  Measured and dropped:
     // the select-based tables (every lane fetches its own block of Y: 4 wavefronts instead of 6) + 6 %, skipping the
-    // operand fetches whose block is still in registers behind run-time flags + 3 %.
+    // operand fetches whose block is still in registers behind run-time flags + 3 %.  A layout searched for THIS kernel's mixed
+    // operand fetch (scratch/conflict_blockmajor.py, mode "grad") gets it from 6 to 5 wavefronts at best, 2.8 % of the
+    // kernel's shared-memory traffic (the kernel runs the MIO pipe at 92 %): not worth a third table set.
     static constexpr int G1 = 569, G2 = 1141, WARP_ELEMS = 1712;
     static_assert(G1 % 8 == 409 % 8 && G2 % 8 == 821 % 8 && WARP_ELEMS % 8 == 0, "bank residues of the searched layout");
     static_assert(G1 >= NBUF * BUF && G2 >= G1 + NBUF * BUF && WARP_ELEMS >= G2 + NBUF * BUF, "layout");

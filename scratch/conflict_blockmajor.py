@@ -21,9 +21,11 @@ def patterns(bi, bj, kord):
         return [(bj, bj), (bi, (bj+1) % 3), ((bj+1) % 3, bj), (bi, (bj+2) % 3), ((bj+2) % 3, bj)]
     if bi != bj:
         k2 = 3 - bi - bj
-        return [(bi, bi), (bj, bj), (bi, k2), (k2, bj)] + ([None] if MODE == "both2" else [])
+        # "grad": the gradient kernel fetches the Y operand of EVERY lane in one instruction (own block off the diagonal,
+        # Y(k1, bi) on it): that mixed pattern is the fifth load class, for all lanes
+        return [(bi, bi), (bj, bj), (bi, k2), (k2, bj)] + ([None] if MODE == "both2" else []) + ([(bi, bj)] if MODE == "grad" else [])
     k1 = (bi + 1 + kord) % 3; k2 = (bi + 2 - kord) % 3
-    if MODE == "both2":
+    if MODE in ("both2", "grad"):
         return [(bi, k1), (bi, bi), (bi, k2), (k2, bj), (k1, bi)]
     return [(bi, k1), (k1, bj), (bi, k2), (k2, bj)]
 
@@ -35,7 +37,7 @@ def cost(st, detail=False):
         g = src // 9
         li = perms[g][src % 9]
         lanes.append((g, li // 3, li % 3, lane < 27, src))
-    npat = 5 if MODE in ("xown", "both2") else 4
+    npat = 5 if MODE in ("xown", "both2", "grad") else 4
     ld = 0
     for pi in range(npat):
         keys = []
